@@ -1,0 +1,392 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+The reference calls `std::tie(en, psi) = dmrg(H, psis, psi0, sweeps, {"Quiet",true,"Weight=",1000.0})`
+(/root/reference/src/dmrg.h:544,563,596) with ITensor's MPO / MPS / Sweeps types.  `dmrg()` below has the same
+argument meaning and return value and forwards to the C ABI (cb200_dmrg); MPS, MPO and Sweeps are thin
+containers of the dense tensors + charge labels that cross that boundary.  No arithmetic happens in Python.
+
+Array convention on the Python side: NumPy arrays indexed A[l, s, r] / W[a, s_out, s_in, a'] (any memory order);
+they are converted to column-major storage right before the call.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ChainB200Error, Index, Tensor, Sweep, MpsC, MpoC, BondStat, ptr, i32ptr
+
+
+class Context:
+    """One device context (cb200_ctx). Fails loudly when the CUDA library / device is unavailable."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = _lib.load(lib_path)
+        h = C.c_void_p()
+        rc = self.lib.cb200_create(C.byref(h), device)
+        if rc != 0:
+            raise ChainB200Error(rc, (self.lib.cb200_last_error(None) or b"").decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise ChainB200Error(rc, (self.lib.cb200_last_error(self.h) or b"").decode())
+
+    @property
+    def backend(self):
+        return self.lib.cb200_backend_name().decode()
+
+    @property
+    def launches(self):
+        return int(self.lib.cb200_launch_count(self.h))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class Sweeps:
+    """itensor::Sweeps: per-sweep maxdim / mindim / cutoff / niter / noise; short lists repeat their last entry."""
+
+    def __init__(self, nsweep, maxdim, cutoff, niter=2, mindim=1, noise=0.0):
+        def ext(x):
+            x = list(x) if isinstance(x, (list, tuple)) else [x]
+            return [x[min(i, len(x) - 1)] for i in range(nsweep)]
+        self.nsweep = nsweep
+        self.maxdim, self.cutoff, self.niter, self.mindim, self.noise = ext(maxdim), ext(cutoff), ext(niter), ext(mindim), ext(noise)
+
+    def to_c(self):
+        arr = (Sweep * self.nsweep)()
+        for i in range(self.nsweep):
+            arr[i].maxdim = int(min(self.maxdim[i], 2 ** 31 - 1))
+            arr[i].mindim = int(self.mindim[i])
+            arr[i].niter = int(self.niter[i])
+            arr[i].cutoff = float(self.cutoff[i])
+            arr[i].noise = float(self.noise[i])
+        return arr
+
+
+class MPS:
+    def __init__(self, sites, link_charges=None, nq=1, center=0):
+        self.sites = [np.asarray(a) for a in sites]
+        n = len(self.sites)
+        if link_charges is None:
+            link_charges = [np.zeros(self.sites[0].shape[0], np.int32)] + [np.zeros(a.shape[2], np.int32) for a in self.sites]
+        self.link_charges = [np.ascontiguousarray(q, dtype=np.int32) for q in link_charges]
+        assert len(self.link_charges) == n + 1
+        self.nq = nq
+        self.center = center
+
+    @property
+    def n(self):
+        return len(self.sites)
+
+    def bond_dims(self):
+        return [a.shape[2] for a in self.sites[:-1]]
+
+    def is_complex(self):
+        return any(np.iscomplexobj(a) for a in self.sites)
+
+    def _to_c(self, keep):
+        dt = np.complex128 if self.is_complex() else np.float64
+        n = self.n
+        ts = (Tensor * n)()
+        ls = (Index * (n + 1))()
+        for j, a in enumerate(self.sites):
+            f = _lib.fcol(a, dt)
+            keep.append(f)
+            ts[j].dtype = 1 if dt is np.complex128 else 0
+            ts[j].rank = 3
+            for k in range(3):
+                ts[j].dims[k] = f.shape[k]
+            ts[j].data = f.ctypes.data
+        for j, q in enumerate(self.link_charges):
+            ls[j].dim = len(q)
+            ls[j].charge = i32ptr(q)
+        keep += [ts, ls]
+        m = MpsC()
+        m.n, m.nq, m.site, m.link, m.ortho_center = n, self.nq, ts, ls, int(self.center or 0)
+        return m
+
+
+class MPO:
+    def __init__(self, sites, link_charges=None, site_charges=None, nq=1):
+        self.sites = [np.asarray(w) for w in sites]
+        n = len(self.sites)
+        d = self.sites[0].shape[1]
+        if link_charges is None:
+            link_charges = [np.zeros(self.sites[0].shape[0], np.int32)] + [np.zeros(w.shape[3], np.int32) for w in self.sites]
+        self.link_charges = [np.ascontiguousarray(q, dtype=np.int32) for q in link_charges]
+        self.site_charges = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
+        self.nq = nq
+        self.d = d
+        assert len(self.link_charges) == n + 1
+
+    @property
+    def n(self):
+        return len(self.sites)
+
+    def is_complex(self):
+        return any(np.iscomplexobj(w) and np.abs(np.imag(w)).max() > 0 for w in self.sites)
+
+    def _to_c(self, keep):
+        dt = np.complex128 if self.is_complex() else np.float64
+        n = self.n
+        ts = (Tensor * n)()
+        ls = (Index * (n + 1))()
+        for j, w in enumerate(self.sites):
+            f = _lib.fcol(np.real(w) if dt is np.float64 else w, dt)
+            keep.append(f)
+            ts[j].dtype = 1 if dt is np.complex128 else 0
+            ts[j].rank = 4
+            for k in range(4):
+                ts[j].dims[k] = f.shape[k]
+            ts[j].data = f.ctypes.data
+        for j, q in enumerate(self.link_charges):
+            ls[j].dim = len(q)
+            ls[j].charge = i32ptr(q)
+        keep += [ts, ls]
+        m = MpoC()
+        m.n, m.nq, m.site, m.link, m.site_charge, m.d = n, self.nq, ts, ls, i32ptr(self.site_charges), self.d
+        return m
+
+
+class DmrgInfo:
+    """What ITensor prints / returns besides (energy, psi): per-bond stats and phase timers."""
+
+    def __init__(self):
+        self.stats = []
+        self.timers = {}
+
+
+def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
+    """(energy, psi) = dmrg(H, psis, psi0, sweeps, {"Weight": weight}) -- same meaning as itensor::dmrg at
+    src/dmrg.h:544: `psis` are the previously found states to be penalised with `weight`."""
+    ctx = ctx or default_context()
+    lib = ctx.lib
+    keep = []
+    Hc = H._to_c(keep)
+    p0 = psi0._to_c(keep)
+    prev = (MpsC * max(len(psis), 1))()
+    for i, p in enumerate(psis):
+        prev[i] = p._to_c(keep)
+    sw = sweeps.to_c()
+    energy = C.c_double()
+    res = C.c_void_p()
+    ctx.check(lib.cb200_dmrg(ctx.h, C.byref(Hc), prev, len(psis), C.byref(p0), sw, sweeps.nsweep, float(weight),
+                             C.byref(energy), C.byref(res)))
+    try:
+        n = lib.cb200_result_nsites(res)
+        cplx = lib.cb200_result_dtype(res) == 1
+        dt = np.complex128 if cplx else np.float64
+        dims = [int(lib.cb200_result_link_dim(res, j)) for j in range(n + 1)]
+        charges = []
+        for j in range(n + 1):
+            q = np.zeros(dims[j], np.int32)
+            ctx.check(lib.cb200_result_link_charges(res, j, i32ptr(q)))
+            charges.append(q)
+        sites = []
+        for j in range(n):
+            a = np.zeros((dims[j], H.d, dims[j + 1]), dtype=dt, order="F")
+            ctx.check(lib.cb200_result_site(res, j, ptr(a)))
+            sites.append(a)
+        if info is not None:
+            ns = lib.cb200_result_nstats(res)
+            arr = (BondStat * max(ns, 1))()
+            ctx.check(lib.cb200_result_stats(res, arr))
+            info.stats = [dict(sweep=arr[i].sweep, bond=arr[i].bond, dir=arr[i].dir, m=arr[i].m, energy=arr[i].energy,
+                               truncerr=arr[i].truncerr) for i in range(ns)]
+            t = (C.c_double * 7)()
+            ctx.check(lib.cb200_result_timers(res, t))
+            info.timers = dict(env=t[0], matvec=t[1], level1=t[2], trunc=t[3], other=t[4], nmatvec=t[5], matvec_flops=t[6])
+    finally:
+        lib.cb200_result_free(res)
+    return energy.value, MPS(sites, charges, nq=H.nq, center=1)
+
+
+class Bond:
+    """One two-site problem resident on the device (cb200_bond): LocalMPO::product, davidson, svdBond, makeL/makeR."""
+
+    def __init__(self, L, W1, W2, R, ql=None, qr=None, qkl=None, qkm=None, qkr=None, site_charges=None, nq=1, ctx=None):
+        self.ctx = ctx or default_context()
+        lib = self.ctx.lib
+        cplx = any(np.iscomplexobj(x) and np.abs(np.imag(x)).max() > 0 for x in (L, W1, W2, R))
+        self.dt = np.complex128 if cplx else np.float64
+        self.cplx = cplx
+        self.Dl, self.kl = L.shape[0], L.shape[1]
+        self.Dr, self.kr = R.shape[0], R.shape[1]
+        self.km, self.d = W1.shape[3], W1.shape[1]
+        self.nq = nq
+        z = lambda n: np.zeros(n, np.int32)
+        self.q = [np.ascontiguousarray(x if x is not None else z(n), dtype=np.int32)
+                  for x, n in ((ql, self.Dl), (qr, self.Dr), (qkl, self.kl), (qkm, self.km), (qkr, self.kr))]
+        self.sq = np.ascontiguousarray(site_charges if site_charges is not None else z(self.d), dtype=np.int32)
+        idx = [Index(len(q), i32ptr(q)) for q in self.q]
+        conv = lambda a: _lib.fcol(a if cplx else np.real(a), self.dt)
+        arrs = [conv(L), conv(W1), conv(W2), conv(R)]
+        h = C.c_void_p()
+        self.ctx.check(lib.cb200_bond_create(self.ctx.h, 1 if cplx else 0, nq, self.d, i32ptr(self.sq), C.byref(idx[0]), C.byref(idx[1]),
+                                             C.byref(idx[2]), C.byref(idx[3]), C.byref(idx[4]), ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]),
+                                             ptr(arrs[3]), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.cb200_bond_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def matvec_flops(self):
+        return float(self.ctx.lib.cb200_bond_matvec_flops(self.h))
+
+    def _phi(self, phi):
+        return _lib.fcol(phi, self.dt)
+
+    def set_penalty(self, vecs, weight):
+        arrs = [self._phi(o) for o in vecs]
+        ps = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        self.ctx.check(self.ctx.lib.cb200_bond_set_penalty(self.h, len(arrs), ps, float(weight)))
+
+    def apply(self, phi):
+        x = self._phi(phi)
+        y = np.zeros_like(x, order="F")
+        self.ctx.check(self.ctx.lib.cb200_bond_apply(self.h, ptr(x), ptr(y)))
+        return y
+
+    def apply_timed(self, phi, reps=5, warmup=3):
+        x = self._phi(phi)
+        ms = C.c_double()
+        self.ctx.check(self.ctx.lib.cb200_bond_apply_timed(self.h, ptr(x), reps, warmup, C.byref(ms)))
+        return ms.value
+
+    def davidson(self, phi, niter=2):
+        x = self._phi(phi).copy(order="F")
+        ev, nmv = C.c_double(), C.c_int32()
+        self.ctx.check(self.ctx.lib.cb200_bond_davidson(self.h, ptr(x), niter, C.byref(ev), C.byref(nmv)))
+        return ev.value, x, nmv.value
+
+    def truncate(self, phi, direction, maxdim, cutoff, mindim=1):
+        """direction 'left' (Fromleft) or 'right'. Returns A, B, charges_mid, spectrum, truncerr."""
+        x = self._phi(phi)
+        d = 0 if direction == "left" else 1
+        cap = min(self.Dl * self.d, self.d * self.Dr)
+        m = C.c_int32()
+        qm = np.zeros(cap, np.int32)
+        terr = C.c_double()
+        spec = np.zeros(cap)
+        lib = self.ctx.lib
+        self.ctx.check(lib.cb200_bond_truncate(self.h, ptr(x), d, int(min(maxdim, 2 ** 31 - 1)), mindim, float(cutoff), C.byref(m), i32ptr(qm),
+                                               C.byref(terr), spec.ctypes.data_as(C.POINTER(C.c_double)), None, None))
+        mm = m.value
+        A = np.zeros((self.Dl, self.d, mm), dtype=self.dt, order="F")
+        B = np.zeros((mm, self.d, self.Dr), dtype=self.dt, order="F")
+        self.ctx.check(lib.cb200_bond_truncate(self.h, ptr(x), d, int(min(maxdim, 2 ** 31 - 1)), mindim, float(cutoff), C.byref(m), i32ptr(qm),
+                                               C.byref(terr), spec.ctypes.data_as(C.POINTER(C.c_double)), ptr(A), ptr(B)))
+        return A, B, qm[:mm].copy(), spec[:mm].copy(), terr.value
+
+    def env_update(self, direction, T, charges_mid=None):
+        """makeL ('left', T = A[Dl,d,m]) or makeR ('right', T = B[m,d,Dr]); returns the new environment [m, km, m]."""
+        d = 0 if direction == "left" else 1
+        m = T.shape[2] if d == 0 else T.shape[0]
+        qm = np.ascontiguousarray(charges_mid if charges_mid is not None else np.zeros(m), dtype=np.int32)
+        t = _lib.fcol(T, self.dt)
+        out = np.zeros((m, self.km, m), dtype=self.dt, order="F")
+        self.ctx.check(self.ctx.lib.cb200_bond_env_update(self.h, d, m, i32ptr(qm), ptr(t), ptr(out)))
+        return out
+
+
+# ---- kernel-level helpers (unit tests / calibration) -------------------------------------------------------------
+def k_gemm(A, B, C0, M, N, Ks, a_offs, b_offs, lda, ldb, c_off, ldc, trans_a=False, trans_b=False, conj_a=False,
+           accumulate=False, reps=0, ctx=None):
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(A) or np.iscomplexobj(B)
+    dt = np.complex128 if cplx else np.float64
+    a = np.ascontiguousarray(A, dtype=dt).ravel()
+    b = np.ascontiguousarray(B, dtype=dt).ravel()
+    c = np.ascontiguousarray(C0, dtype=dt).ravel().copy()
+    K = np.ascontiguousarray(Ks, dtype=np.int32)
+    ao = np.ascontiguousarray(a_offs, dtype=np.int64)
+    bo = np.ascontiguousarray(b_offs, dtype=np.int64)
+    ms = C.c_double()
+    ctx.check(ctx.lib.cb200_k_gemm(ctx.h, 1 if cplx else 0, int(trans_a), int(trans_b), int(conj_a), int(accumulate), M, N, len(K),
+                                   i32ptr(K), ptr(a), a.size, ao.ctypes.data_as(C.POINTER(C.c_int64)), lda, ptr(b), b.size,
+                                   bo.ctypes.data_as(C.POINTER(C.c_int64)), ldb, ptr(c), c.size, c_off, ldc, reps, C.byref(ms)))
+    return c, ms.value
+
+
+def k_jacobi_eig(G, tol=1e-14, ctx=None):
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(G)
+    dt = np.complex128 if cplx else np.float64
+    g = np.ascontiguousarray(np.asarray(G, dtype=dt).transpose(0, 2, 1))   # each matrix column-major
+    q = np.zeros_like(g)
+    rot = C.c_int64()
+    ctx.check(ctx.lib.cb200_k_jacobi_eig(ctx.h, 1 if cplx else 0, g.shape[0], ptr(g), ptr(q), tol, C.byref(rot)))
+    return q.transpose(0, 2, 1), rot.value
+
+
+def k_svd(X, ctx=None):
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(X)
+    dt = np.complex128 if cplx else np.float64
+    rows, cols = X.shape
+    x = _lib.fcol(X, dt).copy(order="F")
+    v = np.zeros((cols, cols), dtype=dt, order="F")
+    w = np.zeros(cols)
+    sw = C.c_int32()
+    ctx.check(ctx.lib.cb200_k_svd(ctx.h, 1 if cplx else 0, rows, cols, ptr(x), ptr(v), w.ctypes.data_as(C.POINTER(C.c_double)), C.byref(sw)))
+    return x, v, w, sw.value
+
+
+def k_dots(xs, y, ctx=None):
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(xs) or np.iscomplexobj(y)
+    dt = np.complex128 if cplx else np.float64
+    x = np.ascontiguousarray(xs, dtype=dt)
+    yy = np.ascontiguousarray(y, dtype=dt)
+    out = np.zeros(2 * x.shape[0])
+    ctx.check(ctx.lib.cb200_k_dots(ctx.h, 1 if cplx else 0, x.shape[0], x.shape[1], ptr(x), ptr(yy), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out[0::2] + 1j * out[1::2] if cplx else out[0::2]
+
+
+def k_lincomb(xs, coefs, dst, beta=0.0, ctx=None):
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(xs) or np.iscomplexobj(dst)
+    dt = np.complex128 if cplx else np.float64
+    x = np.ascontiguousarray(xs, dtype=dt)
+    d = np.ascontiguousarray(dst, dtype=dt).copy()
+    c = np.zeros(2 * x.shape[0])
+    c[0::2] = np.real(coefs)
+    c[1::2] = np.imag(coefs)
+    ctx.check(ctx.lib.cb200_k_lincomb(ctx.h, 1 if cplx else 0, x.shape[0], x.shape[1], ptr(x), c.ctypes.data_as(C.POINTER(C.c_double)),
+                                      float(np.real(beta)), float(np.imag(beta)), ptr(d)))
+    return d
+
+
+def k_gemm_peak(n=8192, reps=5, cplx=False, ctx=None):
+    ctx = ctx or default_context()
+    tf = C.c_double()
+    ctx.check(ctx.lib.cb200_k_gemm_peak(ctx.h, 1 if cplx else 0, n, reps, C.byref(tf)))
+    return tf.value

@@ -1,0 +1,68 @@
+// Device backend interface used by the host-side DMRG engine (engine.cpp).
+//
+// The product library implements it in backend_cuda.cu (sm_100a kernels, one CUDA stream per context).
+// tests/hostemu/backend_emu.cpp implements the same interface with serial CPU loops so that the engine's
+// host logic (block bookkeeping, task-list generation, schedules) can be unit-tested in the GPU-less
+// container; that file is never linked into libchain_b200.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include "tasks.h"
+
+namespace cb200 {
+
+constexpr int MAX_LC = 8;       // max vectors in one multi-dot / linear combination
+constexpr int JB = 32;          // Jacobi block width (columns); inner eigenproblems are 2*JB x 2*JB
+
+struct Backend;                 // opaque per-context state (stream, scratch)
+
+Backend* backend_create(int device, char* err, size_t errlen);
+void backend_destroy(Backend*);
+const char* backend_name();
+int backend_device(Backend*);
+
+void* dev_alloc(Backend*, size_t bytes);              // returns nullptr on failure
+void dev_free(Backend*, void* p);
+void dev_memset0(Backend*, void* p, size_t bytes);
+void dev_h2d(Backend*, void* dst, const void* src, size_t bytes);
+void dev_d2h(Backend*, void* dst, const void* src, size_t bytes);   // synchronises the stream
+void dev_d2d(Backend*, void* dst, const void* src, size_t bytes);
+void dev_sync(Backend*);
+const char* dev_last_error(Backend*);                 // nullptr if no error since last call
+uint64_t dev_launch_count(Backend*);                  // kernels launched so far (for bench's gpu_launches)
+void dev_event_record(Backend*, int slot);            // timing helpers (CUDA events on the context stream)
+float dev_event_elapsed_ms(Backend*, int slot0, int slot1);
+
+// Grouped segment-accumulating GEMM (tasks.h). All tasks of a launch share the transpose flags.
+// narrow = true selects the 64-column tile (tasks must then be tiled with gemm_tile_n(cplx, true)).
+void launch_gemm(Backend*, bool cplx, bool transA, bool transB, bool narrow, const void* A, const void* B, void* C,
+                 const GemmTask* d_tasks, int ntasks, const GemmSeg* d_segs, int total_tiles);
+int gemm_tile_m(bool cplx);
+int gemm_tile_n(bool cplx, bool narrow);
+
+// Sparse MPO "mix" between the GEMM stages.
+void launch_mix(Backend*, bool cplx, const void* in, void* out, const MixPanel* d_panels, int npanels,
+                const MixOut* d_outs, const MixEntry* d_entries, int total_blocks);
+int mix_rows_per_block();
+
+// Strided 3-D copies (permutes, gathers, conj-transposes).
+void launch_copy(Backend*, bool cplx, const void* src, void* dst, const CopyTask* d_tasks, int ntasks, int total_blocks);
+int copy_elems_per_block();
+
+// Level-1: out[j] = sum_i conj(x_j[i]) * y[i], j < nv.  Result (nv complex pairs re,im; im=0 for real) is
+// returned to the host (deterministic two-phase reduction, synchronises).
+void multi_dot(Backend*, bool cplx, int nv, const void* const* x, const void* y, int64_t n, double* out_re_im);
+// dst = beta*dst + sum_j c_j x_j   (c, beta complex given as re,im; imaginary parts ignored for real data)
+void lincomb(Backend*, bool cplx, int nv, const void* const* x, const double* c_re_im, double beta_re, double beta_im,
+             void* dst, int64_t n);
+
+// Jacobi building blocks. G: npairs Hermitian (2JB x 2JB, column-major, ld 2JB) Gram matrices; on exit Q holds
+// the unitary eigenvector matrices.  *d_rot (device int64) is incremented by the number of rotations applied.
+// Columns whose squared norm (diagonal of G) is <= floor2 are treated as numerically zero and never rotated.
+void launch_jacobi_eig(Backend*, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, long long* d_rot);
+// colnorm2[j] = sum_i |X[i + j*ld]|^2
+void launch_colnorm2(Backend*, bool cplx, const void* X, int64_t ld, int64_t rows, int64_t cols, double* d_out);
+// X (n x n, ld) = identity
+void launch_set_identity(Backend*, bool cplx, void* X, int64_t ld, int64_t n);
+
+}  // namespace cb200

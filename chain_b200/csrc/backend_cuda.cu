@@ -1,0 +1,582 @@
+// CUDA (sm_100a) implementation of backend.h: the kernels of the Chain DMRG hot path.
+//   * grouped DMMA GEMM            -> gemm.cuh            (H_eff stages, environment update, rho/Gram, projections)
+//   * mix_kernel                   -> sparse W (x) W application between the GEMM stages (HBM/L2-bandwidth bound)
+//   * copy_kernel                  -> strided permutes / gathers
+//   * dot_partial/dot_final, lincomb_kernel -> Davidson orthogonalisation + penalty projectors, Krylov basis resident in HBM
+//   * jacobi_eig_kernel            -> 2JB x 2JB Hermitian eigensolver in shared memory (block one-sided Jacobi SVD)
+// There is no CPU fallback here: every entry point launches a kernel or reports a CUDA error.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include "backend.h"
+#include "gemm.cuh"
+
+namespace cb200 {
+
+struct Backend {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double* d_partial = nullptr;   // multi_dot partials
+  double* d_dot_out = nullptr;
+  double* h_dot_out = nullptr;   // pinned
+  uint64_t launches = 0;
+  std::string err;
+  bool has_err = false;
+  cudaEvent_t ev[8] = {};
+};
+
+static constexpr int DOT_BLOCKS = 592;   // 4 x 148 SMs
+static constexpr int DOT_THREADS = 256;
+
+static void set_err(Backend* b, const char* what, cudaError_t e) {
+  if (!b->has_err) {
+    b->err = std::string(what) + ": " + cudaGetErrorString(e);
+    b->has_err = true;
+  }
+}
+#define CB_CHECK(b, call)                                   \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) set_err((b), #call, e_);         \
+  } while (0)
+#define CB_LAUNCH_CHECK(b, name)                            \
+  do {                                                      \
+    (b)->launches++;                                        \
+    cudaError_t e_ = cudaGetLastError();                    \
+    if (e_ != cudaSuccess) set_err((b), name, e_);          \
+  } while (0)
+
+const char* backend_name() { return "cuda-sm_100a"; }
+int backend_device(Backend* b) { return b->device; }
+
+Backend* backend_create(int device, char* err, size_t errlen) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    snprintf(err, errlen, "chain_b200: no CUDA device available (%s); this library has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    snprintf(err, errlen, "chain_b200: device %d out of range (%d devices)", device, ndev);
+    return nullptr;
+  }
+  cudaSetDevice(device);
+  Backend* b = new Backend();
+  b->device = device;
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&b->d_partial, sizeof(double) * 2 * MAX_LC * DOT_BLOCKS) != cudaSuccess ||
+      cudaMalloc(&b->d_dot_out, sizeof(double) * 2 * MAX_LC) != cudaSuccess ||
+      cudaMallocHost(&b->h_dot_out, sizeof(double) * 2 * MAX_LC) != cudaSuccess) {
+    snprintf(err, errlen, "chain_b200: backend init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete b;
+    return nullptr;
+  }
+  for (auto& ev : b->ev) cudaEventCreate(&ev);
+  // opt in to the large dynamic shared memory the GEMM / Jacobi kernels need
+  {
+    auto opt = [](const void* f, int bytes) { cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+#define CB_OPT(C, TA, TB)                                                                           \
+    opt((const void*)gemm_grouped_kernel<C, TA, TB, 128>, GemmCfg<C, 128>::SMEM_BYTES);            \
+    opt((const void*)gemm_grouped_kernel<C, TA, TB, 64>, GemmCfg<C, 64>::SMEM_BYTES);
+    CB_OPT(false, false, false) CB_OPT(false, false, true) CB_OPT(false, true, false) CB_OPT(false, true, true)
+    CB_OPT(true, false, false) CB_OPT(true, false, true) CB_OPT(true, true, false) CB_OPT(true, true, true)
+#undef CB_OPT
+  }
+  cudaGetLastError();
+  return b;
+}
+
+void backend_destroy(Backend* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  for (auto& ev : b->ev) cudaEventDestroy(ev);
+  cudaFree(b->d_partial);
+  cudaFree(b->d_dot_out);
+  cudaFreeHost(b->h_dot_out);
+  cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+void* dev_alloc(Backend* b, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(&p, bytes, b->stream);
+  if (e != cudaSuccess) { set_err(b, "cudaMallocAsync", e); return nullptr; }
+  return p;
+}
+void dev_free(Backend* b, void* p) { if (p) CB_CHECK(b, cudaFreeAsync(p, b->stream)); }
+void dev_memset0(Backend* b, void* p, size_t bytes) { if (bytes) CB_CHECK(b, cudaMemsetAsync(p, 0, bytes, b->stream)); }
+void dev_h2d(Backend* b, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  CB_CHECK(b, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream));
+  CB_CHECK(b, cudaStreamSynchronize(b->stream));   // source may be pageable / short-lived
+}
+void dev_d2h(Backend* b, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  CB_CHECK(b, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->stream));
+  CB_CHECK(b, cudaStreamSynchronize(b->stream));
+}
+void dev_d2d(Backend* b, void* dst, const void* src, size_t bytes) {
+  if (bytes) CB_CHECK(b, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, b->stream));
+}
+void dev_sync(Backend* b) { CB_CHECK(b, cudaStreamSynchronize(b->stream)); }
+const char* dev_last_error(Backend* b) { return b->has_err ? b->err.c_str() : nullptr; }
+uint64_t dev_launch_count(Backend* b) { return b->launches; }
+void dev_event_record(Backend* b, int slot) { CB_CHECK(b, cudaEventRecord(b->ev[slot & 7], b->stream)); }
+float dev_event_elapsed_ms(Backend* b, int s0, int s1) {
+  float ms = 0.f;
+  CB_CHECK(b, cudaEventSynchronize(b->ev[s1 & 7]));
+  CB_CHECK(b, cudaEventElapsedTime(&ms, b->ev[s0 & 7], b->ev[s1 & 7]));
+  return ms;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM
+int gemm_tile_m(bool cplx) { return cplx ? GemmCfg<true>::BM : GemmCfg<false>::BM; }
+int gemm_tile_n(bool, bool narrow) { return narrow ? 64 : 128; }
+
+template <bool CPLX, int BN_>
+static void launch_gemm_t(Backend* b, bool ta, bool tb, const void* A, const void* B, void* C, const GemmTask* t, int nt,
+                          const GemmSeg* s, int tiles) {
+  const int smem = GemmCfg<CPLX, BN_>::SMEM_BYTES;
+  const char* a = (const char*)A;
+  const char* bb = (const char*)B;
+  char* c = (char*)C;
+  if (!ta && !tb) gemm_grouped_kernel<CPLX, false, false, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (!ta && tb) gemm_grouped_kernel<CPLX, false, true, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (ta && !tb) gemm_grouped_kernel<CPLX, true, false, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else gemm_grouped_kernel<CPLX, true, true, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
+}
+
+void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const void* A, const void* B, void* C, const GemmTask* t,
+                 int nt, const GemmSeg* s, int tiles) {
+  if (tiles <= 0 || nt <= 0) return;
+  if (cplx) { if (narrow) launch_gemm_t<true, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<true, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
+  else { if (narrow) launch_gemm_t<false, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<false, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
+  CB_LAUNCH_CHECK(b, "gemm_grouped_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ mix
+static constexpr int MIX_ROWS = 128;
+int mix_rows_per_block() { return MIX_ROWS; }
+
+template <bool CPLX>
+__global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ in_, void* __restrict__ out_,
+                                                       const MixPanel* __restrict__ panels, int npanels,
+                                                       const MixOut* __restrict__ outs, const MixEntry* __restrict__ ents) {
+  int lo = 0, hi = npanels - 1;
+  const int blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (panels[mid].blk_begin <= blk) lo = mid; else hi = mid - 1;
+  }
+  const MixPanel p = panels[lo];
+  const int local = blk - p.blk_begin;
+  const int row = (local % p.row_chunks) * MIX_ROWS + threadIdx.x;
+  const int64_t r = local / p.row_chunks;
+  if (row >= p.rows) return;
+  for (int o = p.out_begin; o < p.out_end; ++o) {
+    const MixOut mo = outs[o];
+    if constexpr (!CPLX) {
+      const double* in = (const double*)in_;
+      double acc = 0.0;
+      for (int e = mo.e_begin; e < mo.e_end; ++e) {
+        const MixEntry me = ents[e];
+        acc = fma(me.cre, __ldg(in + me.in_off + r * me.in_rstride + row), acc);
+      }
+      ((double*)out_)[mo.off + r * mo.rstride + row] = acc;
+    } else {
+      const double2* in = (const double2*)in_;
+      double ar = 0.0, ai = 0.0;
+      for (int e = mo.e_begin; e < mo.e_end; ++e) {
+        const MixEntry me = ents[e];
+        const double2 v = __ldg(in + me.in_off + r * me.in_rstride + row);
+        ar = fma(me.cre, v.x, ar); ar = fma(-me.cim, v.y, ar);
+        ai = fma(me.cre, v.y, ai); ai = fma(me.cim, v.x, ai);
+      }
+      ((double2*)out_)[mo.off + r * mo.rstride + row] = make_double2(ar, ai);
+    }
+  }
+}
+
+void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixOut* o, const MixEntry* e,
+                int blocks) {
+  if (blocks <= 0) return;
+  if (cplx) mix_kernel<true><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, o, e);
+  else mix_kernel<false><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, o, e);
+  CB_LAUNCH_CHECK(b, "mix_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ copy
+static constexpr int COPY_THREADS = 256;
+static constexpr int COPY_PER_BLOCK = 2048;
+int copy_elems_per_block() { return COPY_PER_BLOCK; }
+
+template <bool CPLX>
+__global__ void __launch_bounds__(COPY_THREADS) copy_kernel(const void* __restrict__ src_, void* __restrict__ dst_,
+                                                            const CopyTask* __restrict__ tasks, int ntasks) {
+  int lo = 0, hi = ntasks - 1;
+  const int blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].blk_begin <= blk) lo = mid; else hi = mid - 1;
+  }
+  const CopyTask t = tasks[lo];
+  const int64_t total = (int64_t)t.n0 * t.n1 * t.n2;
+  const int64_t base = (int64_t)(blk - t.blk_begin) * COPY_PER_BLOCK;
+  for (int u = threadIdx.x; u < COPY_PER_BLOCK; u += COPY_THREADS) {
+    const int64_t idx = base + u;
+    if (idx >= total) break;
+    const int64_t i = idx % t.n0;
+    const int64_t jk = idx / t.n0;
+    const int64_t j = jk % t.n1, k = jk / t.n1;
+    const int64_t so = t.src_off + i * t.ss0 + j * t.ss1 + k * t.ss2;
+    const int64_t d_o = t.dst_off + i * t.ds0 + j * t.ds1 + k * t.ds2;
+    if constexpr (!CPLX) {
+      ((double*)dst_)[d_o] = ((const double*)src_)[so];
+    } else {
+      double2 v = ((const double2*)src_)[so];
+      if (t.conj) v.y = -v.y;
+      ((double2*)dst_)[d_o] = v;
+    }
+  }
+}
+
+void launch_copy(Backend* b, bool cplx, const void* src, void* dst, const CopyTask* t, int nt, int blocks) {
+  if (blocks <= 0) return;
+  if (cplx) copy_kernel<true><<<blocks, COPY_THREADS, 0, b->stream>>>(src, dst, t, nt);
+  else copy_kernel<false><<<blocks, COPY_THREADS, 0, b->stream>>>(src, dst, t, nt);
+  CB_LAUNCH_CHECK(b, "copy_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ level 1
+struct PtrPack { const void* p[MAX_LC]; };
+struct CoefPack { double re[MAX_LC], im[MAX_LC]; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// partial[(2*j+c)*DOT_BLOCKS + blk] = block-local sum; fixed traversal order => bitwise reproducible
+template <bool CPLX, int NV>
+__global__ void __launch_bounds__(DOT_THREADS) dot_partial_kernel(PtrPack xs, const void* __restrict__ y_, int64_t n,
+                                                                  double* __restrict__ partial) {
+  double sr[NV], si[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) { sr[j] = 0.0; si[j] = 0.0; }
+  const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n; i += stride) {
+    if constexpr (!CPLX) {
+      const double yv = ((const double*)y_)[i];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) sr[j] = fma(((const double*)xs.p[j])[i], yv, sr[j]);
+    } else {
+      const double2 yv = ((const double2*)y_)[i];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double2 xv = ((const double2*)xs.p[j])[i];
+        sr[j] = fma(xv.x, yv.x, sr[j]); sr[j] = fma(xv.y, yv.y, sr[j]);
+        si[j] = fma(xv.x, yv.y, si[j]); si[j] = fma(-xv.y, yv.x, si[j]);
+      }
+    }
+  }
+  __shared__ double red[2 * MAX_LC][DOT_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double a = warp_sum(sr[j]);
+    double c = warp_sum(si[j]);
+    if (lane == 0) { red[2 * j][w] = a; red[2 * j + 1][w] = c; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DOT_THREADS / 32; ++k) s += red[threadIdx.x][k];
+    partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void dot_final_kernel(const double* __restrict__ partial, int nblocks, int nout, double* __restrict__ out) {
+  // one warp per output, fixed-order tree => deterministic
+  const int o = blockIdx.x;
+  if (o >= nout) return;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) s += partial[(int64_t)o * nblocks + i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) out[o] = s;
+}
+
+template <bool CPLX>
+static void dot_dispatch(Backend* b, int nv, const PtrPack& xs, const void* y, int64_t n, int blocks) {
+  switch (nv) {
+#define CASE(N) case N: dot_partial_kernel<CPLX, N><<<blocks, DOT_THREADS, 0, b->stream>>>(xs, y, n, b->d_partial); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+}
+
+void multi_dot(Backend* b, bool cplx, int nv, const void* const* x, const void* y, int64_t n, double* out) {
+  if (nv <= 0) return;
+  if (nv > MAX_LC) { set_err(b, "multi_dot: too many vectors", cudaErrorInvalidValue); return; }
+  PtrPack xs{};
+  for (int j = 0; j < nv; ++j) xs.p[j] = x[j];
+  int blocks = (int)((n + DOT_THREADS * 4 - 1) / (DOT_THREADS * 4));
+  if (blocks > DOT_BLOCKS) blocks = DOT_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  if (cplx) dot_dispatch<true>(b, nv, xs, y, n, blocks); else dot_dispatch<false>(b, nv, xs, y, n, blocks);
+  CB_LAUNCH_CHECK(b, "dot_partial_kernel");
+  dot_final_kernel<<<2 * nv, 32, 0, b->stream>>>(b->d_partial, blocks, 2 * nv, b->d_dot_out);
+  CB_LAUNCH_CHECK(b, "dot_final_kernel");
+  CB_CHECK(b, cudaMemcpyAsync(b->h_dot_out, b->d_dot_out, sizeof(double) * 2 * nv, cudaMemcpyDeviceToHost, b->stream));
+  CB_CHECK(b, cudaStreamSynchronize(b->stream));
+  for (int j = 0; j < 2 * nv; ++j) out[j] = b->h_dot_out[j];
+  if (!cplx) for (int j = 0; j < nv; ++j) out[2 * j + 1] = 0.0;
+}
+
+template <bool CPLX, int NV>
+__global__ void __launch_bounds__(256) lincomb_kernel(PtrPack xs, CoefPack c, double br, double bi, void* __restrict__ dst_, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool has_beta = (br != 0.0) || (bi != 0.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if constexpr (!CPLX) {
+      double acc = has_beta ? br * ((double*)dst_)[i] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc = fma(c.re[j], ((const double*)xs.p[j])[i], acc);
+      ((double*)dst_)[i] = acc;
+    } else {
+      double ar = 0.0, ai = 0.0;
+      if (has_beta) {
+        const double2 d = ((double2*)dst_)[i];
+        ar = br * d.x - bi * d.y; ai = br * d.y + bi * d.x;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const double2 v = ((const double2*)xs.p[j])[i];
+        ar = fma(c.re[j], v.x, ar); ar = fma(-c.im[j], v.y, ar);
+        ai = fma(c.re[j], v.y, ai); ai = fma(c.im[j], v.x, ai);
+      }
+      ((double2*)dst_)[i] = make_double2(ar, ai);
+    }
+  }
+}
+
+void lincomb(Backend* b, bool cplx, int nv, const void* const* x, const double* c, double br, double bi, void* dst, int64_t n) {
+  if (n <= 0) return;
+  if (nv > MAX_LC || nv < 1) { set_err(b, "lincomb: bad vector count", cudaErrorInvalidValue); return; }
+  PtrPack xs{};
+  CoefPack cp{};
+  for (int j = 0; j < nv; ++j) { xs.p[j] = x[j]; cp.re[j] = c[2 * j]; cp.im[j] = c[2 * j + 1]; }
+  int blocks = (int)((n + 256 * 4 - 1) / (256 * 4));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+#define CASE(N) case N: if (cplx) lincomb_kernel<true, N><<<blocks, 256, 0, b->stream>>>(xs, cp, br, bi, dst, n); \
+                        else lincomb_kernel<false, N><<<blocks, 256, 0, b->stream>>>(xs, cp, br, bi, dst, n); break;
+  switch (nv) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
+#undef CASE
+  CB_LAUNCH_CHECK(b, "lincomb_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ Jacobi
+// Cyclic two-sided Jacobi on an NJ x NJ Hermitian matrix held in shared memory, round-robin parallel ordering
+// (NJ/2 disjoint rotations per step).  Used as the inner solver of the block one-sided Jacobi SVD that replaces
+// ITensor's diagHermitian(rho) (LAPACK dsyev/zheev) in MPS::svdBond.
+static constexpr int NJ = 2 * JB;
+static constexpr int LDJ = NJ + 1;
+static constexpr int JAC_THREADS = 256;
+static constexpr int JAC_MAX_SWEEPS = 60;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __restrict__ G_, void* __restrict__ Q_, double tol, double floor2,
+                                                                 unsigned long long* __restrict__ rot_total) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  extern __shared__ __align__(16) char jsm[];
+  T* G = reinterpret_cast<T*>(jsm);
+  T* Q = G + NJ * LDJ;
+  __shared__ double rc[NJ / 2], rs[NJ / 2], rer[NJ / 2], rei[NJ / 2];
+  __shared__ int rp[NJ / 2], rq[NJ / 2];
+  __shared__ int sweep_rot;
+  const int tid = threadIdx.x;
+  const T* Gg = reinterpret_cast<const T*>(G_) + (size_t)blockIdx.x * NJ * NJ;
+  T* Qg = reinterpret_cast<T*>(Q_) + (size_t)blockIdx.x * NJ * NJ;
+
+  // load the upper triangle and mirror it so that G is exactly Hermitian
+  for (int idx = tid; idx < NJ * NJ; idx += JAC_THREADS) {
+    const int r = idx % NJ, c = idx / NJ;
+    T v;
+    if (r <= c) v = Gg[r + c * NJ];
+    else {
+      v = Gg[c + r * NJ];
+      if constexpr (CPLX) v.y = -v.y;
+    }
+    if constexpr (CPLX) { if (r == c) v.y = 0.0; }
+    G[r + c * LDJ] = v;
+    T one;
+    if constexpr (CPLX) one = make_double2(r == c ? 1.0 : 0.0, 0.0); else one = (r == c ? 1.0 : 0.0);
+    Q[r + c * LDJ] = one;
+  }
+  __syncthreads();
+
+  const double tol2 = tol * tol;
+  unsigned long long my_total = 0;
+  for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+    if (tid == 0) sweep_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < NJ - 1; ++step) {
+      // ---- rotation parameters for the NJ/2 disjoint pairs of this step
+      if (tid < NJ / 2) {
+        int p, q;
+        if (tid == 0) { p = step; q = NJ - 1; }
+        else { p = (step + tid) % (NJ - 1); q = (step - tid + (NJ - 1)) % (NJ - 1); }
+        if (p > q) { int t_ = p; p = q; q = t_; }
+        double gpp, gqq, gr, gi;
+        if constexpr (CPLX) { gpp = G[p + p * LDJ].x; gqq = G[q + q * LDJ].x; gr = G[p + q * LDJ].x; gi = G[p + q * LDJ].y; }
+        else { gpp = G[p + p * LDJ]; gqq = G[q + q * LDJ]; gr = G[p + q * LDJ]; gi = 0.0; }
+        const double g2 = gr * gr + gi * gi;
+        double c = 1.0, s = 0.0, er = 1.0, ei = 0.0;
+        if (g2 > tol2 * fabs(gpp * gqq) && g2 > 0.0 && gpp > floor2 && gqq > floor2) {
+          const double ag = sqrt(g2);
+          er = gr / ag; ei = gi / ag;
+          const double tau = (gqq - gpp) / (2.0 * ag);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+          atomicAdd(&sweep_rot, 1);
+        }
+        rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = s; rer[tid] = er; rei[tid] = ei;
+      }
+      __syncthreads();
+      // ---- column phase: G <- G J, Q <- Q J   (J[p,p]=J[q,q]=c, J[p,q]=s e^{i th}, J[q,p]=-s e^{-i th})
+      for (int idx = tid; idx < (NJ / 2) * NJ; idx += JAC_THREADS) {
+        const int k = idx / NJ, r = idx % NJ;
+        const double s = rs[k];
+        if (s == 0.0) continue;
+        const double c = rc[k], er = rer[k], ei = rei[k];
+        const int p = rp[k], q = rq[k];
+        if constexpr (!CPLX) {
+          const double sg = s * er;   // er = +-1
+          double a = G[r + p * LDJ], b = G[r + q * LDJ];
+          G[r + p * LDJ] = c * a - sg * b; G[r + q * LDJ] = sg * a + c * b;
+          a = Q[r + p * LDJ]; b = Q[r + q * LDJ];
+          Q[r + p * LDJ] = c * a - sg * b; Q[r + q * LDJ] = sg * a + c * b;
+        } else {
+          // new_p = c a - s e^{-i th} b ; new_q = s e^{i th} a + c b
+          const double sr = s * er, si = s * ei;
+          double2 a = G[r + p * LDJ], b = G[r + q * LDJ];
+          G[r + p * LDJ] = make_double2(c * a.x - (sr * b.x + si * b.y), c * a.y - (sr * b.y - si * b.x));
+          G[r + q * LDJ] = make_double2((sr * a.x - si * a.y) + c * b.x, (sr * a.y + si * a.x) + c * b.y);
+          a = Q[r + p * LDJ]; b = Q[r + q * LDJ];
+          Q[r + p * LDJ] = make_double2(c * a.x - (sr * b.x + si * b.y), c * a.y - (sr * b.y - si * b.x));
+          Q[r + q * LDJ] = make_double2((sr * a.x - si * a.y) + c * b.x, (sr * a.y + si * a.x) + c * b.y);
+        }
+      }
+      __syncthreads();
+      // ---- row phase: G <- J^H G   (row_p' = c row_p - s e^{i th} row_q ; row_q' = s e^{-i th} row_p + c row_q)
+      for (int idx = tid; idx < (NJ / 2) * NJ; idx += JAC_THREADS) {
+        const int k = idx / NJ, cc = idx % NJ;
+        const double s = rs[k];
+        if (s == 0.0) continue;
+        const double c = rc[k], er = rer[k], ei = rei[k];
+        const int p = rp[k], q = rq[k];
+        if constexpr (!CPLX) {
+          const double sg = s * er;
+          const double a = G[p + cc * LDJ], b = G[q + cc * LDJ];
+          G[p + cc * LDJ] = c * a - sg * b; G[q + cc * LDJ] = sg * a + c * b;
+        } else {
+          const double sr = s * er, si = s * ei;
+          const double2 a = G[p + cc * LDJ], b = G[q + cc * LDJ];
+          G[p + cc * LDJ] = make_double2(c * a.x - (sr * b.x - si * b.y), c * a.y - (sr * b.y + si * b.x));
+          G[q + cc * LDJ] = make_double2((sr * a.x + si * a.y) + c * b.x, (sr * a.y - si * a.x) + c * b.y);
+        }
+      }
+      __syncthreads();
+      // ---- clean the annihilated entries
+      if (tid < NJ / 2 && rs[tid] != 0.0) {
+        const int p = rp[tid], q = rq[tid];
+        if constexpr (CPLX) {
+          G[p + q * LDJ] = make_double2(0.0, 0.0); G[q + p * LDJ] = make_double2(0.0, 0.0);
+          G[p + p * LDJ].y = 0.0; G[q + q * LDJ].y = 0.0;
+        } else { G[p + q * LDJ] = 0.0; G[q + p * LDJ] = 0.0; }
+      }
+      __syncthreads();
+    }
+    const int nrot = sweep_rot;
+    my_total += (unsigned long long)nrot;
+    __syncthreads();
+    if (nrot == 0) break;
+  }
+  for (int idx = tid; idx < NJ * NJ; idx += JAC_THREADS) {
+    const int r = idx % NJ, c = idx / NJ;
+    Qg[r + c * NJ] = Q[r + c * LDJ];
+  }
+  if (tid == 0 && my_total) atomicAdd(rot_total, my_total);
+}
+
+void launch_jacobi_eig(Backend* b, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, long long* d_rot) {
+  if (npairs <= 0) return;
+  const size_t smem = (size_t)2 * NJ * LDJ * (cplx ? 16 : 8);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(jacobi_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NJ * LDJ * 16);
+    cudaFuncSetAttribute(jacobi_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NJ * LDJ * 8);
+    attr_done = true;
+  }
+  if (cplx) jacobi_eig_kernel<true><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, (unsigned long long*)d_rot);
+  else jacobi_eig_kernel<false><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, (unsigned long long*)d_rot);
+  CB_LAUNCH_CHECK(b, "jacobi_eig_kernel");
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) colnorm2_kernel(const void* __restrict__ X_, int64_t ld, int64_t rows, double* __restrict__ out) {
+  const int64_t col = blockIdx.x;
+  double s = 0.0;
+  if constexpr (!CPLX) {
+    const double* x = (const double*)X_ + col * ld;
+    for (int64_t i = threadIdx.x; i < rows; i += 256) s = fma(x[i], x[i], s);
+  } else {
+    const double2* x = (const double2*)X_ + col * ld;
+    for (int64_t i = threadIdx.x; i < rows; i += 256) { const double2 v = x[i]; s = fma(v.x, v.x, s); s = fma(v.y, v.y, s); }
+  }
+  __shared__ double red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    out[col] = t;
+  }
+}
+
+void launch_colnorm2(Backend* b, bool cplx, const void* X, int64_t ld, int64_t rows, int64_t cols, double* d_out) {
+  if (cols <= 0) return;
+  if (cplx) colnorm2_kernel<true><<<(unsigned)cols, 256, 0, b->stream>>>(X, ld, rows, d_out);
+  else colnorm2_kernel<false><<<(unsigned)cols, 256, 0, b->stream>>>(X, ld, rows, d_out);
+  CB_LAUNCH_CHECK(b, "colnorm2_kernel");
+}
+
+template <bool CPLX>
+__global__ void set_identity_kernel(void* X_, int64_t ld, int64_t n) {
+  const int64_t total = n * n;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx % n, c = idx / n;
+    if constexpr (CPLX) ((double2*)X_)[r + c * ld] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    else ((double*)X_)[r + c * ld] = (r == c ? 1.0 : 0.0);
+  }
+}
+
+void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) {
+  if (n <= 0) return;
+  int64_t blocks = (n * n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (cplx) set_identity_kernel<true><<<(unsigned)blocks, 256, 0, b->stream>>>(X, ld, n);
+  else set_identity_kernel<false><<<(unsigned)blocks, 256, 0, b->stream>>>(X, ld, n);
+  CB_LAUNCH_CHECK(b, "set_identity_kernel");
+}
+
+}  // namespace cb200

@@ -1,0 +1,447 @@
+// extern "C" boundary (include/chain_b200.h).  Marshals plain pointers into the engine and turns C++ exceptions
+// into status codes; nothing here touches the CPU for arithmetic.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/chain_b200.h"
+#include "engine.h"
+
+using namespace cb200;
+
+struct cb200_ctx {
+  Ctx c;
+};
+static thread_local std::string g_create_err;
+
+struct cb200_result {
+  std::unique_ptr<DmrgResult> r;
+};
+
+struct cb200_bond {
+  cb200_ctx* ctx = nullptr;
+  bool cplx = false;
+  int nq = 1;
+  SiteInfo S;
+  IndexMap l, r, kl, km, kr;
+  HostW W1, W2;
+  DevEnv L, R;
+  Bond b;
+  std::vector<Buf> pen;
+};
+
+template <class F>
+static int guard(cb200_ctx* ctx, F f) {
+  try {
+    f();
+    const char* e = dev_last_error(ctx->c.be);
+    if (e) { ctx->c.err = e; return CB200_ERR_CUDA; }
+    return CB200_OK;
+  } catch (const EngineError& e) {
+    ctx->c.err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->c.err = std::string("internal error: ") + e.what();
+    return CB200_ERR_INVALID;
+  }
+}
+
+extern "C" {
+
+int cb200_create(cb200_ctx** out, int device) {
+  if (!out) return CB200_ERR_INVALID;
+  *out = nullptr;
+  char err[512] = {0};
+  Backend* be = backend_create(device, err, sizeof(err));
+  if (!be) { g_create_err = err; return CB200_ERR_NO_DEVICE; }
+  cb200_ctx* c = new cb200_ctx();
+  c->c.be = be;
+  *out = c;
+  return CB200_OK;
+}
+void cb200_destroy(cb200_ctx* ctx) {
+  if (!ctx) return;
+  backend_destroy(ctx->c.be);
+  delete ctx;
+}
+const char* cb200_last_error(const cb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+const char* cb200_backend_name(void) { return backend_name(); }
+uint64_t cb200_launch_count(const cb200_ctx* ctx) { return ctx ? dev_launch_count(ctx->c.be) : 0; }
+
+// ---------------------------------------------------------------------------------------------- coarse: dmrg
+static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
+  HostMPS h;
+  h.n = m->n;
+  h.center = m->ortho_center;
+  h.link.resize(m->n + 1);
+  for (int j = 0; j <= m->n; ++j) h.link[j] = IndexMap::from_labels(nq, m->link[j].dim, m->link[j].charge);
+  h.site.resize(m->n);
+  *cplx = false;
+  for (int j = 0; j < m->n; ++j) {
+    const cb200_tensor& t = m->site[j];
+    if (t.rank != 3 || t.dims[0] != m->link[j].dim || t.dims[1] != d || t.dims[2] != m->link[j + 1].dim)
+      fail(CB200_ERR_INVALID, "MPS site tensor " + std::to_string(j) + " has inconsistent dimensions");
+    if (j == 0) *cplx = t.dtype == 1;
+    else if ((t.dtype == 1) != *cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside one MPS");
+    const size_t bytes = (size_t)(t.dtype == 1 ? 16 : 8) * t.dims[0] * t.dims[1] * t.dims[2];
+    h.site[j].assign((const char*)t.data, (const char*)t.data + bytes);
+  }
+  return h;
+}
+
+int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_t nprev, const cb200_mps* psi0,
+               const cb200_sweep* sweeps, int32_t nsweep, double weight, double* energy, cb200_result** out) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (!H || !psi0 || !sweeps || !energy || !out || nsweep < 0 || nprev < 0) fail(CB200_ERR_INVALID, "null argument");
+    MpoIn mi;
+    mi.n = H->n; mi.nq = H->nq; mi.d = H->d; mi.site_charge = H->site_charge;
+    mi.link.resize(H->n + 1);
+    for (int j = 0; j <= H->n; ++j) mi.link[j] = IndexMap::from_labels(H->nq, H->link[j].dim, H->link[j].charge);
+    mi.site.resize(H->n);
+    for (int j = 0; j < H->n; ++j) {
+      const cb200_tensor& t = H->site[j];
+      if (t.rank != 4 || t.dims[0] != H->link[j].dim || t.dims[1] != H->d || t.dims[2] != H->d || t.dims[3] != H->link[j + 1].dim)
+        fail(CB200_ERR_INVALID, "MPO site tensor " + std::to_string(j) + " has inconsistent dimensions");
+      if (j == 0) mi.cplx = t.dtype == 1;
+      else if ((t.dtype == 1) != mi.cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside the MPO");
+      mi.site[j] = t.data;
+    }
+    bool pc = false;
+    HostMPS p0 = to_host_mps(psi0, H->nq, H->d, &pc);
+    std::vector<HostMPS> pv;
+    std::vector<bool> pvc;
+    for (int p = 0; p < nprev; ++p) {
+      bool cx = false;
+      pv.push_back(to_host_mps(&prev[p], H->nq, H->d, &cx));
+      pvc.push_back(cx);
+    }
+    std::vector<SweepParams> sw(nsweep);
+    for (int i = 0; i < nsweep; ++i) sw[i] = {sweeps[i].maxdim, sweeps[i].mindim, sweeps[i].niter, sweeps[i].cutoff, sweeps[i].noise};
+    auto r = run_dmrg(&ctx->c, mi, pv, pvc, p0, pc, sw, weight);
+    *energy = r->energy;
+    cb200_result* res = new cb200_result();
+    res->r = std::move(r);
+    *out = res;
+  });
+}
+
+int32_t cb200_result_nsites(const cb200_result* r) { return r ? r->r->psi.n : 0; }
+int32_t cb200_result_dtype(const cb200_result* r) { return r && r->r->cplx ? 1 : 0; }
+int64_t cb200_result_link_dim(const cb200_result* r, int32_t link) {
+  if (!r || link < 0 || link > r->r->psi.n) return -1;
+  return r->r->psi.link[link].g.total();
+}
+int cb200_result_link_charges(const cb200_result* r, int32_t link, int32_t* out) {
+  if (!r || !out || link < 0 || link > r->r->psi.n) return CB200_ERR_INVALID;
+  const auto& m = r->r->psi.link[link];
+  for (size_t i = 0; i < m.charge_ext.size(); ++i) out[i] = m.charge_ext[i];
+  return CB200_OK;
+}
+int cb200_result_site(const cb200_result* r, int32_t site, void* out) {
+  if (!r || !out || site < 0 || site >= r->r->psi.n) return CB200_ERR_INVALID;
+  const auto& s = r->r->psi.site[site];
+  std::memcpy(out, s.data(), s.size());
+  return CB200_OK;
+}
+int32_t cb200_result_nstats(const cb200_result* r) { return r ? (int32_t)r->r->stats.size() : 0; }
+int cb200_result_stats(const cb200_result* r, cb200_bond_stat* out) {
+  if (!r || !out) return CB200_ERR_INVALID;
+  for (size_t i = 0; i < r->r->stats.size(); ++i) {
+    const BondStat& s = r->r->stats[i];
+    out[i].sweep = s.sweep; out[i].bond = s.bond; out[i].dir = s.dir; out[i].m = s.m;
+    out[i].energy = s.energy; out[i].truncerr = s.truncerr;
+  }
+  return CB200_OK;
+}
+int cb200_result_timers(const cb200_result* r, double* o) {
+  if (!r || !o) return CB200_ERR_INVALID;
+  const Timers& t = r->r->tm;
+  o[0] = t.env; o[1] = t.matvec; o[2] = t.level1; o[3] = t.trunc; o[4] = t.other; o[5] = t.nmatvec; o[6] = t.matvec_flops;
+  return CB200_OK;
+}
+void cb200_result_free(cb200_result* r) { delete r; }
+
+// ---------------------------------------------------------------------------------------------- fine: one bond
+int cb200_bond_create(cb200_ctx* ctx, int32_t dtype, int32_t nq, int32_t d, const int32_t* site_charge, const cb200_index* l,
+                      const cb200_index* r, const cb200_index* kl, const cb200_index* km, const cb200_index* kr, const void* L,
+                      const void* W1, const void* W2, const void* R, cb200_bond** out) {
+  if (!ctx || !out) return CB200_ERR_INVALID;
+  *out = nullptr;
+  cb200_bond* bp = new cb200_bond();
+  int rc = guard(ctx, [&] {
+    cb200_bond& B = *bp;
+    B.ctx = ctx; B.cplx = dtype == 1; B.nq = nq;
+    B.S = SiteInfo::make(nq, d, site_charge);
+    B.l = IndexMap::from_labels(nq, l->dim, l->charge);
+    B.r = IndexMap::from_labels(nq, r->dim, r->charge);
+    B.kl = IndexMap::from_labels(nq, kl->dim, kl->charge);
+    B.km = IndexMap::from_labels(nq, km->dim, km->charge);
+    B.kr = IndexMap::from_labels(nq, kr->dim, kr->charge);
+    B.W1 = import_w(nq, d, B.S, B.kl, B.km, B.cplx, W1);
+    B.W2 = import_w(nq, d, B.S, B.km, B.kr, B.cplx, W2);
+    import_env(&ctx->c, B.cplx, B.l, B.kl, L, B.L);
+    import_env(&ctx->c, B.cplx, B.r, B.kr, R, B.R);
+    Bond& b = B.b;
+    b.ctx = &ctx->c; b.cplx = B.cplx; b.nq = nq; b.S = &B.S;
+    b.Dl = B.l.g; b.Dr = B.r.g; b.Kl = B.kl.g; b.Km = B.km.g; b.Kr = B.kr.g;
+    b.L = B.L.buf.p; b.R = B.R.buf.p; b.W1 = &B.W1; b.W2 = &B.W2;
+    b.plan();
+  });
+  if (rc != CB200_OK) { delete bp; return rc; }
+  *out = bp;
+  return CB200_OK;
+}
+void cb200_bond_free(cb200_bond* b) { delete b; }
+
+int cb200_bond_set_penalty(cb200_bond* B, int32_t nprev, const void* const* o, double weight) {
+  if (!B) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    B->pen.clear();
+    B->b.pen.clear();
+    const size_t es = B->cplx ? 16 : 8;
+    for (int p = 0; p < nprev; ++p) {
+      B->pen.emplace_back(B->ctx->c.be, (int64_t)es * std::max<int64_t>(B->b.philay.total, 1), true);
+      import_phi(&B->ctx->c, B->cplx, B->S, B->l, B->r, B->b.philay, o[p], B->pen.back().p);
+      B->b.pen.push_back(B->pen.back().p);
+    }
+    B->b.weight = weight;
+  });
+}
+int64_t cb200_bond_phi_elems(const cb200_bond* B) { return B ? B->l.g.total() * B->S.d * B->S.d * B->r.g.total() : 0; }
+double cb200_bond_matvec_flops(const cb200_bond* B) { return B ? B->b.flops_alg : 0; }
+
+int cb200_bond_apply(cb200_bond* B, const void* phi, void* out) {
+  if (!B || !phi || !out) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true), y(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    B->b.apply(x.p, y.p);
+    export_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, y.p, out);
+  });
+}
+
+int cb200_bond_apply_timed(cb200_bond* B, const void* phi, int32_t reps, int32_t warmup, double* ms_mean) {
+  if (!B || !phi || !ms_mean || reps < 1) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true), y(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    for (int i = 0; i < warmup; ++i) B->b.apply(x.p, y.p);
+    dev_sync(c->be);
+    dev_event_record(c->be, 0);
+    for (int i = 0; i < reps; ++i) B->b.apply(x.p, y.p);
+    dev_event_record(c->be, 1);
+    *ms_mean = dev_event_elapsed_ms(c->be, 0, 1) / reps;
+  });
+}
+
+int cb200_bond_davidson(cb200_bond* B, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec) {
+  if (!B || !phi || !eigenvalue) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    DavidsonResult dr = davidson(B->b, x.p, niter);
+    *eigenvalue = dr.eigenvalue;
+    if (nmatvec) *nmatvec = dr.nmatvec;
+    export_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, x.p, phi);
+  });
+}
+
+int cb200_bond_truncate(cb200_bond* B, const void* phi, int32_t dir, int32_t maxdim, int32_t mindim, double cutoff, int32_t* m,
+                        int32_t* charges_mid, double* truncerr, double* spectrum, void* A, void* Bout) {
+  if (!B || !phi || !m) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    SplitResult sr = split_bond(c, B->cplx, &B->S, B->b.philay, x.p, dir, maxdim, mindim, cutoff);
+    *m = (int32_t)sr.mid.total();
+    IndexMap mid = IndexMap::from_grading(sr.mid);
+    if (charges_mid)
+      for (int64_t i = 0; i < sr.mid.total(); ++i) charges_mid[i] = mid.charge_ext[i];
+    if (truncerr) *truncerr = sr.truncerr;
+    if (spectrum)
+      for (size_t i = 0; i < sr.spectrum.size(); ++i) spectrum[i] = sr.spectrum[i];
+    if (A) export_site3(c, B->cplx, B->S, B->l, mid, sr.A, A);
+    if (Bout) export_site3(c, B->cplx, B->S, mid, B->r, sr.B, Bout);
+  });
+}
+
+int cb200_bond_env_update(cb200_bond* B, int32_t dir, int32_t m, const int32_t* charges_mid, const void* AorB, void* out) {
+  if (!B || !AorB || !out) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    IndexMap mid = IndexMap::from_labels(B->nq, m, charges_mid);
+    DevSite3 T;
+    DevEnv E;
+    if (dir == 0) {
+      import_site3(c, B->cplx, B->S, B->l, mid, AorB, T);
+      env_update_left(c, B->cplx, &B->S, B->L, T, B->W1, E);
+    } else {
+      import_site3(c, B->cplx, B->S, mid, B->r, AorB, T);
+      env_update_right(c, B->cplx, &B->S, B->R, T, B->W2, E);
+    }
+    export_env(c, B->cplx, mid, B->km, E, out);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------- kernel-level
+int cb200_k_gemm(cb200_ctx* ctx, int32_t dtype, int32_t trans_a, int32_t trans_b, int32_t conj_a, int32_t accumulate, int32_t M,
+                 int32_t N, int32_t nseg, const int32_t* K, const void* A, int64_t a_elems, const int64_t* a_off, int64_t lda,
+                 const void* Bm, int64_t b_elems, const int64_t* b_off, int64_t ldb, void* C, int64_t c_elems, int64_t c_off,
+                 int64_t ldc, int32_t reps, double* ms_mean) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    Buf dA(c->be, (int64_t)es * a_elems), dB(c->be, (int64_t)es * b_elems), dC(c->be, (int64_t)es * c_elems);
+    dev_h2d(c->be, dA.p, A, es * a_elems);
+    dev_h2d(c->be, dB.p, Bm, es * b_elems);
+    dev_h2d(c->be, dC.p, C, es * c_elems);
+    std::vector<GemmTask> tasks(1);
+    std::vector<GemmSeg> segs(nseg);
+    GemmTask& t = tasks[0];
+    t = GemmTask{};
+    t.c_off = c_off; t.c_off2 = c_off; t.ldc = ldc; t.M = M; t.N = N; t.n_split = N;
+    t.seg_begin = 0; t.seg_count = nseg;
+    t.flags = (trans_a ? GEMM_TRANS_A : 0) | (trans_b ? GEMM_TRANS_B : 0) | (conj_a ? GEMM_CONJ_A : 0) | (accumulate ? GEMM_ACCUM : 0);
+    const int tm = gemm_tile_m(cx), tn = gemm_tile_n(cx, false);
+    t.tile_begin = 0; t.tiles_m = (M + tm - 1) / tm;
+    const int tiles = t.tiles_m * ((N + tn - 1) / tn);
+    for (int s = 0; s < nseg; ++s) { segs[s] = GemmSeg{}; segs[s].a_off = a_off[s]; segs[s].b_off = b_off[s]; segs[s].lda = lda; segs[s].ldb = ldb; segs[s].K = K[s]; }
+    DevList<GemmTask> dt; DevList<GemmSeg> dsg;
+    dt.upload(c->be, tasks); dsg.upload(c->be, segs);
+    launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+    dev_d2h(c->be, C, dC.p, es * c_elems);
+    if (reps > 0 && ms_mean) {
+      dev_event_record(c->be, 0);
+      for (int i = 0; i < reps; ++i) launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+      dev_event_record(c->be, 1);
+      *ms_mean = dev_event_elapsed_ms(c->be, 0, 1) / reps;
+    }
+  });
+}
+
+int cb200_k_jacobi_eig(cb200_ctx* ctx, int32_t dtype, int32_t npairs, const void* G, void* Q, double tol, int64_t* rotations) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t bytes = (size_t)(cx ? 16 : 8) * 4 * JB * JB * npairs;
+    Buf dG(c->be, (int64_t)bytes), dQ(c->be, (int64_t)bytes), rot(c->be, 8, true);
+    dev_h2d(c->be, dG.p, G, bytes);
+    launch_jacobi_eig(c->be, cx, dG.p, dQ.p, npairs, tol, 0.0, (long long*)rot.p);
+    dev_d2h(c->be, Q, dQ.p, bytes);
+    long long r = 0;
+    dev_d2h(c->be, &r, rot.p, 8);
+    if (rotations) *rotations = r;
+  });
+}
+
+int cb200_k_svd(cb200_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, void* X, void* V, double* w, int32_t* sweeps) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    Buf dX(c->be, (int64_t)es * std::max<int64_t>(rows * cols, 1));
+    dev_h2d(c->be, dX.p, X, es * rows * cols);
+    JacobiOut jo = jacobi_svd(c, cx, dX.p, rows, cols);
+    // return the `cols` heaviest slots, in descending order of weight
+    std::vector<int64_t> order(jo.w.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int64_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return jo.w[a] > jo.w[b]; });
+    std::vector<char> hx(es * (size_t)jo.ldx * jo.w.size()), hv(es * (size_t)jo.ldv * jo.w.size());
+    dev_d2h(c->be, hx.data(), jo.XV.p, hx.size());
+    dev_d2h(c->be, hv.data(), jo.V.p, hv.size());
+    for (int64_t k = 0; k < cols; ++k) {
+      const int64_t s = order[k];
+      w[k] = jo.w[s];
+      std::memcpy((char*)X + es * (size_t)(k * rows), hx.data() + es * (size_t)(s * jo.ldx), es * (size_t)rows);
+      std::memcpy((char*)V + es * (size_t)(k * cols), hv.data() + es * (size_t)(s * jo.ldv), es * (size_t)cols);
+    }
+    if (sweeps) *sweeps = jo.sweeps;
+  });
+}
+
+int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    Buf dx(c->be, (int64_t)es * n * nv), dy(c->be, (int64_t)es * n);
+    dev_h2d(c->be, dx.p, x, es * n * nv);
+    dev_h2d(c->be, dy.p, y, es * n);
+    std::vector<const void*> xs(nv);
+    for (int j = 0; j < nv; ++j) xs[j] = (const char*)dx.p + es * (size_t)n * j;
+    multi_dot(c->be, cx, nv, xs.data(), dy.p, n, out);
+  });
+}
+
+int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const double* coef, double beta_re,
+                    double beta_im, void* dst) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    Buf dx(c->be, (int64_t)es * n * nv), dd(c->be, (int64_t)es * n);
+    dev_h2d(c->be, dx.p, x, es * n * nv);
+    dev_h2d(c->be, dd.p, dst, es * n);
+    std::vector<const void*> xs(nv);
+    for (int j = 0; j < nv; ++j) xs[j] = (const char*)dx.p + es * (size_t)n * j;
+    lincomb(c->be, cx, nv, xs.data(), coef, beta_re, beta_im, dd.p, n);
+    dev_d2h(c->be, dst, dd.p, es * n);
+  });
+}
+
+int cb200_k_gemm_peak(cb200_ctx* ctx, int32_t dtype, int32_t n, int32_t reps, double* tflops) {
+  if (!ctx || !tflops) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    const int64_t ne = (int64_t)n * n;
+    Buf dA(c->be, (int64_t)es * ne), dB(c->be, (int64_t)es * ne), dC(c->be, (int64_t)es * ne, true);
+    std::vector<double> h((size_t)ne * (cx ? 2 : 1));
+    for (size_t i = 0; i < h.size(); ++i) h[i] = (double)((i * 2654435761u) % 1000) / 1000.0 - 0.5;
+    dev_h2d(c->be, dA.p, h.data(), es * ne);
+    dev_h2d(c->be, dB.p, h.data(), es * ne);
+    std::vector<GemmTask> tasks(1);
+    std::vector<GemmSeg> segs(1);
+    GemmTask& t = tasks[0];
+    t = GemmTask{};
+    t.ldc = n; t.M = n; t.N = n; t.n_split = n; t.seg_count = 1;
+    const int tm = gemm_tile_m(cx), tn = gemm_tile_n(cx, false);
+    t.tiles_m = (n + tm - 1) / tm;
+    const int tiles = t.tiles_m * ((n + tn - 1) / tn);
+    segs[0] = GemmSeg{};
+    segs[0].lda = n; segs[0].ldb = n; segs[0].K = n;
+    DevList<GemmTask> dt; DevList<GemmSeg> dsg;
+    dt.upload(c->be, tasks); dsg.upload(c->be, segs);
+    for (int i = 0; i < 3; ++i) launch_gemm(c->be, cx, false, false, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+    dev_sync(c->be);
+    dev_event_record(c->be, 0);
+    for (int i = 0; i < reps; ++i) launch_gemm(c->be, cx, false, false, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+    dev_event_record(c->be, 1);
+    const double ms = dev_event_elapsed_ms(c->be, 0, 1) / reps;
+    *tflops = (cx ? 8.0 : 2.0) * (double)n * n * n / (ms * 1e-3) / 1e12;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,1163 @@
+// Host-side DMRG engine (see engine.h).  Everything here is bookkeeping: it turns the Z_N block structure of the
+// tensors into flat task lists for the device kernels and sequences them like ITensor's DMRGWorker does
+// (SURVEY.md App. A.1-A.5 restated; reference call sites /root/reference/src/dmrg.h:544,563,596).
+#include "engine.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <random>
+
+namespace cb200 {
+
+void fail(int code, const std::string& msg) { throw EngineError{code, msg}; }
+
+static void check_dev(Ctx* c) {
+  const char* e = dev_last_error(c->be);
+  if (e) fail(-3, std::string("device error: ") + e);
+}
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------ indices
+IndexMap IndexMap::from_labels(int nq, int64_t dim, const int32_t* labels) {
+  IndexMap m;
+  m.g = Grading(nq);
+  m.charge_ext.resize(dim);
+  m.ext2int.resize(dim);
+  m.int2ext.resize(dim);
+  for (int64_t i = 0; i < dim; ++i) {
+    int q = labels ? labels[i] : 0;
+    if (q < 0 || q >= nq) fail(-2, "charge label out of range");
+    m.charge_ext[i] = q;
+    m.g.dim[q]++;
+  }
+  std::vector<int64_t> pos(nq, 0);
+  for (int q = 0; q < nq; ++q) pos[q] = m.g.off(q);
+  m.identity = true;
+  for (int64_t i = 0; i < dim; ++i) {
+    int64_t p = pos[m.charge_ext[i]]++;
+    m.ext2int[i] = p;
+    m.int2ext[p] = i;
+    if (p != i) m.identity = false;
+  }
+  return m;
+}
+
+IndexMap IndexMap::from_grading(const Grading& g) {
+  IndexMap m;
+  m.g = g;
+  int64_t n = g.total();
+  m.charge_ext.resize(n);
+  m.ext2int.resize(n);
+  m.int2ext.resize(n);
+  int64_t i = 0;
+  for (int q = 0; q < g.nq; ++q)
+    for (int64_t k = 0; k < g.dim[q]; ++k, ++i) { m.charge_ext[i] = q; m.ext2int[i] = i; m.int2ext[i] = i; }
+  m.identity = true;
+  return m;
+}
+
+SiteInfo SiteInfo::make(int nq, int d, const int32_t* labels) {
+  SiteInfo s;
+  s.d = d;
+  s.nq = nq;
+  s.map = IndexMap::from_labels(nq, d, labels);
+  s.q_int.resize(d);
+  s.loc_int.resize(d);
+  for (int q = 0, i = 0; q < nq; ++q)
+    for (int64_t k = 0; k < s.map.g.dim[q]; ++k, ++i) { s.q_int[i] = q; s.loc_int[i] = (int)k; }
+  s.srow.assign(nq, {});
+  s.srow_index.assign((size_t)d * d, -1);
+  for (int s2 = 0; s2 < d; ++s2)
+    for (int s1 = 0; s1 < d; ++s1) {
+      int qd = qadd(s.q_int[s1], s.q_int[s2], nq);
+      s.srow_index[(size_t)s1 * d + s2] = (int)s.srow[qd].size();
+      s.srow[qd].push_back({s1, s2});
+    }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------ buffers
+Buf::Buf(Backend* b, int64_t nbytes, bool zero) : be(b), bytes(nbytes) {
+  p = dev_alloc(b, (size_t)std::max<int64_t>(nbytes, 16));
+  if (!p) fail(-4, "device allocation of " + std::to_string(nbytes) + " bytes failed");
+  if (zero && nbytes > 0) dev_memset0(b, p, (size_t)nbytes);
+}
+Buf& Buf::operator=(Buf&& o) noexcept {
+  if (this != &o) {
+    reset();
+    be = o.be; p = o.p; bytes = o.bytes;
+    o.p = nullptr; o.bytes = 0;
+  }
+  return *this;
+}
+Buf::~Buf() { reset(); }
+void Buf::reset() {
+  if (p && be) dev_free(be, p);
+  p = nullptr;
+  bytes = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layouts
+void Site3Layout::build(const Grading& x, const Grading& y, const SiteInfo* s) {
+  X = x; Y = y; S = s;
+  const int nq = x.nq;
+  off.assign((size_t)nq * nq, 0);
+  int64_t t = 0;
+  for (int qx = 0; qx < nq; ++qx)
+    for (int qs = 0; qs < nq; ++qs) {
+      off[qx * nq + qs] = t;
+      t += X.dim[qx] * S->map.g.dim[qs] * Y.dim[qadd(qx, qs, nq)];
+    }
+  total = t;
+}
+int64_t Site3Layout::ncols(int qx) const {
+  int64_t n = 0;
+  for (int qs = 0; qs < X.nq; ++qs) n += S->map.g.dim[qs] * Y.dim[qadd(qx, qs, X.nq)];
+  return n;
+}
+void EnvLayout::build(const Grading& x, const Grading& k) {
+  X = x; K = k;
+  const int nq = x.nq;
+  off.assign((size_t)nq * nq, 0);
+  int64_t t = 0;
+  for (int qxp = 0; qxp < nq; ++qxp)
+    for (int qa = 0; qa < nq; ++qa) {
+      off[qxp * nq + qa] = t;
+      t += X.dim[qxp] * K.dim[qa] * X.dim[qsub(qxp, qa, nq)];
+    }
+  total = t;
+}
+void PhiLayout::build(const Grading& l, const Grading& r, const SiteInfo* s) {
+  L = l; R = r; S = s;
+  const int nq = l.nq;
+  off.assign((size_t)nq * nq, 0);
+  int64_t t = 0;
+  for (int ql = 0; ql < nq; ++ql)
+    for (int qr = 0; qr < nq; ++qr) {
+      off[ql * nq + qr] = t;
+      t += L.dim[ql] * S->ns(qsub(qr, ql, nq)) * R.dim[qr];
+    }
+  total = t;
+}
+int64_t PhiLayout::ncols(int ql) const {
+  int64_t n = 0;
+  for (int qr = 0; qr < L.nq; ++qr) n += ns(ql, qr) * R.dim[qr];
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ plan builders
+namespace {
+
+struct GemmBuilder {
+  std::vector<GemmTask> tasks;
+  std::vector<GemmSeg> segs;
+  bool cplx, narrow;
+  double flops = 0;
+  GemmTask cur{};
+  bool open = false;
+  GemmBuilder(bool cplx_, bool narrow_ = false) : cplx(cplx_), narrow(narrow_) {}
+  void begin(int64_t c_off, int64_t ldc, int64_t M, int64_t N, uint32_t flags) {
+    cur = GemmTask{};
+    cur.c_off = c_off; cur.ldc = ldc; cur.c_off2 = c_off;
+    cur.M = (int32_t)M; cur.N = (int32_t)N;
+    cur.seg_begin = (int32_t)segs.size();
+    cur.flags = flags;
+    cur.n_split = (int32_t)N;
+    open = true;
+  }
+  void split(int32_t n_split, int64_t c_off2) { cur.n_split = n_split; cur.c_off2 = c_off2; }
+  void seg(int64_t a_off, int64_t lda, int64_t b_off, int64_t ldb, int64_t K) {
+    if (K <= 0) return;
+    GemmSeg s{};
+    s.a_off = a_off; s.b_off = b_off; s.lda = lda; s.ldb = ldb; s.K = (int32_t)K;
+    segs.push_back(s);
+    flops += 2.0 * cur.M * cur.N * (double)K;
+  }
+  void end() {
+    open = false;
+    cur.seg_count = (int32_t)segs.size() - cur.seg_begin;
+    if (cur.M <= 0 || cur.N <= 0) { segs.resize(cur.seg_begin); return; }
+    tasks.push_back(cur);
+  }
+  void finish(Backend* be, GemmPlan& p, bool ta, bool tb) {
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, narrow);
+    int tiles = 0;
+    for (auto& t : tasks) {
+      t.tile_begin = tiles;
+      t.tiles_m = (t.M + tm - 1) / tm;
+      tiles += t.tiles_m * ((t.N + tn - 1) / tn);
+    }
+    p.tasks.upload(be, tasks);
+    p.segs.upload(be, segs);
+    p.tiles = tiles;
+    p.ta = ta; p.tb = tb; p.narrow = narrow;
+    p.flops = flops * (cplx ? 4.0 : 1.0);
+  }
+};
+
+void run_gemm(Ctx* c, bool cplx, const GemmPlan& p, const void* A, const void* B, void* C) {
+  launch_gemm(c->be, cplx, p.ta, p.tb, p.narrow, A, B, C, p.tasks.ptr(), p.tasks.n, p.segs.ptr(), p.tiles);
+}
+
+struct MixBuilder {
+  std::vector<MixPanel> panels;
+  std::vector<MixOut> outs;
+  std::vector<MixEntry> ents;
+  double flops = 0;
+  bool cplx;
+  explicit MixBuilder(bool c) : cplx(c) {}
+  void begin_panel(int64_t rows, int64_t nr) {
+    MixPanel p{};
+    p.rows = (int32_t)rows; p.nr = (int32_t)nr;
+    p.out_begin = (int32_t)outs.size();
+    panels.push_back(p);
+  }
+  void begin_out(int64_t off, int64_t rstride) {
+    MixOut o{};
+    o.off = off; o.rstride = rstride; o.e_begin = (int32_t)ents.size();
+    outs.push_back(o);
+  }
+  void entry(int64_t in_off, int64_t in_rstride, cplx_t coef) {
+    MixEntry e{};
+    e.in_off = in_off; e.in_rstride = in_rstride; e.cre = coef.real(); e.cim = coef.imag();
+    ents.push_back(e);
+  }
+  void end_out() { outs.back().e_end = (int32_t)ents.size(); }
+  void end_panel() {
+    MixPanel& p = panels.back();
+    p.out_end = (int32_t)outs.size();
+    int64_t ne = 0;
+    for (int o = p.out_begin; o < p.out_end; ++o) ne += outs[o].e_end - outs[o].e_begin;
+    flops += 2.0 * (double)ne * p.rows * p.nr;
+    if (p.rows <= 0 || p.nr <= 0 || p.out_end == p.out_begin) {
+      outs.resize(p.out_begin);
+      // entries of dropped outs are simply left unused
+      panels.pop_back();
+    }
+  }
+  void finish(Backend* be, MixPlan& mp) {
+    const int rpb = mix_rows_per_block();
+    int blocks = 0;
+    for (auto& p : panels) {
+      p.blk_begin = blocks;
+      p.row_chunks = (p.rows + rpb - 1) / rpb;
+      blocks += p.row_chunks * p.nr;
+    }
+    mp.panels.upload(be, panels);
+    mp.outs.upload(be, outs);
+    mp.ents.upload(be, ents);
+    mp.blocks = blocks;
+    mp.flops = flops * (cplx ? 4.0 : 1.0);
+  }
+};
+
+void run_mix(Ctx* c, bool cplx, const MixPlan& p, const void* in, void* out) {
+  launch_mix(c->be, cplx, in, out, p.panels.ptr(), p.panels.n, p.outs.ptr(), p.ents.ptr(), p.blocks);
+}
+
+struct CopyBuilder {
+  std::vector<CopyTask> tasks;
+  void add(int64_t src_off, int64_t dst_off, int64_t n0, int64_t ss0, int64_t ds0, int64_t n1 = 1, int64_t ss1 = 0, int64_t ds1 = 0,
+           int64_t n2 = 1, int64_t ss2 = 0, int64_t ds2 = 0, bool conj = false) {
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return;
+    CopyTask t{};
+    t.src_off = src_off; t.dst_off = dst_off;
+    t.n0 = (int32_t)n0; t.n1 = (int32_t)n1; t.n2 = (int32_t)n2;
+    t.ss0 = ss0; t.ss1 = ss1; t.ss2 = ss2; t.ds0 = ds0; t.ds1 = ds1; t.ds2 = ds2;
+    t.conj = conj ? 1 : 0;
+    tasks.push_back(t);
+  }
+  void run(Ctx* c, bool cplx, const void* src, void* dst) {
+    if (tasks.empty()) return;
+    const int epb = copy_elems_per_block();
+    int blocks = 0;
+    for (auto& t : tasks) {
+      t.blk_begin = blocks;
+      int64_t tot = (int64_t)t.n0 * t.n1 * t.n2;
+      blocks += (int)((tot + epb - 1) / epb);
+    }
+    DevList<CopyTask> d;
+    d.upload(c->be, tasks);
+    launch_copy(c->be, cplx, src, dst, d.ptr(), d.n, blocks);
+    // the task list must outlive the kernel: stream-ordered free keeps it alive until the kernel has run
+  }
+};
+
+size_t esz(bool cplx) { return cplx ? 16 : 8; }
+
+void scale_inplace(Ctx* c, bool cplx, void* v, int64_t n, double s) {
+  const void* xs[1] = {v};
+  double co[2] = {s, 0.0};
+  lincomb(c->be, cplx, 1, xs, co, 0.0, 0.0, v, n);
+}
+
+double norm2_dev(Ctx* c, bool cplx, const void* v, int64_t n) {
+  const void* xs[1] = {v};
+  double out[2];
+  multi_dot(c->be, cplx, 1, xs, v, n, out);
+  return out[0];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ H_eff matvec
+void Bond::plan() {
+  Backend* be = ctx->be;
+  const int d = S->d;
+  Llay.build(Dl, Kl);
+  Rlay.build(Dr, Kr);
+  philay.build(Dl, Dr, S);
+  // ---- T1 layout: block (qa, ql): rows (l', a), cols = phi columns of left sector ql
+  std::vector<int64_t> t1off((size_t)nq * nq, 0), t1M((size_t)nq * nq, 0);
+  int64_t t1 = 0;
+  for (int qa = 0; qa < nq; ++qa)
+    for (int ql = 0; ql < nq; ++ql) {
+      const int qlp = qadd(ql, qa, nq);
+      const int64_t M = Dl.dim[qlp] * Kl.dim[qa];
+      t1off[qa * nq + ql] = t1;
+      t1M[qa * nq + ql] = M;
+      if (Dl.dim[ql] > 0) t1 += M * philay.ncols(ql);
+    }
+  t1_elems = t1;
+  // ---- T2 layout: block (ql', qa'', qr): rows (l', srow'), cols (a'', r)
+  std::vector<int64_t> t2off((size_t)nq * nq * nq, 0), t2M((size_t)nq * nq * nq, 0);
+  int64_t t2 = 0;
+  for (int qlp = 0; qlp < nq; ++qlp)
+    for (int qa2 = 0; qa2 < nq; ++qa2)
+      for (int qr = 0; qr < nq; ++qr) {
+        const int qrp = qadd(qr, qa2, nq);
+        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp);
+        const size_t id = ((size_t)qlp * nq + qa2) * nq + qr;
+        t2off[id] = t2;
+        t2M[id] = M;
+        t2 += M * Kr.dim[qa2] * Dr.dim[qr];
+      }
+  t2_elems = t2;
+  T1 = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(t1_elems, 1));
+  T2 = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
+
+  // ---- GEMM1: T1(qa,ql) = L(ql+qa, qa) [ (l',a) x l ] * Phi_ql [ l x cols ]
+  {
+    GemmBuilder gb(cplx);
+    for (int qa = 0; qa < nq; ++qa)
+      for (int ql = 0; ql < nq; ++ql) {
+        const int qlp = qadd(ql, qa, nq);
+        const int64_t M = t1M[qa * nq + ql], N = philay.ncols(ql), K = Dl.dim[ql];
+        if (M == 0 || N == 0 || K == 0) continue;
+        gb.begin(t1off[qa * nq + ql], M, M, N, 0);
+        gb.seg(Llay.o(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
+        gb.end();
+      }
+    gb.finish(be, g1, false, false);
+  }
+  // ---- Omega = W1 (x) W2 contracted over the middle MPO link, as a sparse map (a,s1,s2) -> (a'',t1,t2)
+  const int64_t kl = Kl.total(), km = Km.total(), kr = Kr.total();
+  const int64_t nin = kl * d * d, nout = kr * d * d;
+  std::vector<cplx_t> omega((size_t)nin * nout, cplx_t(0, 0));   // omega[in + nin*out]
+  {
+    struct E1 { int64_t a; int t, s; cplx_t v; };
+    struct E2 { int t, s; int64_t app; cplx_t v; };
+    std::vector<std::vector<E1>> n1(km);
+    std::vector<std::vector<E2>> n2(km);
+    for (int64_t ap = 0; ap < km; ++ap)
+      for (int s = 0; s < d; ++s)
+        for (int t = 0; t < d; ++t)
+          for (int64_t a = 0; a < kl; ++a) {
+            cplx_t v = W1->at(a, t, s, ap);
+            if (v != cplx_t(0, 0)) n1[ap].push_back({a, t, s, v});
+          }
+    for (int64_t app = 0; app < kr; ++app)
+      for (int s = 0; s < d; ++s)
+        for (int t = 0; t < d; ++t)
+          for (int64_t ap = 0; ap < km; ++ap) {
+            cplx_t v = W2->at(ap, t, s, app);
+            if (v != cplx_t(0, 0)) n2[ap].push_back({t, s, app, v});
+          }
+    for (int64_t ap = 0; ap < km; ++ap)
+      for (const auto& x : n1[ap])
+        for (const auto& y : n2[ap]) {
+          const int64_t in = x.a + kl * (x.s + (int64_t)d * y.s);
+          const int64_t out = y.app + kr * (x.t + (int64_t)d * y.t);
+          omega[(size_t)in + (size_t)nin * out] += x.v * y.v;
+        }
+  }
+  // ---- mix panels (ql', qr)
+  {
+    MixBuilder mb(cplx);
+    for (int qlp = 0; qlp < nq; ++qlp)
+      for (int qr = 0; qr < nq; ++qr) {
+        mb.begin_panel(Dl.dim[qlp], Dr.dim[qr]);
+        for (int qa2 = 0; qa2 < nq; ++qa2) {
+          const int qrp = qadd(qr, qa2, nq);
+          const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
+          const int64_t M2 = t2M[id2];
+          const int qd_out = qsub(qrp, qlp, nq);
+          for (int64_t a2l = 0; a2l < Kr.dim[qa2]; ++a2l) {
+            const int64_t app = Kr.off(qa2) + a2l;
+            for (int64_t sro = 0; sro < S->ns(qd_out); ++sro) {
+              const int t1s = S->srow[qd_out][sro].first, t2s = S->srow[qd_out][sro].second;
+              const int64_t out = app + kr * (t1s + (int64_t)d * t2s);
+              mb.begin_out(t2off[id2] + Dl.dim[qlp] * sro + M2 * a2l, M2 * Kr.dim[qa2]);
+              const cplx_t* row = &omega[(size_t)nin * out];
+              for (int64_t in = 0; in < nin; ++in) {
+                if (row[in] == cplx_t(0, 0)) continue;
+                const int64_t a = in % kl;
+                const int s1 = (int)((in / kl) % d), s2 = (int)(in / (kl * d));
+                // internal MPO link value a -> (qa, a_loc)
+                int qa = 0;
+                int64_t aloc = a;
+                while (aloc >= Kl.dim[qa]) { aloc -= Kl.dim[qa]; ++qa; }
+                const int ql = qsub(qlp, qa, nq);
+                const int qd_in = qadd(S->q_int[s1], S->q_int[s2], nq);
+                if (qd_in != qsub(qr, ql, nq)) fail(-2, "MPO tensors do not conserve the Z_N charge");
+                const int64_t M1 = t1M[qa * nq + ql];
+                const int64_t sri = S->srow_index[(size_t)s1 * d + s2];
+                const int64_t nsi = S->ns(qd_in);
+                mb.entry(t1off[qa * nq + ql] + Dl.dim[qlp] * aloc + M1 * (philay.colbase(ql, qr) + sri), M1 * nsi, row[in]);
+              }
+              mb.end_out();
+            }
+          }
+        }
+        mb.end_panel();
+      }
+    mb.finish(be, mix);
+  }
+  // ---- GEMM2: out(ql', qr') [ (l',srow') x r' ] = sum_{qa''} T2(ql',qa'',qr'-qa'') [ . x (a'',r) ] * R(qr',qa'')^T
+  {
+    GemmBuilder gb(cplx);
+    for (int qlp = 0; qlp < nq; ++qlp)
+      for (int qrp = 0; qrp < nq; ++qrp) {
+        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
+        if (M == 0 || N == 0) continue;
+        gb.begin(philay.o(qlp, qrp), M, M, N, 0);
+        for (int qa2 = 0; qa2 < nq; ++qa2) {
+          const int qr = qsub(qrp, qa2, nq);
+          const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
+          gb.seg(t2off[id2], M, Rlay.o(qrp, qa2), Dr.dim[qrp], Kr.dim[qa2] * Dr.dim[qr]);
+        }
+        gb.end();
+      }
+    gb.finish(be, g2, false, true);
+  }
+  flops_alg = g1.flops + g2.flops + mix.flops;
+  check_dev(ctx);
+}
+
+void Bond::apply(const void* x, void* y) {
+  run_gemm(ctx, cplx, g1, L, x, T1.p);
+  run_mix(ctx, cplx, mix, T1.p, T2.p);
+  run_gemm(ctx, cplx, g2, T2.p, R, y);
+  if (!pen.empty() && weight != 0.0) {
+    // LocalMPO_MPS::product: y += weight * sum_j <o_j|x> o_j
+    const int np = (int)pen.size();
+    for (int j0 = 0; j0 < np; j0 += MAX_LC) {
+      const int nv = std::min(MAX_LC, np - j0);
+      double z[2 * MAX_LC];
+      multi_dot(ctx->be, cplx, nv, pen.data() + j0, x, philay.total, z);
+      for (int j = 0; j < 2 * nv; ++j) z[j] *= weight;
+      lincomb(ctx->be, cplx, nv, pen.data() + j0, z, 1.0, 0.0, y, philay.total);
+    }
+  }
+  ctx->tm.nmatvec += 1;
+  ctx->tm.matvec_flops += flops_alg;
+}
+
+// ------------------------------------------------------------------------------------------------ Davidson (A.4)
+namespace {
+// lowest eigenpair of a small Hermitian matrix (n <= 16) by cyclic Jacobi; M is row-major n x n
+void small_heig_lowest(int n, const std::vector<cplx_t>& Min, double* lam, std::vector<cplx_t>& u) {
+  std::vector<cplx_t> A = Min, V((size_t)n * n, cplx_t(0, 0));
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) off += std::norm(A[(size_t)p * n + q]);
+    if (off < 1e-300) break;
+    bool any = false;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const cplx_t g = A[(size_t)p * n + q];
+        const double ag = std::abs(g);
+        const double app = A[(size_t)p * n + p].real(), aqq = A[(size_t)q * n + q].real();
+        if (ag <= 1e-17 * std::sqrt(std::fabs(app * aqq)) || ag == 0.0) continue;
+        any = true;
+        const cplx_t e = g / ag;
+        const double tau = (aqq - app) / (2.0 * ag);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = t * cs;
+        // columns: new_p = c a - s conj(e) b ; new_q = s e a + c b
+        for (int r = 0; r < n; ++r) {
+          cplx_t a = A[(size_t)r * n + p], b = A[(size_t)r * n + q];
+          A[(size_t)r * n + p] = cs * a - sn * std::conj(e) * b;
+          A[(size_t)r * n + q] = sn * e * a + cs * b;
+          a = V[(size_t)r * n + p]; b = V[(size_t)r * n + q];
+          V[(size_t)r * n + p] = cs * a - sn * std::conj(e) * b;
+          V[(size_t)r * n + q] = sn * e * a + cs * b;
+        }
+        // rows: row_p' = c row_p - s e row_q ; row_q' = s conj(e) row_p + c row_q
+        for (int cc = 0; cc < n; ++cc) {
+          cplx_t a = A[(size_t)p * n + cc], b = A[(size_t)q * n + cc];
+          A[(size_t)p * n + cc] = cs * a - sn * e * b;
+          A[(size_t)q * n + cc] = sn * std::conj(e) * a + cs * b;
+        }
+        A[(size_t)p * n + q] = 0; A[(size_t)q * n + p] = 0;
+      }
+    if (!any) break;
+  }
+  int best = 0;
+  for (int i = 1; i < n; ++i)
+    if (A[(size_t)i * n + i].real() < A[(size_t)best * n + best].real()) best = i;
+  *lam = A[(size_t)best * n + best].real();
+  u.resize(n);
+  for (int i = 0; i < n; ++i) u[i] = V[(size_t)i * n + best];
+}
+}  // namespace
+
+DavidsonResult davidson(Bond& b, void* phi, int niter) {
+  Ctx* c = b.ctx;
+  Backend* be = c->be;
+  const bool cx = b.cplx;
+  const int64_t n = b.philay.total;
+  const int64_t nbytes = (int64_t)esz(cx) * std::max<int64_t>(n, 1);
+  const double errgoal = 1e-14;
+  const int miniter = 1;
+  const int maxiter = niter;
+  const int actual_maxiter = (int)std::min<int64_t>(maxiter, n - 1);
+  if (actual_maxiter + 1 > MAX_LC) fail(-2, "davidson: niter too large for this build (max " + std::to_string(MAX_LC - 1) + ")");
+
+  double t0 = now_s();
+  double nrm2 = norm2_dev(c, cx, phi, n);
+  if (nrm2 == 0.0) fail(-2, "davidson: zero initial vector");
+  std::vector<Buf> V, AV;
+  V.emplace_back(be, nbytes);
+  AV.emplace_back(be, nbytes);
+  {
+    const void* xs[1] = {phi};
+    double co[2] = {1.0 / std::sqrt(nrm2), 0.0};
+    lincomb(be, cx, 1, xs, co, 0, 0, V[0].p, n);
+  }
+  c->tm.level1 += now_s() - t0;
+  auto matvec = [&](const void* x, void* y) {
+    double t = now_s();
+    b.apply(x, y);
+    dev_sync(be);
+    c->tm.matvec += now_s() - t;
+  };
+  matvec(V[0].p, AV[0].p);
+  t0 = now_s();
+  const int mm = actual_maxiter + 2;
+  std::vector<cplx_t> M((size_t)mm * mm, cplx_t(0, 0));
+  double lam;
+  {
+    const void* xs[1] = {V[0].p};
+    double out[2];
+    multi_dot(be, cx, 1, xs, AV[0].p, n, out);
+    lam = out[0];
+    M[0] = lam;
+  }
+  Buf q(be, nbytes);
+  double last_lam = 1000.0;
+  int nmv = 1;
+  for (int ii = 0; ii <= actual_maxiter; ++ii) {
+    if (ii == 0) {
+      const void* xs[2] = {AV[0].p, V[0].p};
+      double co[4] = {1.0, 0.0, -lam, 0.0};
+      lincomb(be, cx, 2, xs, co, 0, 0, q.p, n);
+      dev_d2d(be, phi, V[0].p, (size_t)nbytes);
+    } else {
+      const int ni = ii + 1;
+      std::vector<cplx_t> Ms((size_t)ni * ni), u;
+      for (int r = 0; r < ni; ++r)
+        for (int cc = 0; cc < ni; ++cc) Ms[(size_t)r * ni + cc] = M[(size_t)r * mm + cc];
+      small_heig_lowest(ni, Ms, &lam, u);
+      if (u[0].real() < 0)
+        for (auto& x : u) x = -x;
+      std::vector<const void*> xs(ni);
+      std::vector<double> co(2 * ni);
+      for (int k = 0; k < ni; ++k) { xs[k] = V[k].p; co[2 * k] = u[k].real(); co[2 * k + 1] = cx ? u[k].imag() : 0.0; }
+      lincomb(be, cx, ni, xs.data(), co.data(), 0, 0, phi, n);
+      for (int k = 0; k < ni; ++k) xs[k] = AV[k].p;
+      lincomb(be, cx, ni, xs.data(), co.data(), 0, 0, q.p, n);
+      const void* ph[1] = {phi};
+      double cl[2] = {-lam, 0.0};
+      lincomb(be, cx, 1, ph, cl, 1.0, 0.0, q.p, n);
+    }
+    const double qnorm = std::sqrt(std::max(0.0, norm2_dev(c, cx, q.p, n)));
+    const bool converged = (qnorm < errgoal && std::fabs(lam - last_lam) < errgoal) || qnorm < std::max(1e-12, errgoal * 1e-3);
+    if (qnorm < 1e-20 || (converged && ii >= miniter) || ii == actual_maxiter) break;
+    last_lam = lam;
+    // classical Gram-Schmidt: all dots first, then the subtractions (one fused pass each)
+    const int ni = ii + 1;
+    std::vector<const void*> xs(ni);
+    for (int k = 0; k < ni; ++k) xs[k] = V[k].p;
+    std::vector<double> vq(2 * ni), co(2 * ni);
+    multi_dot(be, cx, ni, xs.data(), q.p, n, vq.data());
+    for (int k = 0; k < 2 * ni; ++k) co[k] = -vq[k];
+    lincomb(be, cx, ni, xs.data(), co.data(), 1.0, 0.0, q.p, n);
+    double qn = std::sqrt(std::max(0.0, norm2_dev(c, cx, q.p, n)));
+    int passes = 1;
+    while (qn < 1e-10 && passes <= 3) {
+      // ITensor randomises q here; the phi layout holds only allowed blocks, so any fill is symmetry-respecting
+      std::mt19937_64 rng(12345 + ii + 17 * passes);
+      std::normal_distribution<double> nd;
+      std::vector<double> h((size_t)n * (cx ? 2 : 1));
+      for (auto& x : h) x = nd(rng);
+      dev_h2d(be, q.p, h.data(), h.size() * sizeof(double));
+      multi_dot(be, cx, ni, xs.data(), q.p, n, vq.data());
+      for (int k = 0; k < 2 * ni; ++k) co[k] = -vq[k];
+      lincomb(be, cx, ni, xs.data(), co.data(), 1.0, 0.0, q.p, n);
+      qn = std::sqrt(std::max(0.0, norm2_dev(c, cx, q.p, n)));
+      ++passes;
+    }
+    V.emplace_back(be, nbytes);
+    AV.emplace_back(be, nbytes);
+    {
+      const void* qs[1] = {q.p};
+      double cs[2] = {1.0 / qn, 0.0};
+      lincomb(be, cx, 1, qs, cs, 0, 0, V[ii + 1].p, n);
+    }
+    c->tm.level1 += now_s() - t0;
+    matvec(V[ii + 1].p, AV[ii + 1].p);
+    t0 = now_s();
+    ++nmv;
+    {
+      std::vector<const void*> vs(ii + 2);
+      for (int k = 0; k < ii + 2; ++k) vs[k] = V[k].p;
+      std::vector<double> col(2 * (ii + 2));
+      multi_dot(be, cx, ii + 2, vs.data(), AV[ii + 1].p, n, col.data());
+      for (int k = 0; k < ii + 2; ++k) {
+        M[(size_t)k * mm + (ii + 1)] = cplx_t(col[2 * k], col[2 * k + 1]);
+        M[(size_t)(ii + 1) * mm + k] = std::conj(M[(size_t)k * mm + (ii + 1)]);
+      }
+    }
+  }
+  dev_sync(be);
+  c->tm.level1 += now_s() - t0;
+  check_dev(c);
+  return {lam, nmv};
+}
+
+// ------------------------------------------------------------------------------------------------ two-site product
+void two_site(Ctx* c, bool cplx, const DevSite3& A, const DevSite3& B, const PhiLayout& pl, void* phi) {
+  const SiteInfo* S = pl.S;
+  const int nq = pl.L.nq, d = S->d;
+  const Grading& Dl = A.lay.X;
+  const Grading& Dm = A.lay.Y;
+  const Grading& ds = S->map.g;
+  GemmBuilder gb(cplx);
+  for (int ql = 0; ql < nq; ++ql)
+    for (int s1 = 0; s1 < d; ++s1)
+      for (int s2 = 0; s2 < d; ++s2) {
+        const int q1 = S->q_int[s1], q2 = S->q_int[s2];
+        const int qm = qadd(ql, q1, nq), qr = qadd(qm, q2, nq);
+        const int64_t M = Dl.dim[ql], N = pl.R.dim[qr], K = Dm.dim[qm];
+        if (M == 0 || N == 0) continue;
+        const int64_t sr = S->srow_index[(size_t)s1 * d + s2];
+        gb.begin(pl.o(ql, qr) + M * sr, M * pl.ns(ql, qr), M, N, 0);
+        gb.seg(A.lay.o(ql, q1) + M * S->loc_int[s1], M * ds.dim[q1], B.lay.o(qm, q2) + K * S->loc_int[s2], K * ds.dim[q2], K);
+        gb.end();
+      }
+  GemmPlan p;
+  gb.finish(c->be, p, false, false);
+  run_gemm(c, cplx, p, A.buf.p, B.buf.p, phi);
+}
+
+// ------------------------------------------------------------------------------------------------ truncation rule (A.5)
+void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, double cutoff, int64_t* m_out, double* terr_out,
+                    double* docut_out) {
+  const int64_t origm = (int64_t)P.size();
+  int64_t n = origm - 1;
+  for (int64_t zn = n; zn >= 0 && P[zn] < 0; --zn) P[zn] = 0;
+  if (origm == 1) { *m_out = 1; *terr_out = 0; *docut_out = P[0] / 2.0; return; }
+  double truncerr = 0;
+  while (n >= maxdim) { truncerr += P[n]; --n; }
+  double scale = 0;
+  for (double x : P) scale += x;
+  if (scale == 0) scale = 1.0;
+  while (n >= mindim && n >= 0 && truncerr + P[n] < cutoff * scale) { truncerr += P[n]; --n; }
+  truncerr /= scale;
+  if (n < 0) n = 0;
+  const int64_t m = n + 1;
+  double docut = 0;
+  if (m < origm) {
+    docut = (P[m - 1] + P[m]) / 2.0;
+    if (std::fabs(P[m - 1] - P[m]) < 1e-3 * P[m - 1]) docut += 1e-3 * P[m - 1];
+  }
+  *m_out = m; *terr_out = truncerr; *docut_out = docut;
+}
+
+// ------------------------------------------------------------------------------------------------ block Jacobi SVD
+JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) {
+  Backend* be = c->be;
+  const size_t es = esz(cplx);
+  const int NJ = 2 * JB;
+  JacobiOut out;
+  const int64_t npad = ((n + NJ - 1) / NJ) * NJ;
+  const int64_t nb = npad / JB;          // even
+  const int64_t npairs = nb / 2;
+  const int64_t ldx = std::max<int64_t>(rows, 1), ldv = npad;
+  out.ldx = ldx; out.ldv = ldv;
+  Buf Xa(be, (int64_t)es * ldx * npad, true), Xb(be, (int64_t)es * ldx * npad, true);
+  Buf Va(be, (int64_t)es * ldv * npad), Vb(be, (int64_t)es * ldv * npad, true);
+  if (rows > 0 && n > 0) dev_d2d(be, Xa.p, X, es * (size_t)rows * n);
+  launch_set_identity(be, cplx, Va.p, ldv, npad);
+  out.w.assign(n, 0.0);
+  if (rows == 0 || n == 0) {
+    out.XV = std::move(Xa); out.V = std::move(Va);
+    return out;
+  }
+  // slot permutation of the round-robin tournament: pair p occupies slots (2p, 2p+1)
+  auto pos_of_slot = [&](int64_t s) { return (s % 2 == 0) ? s / 2 : nb - 1 - (s - 1) / 2; };
+  auto slot_of_pos = [&](int64_t p) { return (p < nb / 2) ? 2 * p : 2 * (nb - 1 - p) + 1; };
+  auto next_slot = [&](int64_t s) {
+    int64_t p = pos_of_slot(s);
+    if (nb > 2 && p != 0) p = (p == nb - 1) ? 1 : p + 1;
+    return slot_of_pos(p);
+  };
+  GemmPlan gram, appX, appV;
+  {
+    GemmBuilder gb(cplx, true);
+    for (int64_t p = 0; p < npairs; ++p) {
+      gb.begin(p * NJ * NJ, NJ, NJ, NJ, 0);
+      gb.seg(p * NJ * ldx, ldx, p * NJ * ldx, ldx, rows);
+      gb.end();
+    }
+    for (auto& t : gb.tasks) t.flags |= GEMM_TRANS_A | GEMM_CONJ_A;
+    gb.finish(be, gram, true, false);
+  }
+  {
+    GemmBuilder gx(cplx, true), gv(cplx, true);
+    for (int64_t p = 0; p < npairs; ++p) {
+      const int64_t s0 = next_slot(2 * p), s1 = next_slot(2 * p + 1);
+      gx.begin(s0 * JB * ldx, ldx, rows, NJ, 0);
+      gx.split(JB, s1 * JB * ldx);
+      gx.seg(p * NJ * ldx, ldx, p * NJ * NJ, NJ, NJ);
+      gx.end();
+      gv.begin(s0 * JB * ldv, ldv, npad, NJ, 0);
+      gv.split(JB, s1 * JB * ldv);
+      gv.seg(p * NJ * ldv, ldv, p * NJ * NJ, NJ, NJ);
+      gv.end();
+    }
+    gx.finish(be, appX, false, false);
+    gv.finish(be, appV, false, false);
+  }
+  Buf G(be, (int64_t)es * NJ * NJ * npairs), Q(be, (int64_t)es * NJ * NJ * npairs);
+  Buf rot(be, 8, true);
+  const double tol = std::max(1e-14, 8.0 * 1.1e-16 * std::sqrt((double)rows));
+  // columns with norm^2 below 1e-26 ||X||_F^2 are numerically zero (rank-deficient rho): never rotated, always truncated
+  double floor2 = 0;
+  {
+    Buf wd0(be, 8 * npad);
+    launch_colnorm2(be, cplx, Xa.p, ldx, rows, npad, (double*)wd0.p);
+    std::vector<double> w0(npad);
+    dev_d2h(be, w0.data(), wd0.p, 8 * (size_t)npad);
+    double tot = 0;
+    for (double x : w0) tot += x;
+    floor2 = 1e-26 * tot;
+  }
+  void* xc = Xa.p; void* xn = Xb.p; void* vc = Va.p; void* vn = Vb.p;
+  const int max_sweeps = 60;
+  bool done = false;
+  int sweep = 0;
+  for (; sweep < max_sweeps && !done; ++sweep) {
+    dev_memset0(be, rot.p, 8);
+    for (int64_t round = 0; round < std::max<int64_t>(nb - 1, 1); ++round) {
+      run_gemm(c, cplx, gram, xc, xc, G.p);
+      launch_jacobi_eig(be, cplx, G.p, Q.p, (int)npairs, tol, floor2, (long long*)rot.p);
+      run_gemm(c, cplx, appX, xc, Q.p, xn);
+      run_gemm(c, cplx, appV, vc, Q.p, vn);
+      std::swap(xc, xn);
+      std::swap(vc, vn);
+    }
+    long long nrot = 0;
+    dev_d2h(be, &nrot, rot.p, 8);
+    check_dev(c);
+    if (nrot == 0) done = true;
+  }
+  if (!done) fail(-5, "block Jacobi SVD did not converge in " + std::to_string(max_sweeps) + " sweeps");
+  out.sweeps = sweep;
+  Buf wd(be, 8 * npad);
+  launch_colnorm2(be, cplx, xc, ldx, rows, npad, (double*)wd.p);
+  std::vector<double> w(npad);
+  dev_d2h(be, w.data(), wd.p, 8 * (size_t)npad);
+  // the padding columns are exactly zero; report the n largest so that slots are interchangeable
+  out.w = w;   // length npad, slot order (caller selects by value)
+  if (xc == Xa.p) { out.XV = std::move(Xa); } else { out.XV = std::move(Xb); }
+  if (vc == Va.p) { out.V = std::move(Va); } else { out.V = std::move(Vb); }
+  check_dev(c);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------ svdBond
+SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
+                       int64_t mindim, double cutoff) {
+  Backend* be = c->be;
+  const int nq = pl.L.nq, d = S->d;
+  const Grading& Dl = pl.L;
+  const Grading& Dr = pl.R;
+  const Grading& ds = S->map.g;
+  const size_t es = esz(cplx);
+  struct Blk {
+    int64_t rows = 0, n = 0;
+    std::vector<int64_t> rowbase, colbase;   // indexed by q2 / ql (dir 0) or ql / q2 (dir 1)
+    JacobiOut jo;
+    std::vector<int64_t> order;              // slots sorted by descending w
+    int64_t keep = 0;
+  };
+  std::vector<Blk> blk(nq);
+  // sizes: dir 0 orthogonalises (l,s1) [columns], long index (s2,r) [rows]; dir 1 the other way round
+  for (int qm = 0; qm < nq; ++qm) {
+    Blk& b = blk[qm];
+    std::vector<int64_t> lbase(nq, 0), rbase(nq, 0);
+    int64_t nl = 0, nr = 0;
+    for (int ql = 0; ql < nq; ++ql) { lbase[ql] = nl; nl += Dl.dim[ql] * ds.dim[qsub(qm, ql, nq)]; }
+    for (int q2 = 0; q2 < nq; ++q2) { rbase[q2] = nr; nr += ds.dim[q2] * Dr.dim[qadd(qm, q2, nq)]; }
+    if (dir == 0) { b.n = nl; b.rows = nr; b.colbase = lbase; b.rowbase = rbase; }
+    else { b.n = nr; b.rows = nl; b.colbase = rbase; b.rowbase = lbase; }
+  }
+  // ---- gather + Jacobi per middle-charge block
+  std::vector<double> pooled;
+  for (int qm = 0; qm < nq; ++qm) {
+    Blk& b = blk[qm];
+    if (b.n == 0) continue;
+    const int64_t ld = std::max<int64_t>(b.rows, 1);
+    Buf X(be, (int64_t)es * ld * std::max<int64_t>(b.n, 1), true);
+    CopyBuilder cb;
+    for (int ql = 0; ql < nq; ++ql) {
+      const int q1 = qsub(qm, ql, nq);
+      for (int64_t s1l = 0; s1l < ds.dim[q1]; ++s1l)
+        for (int q2 = 0; q2 < nq; ++q2) {
+          const int qr = qadd(qm, q2, nq);
+          for (int64_t s2l = 0; s2l < ds.dim[q2]; ++s2l) {
+            const int s1 = (int)(ds.off(q1) + s1l), s2 = (int)(ds.off(q2) + s2l);
+            const int64_t sr = S->srow_index[(size_t)s1 * d + s2];
+            const int64_t src = pl.o(ql, qr) + Dl.dim[ql] * sr;
+            const int64_t rstride = Dl.dim[ql] * pl.ns(ql, qr);
+            if (dir == 0) {
+              // X[(s2,r), (l,s1)] = conj(phi[l, srow, r])
+              const int64_t dst = (b.rowbase[q2] + Dr.dim[qr] * s2l) + ld * (b.colbase[ql] + Dl.dim[ql] * s1l);
+              cb.add(src, dst, Dl.dim[ql], 1, ld, Dr.dim[qr], rstride, 1, 1, 0, 0, true);
+            } else {
+              // X[(l,s1), (s2,r)] = phi[l, srow, r]
+              const int64_t dst = (b.rowbase[ql] + Dl.dim[ql] * s1l) + ld * (b.colbase[q2] + Dr.dim[qr] * s2l);
+              cb.add(src, dst, Dl.dim[ql], 1, 1, Dr.dim[qr], rstride, ld, 1, 0, 0, false);
+            }
+          }
+        }
+    }
+    cb.run(c, cplx, phi, X.p);
+    b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n);
+    const int64_t npad = (int64_t)b.jo.w.size();
+    b.order.resize(npad);
+    std::iota(b.order.begin(), b.order.end(), 0);
+    std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
+    for (int64_t k = 0; k < b.n; ++k) pooled.push_back(b.jo.w[b.order[k]]);
+  }
+  std::sort(pooled.begin(), pooled.end(), std::greater<double>());
+  int64_t m = 0;
+  double terr = 0, docut = 0;
+  if (pooled.empty()) fail(-2, "split_bond: empty bond");
+  truncate_probs(pooled, maxdim, mindim, cutoff, &m, &terr, &docut);
+  SplitResult res;
+  res.truncerr = terr;
+  res.mid = Grading(nq);
+  int64_t total_keep = 0;
+  for (int qm = 0; qm < nq; ++qm) {
+    Blk& b = blk[qm];
+    int64_t keep = 0;
+    while (keep < b.n && b.jo.w[b.order[keep]] > docut) ++keep;
+    b.keep = keep;
+    total_keep += keep;
+  }
+  if (total_keep == 0) {   // keep the single largest state
+    int best = -1;
+    for (int qm = 0; qm < nq; ++qm)
+      if (blk[qm].n > 0 && (best < 0 || blk[qm].jo.w[blk[qm].order[0]] > blk[best].jo.w[blk[best].order[0]])) best = qm;
+    blk[best].keep = 1;
+  }
+  double kept_w = 0;
+  for (int qm = 0; qm < nq; ++qm) {
+    res.mid.dim[qm] = blk[qm].keep;
+    for (int64_t k = 0; k < blk[qm].keep; ++k) { kept_w += blk[qm].jo.w[blk[qm].order[k]]; res.spectrum.push_back(blk[qm].jo.w[blk[qm].order[k]]); }
+    res.sweeps = std::max(res.sweeps, blk[qm].jo.sweeps);
+  }
+  std::sort(res.spectrum.begin(), res.spectrum.end(), std::greater<double>());
+  res.A.lay.build(Dl, res.mid, S);
+  res.B.lay.build(res.mid, Dr, S);
+  res.A.buf = Buf(be, (int64_t)es * std::max<int64_t>(res.A.lay.total, 1), true);
+  res.B.buf = Buf(be, (int64_t)es * std::max<int64_t>(res.B.lay.total, 1), true);
+  // ---- compaction of the kept columns (sorted by weight) and scatter into the two site tensors
+  for (int qm = 0; qm < nq; ++qm) {
+    Blk& b = blk[qm];
+    const int64_t keep = b.keep;
+    if (keep == 0) continue;
+    const int64_t ldxk = std::max<int64_t>(b.rows, 1), ldvk = b.n;
+    Buf Xk(be, (int64_t)es * ldxk * keep), Vk(be, (int64_t)es * ldvk * keep);
+    {
+      CopyBuilder cx_, cv_;
+      for (int64_t k = 0; k < keep; ++k) {
+        cx_.add(b.order[k] * b.jo.ldx, k * ldxk, b.rows, 1, 1);
+        cv_.add(b.order[k] * b.jo.ldv, k * ldvk, b.n, 1, 1);
+      }
+      cx_.run(c, cplx, b.jo.XV.p, Xk.p);
+      cv_.run(c, cplx, b.jo.V.p, Vk.p);
+    }
+    // isometry from V (columns = orthogonalised index), weight tensor from X V (rows = long index)
+    CopyBuilder toA_V, toA_X, toB_V, toB_X;
+    for (int ql = 0; ql < nq; ++ql) {
+      const int q1 = qsub(qm, ql, nq);
+      const int64_t blkrows = Dl.dim[ql] * ds.dim[q1];
+      // A block (ql,q1): element (l + Dl*s1l) + blkrows*j
+      if (dir == 0) toA_V.add(b.colbase[ql], res.A.lay.o(ql, q1), blkrows, 1, 1, keep, ldvk, blkrows);
+      else toA_X.add(b.rowbase[ql], res.A.lay.o(ql, q1), blkrows, 1, 1, keep, ldxk, blkrows);
+    }
+    for (int q2 = 0; q2 < nq; ++q2) {
+      const int qr = qadd(qm, q2, nq);
+      // B block (qm,q2): element j + keep*(s2l + ds*r)  <-  conj(M[(base + Dr*s2l + r), j])
+      if (dir == 0) toB_X.add(b.rowbase[q2], res.B.lay.o(qm, q2), keep, ldxk, 1, ds.dim[q2], Dr.dim[qr], keep, Dr.dim[qr], 1, keep * ds.dim[q2], true);
+      else toB_V.add(b.colbase[q2], res.B.lay.o(qm, q2), keep, ldvk, 1, ds.dim[q2], Dr.dim[qr], keep, Dr.dim[qr], 1, keep * ds.dim[q2], true);
+    }
+    toA_V.run(c, cplx, Vk.p, res.A.buf.p);
+    toA_X.run(c, cplx, Xk.p, res.A.buf.p);
+    toB_V.run(c, cplx, Vk.p, res.B.buf.p);
+    toB_X.run(c, cplx, Xk.p, res.B.buf.p);
+  }
+  // DoNormalize: the weight-carrying tensor has squared norm = sum of kept eigenvalues
+  if (kept_w > 0) {
+    const double s = 1.0 / std::sqrt(kept_w);
+    if (dir == 0) scale_inplace(c, cplx, res.B.buf.p, res.B.lay.total, s);
+    else scale_inplace(c, cplx, res.A.buf.p, res.A.lay.total, s);
+  }
+  dev_sync(be);
+  check_dev(c);
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------------ environment updates
+void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, const DevSite3& A, const HostW& W, DevEnv& out) {
+  Backend* be = c->be;
+  const int nq = S->nq, d = S->d;
+  const Grading& Dl = A.lay.X;
+  const Grading& Dm = A.lay.Y;
+  const Grading& ds = S->map.g;
+  const Grading& Kl = W.KL;
+  const Grading& Km = W.KR;
+  const size_t es = esz(cplx);
+  out.lay.build(Dm, Km);
+  out.buf = Buf(be, (int64_t)es * std::max<int64_t>(out.lay.total, 1), true);
+  // X block (qa, ql): rows (l', a), cols (qs; s, m) of A's right-form matrix for left sector ql
+  std::vector<int64_t> xoff((size_t)nq * nq, 0), xM((size_t)nq * nq, 0);
+  int64_t xt = 0;
+  for (int qa = 0; qa < nq; ++qa)
+    for (int ql = 0; ql < nq; ++ql) {
+      const int64_t M = Dl.dim[qadd(ql, qa, nq)] * Kl.dim[qa];
+      xoff[qa * nq + ql] = xt; xM[qa * nq + ql] = M;
+      xt += M * A.lay.ncols(ql);
+    }
+  Buf X(be, (int64_t)es * std::max<int64_t>(xt, 1));
+  GemmPlan p1;
+  {
+    GemmBuilder gb(cplx);
+    for (int qa = 0; qa < nq; ++qa)
+      for (int ql = 0; ql < nq; ++ql) {
+        const int64_t M = xM[qa * nq + ql], N = A.lay.ncols(ql), K = Dl.dim[ql];
+        if (M == 0 || N == 0 || K == 0) continue;
+        gb.begin(xoff[qa * nq + ql], M, M, N, 0);
+        gb.seg(L.lay.o(qadd(ql, qa, nq), qa), M, A.lay.o(ql, 0), K, K);
+        gb.end();
+      }
+    gb.finish(be, p1, false, false);
+  }
+  // Y block (ql', qs', qa'): rows (l', s'), cols (a', m) with qm = ql'+qs'-qa'
+  std::vector<int64_t> yoff((size_t)nq * nq * nq, 0);
+  int64_t yt = 0;
+  for (int qlp = 0; qlp < nq; ++qlp)
+    for (int qsp = 0; qsp < nq; ++qsp)
+      for (int qap = 0; qap < nq; ++qap) {
+        const int qm = qsub(qadd(qlp, qsp, nq), qap, nq);
+        yoff[((size_t)qlp * nq + qsp) * nq + qap] = yt;
+        yt += Dl.dim[qlp] * ds.dim[qsp] * Km.dim[qap] * Dm.dim[qm];
+      }
+  Buf Y(be, (int64_t)es * std::max<int64_t>(yt, 1));
+  MixPlan mp;
+  {
+    MixBuilder mb(cplx);
+    const int64_t kl = Kl.total();
+    for (int qlp = 0; qlp < nq; ++qlp)
+      for (int qm = 0; qm < nq; ++qm) {
+        mb.begin_panel(Dl.dim[qlp], Dm.dim[qm]);
+        for (int qsp = 0; qsp < nq; ++qsp) {
+          const int qap = qsub(qadd(qlp, qsp, nq), qm, nq);
+          const int64_t MY = Dl.dim[qlp] * ds.dim[qsp];
+          const int64_t yo = yoff[((size_t)qlp * nq + qsp) * nq + qap];
+          for (int64_t spl = 0; spl < ds.dim[qsp]; ++spl)
+            for (int64_t apl = 0; apl < Km.dim[qap]; ++apl) {
+              const int t = (int)(ds.off(qsp) + spl);
+              const int64_t ap = Km.off(qap) + apl;
+              mb.begin_out(yo + Dl.dim[qlp] * spl + MY * apl, MY * Km.dim[qap]);
+              for (int s = 0; s < d; ++s)
+                for (int64_t a = 0; a < kl; ++a) {
+                  const cplx_t v = W.at(a, t, s, ap);
+                  if (v == cplx_t(0, 0)) continue;
+                  const int qa = W.qa_l[a];
+                  const int64_t aloc = a - Kl.off(qa);
+                  const int ql = qsub(qlp, qa, nq);
+                  const int qs = S->q_int[s];
+                  if (qadd(ql, qs, nq) != qm) fail(-2, "MPO tensor does not conserve the Z_N charge (env update)");
+                  const int64_t M = xM[qa * nq + ql];
+                  // column of A's right-form matrix: cb(ql,qs) + s_loc + ds*m
+                  const int64_t cb = (A.lay.o(ql, qs) - A.lay.o(ql, 0)) / std::max<int64_t>(Dl.dim[ql], 1);
+                  mb.entry(xoff[qa * nq + ql] + Dl.dim[qlp] * aloc + M * (cb + S->loc_int[s]), M * ds.dim[qs], v);
+                }
+              mb.end_out();
+            }
+        }
+        mb.end_panel();
+      }
+    mb.finish(be, mp);
+  }
+  GemmPlan p3;
+  {
+    GemmBuilder gb(cplx);
+    for (int qmp = 0; qmp < nq; ++qmp)
+      for (int qap = 0; qap < nq; ++qap) {
+        const int qm = qsub(qmp, qap, nq);
+        const int64_t M = Dm.dim[qmp], N = Km.dim[qap] * Dm.dim[qm];
+        if (M == 0 || N == 0) continue;
+        gb.begin(out.lay.o(qmp, qap), M, M, N, GEMM_TRANS_A | GEMM_CONJ_A);
+        for (int qlp = 0; qlp < nq; ++qlp) {
+          const int qsp = qsub(qmp, qlp, nq);
+          const int64_t K = Dl.dim[qlp] * ds.dim[qsp];
+          gb.seg(A.lay.o(qlp, qsp), K, yoff[((size_t)qlp * nq + qsp) * nq + qap], K, K);
+        }
+        gb.end();
+      }
+    gb.finish(be, p3, true, false);
+  }
+  run_gemm(c, cplx, p1, L.buf.p, A.buf.p, X.p);
+  run_mix(c, cplx, mp, X.p, Y.p);
+  run_gemm(c, cplx, p3, A.buf.p, Y.p, out.buf.p);
+  dev_sync(be);
+  check_dev(c);
+}
+
+void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, const DevSite3& B, const HostW& W, DevEnv& out) {
+  Backend* be = c->be;
+  const int nq = S->nq, d = S->d;
+  const Grading& Dm = B.lay.X;
+  const Grading& Dr = B.lay.Y;
+  const Grading& ds = S->map.g;
+  const Grading& Km = W.KL;
+  const Grading& Kr = W.KR;
+  const size_t es = esz(cplx);
+  out.lay.build(Dm, Km);
+  out.buf = Buf(be, (int64_t)es * std::max<int64_t>(out.lay.total, 1), true);
+  // X block (qa'', qm, qs): element r' + Dr'*a'' + M*(m + Dm*s_loc), qr = qm+qs, qr' = qr+qa''
+  std::vector<int64_t> xoff((size_t)nq * nq * nq, 0), xM((size_t)nq * nq * nq, 0);
+  int64_t xt = 0;
+  for (int qa2 = 0; qa2 < nq; ++qa2)
+    for (int qm = 0; qm < nq; ++qm)
+      for (int qs = 0; qs < nq; ++qs) {
+        const int qr = qadd(qm, qs, nq), qrp = qadd(qr, qa2, nq);
+        const size_t id = ((size_t)qa2 * nq + qm) * nq + qs;
+        const int64_t M = Dr.dim[qrp] * Kr.dim[qa2];
+        xoff[id] = xt; xM[id] = M;
+        xt += M * Dm.dim[qm] * ds.dim[qs];
+      }
+  Buf X(be, (int64_t)es * std::max<int64_t>(xt, 1));
+  GemmPlan p1;
+  {
+    GemmBuilder gb(cplx);
+    for (int qa2 = 0; qa2 < nq; ++qa2)
+      for (int qm = 0; qm < nq; ++qm)
+        for (int qs = 0; qs < nq; ++qs) {
+          const int qr = qadd(qm, qs, nq), qrp = qadd(qr, qa2, nq);
+          const size_t id = ((size_t)qa2 * nq + qm) * nq + qs;
+          const int64_t M = xM[id], N = Dm.dim[qm] * ds.dim[qs], K = Dr.dim[qr];
+          if (M == 0 || N == 0 || K == 0) continue;
+          gb.begin(xoff[id], M, M, N, 0);
+          gb.seg(R.lay.o(qrp, qa2), M, B.lay.o(qm, qs), N, K);   // B^T: element (k=r, n=(m,s)) at n + N*k
+          gb.end();
+        }
+    gb.finish(be, p1, false, true);
+  }
+  // Y block (qr', qs', qa): element r' + Dr'*(s' + ds*(a + km*m)); qm' = qr'-qs', qm = qm'-qa
+  std::vector<int64_t> yoff((size_t)nq * nq * nq, 0);
+  int64_t yt = 0;
+  for (int qrp = 0; qrp < nq; ++qrp)
+    for (int qsp = 0; qsp < nq; ++qsp)
+      for (int qa = 0; qa < nq; ++qa) {
+        const int qm = qsub(qsub(qrp, qsp, nq), qa, nq);
+        yoff[((size_t)qrp * nq + qsp) * nq + qa] = yt;
+        yt += Dr.dim[qrp] * ds.dim[qsp] * Km.dim[qa] * Dm.dim[qm];
+      }
+  Buf Y(be, (int64_t)es * std::max<int64_t>(yt, 1));
+  MixPlan mp;
+  {
+    MixBuilder mb(cplx);
+    const int64_t kr = Kr.total();
+    for (int qrp = 0; qrp < nq; ++qrp)
+      for (int qm = 0; qm < nq; ++qm) {
+        mb.begin_panel(Dr.dim[qrp], Dm.dim[qm]);
+        for (int qsp = 0; qsp < nq; ++qsp) {
+          const int qa = qsub(qsub(qrp, qsp, nq), qm, nq);
+          const int64_t yo = yoff[((size_t)qrp * nq + qsp) * nq + qa];
+          const int64_t rs = Dr.dim[qrp] * ds.dim[qsp];
+          for (int64_t spl = 0; spl < ds.dim[qsp]; ++spl)
+            for (int64_t al = 0; al < Km.dim[qa]; ++al) {
+              const int t = (int)(ds.off(qsp) + spl);
+              const int64_t a = Km.off(qa) + al;
+              mb.begin_out(yo + Dr.dim[qrp] * spl + rs * al, rs * Km.dim[qa]);
+              for (int s = 0; s < d; ++s)
+                for (int64_t a2 = 0; a2 < kr; ++a2) {
+                  const cplx_t v = W.at(a, t, s, a2);
+                  if (v == cplx_t(0, 0)) continue;
+                  const int qa2 = W.qa_r[a2];
+                  const int64_t a2loc = a2 - Kr.off(qa2);
+                  const int qs = S->q_int[s];
+                  const int qr = qsub(qrp, qa2, nq);
+                  if (qadd(qm, qs, nq) != qr) fail(-2, "MPO tensor does not conserve the Z_N charge (env update)");
+                  const size_t id = ((size_t)qa2 * nq + qm) * nq + qs;
+                  const int64_t M = xM[id];
+                  mb.entry(xoff[id] + Dr.dim[qrp] * a2loc + M * Dm.dim[qm] * S->loc_int[s], M, v);
+                }
+              mb.end_out();
+            }
+        }
+        mb.end_panel();
+      }
+    mb.finish(be, mp);
+  }
+  GemmPlan p3;
+  {
+    GemmBuilder gb(cplx);
+    for (int qmp = 0; qmp < nq; ++qmp)
+      for (int qa = 0; qa < nq; ++qa) {
+        const int qm = qsub(qmp, qa, nq);
+        const int64_t M = Dm.dim[qmp], N = Km.dim[qa] * Dm.dim[qm];
+        if (M == 0 || N == 0) continue;
+        gb.begin(out.lay.o(qmp, qa), M, M, N, GEMM_CONJ_A);
+        for (int qsp = 0; qsp < nq; ++qsp) {
+          const int qrp = qadd(qmp, qsp, nq);
+          for (int64_t spl = 0; spl < ds.dim[qsp]; ++spl)
+            gb.seg(B.lay.o(qmp, qsp) + M * spl, M * ds.dim[qsp], yoff[((size_t)qrp * nq + qsp) * nq + qa] + Dr.dim[qrp] * spl,
+                   Dr.dim[qrp] * ds.dim[qsp], Dr.dim[qrp]);
+        }
+        gb.end();
+      }
+    gb.finish(be, p3, false, false);
+  }
+  run_gemm(c, cplx, p1, R.buf.p, B.buf.p, X.p);
+  run_mix(c, cplx, mp, X.p, Y.p);
+  run_gemm(c, cplx, p3, B.buf.p, Y.p, out.buf.p);
+  dev_sync(be);
+  check_dev(c);
+}
+
+}  // namespace cb200

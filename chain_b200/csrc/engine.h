@@ -1,0 +1,257 @@
+// Host-side DMRG engine: block (Z_N charge) bookkeeping, task-list planning and the sweep driver.
+// Backend-agnostic: all device work goes through backend.h.  Restates, B200-first, what ITensor's
+// DMRGWorker / LocalMPO / LocalMPO_MPS / davidson / MPS::svdBond do for the call at
+// /root/reference/src/dmrg.h:544,563,596.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+#include "backend.h"
+
+namespace cb200 {
+
+using cplx_t = std::complex<double>;
+
+struct EngineError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string& msg);
+
+inline int qadd(int a, int b, int nq) { return (a + b) % nq; }
+inline int qsub(int a, int b, int nq) { return ((a - b) % nq + nq) % nq; }
+
+// A graded index in internal (charge-sorted) order.
+struct Grading {
+  int nq = 1;
+  std::vector<int64_t> dim;
+  Grading() {}
+  explicit Grading(int nq_) : nq(nq_), dim(nq_, 0) {}
+  int64_t total() const { int64_t t = 0; for (auto d : dim) t += d; return t; }
+  int64_t off(int q) const { int64_t t = 0; for (int i = 0; i < q; ++i) t += dim[i]; return t; }
+  bool operator==(const Grading& o) const { return nq == o.nq && dim == o.dim; }
+};
+
+// External index (arbitrary charge order, one label per value) <-> internal order.
+struct IndexMap {
+  Grading g;
+  std::vector<int32_t> charge_ext;
+  std::vector<int64_t> ext2int, int2ext;
+  bool identity = true;
+  static IndexMap from_labels(int nq, int64_t dim, const int32_t* labels);
+  static IndexMap from_grading(const Grading& g);   // external order == internal order
+};
+
+struct SiteInfo {
+  int d = 0, nq = 1;
+  IndexMap map;
+  std::vector<int> q_int;                                  // charge of internal site value
+  std::vector<int> loc_int;                                // position inside its sector
+  std::vector<std::vector<std::pair<int, int>>> srow;      // [qdiff] -> list of internal (s1, s2), s2-major
+  std::vector<int> srow_index;                             // [s1*d+s2] -> index inside srow[q(s1)+q(s2)]
+  int64_t ns(int qdiff) const { return (int64_t)srow[qdiff].size(); }
+  static SiteInfo make(int nq, int d, const int32_t* labels);
+};
+
+// RAII device buffer
+struct Buf {
+  Backend* be = nullptr;
+  void* p = nullptr;
+  int64_t bytes = 0;
+  Buf() {}
+  Buf(Backend* b, int64_t nbytes, bool zero = false);
+  Buf(Buf&& o) noexcept { *this = std::move(o); }
+  Buf& operator=(Buf&& o) noexcept;
+  Buf(const Buf&) = delete;
+  Buf& operator=(const Buf&) = delete;
+  ~Buf();
+  void reset();
+};
+
+template <class T>
+struct DevList {
+  Buf buf;
+  int n = 0;
+  const T* ptr() const { return (const T*)buf.p; }
+  void upload(Backend* be, const std::vector<T>& v) {
+    n = (int)v.size();
+    buf = Buf(be, (int64_t)sizeof(T) * (v.empty() ? 1 : v.size()));
+    if (!v.empty()) dev_h2d(be, buf.p, v.data(), sizeof(T) * v.size());
+  }
+};
+
+// ---- layouts (element offsets) ------------------------------------------------------------------------------
+struct Site3Layout {   // T[x, s, y], q(y) = q(x)+q(s); blocks (qx, qs) qx-major; element x + Dx*(s + ds*y)
+  Grading X, Y;
+  const SiteInfo* S = nullptr;
+  std::vector<int64_t> off;
+  int64_t total = 0;
+  void build(const Grading& x, const Grading& y, const SiteInfo* s);
+  int64_t o(int qx, int qs) const { return off[qx * X.nq + qs]; }
+  int64_t ncols(int qx) const;   // sum_qs ds*Dy
+};
+struct EnvLayout {     // E[x', a, x], q(x') = q(x)+q(a); blocks (qx', qa) qx'-major; element x' + Dx'*(a + k*x)
+  Grading X, K;
+  std::vector<int64_t> off;
+  int64_t total = 0;
+  void build(const Grading& x, const Grading& k);
+  int64_t o(int qxp, int qa) const { return off[qxp * X.nq + qa]; }
+};
+struct PhiLayout {     // phi[l, srow, r], blocks (ql, qr) ql-major; element l + Dl*(srow + ns*r)
+  Grading L, R;
+  const SiteInfo* S = nullptr;
+  std::vector<int64_t> off;
+  int64_t total = 0;
+  void build(const Grading& l, const Grading& r, const SiteInfo* s);
+  int64_t o(int ql, int qr) const { return off[ql * L.nq + qr]; }
+  int64_t ns(int ql, int qr) const { return S->ns(qsub(qr, ql, L.nq)); }
+  int64_t colbase(int ql, int qr) const { return L.dim[ql] ? (o(ql, qr) - o(ql, 0)) / L.dim[ql] : 0; }
+  int64_t ncols(int ql) const;
+};
+
+struct HostW {         // MPO site tensor in internal orders, W[a + kl*(t + d*(s + d*a'))]  (t = s_out, s = s_in)
+  Grading KL, KR;
+  int d = 0;
+  std::vector<cplx_t> w;
+  std::vector<int> qa_l, qa_r;   // charge of internal MPO link values
+  cplx_t at(int64_t a, int t, int s, int64_t ap) const { return w[a + KL.total() * (t + (int64_t)d * (s + (int64_t)d * ap))]; }
+};
+
+struct GemmPlan {
+  DevList<GemmTask> tasks;
+  DevList<GemmSeg> segs;
+  int tiles = 0;
+  bool ta = false, tb = false, narrow = false;
+  double flops = 0;   // real flops (x4 already applied for complex by the caller of finish())
+};
+struct MixPlan {
+  DevList<MixPanel> panels;
+  DevList<MixOut> outs;
+  DevList<MixEntry> ents;
+  int blocks = 0;
+  double flops = 0;
+};
+struct CopyPlan {
+  DevList<CopyTask> tasks;
+  int blocks = 0;
+};
+
+struct Timers {
+  double env = 0, matvec = 0, level1 = 0, trunc = 0, other = 0, nmatvec = 0, matvec_flops = 0;
+};
+
+struct Ctx {
+  Backend* be = nullptr;
+  std::string err;
+  Timers tm;
+};
+
+// One two-site problem with everything resident on the device.
+struct Bond {
+  Ctx* ctx = nullptr;
+  bool cplx = false;
+  int nq = 1;
+  const SiteInfo* S = nullptr;
+  Grading Dl, Dr, Kl, Km, Kr;
+  EnvLayout Llay, Rlay;
+  PhiLayout philay;
+  const void* L = nullptr;   // not owned
+  const void* R = nullptr;
+  const HostW* W1 = nullptr;
+  const HostW* W2 = nullptr;
+  // matvec plan
+  GemmPlan g1, g2;
+  MixPlan mix;
+  Buf T1, T2;
+  int64_t t1_elems = 0, t2_elems = 0;
+  double flops_alg = 0;      // SURVEY 8(d) F_alg
+  // penalty
+  std::vector<const void*> pen;   // device phi-layout vectors (not owned)
+  double weight = 0;
+  void plan();
+  void apply(const void* x, void* y);   // y = H_eff x (+ penalty)
+};
+
+struct DavidsonResult { double eigenvalue; int nmatvec; };
+DavidsonResult davidson(Bond& b, void* phi /* device, phi layout, in/out */, int niter);
+
+// ---- MPS-level device objects -----------------------------------------------------------------------------------
+struct DevSite3 {
+  Site3Layout lay;
+  Buf buf;
+};
+struct DevEnv {
+  EnvLayout lay;
+  Buf buf;
+};
+
+void two_site(Ctx* c, bool cplx, const DevSite3& A, const DevSite3& B, const PhiLayout& pl, void* phi);
+
+struct SplitResult {
+  Grading mid;
+  DevSite3 A, B;
+  double truncerr = 0;
+  std::vector<double> spectrum;   // kept eigenvalues of rho, descending (pooled)
+  int sweeps = 0;
+};
+// MPS::svdBond. dir 0: Fromleft (A isometry), 1: Fromright (B isometry). The weight-carrying tensor is normalised.
+SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
+                       int64_t mindim, double cutoff);
+
+void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, const DevSite3& A, const HostW& W, DevEnv& out);
+void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, const DevSite3& B, const HostW& W, DevEnv& out);
+
+// one-sided block Jacobi SVD: X (rows x n, ld = rows) on device; returns X V and V (n x n, ld n) and w = column norms^2
+struct JacobiOut {
+  Buf XV, V;
+  int64_t ldx = 0, ldv = 0;
+  std::vector<double> w;
+  int sweeps = 0;
+};
+JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n);
+
+// ITensor truncate() on a descending spectrum
+void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, double cutoff, int64_t* m, double* truncerr, double* docut);
+
+// ---- import / export ---------------------------------------------------------------------------------------------
+HostW import_w(int nq, int d, const SiteInfo& S, const IndexMap& kl, const IndexMap& kr, bool cplx, const void* data);
+void import_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext, DevSite3& out);
+void export_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const DevSite3& in, void* ext);
+void import_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const void* ext, DevEnv& out);
+void export_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const DevEnv& in, void* ext);
+void import_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev);
+void export_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext);
+
+// ---- the sweep driver (itensor::dmrg) --------------------------------------------------------------------------
+struct SweepParams { int maxdim, mindim, niter; double cutoff, noise; };
+struct BondStat { int sweep, bond, dir, m; double energy, truncerr; };
+
+struct HostMPS {       // an MPS in external dense form (what crosses the C ABI)
+  int n = 0;
+  std::vector<IndexMap> link;                 // n+1
+  std::vector<std::vector<char>> site;        // dense [Dl,d,Dr] bytes
+  int center = 0;
+};
+
+struct DmrgResult {
+  double energy = 0;
+  HostMPS psi;
+  std::vector<BondStat> stats;
+  Timers tm;
+  bool cplx = false;
+};
+
+struct MpoIn {
+  int n = 0, nq = 1, d = 0;
+  std::vector<IndexMap> link;                 // n+1
+  std::vector<const void*> site;              // dense [kl,d,d,kr]
+  bool cplx = false;
+  const int32_t* site_charge = nullptr;
+};
+
+std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<HostMPS>& prev, const std::vector<bool>& prev_cplx,
+                                     const HostMPS& psi0, bool psi0_cplx, const std::vector<SweepParams>& sweeps, double weight);
+
+}  // namespace cb200

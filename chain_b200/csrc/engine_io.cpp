@@ -1,0 +1,492 @@
+// Import/export between the dense external tensors that cross the C ABI (ITensor's column-major storage,
+// arbitrary charge order per index) and the internal block layouts; and the sweep driver itensor::dmrg().
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include "engine.h"
+
+namespace cb200 {
+
+static size_t esz(bool cplx) { return cplx ? 16 : 8; }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void check_dev(Ctx* c) {
+  const char* e = dev_last_error(c->be);
+  if (e) fail(-3, std::string("device error: ") + e);
+}
+
+// read element i of an external array of given dtype as complex
+static inline cplx_t rd(const void* p, bool cplx, int64_t i) {
+  if (cplx) return cplx_t(((const double*)p)[2 * i], ((const double*)p)[2 * i + 1]);
+  return cplx_t(((const double*)p)[i], 0.0);
+}
+static inline void wr(void* p, bool cplx, int64_t i, cplx_t v) {
+  if (cplx) { ((double*)p)[2 * i] = v.real(); ((double*)p)[2 * i + 1] = v.imag(); }
+  else ((double*)p)[i] = v.real();
+}
+
+HostW import_w(int nq, int d, const SiteInfo& S, const IndexMap& kl, const IndexMap& kr, bool cplx, const void* data) {
+  HostW W;
+  W.KL = kl.g; W.KR = kr.g; W.d = d;
+  const int64_t nl = kl.g.total(), nr = kr.g.total();
+  W.w.assign((size_t)nl * d * d * nr, cplx_t(0, 0));
+  W.qa_l.resize(nl); W.qa_r.resize(nr);
+  for (int64_t a = 0; a < nl; ++a) W.qa_l[kl.ext2int[a]] = kl.charge_ext[a];
+  for (int64_t a = 0; a < nr; ++a) W.qa_r[kr.ext2int[a]] = kr.charge_ext[a];
+  for (int64_t ap = 0; ap < nr; ++ap)
+    for (int s = 0; s < d; ++s)
+      for (int t = 0; t < d; ++t)
+        for (int64_t a = 0; a < nl; ++a) {
+          const cplx_t v = rd(data, cplx, a + nl * (t + (int64_t)d * (s + (int64_t)d * ap)));
+          if (v == cplx_t(0, 0)) continue;
+          const int64_t ai = kl.ext2int[a], api = kr.ext2int[ap];
+          const int ti = (int)S.map.ext2int[t], si = (int)S.map.ext2int[s];
+          // charge rule q(a') = q(a) + q(s_out) - q(s_in)
+          if (qadd(W.qa_l[ai], S.q_int[ti], nq) != qadd(W.qa_r[api], S.q_int[si], nq))
+            fail(-2, "MPO tensor has a non-zero element that violates q(a)+q(s_out) = q(s_in)+q(a')");
+          W.w[ai + nl * (ti + (int64_t)d * (si + (int64_t)d * api))] = v;
+        }
+  return W;
+}
+
+// generic 3-index transfer: ext[xe + Dx*(se + d*ye)] <-> block (qx,qs) element xi_loc + Dx_q*(s_loc + ds*y_loc)
+template <class F>
+static void for_site3(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const Site3Layout& lay, F f) {
+  const int nq = S.nq, d = S.d;
+  const int64_t Dx = l.g.total();
+  for (int qx = 0; qx < nq; ++qx)
+    for (int qs = 0; qs < nq; ++qs) {
+      const int qy = qadd(qx, qs, nq);
+      const int64_t dx = l.g.dim[qx], dsq = S.map.g.dim[qs], dy = r.g.dim[qy];
+      const int64_t bo = lay.o(qx, qs);
+      for (int64_t y = 0; y < dy; ++y) {
+        const int64_t ye = r.int2ext[r.g.off(qy) + y];
+        for (int64_t s = 0; s < dsq; ++s) {
+          const int64_t se = S.map.int2ext[S.map.g.off(qs) + s];
+          for (int64_t x = 0; x < dx; ++x) {
+            const int64_t xe = l.int2ext[l.g.off(qx) + x];
+            f(xe + Dx * (se + (int64_t)d * ye), bo + x + dx * (s + dsq * y));
+          }
+        }
+      }
+    }
+}
+
+static void import_site3_t(Ctx* c, bool cplx, bool src_cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext,
+                           DevSite3& out) {
+  out.lay.build(l.g, r.g, &S);
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(out.lay.total, 1), 0);
+  for_site3(S, l, r, out.lay, [&](int64_t e, int64_t i) { wr(h.data(), cplx, i, rd(ext, src_cplx, e)); });
+  out.buf = Buf(c->be, (int64_t)h.size());
+  dev_h2d(c->be, out.buf.p, h.data(), h.size());
+}
+void import_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext, DevSite3& out) {
+  import_site3_t(c, cplx, cplx, S, l, r, ext, out);
+}
+void export_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const DevSite3& in, void* ext) {
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(in.lay.total, 1));
+  dev_d2h(c->be, h.data(), in.buf.p, esz(cplx) * (size_t)in.lay.total);
+  const int64_t tot = l.g.total() * S.d * r.g.total();
+  std::memset(ext, 0, esz(cplx) * (size_t)tot);
+  for_site3(S, l, r, in.lay, [&](int64_t e, int64_t i) { wr(ext, cplx, e, rd(h.data(), cplx, i)); });
+}
+
+template <class F>
+static void for_env(const IndexMap& x, const IndexMap& k, const EnvLayout& lay, F f) {
+  const int nq = x.g.nq;
+  const int64_t Dx = x.g.total(), Kt = k.g.total();
+  for (int qxp = 0; qxp < nq; ++qxp)
+    for (int qa = 0; qa < nq; ++qa) {
+      const int qx = qsub(qxp, qa, nq);
+      const int64_t dxp = x.g.dim[qxp], ka = k.g.dim[qa], dx = x.g.dim[qx];
+      const int64_t bo = lay.o(qxp, qa);
+      for (int64_t xi = 0; xi < dx; ++xi) {
+        const int64_t xe = x.int2ext[x.g.off(qx) + xi];
+        for (int64_t a = 0; a < ka; ++a) {
+          const int64_t ae = k.int2ext[k.g.off(qa) + a];
+          for (int64_t xp = 0; xp < dxp; ++xp) {
+            const int64_t xpe = x.int2ext[x.g.off(qxp) + xp];
+            f(xpe + Dx * (ae + Kt * xe), bo + xp + dxp * (a + ka * xi));
+          }
+        }
+      }
+    }
+}
+void import_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const void* ext, DevEnv& out) {
+  out.lay.build(x.g, k.g);
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(out.lay.total, 1), 0);
+  for_env(x, k, out.lay, [&](int64_t e, int64_t i) { wr(h.data(), cplx, i, rd(ext, cplx, e)); });
+  out.buf = Buf(c->be, (int64_t)h.size());
+  dev_h2d(c->be, out.buf.p, h.data(), h.size());
+}
+void export_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const DevEnv& in, void* ext) {
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(in.lay.total, 1));
+  dev_d2h(c->be, h.data(), in.buf.p, esz(cplx) * (size_t)in.lay.total);
+  const int64_t tot = x.g.total() * k.g.total() * x.g.total();
+  std::memset(ext, 0, esz(cplx) * (size_t)tot);
+  for_env(x, k, in.lay, [&](int64_t e, int64_t i) { wr(ext, cplx, e, rd(h.data(), cplx, i)); });
+}
+
+template <class F>
+static void for_phi(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, F f) {
+  const int nq = S.nq, d = S.d;
+  const int64_t Dl = l.g.total();
+  for (int ql = 0; ql < nq; ++ql)
+    for (int qr = 0; qr < nq; ++qr) {
+      const int qd = qsub(qr, ql, nq);
+      const int64_t dl = l.g.dim[ql], dr = r.g.dim[qr], ns = S.ns(qd);
+      const int64_t bo = pl.o(ql, qr);
+      for (int64_t rr = 0; rr < dr; ++rr) {
+        const int64_t re = r.int2ext[r.g.off(qr) + rr];
+        for (int64_t sr = 0; sr < ns; ++sr) {
+          const int64_t s1e = S.map.int2ext[S.srow[qd][sr].first], s2e = S.map.int2ext[S.srow[qd][sr].second];
+          for (int64_t ll = 0; ll < dl; ++ll) {
+            const int64_t le = l.int2ext[l.g.off(ql) + ll];
+            f(le + Dl * (s1e + (int64_t)d * (s2e + (int64_t)d * re)), bo + ll + dl * (sr + ns * rr));
+          }
+        }
+      }
+    }
+}
+void import_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev) {
+  if (S.nq == 1 && l.identity && r.identity && S.map.identity) {   // dense: the phi layout IS the column-major [l,s1,s2,r] array
+    dev_h2d(c->be, dev, ext, esz(cplx) * (size_t)pl.total);
+    return;
+  }
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(pl.total, 1), 0);
+  for_phi(S, l, r, pl, [&](int64_t e, int64_t i) { wr(h.data(), cplx, i, rd(ext, cplx, e)); });
+  dev_h2d(c->be, dev, h.data(), esz(cplx) * (size_t)pl.total);
+}
+void export_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext) {
+  if (S.nq == 1 && l.identity && r.identity && S.map.identity) {
+    dev_d2h(c->be, ext, dev, esz(cplx) * (size_t)pl.total);
+    return;
+  }
+  std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(pl.total, 1));
+  dev_d2h(c->be, h.data(), dev, esz(cplx) * (size_t)pl.total);
+  const int64_t tot = l.g.total() * S.d * S.d * r.g.total();
+  std::memset(ext, 0, esz(cplx) * (size_t)tot);
+  for_phi(S, l, r, pl, [&](int64_t e, int64_t i) { wr(ext, cplx, e, rd(h.data(), cplx, i)); });
+}
+
+// ------------------------------------------------------------------------------------------------ overlap environments
+namespace {
+
+struct DevMat {   // block-diagonal matrix F[x, j] (same charge on both sides): block q is X[q] x J[q], column-major
+  Grading X, J;
+  std::vector<int64_t> off;
+  int64_t total = 0;
+  Buf buf;
+  void build(const Grading& x, const Grading& j) {
+    X = x; J = j;
+    off.assign(x.nq, 0);
+    int64_t t = 0;
+    for (int q = 0; q < x.nq; ++q) { off[q] = t; t += X.dim[q] * J.dim[q]; }
+    total = t;
+  }
+};
+
+struct PlanBits {
+  std::vector<GemmTask> tasks;
+  std::vector<GemmSeg> segs;
+};
+
+// tiny local copy of the GEMM builder (the one in engine.cpp is file-local)
+struct GB {
+  std::vector<GemmTask> tasks;
+  std::vector<GemmSeg> segs;
+  bool cplx;
+  GemmTask cur{};
+  explicit GB(bool c) : cplx(c) {}
+  void begin(int64_t c_off, int64_t ldc, int64_t M, int64_t N, uint32_t flags) {
+    cur = GemmTask{};
+    cur.c_off = c_off; cur.c_off2 = c_off; cur.ldc = ldc; cur.M = (int32_t)M; cur.N = (int32_t)N; cur.n_split = (int32_t)N;
+    cur.seg_begin = (int32_t)segs.size(); cur.flags = flags;
+  }
+  void seg(int64_t a_off, int64_t lda, int64_t b_off, int64_t ldb, int64_t K) {
+    if (K <= 0) return;
+    GemmSeg s{};
+    s.a_off = a_off; s.b_off = b_off; s.lda = lda; s.ldb = ldb; s.K = (int32_t)K;
+    segs.push_back(s);
+  }
+  void end() {
+    cur.seg_count = (int32_t)segs.size() - cur.seg_begin;
+    if (cur.M <= 0 || cur.N <= 0) { segs.resize(cur.seg_begin); return; }
+    tasks.push_back(cur);
+  }
+  void run(Ctx* c, bool ta, bool tb, const void* A, const void* B, void* C) {
+    if (tasks.empty()) return;
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, false);
+    int tiles = 0;
+    for (auto& t : tasks) {
+      t.tile_begin = tiles;
+      t.tiles_m = (t.M + tm - 1) / tm;
+      tiles += t.tiles_m * ((t.N + tn - 1) / tn);
+    }
+    DevList<GemmTask> dt;
+    DevList<GemmSeg> dsg;
+    dt.upload(c->be, tasks);
+    dsg.upload(c->be, segs);
+    launch_gemm(c->be, cplx, ta, tb, false, A, B, C, dt.ptr(), dt.n, dsg.ptr(), tiles);
+  }
+};
+
+// Y[x, s, n] = sum_j F[x, j] P[j, s, n]      (Site3 with left grading F.X, right grading P.Y)
+void mat_times_site3(Ctx* c, bool cplx, const SiteInfo* S, const DevMat& F, const DevSite3& P, DevSite3& Y) {
+  const int nq = S->nq;
+  Y.lay.build(F.X, P.lay.Y, S);
+  Y.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(Y.lay.total, 1), true);
+  GB gb(cplx);
+  for (int q = 0; q < nq; ++q) {
+    const int64_t M = F.X.dim[q], K = F.J.dim[q], N = P.lay.ncols(q);
+    if (M == 0 || N == 0) continue;
+    gb.begin(Y.lay.o(q, 0), M, M, N, 0);
+    gb.seg(F.off[q], M, P.lay.o(q, 0), K, K);
+    gb.end();
+  }
+  gb.run(c, false, false, F.buf.p, P.buf.p, Y.buf.p);
+}
+
+// Y[n, s, r] = sum_p P[n, s, p] F[r, p]      (Site3 with left grading P.X, right grading F.X)
+void site3_times_matT(Ctx* c, bool cplx, const SiteInfo* S, const DevSite3& P, const DevMat& F, DevSite3& Y) {
+  const int nq = S->nq;
+  const Grading& ds = S->map.g;
+  Y.lay.build(P.lay.X, F.X, S);
+  Y.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(Y.lay.total, 1), true);
+  GB gb(cplx);
+  for (int qn = 0; qn < nq; ++qn)
+    for (int qs = 0; qs < nq; ++qs) {
+      const int qr = qadd(qn, qs, nq);
+      const int64_t M = P.lay.X.dim[qn] * ds.dim[qs], N = F.X.dim[qr], K = F.J.dim[qr];
+      if (M == 0 || N == 0) continue;
+      gb.begin(Y.lay.o(qn, qs), M, M, N, 0);
+      gb.seg(P.lay.o(qn, qs), M, F.off[qr], N, K);   // B^T: element (k=p, n=r) at r + N*p
+      gb.end();
+    }
+  gb.run(c, false, true, P.buf.p, F.buf.p, Y.buf.p);
+}
+
+// F'[m, n] = sum_{l,s} conj(A[l,s,m]) X[l,s,n]   (A: Dl->Dm, X: Dl->Dn)
+void site3H_times_site3(Ctx* c, bool cplx, const SiteInfo* S, const DevSite3& A, const DevSite3& X, DevMat& F) {
+  const int nq = S->nq;
+  const Grading& ds = S->map.g;
+  F.build(A.lay.Y, X.lay.Y);
+  F.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(F.total, 1), true);
+  GB gb(cplx);
+  for (int qm = 0; qm < nq; ++qm) {
+    const int64_t M = A.lay.Y.dim[qm], N = X.lay.Y.dim[qm];
+    if (M == 0 || N == 0) continue;
+    gb.begin(F.off[qm], M, M, N, GEMM_TRANS_A | GEMM_CONJ_A);
+    for (int ql = 0; ql < nq; ++ql) {
+      const int qs = qsub(qm, ql, nq);
+      const int64_t K = A.lay.X.dim[ql] * ds.dim[qs];
+      gb.seg(A.lay.o(ql, qs), K, X.lay.o(ql, qs), K, K);
+    }
+    gb.end();
+  }
+  gb.run(c, true, false, A.buf.p, X.buf.p, F.buf.p);
+}
+
+// F'[m, n] = sum_{s,r} conj(B[m,s,r]) X[n,s,r]   (B: Dm->Dr, X: Dn->Dr)
+void site3_times_site3H_right(Ctx* c, bool cplx, const SiteInfo* S, const DevSite3& B, const DevSite3& X, DevMat& F) {
+  const int nq = S->nq;
+  const Grading& ds = S->map.g;
+  F.build(B.lay.X, X.lay.X);
+  F.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(F.total, 1), true);
+  GB gb(cplx);
+  for (int qm = 0; qm < nq; ++qm) {
+    const int64_t M = B.lay.X.dim[qm], N = X.lay.X.dim[qm];
+    if (M == 0 || N == 0) continue;
+    // F'[m,n] = sum_k conj(B[m,k]) X[n,k]: A = B block as M x K (m contiguous) with CONJ_A, B-op = X^T (n contiguous)
+    gb.begin(F.off[qm], M, M, N, GEMM_CONJ_A);
+    for (int qs = 0; qs < nq; ++qs) {
+      const int qr = qadd(qm, qs, nq);
+      const int64_t K = ds.dim[qs] * B.lay.Y.dim[qr];
+      gb.seg(B.lay.o(qm, qs), M, X.lay.o(qm, qs), N, K);
+    }
+    gb.end();
+  }
+  gb.run(c, false, true, B.buf.p, X.buf.p, F.buf.p);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ the sweep driver
+std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<HostMPS>& prev, const std::vector<bool>& prev_cplx,
+                                     const HostMPS& psi0, bool psi0_cplx, const std::vector<SweepParams>& sweeps, double weight) {
+  Backend* be = c->be;
+  const int n = H.n, nq = H.nq;
+  if (n < 2) fail(-2, "dmrg needs at least 2 sites");
+  if (psi0.n != n) fail(-2, "MPS / MPO length mismatch");
+  bool cplx = H.cplx || psi0_cplx;
+  for (bool b : prev_cplx) cplx = cplx || b;
+  c->tm = Timers{};
+  double t_other0 = now_s();
+
+  SiteInfo S = SiteInfo::make(nq, H.d, H.site_charge);
+  std::vector<HostW> W(n);
+  for (int j = 0; j < n; ++j) W[j] = import_w(nq, H.d, S, H.link[j], H.link[j + 1], H.cplx, H.site[j]);
+
+  // current state
+  std::vector<IndexMap> link = psi0.link;
+  std::vector<DevSite3> A(n);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, psi0_cplx, S, link[j], link[j + 1], psi0.site[j].data(), A[j]);
+  if (link[0].g.total() != 1 || link[n].g.total() != 1) fail(-2, "outer MPS links must have dimension 1");
+  // previous states
+  const int np = (int)prev.size();
+  std::vector<std::vector<DevSite3>> P(np);
+  for (int p = 0; p < np; ++p) {
+    if (prev[p].n != n) fail(-2, "previous state length mismatch");
+    P[p].resize(n);
+    for (int j = 0; j < n; ++j) import_site3_t(c, cplx, prev_cplx[p], S, prev[p].link[j], prev[p].link[j + 1], prev[p].site[j].data(), P[p][j]);
+  }
+
+  auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {   // sites i, i+1 (0-based)
+    pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
+    phi = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
+    two_site(c, cplx, A[i], A[i + 1], pl, phi.p);
+  };
+
+  // psi.position(1) for a non-canonical start: exact (untruncated) splits from the right
+  if (psi0.center != 1) {
+    for (int i = n - 2; i >= 0; --i) {
+      PhiLayout pl; Buf phi;
+      phi_of(i, pl, phi);
+      // tiny relative cutoff: drops only the numerically-zero directions, so a product state keeps bond dimension 1
+      SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 1, INT64_MAX / 4, 1, 1e-20);
+      A[i] = std::move(sr.A);
+      A[i + 1] = std::move(sr.B);
+    }
+  }
+
+  // environments: LE[b] covers sites 1..b, RE[b] covers sites b+1..n (cut index b = 0..n)
+  std::vector<DevEnv> LE(n + 1), RE(n + 1);
+  auto unit_env = [&](DevEnv& e, const Grading& x, const Grading& k) {
+    e.lay.build(x, k);
+    if (e.lay.total != 1) fail(-2, "boundary environment is not 1x1x1");
+    std::vector<char> one(esz(cplx), 0);
+    wr(one.data(), cplx, 0, cplx_t(1, 0));
+    e.buf = Buf(be, (int64_t)esz(cplx));
+    dev_h2d(be, e.buf.p, one.data(), one.size());
+  };
+  unit_env(LE[0], A[0].lay.X, W[0].KL);
+  unit_env(RE[n], A[n - 1].lay.Y, W[n - 1].KR);
+  std::vector<std::vector<DevMat>> FL(np), FR(np);
+  for (int p = 0; p < np; ++p) { FL[p] = std::vector<DevMat>(n + 1); FR[p] = std::vector<DevMat>(n + 1); }
+  for (int p = 0; p < np; ++p) {
+    for (DevMat* f : {&FL[p][0], &FR[p][n]}) {
+      const Grading& x = (f == &FL[p][0]) ? A[0].lay.X : A[n - 1].lay.Y;
+      const Grading& j = (f == &FL[p][0]) ? P[p][0].lay.X : P[p][n - 1].lay.Y;
+      f->build(x, j);
+      if (f->total != 1) fail(-2, "previous state lives in a different charge sector");
+      std::vector<char> one(esz(cplx), 0);
+      wr(one.data(), cplx, 0, cplx_t(1, 0));
+      f->buf = Buf(be, (int64_t)esz(cplx));
+      dev_h2d(be, f->buf.p, one.data(), one.size());
+    }
+  }
+  auto ovl_right = [&](int p, int b) {   // FR[p][b] from FR[p][b+1] and site b+1 (0-based b)
+    DevSite3 X;
+    site3_times_matT(c, cplx, &S, P[p][b], FR[p][b + 1], X);          // X[n,s,r] = P[n,s,p] F[r,p]
+    site3_times_site3H_right(c, cplx, &S, A[b], X, FR[p][b]);
+  };
+  auto ovl_left = [&](int p, int b) {    // FL[p][b] from FL[p][b-1] and site b (1-based b) = index b-1
+    DevSite3 X;
+    mat_times_site3(c, cplx, &S, FL[p][b - 1], P[p][b - 1], X);       // X[l,s,n] = F[l,j] P[j,s,n]
+    site3H_times_site3(c, cplx, &S, A[b - 1], X, FL[p][b]);
+  };
+  {
+    double t = now_s();
+    for (int b = n - 1; b >= 2; --b) {
+      env_update_right(c, cplx, &S, RE[b + 1], A[b], W[b], RE[b]);
+      for (int p = 0; p < np; ++p) ovl_right(p, b);
+    }
+    dev_sync(be);
+    c->tm.env += now_s() - t;
+  }
+  c->tm.other += now_s() - t_other0 - c->tm.env - c->tm.trunc;
+
+  auto res = std::make_unique<DmrgResult>();
+  res->cplx = cplx;
+  double energy = 0;
+  for (int sw = 0; sw < (int)sweeps.size(); ++sw) {
+    const SweepParams& sp = sweeps[sw];
+    if (sp.noise != 0.0) fail(-2, "noise != 0 is not supported (Chain always runs with noise 0, src/dmrg.h:350)");
+    for (int half = 0; half < 2; ++half)
+      for (int k = 0; k < n - 1; ++k) {
+        const int b = half == 0 ? k + 1 : n - 1 - k;     // 1-based bond (sites b, b+1)
+        const int dir = half;                            // 0 Fromleft, 1 Fromright
+        const int i = b - 1;
+        double t0 = now_s();
+        PhiLayout pl; Buf phi;
+        phi_of(i, pl, phi);
+        Bond bond;
+        bond.ctx = c; bond.cplx = cplx; bond.nq = nq; bond.S = &S;
+        bond.Dl = A[i].lay.X; bond.Dr = A[i + 1].lay.Y;
+        bond.Kl = W[i].KL; bond.Km = W[i].KR; bond.Kr = W[i + 1].KR;
+        bond.L = LE[b - 1].buf.p; bond.R = RE[b + 1].buf.p;
+        bond.W1 = &W[i]; bond.W2 = &W[i + 1];
+        bond.plan();
+        // penalty vectors o_j = FL . Psi_b . Psi_{b+1} . FR^T (built once per bond, LocalMPO_MPS)
+        std::vector<Buf> pen(np);
+        for (int p = 0; p < np; ++p) {
+          DevSite3 X1, X2;
+          mat_times_site3(c, cplx, &S, FL[p][b - 1], P[p][i], X1);
+          site3_times_matT(c, cplx, &S, P[p][i + 1], FR[p][b + 1], X2);
+          pen[p] = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
+          two_site(c, cplx, X1, X2, pl, pen[p].p);
+          bond.pen.push_back(pen[p].p);
+        }
+        bond.weight = weight;
+        dev_sync(be);
+        c->tm.other += now_s() - t0;
+        DavidsonResult dr = davidson(bond, phi.p, sp.niter);
+        energy = dr.eigenvalue;
+        t0 = now_s();
+        SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, dir, sp.maxdim, sp.mindim, sp.cutoff);
+        c->tm.trunc += now_s() - t0;
+        A[i] = std::move(sr.A);
+        A[i + 1] = std::move(sr.B);
+        t0 = now_s();
+        if (dir == 0) {
+          env_update_left(c, cplx, &S, LE[b - 1], A[i], W[i], LE[b]);
+          for (int p = 0; p < np; ++p) ovl_left(p, b);
+        } else {
+          env_update_right(c, cplx, &S, RE[b + 1], A[i + 1], W[i + 1], RE[b]);
+          for (int p = 0; p < np; ++p) ovl_right(p, b);
+        }
+        dev_sync(be);
+        c->tm.env += now_s() - t0;
+        res->stats.push_back({sw, b, dir, (int)sr.mid.total(), energy, sr.truncerr});
+        check_dev(c);
+      }
+  }
+  // psi.normalize(): the orthogonality centre is site 1
+  {
+    const void* xs[1] = {A[0].buf.p};
+    double nn[2];
+    multi_dot(be, cplx, 1, xs, A[0].buf.p, A[0].lay.total, nn);
+    if (nn[0] > 0) {
+      double co[2] = {1.0 / std::sqrt(nn[0]), 0.0};
+      lincomb(be, cplx, 1, xs, co, 0, 0, A[0].buf.p, A[0].lay.total);
+    }
+  }
+  // export
+  res->energy = energy;
+  res->psi.n = n;
+  res->psi.center = 1;
+  res->psi.link.resize(n + 1);
+  res->psi.site.resize(n);
+  for (int j = 0; j <= n; ++j) res->psi.link[j] = IndexMap::from_grading(j == 0 ? A[0].lay.X : A[j - 1].lay.Y);
+  for (int j = 0; j < n; ++j) {
+    const int64_t tot = A[j].lay.X.total() * S.d * A[j].lay.Y.total();
+    res->psi.site[j].assign(esz(cplx) * (size_t)tot, 0);
+    // site index is exported in the caller's order (S.map), links in internal (charge-sorted) order
+    export_site3(c, cplx, S, res->psi.link[j], res->psi.link[j + 1], A[j], res->psi.site[j].data());
+  }
+  res->tm = c->tm;
+  check_dev(c);
+  return res;
+}
+
+}  // namespace cb200

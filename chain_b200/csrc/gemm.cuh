@@ -1,0 +1,273 @@
+// Grouped, segment-accumulating FP64 GEMM on the sm_100a DMMA pipe.
+//
+// One launch executes a whole task list (tasks.h): every CTA owns one 128x128 (real) or 64x128 (complex)
+// tile of one task's C and runs a single multi-stage cp.async pipeline over the concatenation of all of that
+// task's K-segments, so that  C = sum_seg op(A_seg) * op(B_seg)  is formed in registers without ever
+// materialising the per-segment products.  This is how the environment x MPO x wavefunction contractions of
+// LocalMPO::product / makeL / makeR (ITensor, called from /root/reference/src/dmrg.h:544,563,596) are executed:
+// the index permutations ITensor performs as explicit copies are absorbed into the (lda, ldb, transpose)
+// addressing of the tile loads.
+//
+// FP64 on sm_100a has no tcgen05 kind; the tensor instruction is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).
+// Fragment layout (PTX ISA): A[row=lane>>2][k=lane&3], B[k=lane&3][col=lane>>2], C[row=lane>>2][col=2*(lane&3)+{0,1}].
+// Shared-memory tiles are padded so that the 64-bit (half-warp) / 128-bit (quarter-warp) fragment loads are
+// bank-conflict free in both operand orientations ("DMMA GEMM").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "tasks.h"
+
+namespace cb200 {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <bool CPLX, int BN_ = 128>
+struct GemmCfg {
+  // real:    CTA 128x128x16, 8 warps as 2(m) x 4(n), warp tile 64x32  -> 8x4 DMMA tiles
+  // complex: CTA  64x128x8,  8 warps as 2(m) x 4(n), warp tile 32x32  -> 4x4 complex tiles (4 DMMA each)
+  static constexpr int BM = CPLX ? 64 : 128;
+  static constexpr int BN = BN_;                     // 128 (default) or 64 (narrow outputs: Jacobi rotations, Gram blocks)
+  static constexpr int BK = CPLX ? 8 : 16;
+  static constexpr int WM = CPLX ? 32 : 64;
+  static constexpr int WN = BN_ / 4;
+  static constexpr int MT = WM / 8;
+  static constexpr int NT = WN / 8;
+  static constexpr int ES = CPLX ? 16 : 8;           // element bytes
+  static constexpr int PAD_MN = CPLX ? 2 : 4;        // [k][mn] layout: LD = B{M,N} + PAD_MN
+  static constexpr int LDK = BK + 4;                 // [mn][k] layout
+  static constexpr int A_ELEMS = (BK * (BM + PAD_MN) > BM * LDK) ? BK * (BM + PAD_MN) : BM * LDK;
+  static constexpr int B_ELEMS = (BK * (BN + PAD_MN) > BN * LDK) ? BK * (BN + PAD_MN) : BN * LDK;
+  static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * ES;
+  static constexpr int STAGES = 4;
+  static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES;
+  static constexpr int THREADS = 256;
+};
+
+// Load one operand tile (BMN x BK elements) into shared memory.
+//   MN_CONTIG = true : global element (mn,k) at g[mn + k*ld]; smem layout [k][mn], LD = BMN+PAD
+//   MN_CONTIG = false: global element (mn,k) at g[k + mn*ld]; smem layout [mn][k], LD = BK+4
+// Out-of-range elements are zero-filled by cp.async's src-size operand.
+template <bool CPLX, int BN_, int BMN, bool MN_CONTIG>
+__device__ __forceinline__ void load_operand_tile(char* smem, const char* g, int64_t ld, int mn0, int MN, int k0, int K,
+                                                  bool vec_ok, int tid) {
+  using Cfg = GemmCfg<CPLX, BN_>;
+  constexpr int BK = Cfg::BK;
+  constexpr int ES = Cfg::ES;
+  constexpr int LD = MN_CONTIG ? (BMN + Cfg::PAD_MN) : Cfg::LDK;
+  if constexpr (CPLX) {
+    // one 16-byte element per copy
+    constexpr int TOTAL = BMN * BK;
+#pragma unroll
+    for (int c = tid; c < TOTAL; c += Cfg::THREADS) {
+      int mn, k;
+      if constexpr (MN_CONTIG) { k = c / BMN; mn = c % BMN; } else { mn = c / BK; k = c % BK; }
+      const bool ok = (mn0 + mn < MN) && (k0 + k < K);
+      const int64_t goff = MN_CONTIG ? ((int64_t)(mn0 + mn) + (int64_t)(k0 + k) * ld) : ((int64_t)(k0 + k) + (int64_t)(mn0 + mn) * ld);
+      const int soff = MN_CONTIG ? (k * LD + mn) : (mn * LD + k);
+      cp_async16(smem + (size_t)soff * ES, ok ? (g + goff * ES) : g, ok ? 16 : 0);
+    }
+  } else {
+    // two doubles per 16-byte copy along the contiguous direction
+    constexpr int TOTAL = BMN * BK / 2;
+#pragma unroll
+    for (int c = tid; c < TOTAL; c += Cfg::THREADS) {
+      int mn, k, rem;
+      int64_t goff;
+      int soff;
+      if constexpr (MN_CONTIG) {
+        k = c / (BMN / 2); mn = (c % (BMN / 2)) * 2;
+        rem = (k0 + k < K) ? (MN - (mn0 + mn)) : 0;
+        goff = (int64_t)(mn0 + mn) + (int64_t)(k0 + k) * ld;
+        soff = k * LD + mn;
+      } else {
+        mn = c / (BK / 2); k = (c % (BK / 2)) * 2;
+        rem = (mn0 + mn < MN) ? (K - (k0 + k)) : 0;
+        goff = (int64_t)(k0 + k) + (int64_t)(mn0 + mn) * ld;
+        soff = mn * LD + k;
+      }
+      rem = rem < 0 ? 0 : (rem > 2 ? 2 : rem);
+      char* sp = smem + (size_t)soff * 8;
+      const char* gp = rem ? (g + goff * 8) : g;
+      if (vec_ok) {
+        cp_async16(sp, gp, rem * 8);
+      } else {
+        cp_async8(sp, gp, rem >= 1 ? 8 : 0);
+        cp_async8(sp + 8, rem >= 2 ? gp + 8 : g, rem >= 2 ? 8 : 0);
+      }
+    }
+  }
+}
+
+template <bool CPLX, bool TA, bool TB, int BN_ = 128>
+__global__ void __launch_bounds__(256, 1)
+gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
+                    const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs) {
+  using Cfg = GemmCfg<CPLX, BN_>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, MT = Cfg::MT, NT = Cfg::NT, ES = Cfg::ES, STAGES = Cfg::STAGES;
+  // smem strides (elements) of the fragment reads
+  constexpr int A_SM = TA ? Cfg::LDK : 1;                       // stride along m
+  constexpr int A_SK = TA ? 1 : (BM + Cfg::PAD_MN);             // stride along k
+  constexpr int B_SN = TB ? 1 : Cfg::LDK;                       // stride along n
+  constexpr int B_SK = TB ? (BN + Cfg::PAD_MN) : 1;             // stride along k
+
+  extern __shared__ __align__(16) char smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wm0 = (warp & 1) * Cfg::WM;
+  const int wn0 = (warp >> 1) * Cfg::WN;
+
+  // locate the task owning this tile (tile_begin is ascending)
+  int lo = 0, hi = ntasks - 1;
+  const int tile = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+  }
+  const GemmTask t = tasks[lo];
+  const int lt = tile - t.tile_begin;
+  const int m0 = (lt % t.tiles_m) * BM;
+  const int n0 = (lt / t.tiles_m) * BN;
+  const GemmSeg* sg = segs + t.seg_begin;
+
+  int total_kt = 0;
+  for (int s = 0; s < t.seg_count; ++s) total_kt += (sg[s].K + BK - 1) / BK;
+
+  // producer cursor
+  int ps = 0, pk = 0;
+  auto issue_load = [&](int stage) {
+    const GemmSeg s = sg[ps];
+    char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+    char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
+    const char* ga = Abase + s.a_off * ES;
+    const char* gb = Bbase + s.b_off * ES;
+    bool va = true, vb = true;
+    if constexpr (!CPLX) {
+      va = ((((uintptr_t)ga) & 15) == 0) && ((s.lda & 1) == 0);
+      vb = ((((uintptr_t)gb) & 15) == 0) && ((s.ldb & 1) == 0);
+    }
+    load_operand_tile<CPLX, BN_, BM, !TA>(sa, ga, s.lda, m0, t.M, pk, s.K, va, tid);
+    load_operand_tile<CPLX, BN_, BN, TB>(sb, gb, s.ldb, n0, t.N, pk, s.K, vb, tid);
+    pk += BK;
+    if (pk >= s.K) { pk = 0; ++ps; }
+  };
+
+  double acc_re[MT][NT][2];
+  double acc_im[CPLX ? MT : 1][CPLX ? NT : 1][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      acc_re[i][j][0] = 0.0; acc_re[i][j][1] = 0.0;
+      if constexpr (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
+    }
+
+  int issued = 0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (issued < total_kt) { issue_load(s); ++issued; }
+    cp_async_commit();
+  }
+
+  const bool conjA = (t.flags & GEMM_CONJ_A) != 0;
+  for (int it = 0; it < total_kt; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (issued < total_kt) { issue_load((it + STAGES - 1) % STAGES); ++issued; }
+    cp_async_commit();
+
+    const char* sa = smem + (size_t)(it % STAGES) * Cfg::STAGE_BYTES;
+    const char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
+    if constexpr (!CPLX) {
+      const double* As = reinterpret_cast<const double*>(sa) + (wm0 + g) * A_SM + tq * A_SK;
+      const double* Bs = reinterpret_cast<const double*>(sb) + (wn0 + g) * B_SN + tq * B_SK;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MT], b[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) a[i] = As[i * 8 * A_SM + kk * 4 * A_SK];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = Bs[j * 8 * B_SN + kk * 4 * B_SK];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i], b[j]);
+      }
+    } else {
+      const double2* As = reinterpret_cast<const double2*>(sa) + (wm0 + g) * A_SM + tq * A_SK;
+      const double2* Bs = reinterpret_cast<const double2*>(sb) + (wn0 + g) * B_SN + tq * B_SK;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double2 a[MT], b[NT];
+        double nai[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          a[i] = As[i * 8 * A_SM + kk * 4 * A_SK];
+          if (conjA) a[i].y = -a[i].y;
+          nai[i] = -a[i].y;
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = Bs[j * 8 * B_SN + kk * 4 * B_SK];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+            dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+            dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
+            dmma884(acc_re[i][j][0], acc_re[i][j][1], nai[i], b[j].y);
+            dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
+          }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: direct stores from the accumulator fragments
+  const bool accum = (t.flags & GEMM_ACCUM) != 0;
+  const bool conj_out = (t.flags & GEMM_CONJ_OUT) != 0;
+  char* Cp = Cbase + t.c_off * ES;
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int m = m0 + wm0 + i * 8 + g;
+    if (m >= t.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 + wn0 + j * 8 + tq * 2 + e;
+        if (n >= t.N) continue;
+        const int64_t off = (n < t.n_split) ? ((int64_t)m + (int64_t)n * t.ldc)
+                                            : ((t.c_off2 - t.c_off) + (int64_t)m + (int64_t)(n - t.n_split) * t.ldc);
+        if constexpr (!CPLX) {
+          double* p = reinterpret_cast<double*>(Cp) + off;
+          double v = acc_re[i][j][e];
+          if (accum) v += *p;
+          *p = v;
+        } else {
+          double2* p = reinterpret_cast<double2*>(Cp) + off;
+          double2 v = make_double2(acc_re[i][j][e], conj_out ? -acc_im[i][j][e] : acc_im[i][j][e]);
+          if (accum) { double2 o = *p; v.x += o.x; v.y += o.y; }
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace cb200

@@ -1,0 +1,160 @@
+/* chain_b200 -- C ABI of the B200-native DMRG hot path for tzu-chen/Chain.
+ *
+ * The reference has no FFI of its own: its seam is the C++ call
+ *     std::tie(en_, psi_) = dmrg(H, dmrg_progress_.DoneStates(), psi, sweeps, {"Quiet",true,"Weight=",1000.0});
+ * at /root/reference/src/dmrg.h:544, :563 and :596 (ITensor's itensor::dmrg).  cb200_dmrg() below is what an adapter
+ * for that call binds (INTEGRATION.md shows the adapter); the finer-grained entry points expose the individual
+ * steps of that call (LocalMPO::product, davidson, MPS::svdBond, LocalMPO::position) for tests and profiling.
+ *
+ * Conventions
+ *   - all arrays are column-major (first index fastest), exactly like ITensor's dense storage;
+ *   - dtype 0 = float64, 1 = complex128 (interleaved re,im);
+ *   - MPS site tensor A[l, s, r]; MPO site tensor W[a, s_out, s_in, a']; (s_in is the ket index ITensor calls s,
+ *     s_out the primed index s');
+ *   - Z_N symmetry is described by one charge label per index value (cb200_index), the block structure is
+ *     derived from the labels: A[l,s,r] != 0 only if q(l)+q(s) = q(r), W != 0 only if q(a)+q(s_out) = q(s_in)+q(a')
+ *     ... all mod N.  N = 1 (all labels 0) is the dense case (golden, haagerup); N = 3 is haagerupq;
+ *   - every function returns 0 on success, a negative cb200_status otherwise; cb200_last_error() gives the text.
+ *     No exception crosses this boundary and there is no CPU fallback: without a usable sm_100 device
+ *     cb200_create() fails.
+ */
+#ifndef CHAIN_B200_H
+#define CHAIN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb200_ctx cb200_ctx;
+
+enum cb200_status {
+  CB200_OK = 0,
+  CB200_ERR_NO_DEVICE = -1,
+  CB200_ERR_INVALID = -2,
+  CB200_ERR_CUDA = -3,
+  CB200_ERR_NOMEM = -4,
+  CB200_ERR_NOCONV = -5,
+  CB200_ERR_RANGE = -6   /* the adapter rethrows this one as std::out_of_range, which DMRG::Simulate catches (src/dmrg.h:454) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int cb200_create(cb200_ctx** out, int device);
+void cb200_destroy(cb200_ctx* ctx);
+const char* cb200_last_error(const cb200_ctx* ctx);   /* ctx may be NULL: error of the last failed cb200_create */
+const char* cb200_backend_name(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t cb200_launch_count(const cb200_ctx* ctx);
+
+/* ---- problem description -------------------------------------------------------------------------------------- */
+typedef struct cb200_index {
+  int64_t dim;
+  const int32_t* charge;      /* dim labels in [0, nq); NULL means all zero */
+} cb200_index;
+
+typedef struct cb200_tensor {
+  int32_t dtype;              /* 0 f64, 1 c128 */
+  int32_t rank;               /* 3 (MPS) or 4 (MPO) */
+  int64_t dims[4];
+  const void* data;           /* column-major, dense with exact zeros in forbidden blocks */
+} cb200_tensor;
+
+/* per-sweep parameters: what itensor::Sweeps holds (src/dmrg.h:538-543, :589-593) */
+typedef struct cb200_sweep {
+  int32_t maxdim, mindim, niter;
+  int32_t pad_;
+  double cutoff, noise;
+} cb200_sweep;
+
+typedef struct cb200_bond_stat {
+  int32_t sweep, bond, dir, m;       /* dir 0 = Fromleft, 1 = Fromright */
+  double energy, truncerr;
+} cb200_bond_stat;
+
+/* An MPS handed across the boundary: n site tensors + n+1 link indices (link[0] and link[n] have dim 1). */
+typedef struct cb200_mps {
+  int32_t n, nq;
+  const cb200_tensor* site;          /* n tensors [Dl, d, Dr] */
+  const cb200_index* link;           /* n+1 */
+  int32_t ortho_center;              /* 1-based; 0 = unknown (the library orthogonalises to site 1) */
+  int32_t pad_;
+} cb200_mps;
+
+typedef struct cb200_mpo {
+  int32_t n, nq;
+  const cb200_tensor* site;          /* n tensors [kl, d, d, kr] */
+  const cb200_index* link;           /* n+1 MPO link indices */
+  const int32_t* site_charge;        /* d labels of the physical index (same on every site) */
+  int32_t d, pad_;
+} cb200_mpo;
+
+/* ---- coarse entry point: replaces itensor::dmrg(H, psis, psi0, sweeps, {"Weight",w}) -------------------------- */
+typedef struct cb200_result cb200_result;   /* owns the optimised MPS until cb200_result_free */
+
+int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_t nprev, const cb200_mps* psi0,
+               const cb200_sweep* sweeps, int32_t nsweep, double weight, double* energy, cb200_result** out);
+int32_t cb200_result_nsites(const cb200_result* r);
+int32_t cb200_result_dtype(const cb200_result* r);                                  /* 0 f64, 1 c128 */
+int64_t cb200_result_link_dim(const cb200_result* r, int32_t link);                 /* link in [0, n] */
+int cb200_result_link_charges(const cb200_result* r, int32_t link, int32_t* out);  /* dim labels */
+int cb200_result_site(const cb200_result* r, int32_t site, void* out);             /* dense [Dl,d,Dr], caller-sized */
+int32_t cb200_result_nstats(const cb200_result* r);
+int cb200_result_stats(const cb200_result* r, cb200_bond_stat* out);
+/* seconds spent in: [0] env update, [1] H_eff matvec, [2] Davidson level-1, [3] truncation, [4] other; [5] matvec count, [6] matvec flop */
+int cb200_result_timers(const cb200_result* r, double* out7);
+void cb200_result_free(cb200_result* r);
+
+/* ---- fine-grained entry points (one bond of the path; used by tests, bench.py and ncu) ------------------------- */
+/* A "bond problem" keeps L, W_b, W_{b+1}, R (and penalty vectors) resident on the device. */
+typedef struct cb200_bond cb200_bond;
+
+int cb200_bond_create(cb200_ctx* ctx, int32_t dtype, int32_t nq, int32_t d, const int32_t* site_charge,
+                      const cb200_index* l, const cb200_index* r,          /* MPS links left / right of the two sites */
+                      const cb200_index* kl, const cb200_index* km, const cb200_index* kr,   /* MPO links */
+                      const void* L,   /* [Dl, kl, Dl]  (bra, mpo, ket) */
+                      const void* W1,  /* [kl, d, d, km] */
+                      const void* W2,  /* [km, d, d, kr] */
+                      const void* R,   /* [Dr, kr, Dr] */
+                      cb200_bond** out);
+void cb200_bond_free(cb200_bond* b);
+/* penalty vectors o_j (phi-shaped, dense [Dl,d,d,Dr]) with weight: H_eff += weight * sum_j |o_j><o_j| */
+int cb200_bond_set_penalty(cb200_bond* b, int32_t nprev, const void* const* o, double weight);
+int64_t cb200_bond_phi_elems(const cb200_bond* b);   /* Dl*d*d*Dr */
+double cb200_bond_matvec_flops(const cb200_bond* b); /* F_alg of SURVEY 8(d): block-sparse, sparse-W */
+/* LocalMPO(_MPS)::product: host phi in, host H_eff*phi out (copies included) */
+int cb200_bond_apply(cb200_bond* b, const void* phi, void* out);
+/* same product, device-resident, repeated `reps` times; returns mean milliseconds (CUDA events) */
+int cb200_bond_apply_timed(cb200_bond* b, const void* phi, int32_t reps, int32_t warmup, double* ms_mean);
+/* itensor::davidson (MaxIter = niter): phi in/out (host), eigenvalue out */
+int cb200_bond_davidson(cb200_bond* b, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec);
+/* MPS::svdBond: phi (host) -> A [Dl,d,m], B [m,d,Dr]; call with A=B=NULL first to get m and charges_mid
+ * (caller-sized to min(Dl*d, d*Dr)), then again with buffers.  dir 0 Fromleft, 1 Fromright; use_svd != 0 selects
+ * ITensor's "cutoff < 1e-12" branch (identical on this path: the SVD is always used). */
+int cb200_bond_truncate(cb200_bond* b, const void* phi, int32_t dir, int32_t maxdim, int32_t mindim, double cutoff,
+                        int32_t* m, int32_t* charges_mid, double* truncerr, double* spectrum, void* A, void* B);
+/* LocalMPO::makeL / makeR: new environment from the bond's L (dir 0, uses A [Dl,d,m] and W1) or R (dir 1, B [m,d,Dr], W2);
+ * out is [m, km, m] */
+int cb200_bond_env_update(cb200_bond* b, int32_t dir, int32_t m, const int32_t* charges_mid, const void* AorB, void* out);
+
+/* ---- kernel-level entry points (unit tests of the device kernels; all pointers are HOST pointers) ------------- */
+/* C[M x N] (ldc) = (accumulate? C : 0) + sum_seg op(A_seg) op(B_seg); segment s has K[s] columns, A_seg at A + a_off[s]. */
+int cb200_k_gemm(cb200_ctx* ctx, int32_t dtype, int32_t trans_a, int32_t trans_b, int32_t conj_a, int32_t accumulate,
+                 int32_t M, int32_t N, int32_t nseg, const int32_t* K, const void* A, int64_t a_elems, const int64_t* a_off,
+                 int64_t lda, const void* B, int64_t b_elems, const int64_t* b_off, int64_t ldb, void* C, int64_t c_elems,
+                 int64_t c_off, int64_t ldc, int32_t reps, double* ms_mean);
+/* Hermitian eigensolver used inside the truncation: G [npairs][64 x 64] -> Q; returns rotation count */
+int cb200_k_jacobi_eig(cb200_ctx* ctx, int32_t dtype, int32_t npairs, const void* G, void* Q, double tol, int64_t* rotations);
+/* full one-sided block-Jacobi SVD of X [rows x cols]: X <- X V (columns orthogonal), V [cols x cols], w[cols] = column norms^2 */
+int cb200_k_svd(cb200_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, void* X, void* V, double* w, int32_t* sweeps);
+/* out[j] = <x_j | y>, dst = beta*dst + sum c_j x_j */
+int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out_re_im);
+int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const double* c_re_im, double beta_re,
+                    double beta_im, void* dst);
+/* FP64 calibration: achieved TFLOP/s of the DMMA GEMM kernel on a square problem (device-resident, CUDA events) */
+int cb200_k_gemm_peak(cb200_ctx* ctx, int32_t dtype, int32_t n, int32_t reps, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHAIN_B200_H */

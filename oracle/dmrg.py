@@ -330,7 +330,8 @@ def dmrg(W, prev_states, psi0, sweeps, weight=1.0, stats=None, matvec_hook=None)
                     y = y + weight * np.vdot(o, x) * o
                 return y
             if matvec_hook is not None:
-                matvec_hook(b, direction, L, W1, W2, R, phi, proj)
+                matvec_hook(dict(bond=b, dir=direction, L=L, W1=W1, W2=W2, R=R, phi=phi, proj=proj, ql=psi.q[b - 1], qr=psi.q[b + 1],
+                                 sweep=sw, maxdim=maxdim, mindim=mindim, cutoff=cutoff, niter=niter, weight=weight))
             energy, phi, nmv = davidson(mv, phi, maxiter=niter)
             A1, A2, qmid, spec, terr = split_bond(phi, psi.q[b - 1], psi.q[b + 1], sq, nq, direction,
                                                   maxdim, mindim, cutoff, use_svd=use_svd)

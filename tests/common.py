@@ -1,0 +1,187 @@
+"""Shared bodies of the parity tests: the same checks run against the host-emulation build (CPU, host logic only)
+and against the product library on a B200 (-m gpu).  The oracle (oracle/) is the checker."""
+import json
+import os
+
+import numpy as np
+
+import chain_b200 as cb
+from oracle import models, mpo as ompo, dmrg as od
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+PRODUCT_LIB = os.path.join(ROOT, "chain_b200", "libchain_b200.so")
+
+
+def golden():
+    with open(os.path.join(HERE, "golden", "ed_levels.json")) as f:
+        return json.load(f)
+
+
+def ed_level(site, bc, n, couplings, charge):
+    for c in golden()["levels"]:
+        if c["site"] == site and c["bc"] == bc and c["n"] == n and c["couplings"] == list(couplings) and c["charge"] == charge:
+            return c["levels"]
+    raise KeyError((site, bc, n, couplings, charge))
+
+
+def build_model(st, bc, n, couplings, U=2.0):
+    site = models.make_site(st)
+    W, qk = ompo.build_mpo(models.hamiltonian_terms(st, bc, n, U, couplings), site, n)
+    return site, W, qk
+
+
+def to_cb(psi):
+    return cb.MPS(psi.A, psi.q, nq=psi.nq, center=psi.center or 0)
+
+
+def to_oracle(m, site):
+    return od.MPS([np.array(a) for a in m.sites], [np.array(q, dtype=np.int64) for q in m.link_charges], site.charges, site.nq, center=m.center)
+
+
+def warm_start(site, W, n, charge, seed, maxdim=8, nsweep=2):
+    """A non-trivial common start state: a couple of oracle sweeps from the reference's product state.
+    (For QN sites the product state itself triggers Davidson's random restart, which no two implementations share.)"""
+    rng = np.random.default_rng(seed)
+    psi0 = od.product_mps(site, n, charge, rng, dtype=complex if np.iscomplexobj(W[1]) else float)
+    _, psi = od.dmrg(W, [], psi0, od.Sweeps(nsweep, maxdim, 1e-10))
+    return psi
+
+
+def capture_bond(st, bc, n, couplings, charge, bond, seed=3, nsw=3, maxdims=(10, 20, 40)):
+    """Run the oracle a few sweeps and capture L, W, R, phi of one bond update (realistic block structure)."""
+    site, W, qk = build_model(st, bc, n, couplings)
+    rng = np.random.default_rng(seed)
+    psi0 = od.product_mps(site, n, charge, rng, dtype=complex if np.iscomplexobj(W[1]) else float)
+    caps = []
+    od.dmrg(W, [], psi0, od.Sweeps(nsw, list(maxdims), 1e-10), matvec_hook=caps.append)
+    c = [x for x in caps if x["bond"] == bond][-1]
+    return site, W, qk, c
+
+
+def make_bond(ctx, site, qk, c):
+    b = c["bond"]
+    return cb.Bond(c["L"], c["W1"], c["W2"], c["R"], ql=c["ql"], qr=c["qr"], qkl=qk[b - 1], qkm=qk[b], qkr=qk[b + 1],
+                   site_charges=site.charges, nq=site.nq, ctx=ctx)
+
+
+BOND_CASES = [
+    ("golden", "p", 6, [-1.0], 0, 3),
+    ("golden", "s", 8, [-1.0], 0, 4),
+    ("haagerup", "p", 6, [0.0, -1.0, 0.0], 0, 3),
+    ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 1, 3),
+    ("haagerupq", "p", 6, [0.0, -1.0, 0.3], 2, 3),     # complex
+    ("haagerupq", "o", 6, [0.0, 0.0, -1.0], 0, 2),     # complex, open chain, off-centre bond
+]
+
+
+def check_bond_ops(ctx, case, rtol=1e-12):
+    st, bc, n, cp, q, bond = case
+    site, W, qk, c = capture_bond(st, bc, n, cp, q, bond)
+    B = make_bond(ctx, site, qk, c)
+    phi = c["phi"]
+    # LocalMPO::product
+    y = B.apply(phi)
+    yo = od.heff_apply(c["L"], c["W1"], c["W2"], c["R"], phi)
+    assert np.abs(y - yo).max() <= rtol * np.abs(yo).max()
+    # Hermiticity of H_eff on random allowed vectors (size-independent property)
+    rng = np.random.default_rng(11)
+    mask = (np.abs(phi) > 0) | (np.abs(yo) > 0)
+    x1 = rng.standard_normal(phi.shape) * mask
+    x2 = rng.standard_normal(phi.shape) * mask
+    h12 = np.vdot(x1, B.apply(x2))
+    h21 = np.vdot(x2, B.apply(x1))
+    assert abs(h12 - np.conj(h21)) <= 1e-11 * max(1.0, abs(h12))
+    # davidson
+    mv = lambda v: od.heff_apply(c["L"], c["W1"], c["W2"], c["R"], v)
+    evo, xo, nmvo = od.davidson(mv, phi.astype(yo.dtype), 2)
+    ev, x, nmv = B.davidson(phi, 2)
+    assert nmv == nmvo
+    assert abs(ev - evo) <= 1e-12 * abs(evo)
+    assert abs(abs(np.vdot(xo, x)) - 1) <= 1e-10
+    # penalty projector (LocalMPO_MPS): y += w <o|x> o
+    o = rng.standard_normal(phi.shape) * mask
+    o = o / np.linalg.norm(o)
+    B.set_penalty([o], 1000.0)
+    yp = B.apply(phi)
+    assert np.abs(yp - (yo + 1000.0 * np.vdot(o, phi) * o)).max() <= 1e-11 * max(1.0, np.abs(yp).max())
+    B.set_penalty([], 0.0)
+    # svdBond + makeL/makeR
+    for d in ("left", "right"):
+        A, Bt, qm, spec, terr = B.truncate(xo, d, 40, 1e-8)
+        A1, A2, qmo, speco, terro = od.split_bond(xo, c["ql"], c["qr"], site.charges, site.nq, d, 40, 1, 1e-8)
+        assert A.shape[2] == A1.shape[2]
+        assert np.array_equal(np.bincount(qm, minlength=site.nq), np.bincount(qmo, minlength=site.nq))
+        assert abs(terr - terro) <= 1e-14
+        assert np.abs(np.sort(spec) - np.sort(speco)).max() <= 1e-13
+        iso = A if d == "left" else Bt
+        m = iso.shape[2] if d == "left" else iso.shape[0]
+        g = np.tensordot(iso.conj(), iso, axes=([0, 1], [0, 1])) if d == "left" else np.tensordot(iso, iso.conj(), axes=([1, 2], [1, 2]))
+        assert np.abs(g - np.eye(m)).max() <= 1e-12
+        rec = np.tensordot(A, Bt, axes=([2], [0]))
+        reco = np.tensordot(A1, A2, axes=([2], [0]))
+        assert np.abs(rec - reco).max() <= 1e-9     # eigh(rho) resolves small eigenvectors only to ~eps/gap
+        T = A if d == "left" else Bt
+        E = B.env_update(d, T, qm)
+        Eo = od.update_left(c["L"], T, c["W1"]) if d == "left" else od.update_right(c["R"], T, c["W2"])
+        assert np.abs(E - Eo).max() <= rtol * max(1.0, np.abs(Eo).max())
+    B.close()
+
+
+DMRG_CASES = [
+    # site, bc, n, couplings, charge, nstates, product-state start?
+    ("golden", "p", 6, [-1.0], 0, 3, True),
+    ("golden", "o", 7, [-1.0], 0, 1, True),
+    ("haagerup", "p", 6, [0.0, -1.0, 0.0], 0, 1, True),
+    ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 1, 2, False),
+    ("haagerupq", "p", 6, [0.0, -1.0, 0.0], 0, 1, False),   # complex128 block-sparse (README example model)
+]
+
+
+def check_dmrg_trajectory(ctx, case, nsweep=4):
+    """Same start, same schedule => per-bond energies 1e-10 relative, EE 1e-8 (BASELINE.json tolerances)."""
+    st, bc, n, cp, q, nst, product = case
+    site, W, qk = build_model(st, bc, n, cp)
+    H = cb.MPO(W, qk, site.charges, nq=site.nq)
+    rng = np.random.default_rng(5)
+    done_o, done_g = [], []
+    maxd = [10, 20, 40, 80][:nsweep]
+    cut = [1e-5, 1e-6, 1e-7, 1e-8][:nsweep]
+    for s in range(nst):
+        if product:
+            psi0 = od.product_mps(site, n, q, rng, dtype=complex if np.iscomplexobj(W[1]) else float)
+        else:
+            psi0 = warm_start(site, W, n, q, seed=7 + s)
+        so = []
+        eo, po = od.dmrg(W, done_o, psi0, od.Sweeps(nsweep, maxd, cut), weight=1000.0, stats=so)
+        info = cb.DmrgInfo()
+        eg, pg = cb.dmrg(H, done_g, to_cb(psi0), cb.Sweeps(nsweep, maxd, cut), weight=1000.0, ctx=ctx, info=info)
+        assert len(so) == len(info.stats)
+        for a, b in zip(so, info.stats):
+            assert a["m"] == b["m"], (a, b)
+            # intermediate Davidson values of penalised (Weight=1000) problems amplify rounding; the contract is on the result
+            assert abs(a["energy"] - b["energy"]) <= 1e-8 * max(1.0, abs(a["energy"])), (a, b)
+        assert abs(eo - eg) <= 1e-10 * max(1.0, abs(eo))
+        pgo = to_oracle(pg, site)
+        assert abs(abs(od.overlap(po, pgo)) - 1) <= 1e-9
+        assert np.abs(np.array(od.calc_ee(po)) - np.array(od.calc_ee(pgo))).max() <= 1e-8
+        assert abs(od.overlap(pgo, pgo) - 1) <= 1e-12
+        done_o.append(po)
+        done_g.append(pg)
+    return done_g
+
+
+def check_ground_state_kat(ctx, st, bc, n, cp, q, tol, nrep=12, seed=1):
+    """Warm-up + reps of src/dmrg.h:538-609 through the C ABI; compare with the ED known answer."""
+    site, W, qk = build_model(st, bc, n, cp)
+    H = cb.MPO(W, qk, site.charges, nq=site.nq)
+    rng = np.random.default_rng(seed)
+    psi0 = od.product_mps(site, n, q, rng, dtype=complex if np.iscomplexobj(W[1]) else float)
+    c = float(np.float32(1e-8))
+    sw = cb.Sweeps(5, [10, 20, 40, 80, 200], [max(1e-5, c), max(1e-6, c), max(1e-7, c), max(1e-8, c), max(1e-9, c)])
+    en, psi = cb.dmrg(H, [], to_cb(psi0), sw, weight=1000.0, ctx=ctx)
+    for _ in range(nrep):
+        en, psi = cb.dmrg(H, [], psi, cb.Sweeps(1, 400, c), weight=1000.0, ctx=ctx)
+    e_ed = ed_level(st, bc, n, cp, q if site.nq > 1 else None)[0]
+    assert abs(en - e_ed) <= tol * abs(e_ed), (en, e_ed)
+    return en, psi, site

@@ -1,0 +1,234 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libchain_b200.so.
+// Serial CPU implementation of chain_b200/csrc/backend.h so that the engine's HOST logic (block bookkeeping,
+// task-list generation, Davidson/truncation sequencing, sweep driver) can be exercised by `pytest -m "not gpu"`
+// in the GPU-less container.  Each function executes the same task lists the CUDA kernels execute, with the
+// simplest possible loops; it makes no attempt to mirror the kernels' arithmetic order.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../chain_b200/csrc/backend.h"
+
+namespace cb200 {
+
+using cd = std::complex<double>;
+
+struct Backend {
+  uint64_t launches = 0;
+  double ev[8] = {0};
+};
+
+Backend* backend_create(int, char*, size_t) { return new Backend(); }
+void backend_destroy(Backend* b) { delete b; }
+const char* backend_name() { return "host-emulation (tests only)"; }
+int backend_device(Backend*) { return -1; }
+void* dev_alloc(Backend*, size_t bytes) { return std::malloc(bytes ? bytes : 16); }
+void dev_free(Backend*, void* p) { std::free(p); }
+void dev_memset0(Backend*, void* p, size_t bytes) { std::memset(p, 0, bytes); }
+void dev_h2d(Backend*, void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+void dev_d2h(Backend*, void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
+void dev_d2d(Backend*, void* d, const void* s, size_t n) { std::memmove(d, s, n); }
+void dev_sync(Backend*) {}
+const char* dev_last_error(Backend*) { return nullptr; }
+uint64_t dev_launch_count(Backend* b) { return b->launches; }
+void dev_event_record(Backend*, int) {}
+float dev_event_elapsed_ms(Backend*, int, int) { return 0.f; }
+int gemm_tile_m(bool cplx) { return cplx ? 64 : 128; }
+int gemm_tile_n(bool, bool narrow) { return narrow ? 64 : 128; }
+int mix_rows_per_block() { return 128; }
+int copy_elems_per_block() { return 2048; }
+
+template <class T>
+static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTask* tasks, int nt, const GemmSeg* segs) {
+  for (int ti = 0; ti < nt; ++ti) {
+    const GemmTask& t = tasks[ti];
+    const bool conjA = t.flags & GEMM_CONJ_A, acc = t.flags & GEMM_ACCUM, conjOut = t.flags & GEMM_CONJ_OUT;
+    if (bool(t.flags & GEMM_TRANS_A) != ta && t.seg_count) { std::fprintf(stderr, "emu: transA flag mismatch\n"); std::abort(); }
+    std::vector<T> tmp((size_t)t.M * t.N, T(0));
+    for (int s = 0; s < t.seg_count; ++s) {
+      const GemmSeg& g = segs[t.seg_begin + s];
+      for (int n = 0; n < t.N; ++n)
+        for (int k = 0; k < g.K; ++k) {
+          const T b = tb ? B[g.b_off + n + (int64_t)k * g.ldb] : B[g.b_off + k + (int64_t)n * g.ldb];
+          if (b == T(0)) continue;
+          for (int m = 0; m < t.M; ++m) {
+            T a = ta ? A[g.a_off + k + (int64_t)m * g.lda] : A[g.a_off + m + (int64_t)k * g.lda];
+            if constexpr (std::is_same<T, cd>::value) { if (conjA) a = std::conj(a); }
+            tmp[(size_t)m + (size_t)n * t.M] += a * b;
+          }
+        }
+    }
+    for (int n = 0; n < t.N; ++n)
+      for (int m = 0; m < t.M; ++m) {
+        T v = tmp[(size_t)m + (size_t)n * t.M];
+        if constexpr (std::is_same<T, cd>::value) { if (conjOut) v = std::conj(v); }
+        T* p = (n < t.n_split) ? &C[t.c_off + m + (int64_t)n * t.ldc] : &C[t.c_off2 + m + (int64_t)(n - t.n_split) * t.ldc];
+        *p = acc ? *p + v : v;
+      }
+  }
+}
+
+void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool, const void* A, const void* B, void* C, const GemmTask* t, int nt,
+                 const GemmSeg* s, int tiles) {
+  if (tiles <= 0 || nt <= 0) return;
+  b->launches++;
+  if (cplx) gemm_t<cd>(ta, tb, (const cd*)A, (const cd*)B, (cd*)C, t, nt, s);
+  else gemm_t<double>(ta, tb, (const double*)A, (const double*)B, (double*)C, t, nt, s);
+}
+
+template <class T>
+static void mix_t(const T* in, T* out, const MixPanel* panels, int np, const MixOut* outs, const MixEntry* ents) {
+  for (int pi = 0; pi < np; ++pi) {
+    const MixPanel& p = panels[pi];
+    for (int64_t r = 0; r < p.nr; ++r)
+      for (int o = p.out_begin; o < p.out_end; ++o) {
+        const MixOut& mo = outs[o];
+        for (int row = 0; row < p.rows; ++row) {
+          T acc(0);
+          for (int e = mo.e_begin; e < mo.e_end; ++e) {
+            const MixEntry& me = ents[e];
+            T c;
+            if constexpr (std::is_same<T, cd>::value) c = cd(me.cre, me.cim); else c = me.cre;
+            acc += c * in[me.in_off + r * me.in_rstride + row];
+          }
+          out[mo.off + r * mo.rstride + row] = acc;
+        }
+      }
+  }
+}
+
+void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixOut* o, const MixEntry* e, int blocks) {
+  if (blocks <= 0) return;
+  b->launches++;
+  if (cplx) mix_t<cd>((const cd*)in, (cd*)out, p, np, o, e); else mix_t<double>((const double*)in, (double*)out, p, np, o, e);
+}
+
+template <class T>
+static void copy_t(const T* src, T* dst, const CopyTask* tasks, int nt) {
+  for (int ti = 0; ti < nt; ++ti) {
+    const CopyTask& t = tasks[ti];
+    for (int64_t k = 0; k < t.n2; ++k)
+      for (int64_t j = 0; j < t.n1; ++j)
+        for (int64_t i = 0; i < t.n0; ++i) {
+          T v = src[t.src_off + i * t.ss0 + j * t.ss1 + k * t.ss2];
+          if constexpr (std::is_same<T, cd>::value) { if (t.conj) v = std::conj(v); }
+          dst[t.dst_off + i * t.ds0 + j * t.ds1 + k * t.ds2] = v;
+        }
+  }
+}
+
+void launch_copy(Backend* b, bool cplx, const void* src, void* dst, const CopyTask* t, int nt, int blocks) {
+  if (blocks <= 0) return;
+  b->launches++;
+  if (cplx) copy_t<cd>((const cd*)src, (cd*)dst, t, nt); else copy_t<double>((const double*)src, (double*)dst, t, nt);
+}
+
+void multi_dot(Backend* b, bool cplx, int nv, const void* const* x, const void* y, int64_t n, double* out) {
+  b->launches += 2;
+  for (int j = 0; j < nv; ++j) {
+    if (cplx) {
+      cd s(0);
+      for (int64_t i = 0; i < n; ++i) s += std::conj(((const cd*)x[j])[i]) * ((const cd*)y)[i];
+      out[2 * j] = s.real(); out[2 * j + 1] = s.imag();
+    } else {
+      double s = 0;
+      for (int64_t i = 0; i < n; ++i) s += ((const double*)x[j])[i] * ((const double*)y)[i];
+      out[2 * j] = s; out[2 * j + 1] = 0;
+    }
+  }
+}
+
+void lincomb(Backend* b, bool cplx, int nv, const void* const* x, const double* c, double br, double bi, void* dst, int64_t n) {
+  b->launches++;
+  for (int64_t i = 0; i < n; ++i) {
+    if (cplx) {
+      cd acc = (br != 0 || bi != 0) ? cd(br, bi) * ((cd*)dst)[i] : cd(0);
+      for (int j = 0; j < nv; ++j) acc += cd(c[2 * j], c[2 * j + 1]) * ((const cd*)x[j])[i];
+      ((cd*)dst)[i] = acc;
+    } else {
+      double acc = (br != 0) ? br * ((double*)dst)[i] : 0.0;
+      for (int j = 0; j < nv; ++j) acc += c[2 * j] * ((const double*)x[j])[i];
+      ((double*)dst)[i] = acc;
+    }
+  }
+}
+
+// serial cyclic Jacobi on one NJ x NJ Hermitian matrix
+static long long jacobi_one(int n, std::vector<cd>& G, std::vector<cd>& Q, double tol, double floor2) {
+  long long total = 0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    long long nrot = 0;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const cd g = G[p + (size_t)q * n];
+        const double g2 = std::norm(g), gpp = G[p + (size_t)p * n].real(), gqq = G[q + (size_t)q * n].real();
+        if (!(g2 > tol * tol * std::fabs(gpp * gqq)) || g2 == 0.0 || !(gpp > floor2) || !(gqq > floor2)) continue;
+        ++nrot;
+        const double ag = std::sqrt(g2);
+        const cd e = g / ag;
+        const double tau = (gqq - gpp) / (2.0 * ag);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+        for (int r = 0; r < n; ++r) {
+          cd a = G[r + (size_t)p * n], b = G[r + (size_t)q * n];
+          G[r + (size_t)p * n] = c * a - s * std::conj(e) * b;
+          G[r + (size_t)q * n] = s * e * a + c * b;
+          a = Q[r + (size_t)p * n]; b = Q[r + (size_t)q * n];
+          Q[r + (size_t)p * n] = c * a - s * std::conj(e) * b;
+          Q[r + (size_t)q * n] = s * e * a + c * b;
+        }
+        for (int cc = 0; cc < n; ++cc) {
+          const cd a = G[p + (size_t)cc * n], b = G[q + (size_t)cc * n];
+          G[p + (size_t)cc * n] = c * a - s * e * b;
+          G[q + (size_t)cc * n] = s * std::conj(e) * a + c * b;
+        }
+        G[p + (size_t)q * n] = 0; G[q + (size_t)p * n] = 0;
+      }
+    total += nrot;
+    if (!nrot) break;
+  }
+  return total;
+}
+
+void launch_jacobi_eig(Backend* b, bool cplx, const void* G_, void* Q_, int npairs, double tol, double floor2, long long* d_rot) {
+  b->launches++;
+  const int n = 2 * JB;
+  for (int pi = 0; pi < npairs; ++pi) {
+    std::vector<cd> G((size_t)n * n), Q((size_t)n * n, cd(0));
+    for (int c = 0; c < n; ++c)
+      for (int r = 0; r < n; ++r) {
+        const int rr = r <= c ? r : c, cc = r <= c ? c : r;
+        cd v = cplx ? ((const cd*)G_)[(size_t)pi * n * n + rr + (size_t)cc * n] : cd(((const double*)G_)[(size_t)pi * n * n + rr + (size_t)cc * n], 0);
+        if (r > c) v = std::conj(v);
+        if (r == c) v = cd(v.real(), 0);
+        G[r + (size_t)c * n] = v;
+      }
+    for (int i = 0; i < n; ++i) Q[i + (size_t)i * n] = 1;
+    *d_rot += jacobi_one(n, G, Q, tol, floor2);
+    for (size_t i = 0; i < (size_t)n * n; ++i) {
+      if (cplx) ((cd*)Q_)[(size_t)pi * n * n + i] = Q[i]; else ((double*)Q_)[(size_t)pi * n * n + i] = Q[i].real();
+    }
+  }
+}
+
+void launch_colnorm2(Backend* b, bool cplx, const void* X, int64_t ld, int64_t rows, int64_t cols, double* out) {
+  b->launches++;
+  for (int64_t c = 0; c < cols; ++c) {
+    double s = 0;
+    for (int64_t i = 0; i < rows; ++i) s += cplx ? std::norm(((const cd*)X)[i + c * ld]) : ((const double*)X)[i + c * ld] * ((const double*)X)[i + c * ld];
+    out[c] = s;
+  }
+}
+
+void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) {
+  b->launches++;
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = 0; r < n; ++r) {
+      if (cplx) ((cd*)X)[r + c * ld] = cd(r == c ? 1.0 : 0.0, 0); else ((double*)X)[r + c * ld] = (r == c ? 1.0 : 0.0);
+    }
+}
+
+}  // namespace cb200

@@ -1,0 +1,50 @@
+"""Host-logic tests (CPU): the engine's block bookkeeping / task-list generation / sequencing, executed on the
+serial emulation backend (tests/hostemu) and compared with the oracle.  These do NOT test the CUDA kernels; the
+-m gpu tests run the same bodies through the product library."""
+import numpy as np
+import pytest
+
+import chain_b200 as cb
+import common
+
+
+@pytest.mark.parametrize("case", common.BOND_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
+def test_bond_ops_match_oracle(emu_ctx, case):
+    common.check_bond_ops(emu_ctx, case)
+
+
+@pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
+def test_dmrg_trajectory_matches_oracle(emu_ctx, case):
+    common.check_dmrg_trajectory(emu_ctx, case, nsweep=3)
+
+
+def test_task_list_gemm_segments_and_split(emu_ctx):
+    rng = np.random.default_rng(0)
+    M, N = 37, 29
+    Ks = [5, 0, 13]
+    A = rng.standard_normal(M * 40)
+    B = rng.standard_normal(40 * N)
+    a_off, b_off = [0, 0, M * 7], [0, 0, 9]
+    c, _ = cb.k_gemm(A, B, np.zeros(M * N), M, N, Ks, a_off, b_off, M, 40, 0, M, ctx=emu_ctx)
+    want = sum(A[ao:ao + M * k].reshape(k, M).T @ np.stack([B[bo + j * 40: bo + j * 40 + k] for j in range(N)], axis=1)
+               for ao, bo, k in zip(a_off, b_off, Ks) if k)
+    assert np.abs(c.reshape(N, M).T - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("rows,cols", [(90, 70), (30, 70), (10, 100), (64, 64), (5, 3), (1, 1)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_block_jacobi_svd_driver(emu_ctx, rows, cols, cplx):
+    rng = np.random.default_rng(rows * 100 + cols)
+    X = rng.standard_normal((rows, cols)) + (1j * rng.standard_normal((rows, cols)) if cplx else 0)
+    if cols > 5:
+        X[:, 5] = 0
+    xv, v, w, sweeps = cb.k_svd(X, ctx=emu_ctx)
+    s = np.linalg.svd(X, compute_uv=False)
+    k = min(rows, cols)
+    assert np.abs(w[:k] - s ** 2).max() < 1e-11 * max(1.0, s[0] ** 2)
+    assert np.abs(v.conj().T @ v - np.eye(cols)).max() < 1e-12
+    assert np.abs(X @ v - xv).max() < 1e-12 * max(1.0, s[0])
+
+
+def test_ground_state_kat_golden(emu_ctx):
+    common.check_ground_state_kat(emu_ctx, "golden", "p", 6, [-1.0], 0, tol=2e-9)
