@@ -78,6 +78,7 @@ SYMBOLS = [
     ("cb200_k_dots", C.c_int, [vp, i32, i32, i64, vp, vp, C.POINTER(dbl)]),
     ("cb200_k_lincomb", C.c_int, [vp, i32, i32, i64, vp, C.POINTER(dbl), dbl, dbl, vp]),
     ("cb200_k_gemm_peak", C.c_int, [vp, i32, i32, i32, C.POINTER(dbl)]),
+    ("cb200_k_fp64_peak", C.c_int, [vp, i32, i32, C.POINTER(dbl)]),
 ]
 
 

@@ -390,3 +390,11 @@ def k_gemm_peak(n=8192, reps=5, cplx=False, ctx=None):
     tf = C.c_double()
     ctx.check(ctx.lib.cb200_k_gemm_peak(ctx.h, 1 if cplx else 0, n, reps, C.byref(tf)))
     return tf.value
+
+
+def k_fp64_peak(which=0, iters=20000, ctx=None):
+    """Issue-rate peak of the FP64 pipes (0 = DMMA.8x8x4, 1 = DFMA) in TFLOP/s."""
+    ctx = ctx or default_context()
+    tf = C.c_double()
+    ctx.check(ctx.lib.cb200_k_fp64_peak(ctx.h, which, iters, C.byref(tf)))
+    return tf.value

@@ -65,4 +65,7 @@ void launch_colnorm2(Backend*, bool cplx, const void* X, int64_t ld, int64_t row
 // X (n x n, ld) = identity
 void launch_set_identity(Backend*, bool cplx, void* X, int64_t ld, int64_t n);
 
+// FP64 issue-rate calibration (0 = DMMA.8x8x4, 1 = DFMA); TFLOP/s.  Device-only, used by bench.py for the roofline denominator.
+double fp64_pipe_peak(Backend*, int which, int iters);
+
 }  // namespace cb200

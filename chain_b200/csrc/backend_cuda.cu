@@ -579,4 +579,59 @@ void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) 
   CB_LAUNCH_CHECK(b, "set_identity_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------ FP64 pipe calibration
+// Pure issue-rate loops (no memory traffic): the roofline denominators for the DMMA GEMM (MEASURED_PEAKS.json has no FP64 entry).
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i * 1e-9; }
+  double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-9 + i;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 123.456) sink[0] = s;
+}
+
+// which: 0 = DMMA.8x8x4 loop, 1 = DFMA loop; returns TFLOP/s
+double fp64_pipe_peak(Backend* b, int which, int iters) {
+  double* sink = nullptr;
+  CB_CHECK(b, cudaMalloc(&sink, 8));
+  const int blocks = 148 * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 2; ++rep) {
+    if (rep == 1) cudaEventRecord(e0, b->stream);
+    if (which == 0) dmma_peak_kernel<<<blocks, 256, 0, b->stream>>>(iters, sink);
+    else dfma_peak_kernel<<<blocks, 256, 0, b->stream>>>(iters, sink);
+    CB_LAUNCH_CHECK(b, "fp64_peak_kernel");
+  }
+  cudaEventRecord(e1, b->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  const double warps = (double)blocks * 8;
+  const double flops = which == 0 ? warps * iters * 16.0 * 512.0 : warps * 32.0 * iters * 16.0 * 2.0;
+  return flops / (ms * 1e-3) / 1e12;
+}
+
 }  // namespace cb200

@@ -444,4 +444,9 @@ int cb200_k_gemm_peak(cb200_ctx* ctx, int32_t dtype, int32_t n, int32_t reps, do
   });
 }
 
+int cb200_k_fp64_peak(cb200_ctx* ctx, int32_t which, int32_t iters, double* tflops) {
+  if (!ctx || !tflops) return CB200_ERR_INVALID;
+  return guard(ctx, [&] { *tflops = fp64_pipe_peak(ctx->c.be, which, iters); });
+}
+
 }  // extern "C"

@@ -153,6 +153,8 @@ int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const 
                     double beta_im, void* dst);
 /* FP64 calibration: achieved TFLOP/s of the DMMA GEMM kernel on a square problem (device-resident, CUDA events) */
 int cb200_k_gemm_peak(cb200_ctx* ctx, int32_t dtype, int32_t n, int32_t reps, double* tflops);
+/* FP64 pipe issue-rate loops without memory traffic: which 0 = DMMA.8x8x4 (mma.sync.m8n8k4.f64), 1 = DFMA */
+int cb200_k_fp64_peak(cb200_ctx* ctx, int32_t which, int32_t iters, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,112 @@
+"""-m gpu: the device kernels through the C ABI, against NumPy on the same seeded inputs (bit-tolerance 1e-12..1e-13
+relative: FP64 accumulation order differs from BLAS)."""
+import numpy as np
+import pytest
+
+import chain_b200 as cb
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, shape, cplx):
+    x = rng.standard_normal(shape)
+    return x + 1j * rng.standard_normal(shape) if cplx else x
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (257, 131, 95), (1, 1, 1), (70, 45, 33), (533, 300, 534), (64, 640, 7)])
+def test_gemm_single_segment(gpu_ctx, cplx, ta, tb, M, N, K):
+    rng = np.random.default_rng(M * 7 + N * 3 + K + cplx)
+    A = _rand(rng, (M, K), cplx)
+    B = _rand(rng, (K, N), cplx)
+    a = (A.T if ta else A).ravel(order="F")      # ta: stored K x M column-major
+    b = (B.T if tb else B).ravel(order="F")
+    lda = K if ta else M
+    ldb = N if tb else K
+    c, _ = cb.k_gemm(a, b, np.zeros(M * N), M, N, [K], [0], [0], lda, ldb, 0, M, trans_a=ta, trans_b=tb, ctx=gpu_ctx)
+    want = A @ B
+    assert np.abs(c.reshape(N, M).T - want).max() <= 1e-13 * K * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gemm_conj_accumulate_offsets_segments(gpu_ctx, cplx):
+    rng = np.random.default_rng(5 + cplx)
+    M, N = 150, 77
+    Ks = [33, 0, 129, 5]
+    lda, ldb, ldc = 161, 140, 157           # odd leading dimensions + odd offsets: exercises the unaligned (8-byte) load path
+    A = _rand(rng, lda * 140 + 50, cplx)
+    B = _rand(rng, ldb * N + 50, cplx)
+    C0 = _rand(rng, ldc * N + 9, cplx)
+    a_off, b_off = [3, 0, 11, 1000], [1, 0, 7, 2]
+    c, _ = cb.k_gemm(A, B, C0, M, N, Ks, a_off, b_off, lda, ldb, 5, ldc, trans_a=True, conj_a=True, accumulate=True, ctx=gpu_ctx)
+    want = C0.copy()
+    Cm = np.zeros((M, N), dtype=want.dtype)
+    for ao, bo, k in zip(a_off, b_off, Ks):
+        if k == 0:
+            continue
+        Aseg = np.array([[A[ao + kk + m * lda] for kk in range(k)] for m in range(M)])     # element (m,k) at k + m*lda
+        Bseg = np.array([[B[bo + kk + n * ldb] for n in range(N)] for kk in range(k)])
+        Cm += Aseg.conj() @ Bseg
+    for n in range(N):
+        want[5 + n * ldc: 5 + n * ldc + M] += Cm[:, n]
+    assert np.abs(c - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
+    # untouched padding must be bit-identical
+    mask = np.ones(len(want), bool)
+    for n in range(N):
+        mask[5 + n * ldc: 5 + n * ldc + M] = False
+    assert np.array_equal(c[mask], C0[mask])
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_dots_and_lincomb(gpu_ctx, cplx):
+    rng = np.random.default_rng(9)
+    for n in (1, 1000, 1 << 20 | 3):
+        xs = _rand(rng, (5, n), cplx)
+        y = _rand(rng, n, cplx)
+        d = cb.k_dots(xs, y, ctx=gpu_ctx)
+        want = xs.conj() @ y
+        assert np.abs(d - want).max() <= 1e-12 * max(1.0, np.abs(want).max()) * np.sqrt(n)
+        d2 = cb.k_dots(xs, y, ctx=gpu_ctx)
+        assert np.array_equal(d, d2)          # deterministic reduction (replicated Krylov vectors stay bit-identical)
+        co = _rand(rng, 5, cplx)
+        out = cb.k_lincomb(xs, co, y, beta=0.5, ctx=gpu_ctx)
+        assert np.abs(out - (0.5 * y + co @ xs)).max() <= 1e-13 * 10
+        out = cb.k_lincomb(xs[:1], co[:1], y, beta=0.0, ctx=gpu_ctx)
+        assert np.abs(out - co[0] * xs[0]).max() <= 1e-14 * 10
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_jacobi_eig_kernel(gpu_ctx, cplx):
+    rng = np.random.default_rng(3)
+    Y = _rand(rng, (7, 200, 64), cplx)
+    Y[3, :, 10:] *= 1e-6                 # graded columns
+    Y[4, :, 40:] = 0                     # rank deficient
+    G = np.einsum("pki,pkj->pij", Y.conj(), Y)
+    Q, rot = cb.k_jacobi_eig(G, 1e-14, ctx=gpu_ctx)
+    assert rot > 0
+    for p in range(7):
+        assert np.abs(Q[p].conj().T @ Q[p] - np.eye(64)).max() <= 1e-13
+        D = Q[p].conj().T @ G[p] @ Q[p]
+        dd = np.sqrt(np.abs(np.outer(np.diag(D).real, np.diag(D).real))) + 1e-300
+        off = np.abs(D - np.diag(np.diag(D))) / dd
+        ok = (np.abs(np.diag(D))[:, None] > 1e-20 * np.abs(D).max()) & (np.abs(np.diag(D))[None, :] > 1e-20 * np.abs(D).max())
+        assert (off[ok]).max() <= 1e-12
+        assert np.allclose(np.sort(np.diag(D).real), np.linalg.eigvalsh(G[p]), atol=1e-12 * np.abs(D).max())
+
+
+@pytest.mark.parametrize("rows,cols", [(90, 70), (30, 70), (64, 64), (5, 3), (1, 1), (600, 300), (300, 500)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_block_jacobi_svd(gpu_ctx, rows, cols, cplx):
+    rng = np.random.default_rng(rows * 100 + cols)
+    X = _rand(rng, (rows, cols), cplx)
+    if cols > 5:
+        X[:, 5] = 0
+    xv, v, w, sweeps = cb.k_svd(X, ctx=gpu_ctx)
+    s = np.linalg.svd(X, compute_uv=False)
+    k = min(rows, cols)
+    assert np.abs(w[:k] - s ** 2).max() <= 1e-11 * max(1.0, s[0] ** 2)
+    assert np.abs(v.conj().T @ v - np.eye(cols)).max() <= 1e-12
+    assert np.abs(X @ v - xv).max() <= 1e-12 * max(1.0, s[0])
+    g = xv.conj().T @ xv
+    assert np.abs(g - np.diag(np.diag(g))).max() <= 1e-11 * max(1.0, s[0] ** 2)

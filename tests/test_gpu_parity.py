@@ -1,0 +1,131 @@
+"""-m gpu: the hot path through the C ABI on a B200 against the oracle (same seeded inputs), the ED known answers,
+and size-independent properties at sizes the oracle cannot reach quickly."""
+import numpy as np
+import pytest
+
+import chain_b200 as cb
+import common
+from oracle import dmrg as od
+
+pytestmark = pytest.mark.gpu
+
+
+def test_backend_is_cuda(gpu_ctx):
+    assert gpu_ctx.backend == "cuda-sm_100a"
+    before = gpu_ctx.launches
+    cb.k_dots(np.ones((1, 8)), np.ones(8), ctx=gpu_ctx)
+    assert gpu_ctx.launches > before
+
+
+@pytest.mark.parametrize("case", common.BOND_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
+def test_bond_ops_match_oracle(gpu_ctx, case):
+    common.check_bond_ops(gpu_ctx, case)
+
+
+@pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
+def test_dmrg_trajectory_matches_oracle(gpu_ctx, case):
+    common.check_dmrg_trajectory(gpu_ctx, case, nsweep=4)
+
+
+def test_ground_state_kat_golden_config1(gpu_ctx):
+    # BASELINE config 1: golden periodic L=6 -d 100 -c 1e-8, ground state
+    en, psi, site = common.check_ground_state_kat(gpu_ctx, "golden", "p", 6, [-1.0], 0, tol=2e-9)
+    want = [c for c in common.golden()["ee"] if c["site"] == "golden"][0]["ee"]
+    assert np.allclose(od.calc_ee(common.to_oracle(psi, site)), want, atol=5e-7)
+
+
+def test_ground_state_kat_haagerupq_readme_example(gpu_ctx):
+    # BASELINE config 2's physical run: haagerupq periodic L=6, j=(0,-1,0), q=0 -- complex128, Z3 block-sparse
+    en, psi, site = common.check_ground_state_kat(gpu_ctx, "haagerupq", "p", 6, [0.0, -1.0, 0.0], 0, tol=2e-8, nrep=8)
+    assert max(psi.bond_dims()) <= 216
+    want = [c for c in common.golden()["ee"] if c["site"] == "haagerupq" and c["couplings"][1] == -1.0][0]["ee"]
+    assert np.allclose(od.calc_ee(common.to_oracle(psi, site)), want, atol=5e-6)
+
+
+def test_excited_states_golden_l8(gpu_ctx):
+    # penalty term (Weight = 1000, src/dmrg.h:351): three lowest levels of the golden chain
+    site, W, qk = common.build_model("golden", "p", 8, [-1.0])
+    H = cb.MPO(W, qk, site.charges, nq=1)
+    rng = np.random.default_rng(2)
+    done, ens = [], []
+    for s in range(3):
+        psi = common.to_cb(od.product_mps(site, 8, 0, rng))
+        en, psi = cb.dmrg(H, done, psi, cb.Sweeps(5, [10, 20, 40, 80, 200], [1e-5, 1e-6, 1e-7, 1e-8, 1e-9]), weight=1000.0, ctx=gpu_ctx)
+        for _ in range(10):
+            en, psi = cb.dmrg(H, done, psi, cb.Sweeps(1, 200, 1e-9), weight=1000.0, ctx=gpu_ctx)
+        done.append(psi)
+        ens.append(en)
+    assert np.allclose(ens, common.ed_level("golden", "p", 8, [-1.0], None)[:3], atol=2e-7)
+
+
+def _synthetic_bond(rng, D, d, k, cplx=False):
+    """Random Hermitian-structured dense bond problem: L[a] and R[a] Hermitian per slice pair so that H_eff is Hermitian
+    when W1 (x) W2 is built from Hermitian operator pairs."""
+    def herm(n):
+        x = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+        return (x + x.conj().T) / 2
+    L = np.stack([herm(D) for _ in range(k)], axis=1)                # [D, k, D]
+    R = np.stack([herm(D) for _ in range(k)], axis=1)
+    W1 = np.zeros((k, d, d, k), dtype=complex if cplx else float)
+    W2 = np.zeros((k, d, d, k), dtype=complex if cplx else float)
+    for a in range(k):
+        h = rng.standard_normal((d, d)); W1[a, :, :, a] = (h + h.T) / 2
+        h = rng.standard_normal((d, d)); W2[a, :, :, a] = (h + h.T) / 2
+    return L, W1, W2, R
+
+
+@pytest.mark.parametrize("D,d,k,cplx", [(64, 2, 10, False), (200, 6, 14, False), (96, 6, 5, True)])
+def test_matvec_matches_oracle_on_synthetic_dense(gpu_ctx, D, d, k, cplx):
+    # SURVEY 7 step 3 gate: (D,d,k) = (64,2,10), (200,6,14) on random inputs, <= 1e-13 relative
+    rng = np.random.default_rng(D + d + k)
+    L, W1, W2, R = _synthetic_bond(rng, D, d, k, cplx)
+    phi = rng.standard_normal((D, d, d, D)) + (1j * rng.standard_normal((D, d, d, D)) if cplx else 0)
+    B = cb.Bond(L, W1, W2, R, ctx=gpu_ctx)
+    y = B.apply(phi)
+    yo = od.heff_apply(L, W1, W2, R, phi)
+    assert np.abs(y - yo).max() <= 1e-13 * np.sqrt(D * k) * np.abs(yo).max()
+    B.close()
+
+
+def test_matvec_properties_at_large_d(gpu_ctx):
+    # D = 800, golden-like (d=2, k=10): sizes where the oracle is slow; linearity + Hermiticity + timing sanity
+    rng = np.random.default_rng(1)
+    D, d, k = 800, 2, 10
+    L, W1, W2, R = _synthetic_bond(rng, D, d, k)
+    B = cb.Bond(L, W1, W2, R, ctx=gpu_ctx)
+    x1 = rng.standard_normal((D, d, d, D))
+    x2 = rng.standard_normal((D, d, d, D))
+    y1, y2 = B.apply(x1), B.apply(x2)
+    y12 = B.apply(2.0 * x1 - 3.0 * x2)
+    assert np.abs(y12 - (2.0 * y1 - 3.0 * y2)).max() <= 1e-11 * np.abs(y12).max()
+    h12, h21 = np.vdot(x1, y2), np.vdot(x2, y1)
+    assert abs(h12 - h21) <= 1e-11 * abs(h12)
+    # one slice cross-checked against NumPy: out[:, :, :, r'] needs everything, so check a full small contraction instead
+    yo = od.heff_apply(L[:64, :, :64], W1, W2, R[:64, :, :64], x1[:64, :, :, :64])
+    Bs = cb.Bond(L[:64, :, :64], W1, W2, R[:64, :, :64], ctx=gpu_ctx)
+    assert np.abs(Bs.apply(x1[:64, :, :, :64]) - yo).max() <= 1e-12 * np.abs(yo).max()
+    ms = B.apply_timed(x1, reps=3, warmup=2)
+    assert ms > 0
+    B.close(); Bs.close()
+
+
+def test_truncation_roundtrip_large(gpu_ctx):
+    # phi of exact rank r: svdBond must recover it (encode -> decode round trip) and produce an isometry
+    rng = np.random.default_rng(4)
+    D, d, r = 300, 2, 40
+    A = rng.standard_normal((D * d, r))
+    Bm = rng.standard_normal((r, d * D))
+    phi = (A @ Bm).reshape(D, d, d, D)
+    phi /= np.linalg.norm(phi)
+    L = np.zeros((D, 1, D)); L[:, 0, :] = np.eye(D)
+    W = np.zeros((1, d, d, 1)); W[0, :, :, 0] = np.eye(d)
+    B = cb.Bond(L, W, W, L, ctx=gpu_ctx)
+    for direction in ("left", "right"):
+        A1, B1, qm, spec, terr = B.truncate(phi, direction, 1000, 1e-14)
+        assert A1.shape[2] == r
+        assert terr <= 1e-14
+        rec = np.tensordot(A1, B1, axes=([2], [0]))
+        assert np.abs(rec - phi).max() <= 1e-12
+        s = np.linalg.svd(phi.reshape(D * d, d * D), compute_uv=False)[:r]
+        assert np.allclose(np.sort(spec)[::-1], s ** 2, atol=1e-13)
+    B.close()
