@@ -1,10 +1,8 @@
 # Builds, in-tree:
 #   chain_b200/libchain_b200.so        the product: sm_100a kernels + C++ engine + C ABI (include/chain_b200.h)
 #   tests/hostemu/libcb200_hostemu.so  TEST ONLY: the same engine linked against a serial CPU backend (host-logic tests)
-#   oracle/_ref/libchain_oracle.so     TEST ONLY: C restatement of the hot-path contractions (CPU baseline timing)
 NVCC      ?= nvcc
 CXX       ?= g++
-CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Wno-sign-compare
@@ -14,7 +12,7 @@ OBJ       := build
 ENGINE_SRCS := $(SRC)/engine.cpp $(SRC)/engine_io.cpp $(SRC)/capi.cpp
 HDRS := $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.cuh) include/chain_b200.h
 
-all: chain_b200/libchain_b200.so tests/hostemu/libcb200_hostemu.so oracle/_ref/libchain_oracle.so
+all: chain_b200/libchain_b200.so tests/hostemu/libcb200_hostemu.so
 
 $(OBJ):
 	mkdir -p $(OBJ)
@@ -31,11 +29,7 @@ chain_b200/libchain_b200.so: $(OBJ)/backend_cuda.o $(OBJ)/engine.o $(OBJ)/engine
 tests/hostemu/libcb200_hostemu.so: $(ENGINE_SRCS) tests/hostemu/backend_emu.cpp $(HDRS)
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(ENGINE_SRCS) tests/hostemu/backend_emu.cpp
 
-oracle/_ref/libchain_oracle.so: oracle/c/heff_ref.c
-	mkdir -p oracle/_ref
-	$(CC) -O3 -march=native -fopenmp -fPIC -shared -o $@ $<
-
 clean:
-	rm -rf $(OBJ) chain_b200/libchain_b200.so tests/hostemu/libcb200_hostemu.so oracle/_ref
+	rm -rf $(OBJ) chain_b200/libchain_b200.so tests/hostemu/libcb200_hostemu.so
 
 .PHONY: all clean

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- H_eff matvec throughput of the Chain DMRG hot path on B200 (BASELINE.json metric).
+
+A "step" is one application of the two-site effective Hamiltonian (ITensor LocalMPO::product, the call made three
+times per bond by davidson at /root/reference/src/dmrg.h:544,563,596) on the synthetic form of BASELINE config 2:
+haagerupq periodic, j=(0,-1,0), the model's true compressed MPO (k = 26 = Z3 sectors 10/8/8) at a central bond,
+bond dimension D = 1600 as Z3 sectors (534,533,533), complex128, block-sparse.  Environments and phi are seeded N(0,1)
+in the allowed charge blocks.
+
+  value  : algorithmic FP64 TFLOP/s (F_alg of SURVEY 8d: block-sparse, sparse-W flops only) with phi resident in HBM
+  e2e    : the same through the C-ABI call cb200_bond_apply with pinned HOST buffers (H2D phi + D2H result per step)
+  roofline: the DMMA GEMM kernel (both D^3 stages) against the FP64 peak measured live (cuBLAS DGEMM 8192^3)
+  cpu_baseline / --impl reference: the oracle's port of ITensor's block-pair permute+zgemm loop on the host cores
+
+N > 1 (torchrun): every rank owns one GPU and applies H_eff to its own phi (weak scaling; the row-sharded matvec
+with an all-gather is the next step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (site, bc, L, couplings, D, description)
+    "cfg2": ("haagerupq", "p", 8, [0.0, -1.0, 0.0], 1600, "haagerupq p j=(0,-1,0) synthetic D=1600 Z3(534,533,533) k=26(10,8,8) c128 (BASELINE configs[1])"),
+    "cfg5": ("haagerupq", "p", 8, [-1.0, 0.0, 0.0], 4000, "haagerupq p j=(-1,0,0) synthetic D=4000 Z3(1334,1333,1333) k=26(10,8,8) f64 (BASELINE configs[4])"),
+    "cfg3": ("golden", "p", 24, [-1.0], 800, "golden p synthetic D=800 k=10 f64 dense (BASELINE configs[2])"),
+    "cfg4": ("haagerup", "o", 12, [0.0, -1.0, 0.0], 3000, "haagerup o synthetic D=3000 k=14 f64 dense (BASELINE configs[3])"),
+    "tiny": ("haagerupq", "p", 8, [0.0, -1.0, 0.0], 96, "haagerupq p j=(0,-1,0) synthetic D=96 (smoke size)"),
+}
+
+
+def sectors(D, nq):
+    base, rem = divmod(D, nq)
+    return [base + (1 if q < rem else 0) for q in range(nq)]
+
+
+def labels(dims):
+    return np.concatenate([np.full(n, q, np.int32) for q, n in enumerate(dims)])
+
+
+def build_workload(name, seed):
+    """Synthetic bond problem: true MPO tensors of the model, N(0,1) in the allowed blocks of L, R, phi."""
+    from chain_b200 import models
+    st, bc, L, cp, D, desc = WORKLOADS[name]
+    ss = models.make_siteset(st, L)
+    mpo = ss.hamiltonian(bc, L, 2.0, cp)
+    b = L // 2                                # central bond: sites b, b+1
+    W1, W2 = mpo.sites[b - 1], mpo.sites[b]
+    qkl, qkm, qkr = mpo.link_charges[b - 1], mpo.link_charges[b], mpo.link_charges[b + 1]
+    nq = ss.nq
+    cplx = mpo.is_complex()
+    dl = sectors(D, nq)
+    ql = labels(dl)
+    qr = (ql + 0) % nq                        # right link: same sector sizes
+    sq = ss.charges
+    rng = np.random.default_rng(seed)
+
+    def rnd(shape, mask):
+        x = rng.standard_normal(shape)
+        if cplx:
+            x = x + 1j * rng.standard_normal(shape)
+        return np.asfortranarray(x * mask)
+    Lm = (ql[:, None, None] - qkl[None, :, None] - ql[None, None, :]) % nq == 0          # q(l') = q(l) + q(a)
+    Rm = (qr[:, None, None] - qkr[None, :, None] - qr[None, None, :]) % nq == 0
+    Lenv, Renv = rnd((D, len(qkl), D), Lm), rnd((D, len(qkr), D), Rm)
+    pm = (ql[:, None, None, None] + sq[None, :, None, None] + sq[None, None, :, None] - qr[None, None, None, :]) % nq == 0
+    phi = rnd((D, ss.d, ss.d, D), pm)
+    phi /= np.linalg.norm(phi)
+    dims = dict(Dl=dl, Dr=dl, kl=np.bincount(qkl, minlength=nq).tolist(), km=np.bincount(qkm, minlength=nq).tolist(),
+                kr=np.bincount(qkr, minlength=nq).tolist(), ds=np.bincount(sq, minlength=nq).tolist(), d=ss.d, nq=nq, cplx=bool(cplx), D=D)
+    return dict(L=Lenv, W1=W1, W2=W2, R=Renv, phi=phi, ql=ql, qr=qr, qkl=qkl, qkm=qkm, qkr=qkr, sq=sq, nq=nq, desc=desc, dims=dims)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_ev = gpu, [], threading.Event()
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        self.stop_ev.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path (oracle port of ITensor's block-pair loop), one bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as cbz
+    st, bc, L, cp, D, desc = WORKLOADS[args.workload]
+    w = build_dims_only(args.workload)
+    budget = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cbz.matvec_sample(w["Dl"], w["Dr"], w["kl"], w["kr"], w["ds"], w["cplx"], budget_s=budget / 4)
+    fl, secs, sample = 0.0, 0.0, ""
+    for s in range(args.steps):
+        r = cbz.matvec_sample(w["Dl"], w["Dr"], w["kl"], w["kr"], w["ds"], w["cplx"], budget_s=budget, seed=s)
+        fl += r["flops"]; secs += r["seconds"]; sample = r["sample"]
+    v = fl / secs / 1e12
+    line = {"impl": "reference", "metric": "heff_matvec_fp64_tflops", "value": v, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128" if w["cplx"] else "f64", "data": "synthetic",
+            "config": {"workload": desc, "note": "each step = a bounded sample of the matvec's block-pair GEMMs on the host cores"},
+            "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": cbz.host_threads(), "kind": "port", "sample": sample + " per step"},
+            "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def build_dims_only(name):
+    from chain_b200 import models
+    st, bc, L, cp, D, desc = WORKLOADS[name]
+    ss = models.make_siteset(st, L)
+    mpo = ss.hamiltonian(bc, L, 2.0, cp)
+    b = L // 2
+    nq = ss.nq
+    return dict(Dl=sectors(D, nq), Dr=sectors(D, nq), kl=np.bincount(mpo.link_charges[b - 1], minlength=nq).tolist(),
+                kr=np.bincount(mpo.link_charges[b + 1], minlength=nq).tolist(), ds=np.bincount(ss.charges, minlength=nq).tolist(),
+                cplx=bool(mpo.is_complex()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import chain_b200 as cb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = build_workload(args.workload, seed=1000 * 2 + rank)
+    ctx = cb.Context(device=local_rank)
+    bond = cb.Bond(w["L"], w["W1"], w["W2"], w["R"], ql=w["ql"], qr=w["qr"], qkl=w["qkl"], qkm=w["qkm"], qkr=w["qkr"],
+                   site_charges=w["sq"], nq=w["nq"], ctx=ctx)
+    falg = bond.matvec_flops
+    dt = np.complex128 if w["dims"]["cplx"] else np.float64
+    phi = np.asfortranarray(w["phi"].astype(dt))
+
+    # FP64 peaks measured live (MEASURED_PEAKS.json carries no FP64 number)
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, a)
+    torch.cuda.synchronize()
+    cublas = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, a); e1.record(); torch.cuda.synchronize()
+        cublas = max(cublas, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a
+    torch.cuda.empty_cache()
+    dmma_pipe = cb.k_fp64_peak(0, 20000, ctx=ctx)
+
+    # ---- timed region 1: device-resident matvecs (CUDA events on the library's launching stream)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    ms = bond.apply_timed(phi, reps=args.steps, warmup=args.warmup)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = (ctx.launches - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.summary()
+    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = falg * world / (ms_max * 1e-3) / 1e12
+
+    # ---- per-stage times -> roofline of the dominant kernel (the DMMA GEMM: L-stage + R-stage launches)
+    st_ms, st_fl = bond.stage_times(phi, reps=3)
+    gemm_ms = st_ms[0] + st_ms[2]
+    gemm_fl = st_fl[0] + st_fl[2]
+    roofline = {"kernel": "gemm_grouped_kernel (L-stage + R-stage launches of one matvec)", "bound": "tensor", "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12,
+                "peak": cublas, "unit": "TFLOP/s", "frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / cublas, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "dmma_issue_loop_tflops": dmma_pipe, "share_of_step": gemm_ms / sum(st_ms),
+                "stage_ms": {"gemm_L": st_ms[0], "mix": st_ms[1], "gemm_R": st_ms[2]},
+                "stage_flops": {"gemm_L": st_fl[0], "mix": st_fl[1], "gemm_R": st_fl[2]}}
+
+    # ---- timed region 2: end to end through the C ABI with pinned host buffers (H2D + compute + D2H every step)
+    xh = torch.empty(phi.size * (2 if w["dims"]["cplx"] else 1), dtype=torch.float64, pin_memory=True)
+    yh = torch.empty_like(xh, pin_memory=True)
+    xn = xh.numpy().view(dt).reshape(phi.shape, order="F")
+    yn = yh.numpy().view(dt).reshape(phi.shape, order="F")
+    xn[...] = phi
+    for _ in range(2):
+        bond.apply(xn, out=yn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bond.apply(xn, out=yn)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_v = falg * world * args.steps / float(e2e_t.item()) / 1e12
+    nbytes = int(phi.size * phi.itemsize)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import cpu_baseline as cbz     # the one place bench.py touches the oracle: the reported CPU baseline
+            d = w["dims"]
+            r = cbz.matvec_sample(d["Dl"], d["Dr"], d["kl"], d["kr"], d["ds"], d["cplx"], budget_s=12.0)
+            cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": cbz.host_threads(), "kind": "port", "sample": r["sample"]}
+        line = {"metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "c128" if w["dims"]["cplx"] else "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "dims": w["dims"], "f_alg_per_matvec": falg,
+                           "l2": "inputs larger than L2 (phi + environments + intermediates >> 126 MB)", "parallelism": "replicas x%d" % world},
+                "clocks": clocks,
+                "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+        print(json.dumps(line), flush=True)
+    bond.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

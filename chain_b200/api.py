@@ -269,9 +269,9 @@ class Bond:
         ps = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
         self.ctx.check(self.ctx.lib.cb200_bond_set_penalty(self.h, len(arrs), ps, float(weight)))
 
-    def apply(self, phi):
+    def apply(self, phi, out=None):
         x = self._phi(phi)
-        y = np.zeros_like(x, order="F")
+        y = out if out is not None else np.zeros_like(x, order="F")
         self.ctx.check(self.ctx.lib.cb200_bond_apply(self.h, ptr(x), ptr(y)))
         return y
 
@@ -280,6 +280,14 @@ class Bond:
         ms = C.c_double()
         self.ctx.check(self.ctx.lib.cb200_bond_apply_timed(self.h, ptr(x), reps, warmup, C.byref(ms)))
         return ms.value
+
+    def stage_times(self, phi, reps=3):
+        """(ms[3], flops[3]) for [L-stage GEMM, W(x)W mix, R-stage GEMM], CUDA events on the library's stream."""
+        x = self._phi(phi)
+        ms = (C.c_double * 3)()
+        fl = (C.c_double * 3)()
+        self.ctx.check(self.ctx.lib.cb200_bond_stage_times(self.h, ptr(x), reps, ms, fl))
+        return list(ms), list(fl)
 
     def davidson(self, phi, niter=2):
         x = self._phi(phi).copy(order="F")

@@ -243,6 +243,21 @@ int cb200_bond_apply_timed(cb200_bond* B, const void* phi, int32_t reps, int32_t
   });
 }
 
+int cb200_bond_stage_times(cb200_bond* B, const void* phi, int32_t reps, double* ms3, double* flops3) {
+  if (!B || !phi || !ms3 || reps < 1) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true), y(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    B->b.apply(x.p, y.p);
+    dev_sync(c->be);
+    B->b.stage_times(x.p, y.p, reps, ms3);
+    if (flops3) { flops3[0] = B->b.g1.flops; flops3[1] = B->b.mix.flops; flops3[2] = B->b.g2.flops; }
+  });
+}
+
 int cb200_bond_davidson(cb200_bond* B, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec) {
   if (!B || !phi || !eigenvalue) return CB200_ERR_INVALID;
   return guard(B->ctx, [&] {

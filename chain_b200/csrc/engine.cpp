@@ -348,7 +348,7 @@ void Bond::plan() {
       for (int ql = 0; ql < nq; ++ql) {
         const int qlp = qadd(ql, qa, nq);
         const int64_t M = t1M[qa * nq + ql], N = philay.ncols(ql), K = Dl.dim[ql];
-        if (M == 0 || N == 0 || K == 0) continue;
+        if (M == 0 || N == 0) continue;   // K == 0 still emits the task: it zero-fills the block the mix stage reads
         gb.begin(t1off[qa * nq + ql], M, M, N, 0);
         gb.seg(Llay.o(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
         gb.end();
@@ -466,6 +466,24 @@ void Bond::apply(const void* x, void* y) {
   }
   ctx->tm.nmatvec += 1;
   ctx->tm.matvec_flops += flops_alg;
+}
+
+void Bond::stage_times(const void* x, void* y, int reps, double* ms3) {
+  Backend* be = ctx->be;
+  ms3[0] = ms3[1] = ms3[2] = 0;
+  for (int i = 0; i < reps; ++i) {
+    dev_event_record(be, 0);
+    run_gemm(ctx, cplx, g1, L, x, T1.p);
+    dev_event_record(be, 1);
+    run_mix(ctx, cplx, mix, T1.p, T2.p);
+    dev_event_record(be, 2);
+    run_gemm(ctx, cplx, g2, T2.p, R, y);
+    dev_event_record(be, 3);
+    ms3[0] += dev_event_elapsed_ms(be, 0, 1);
+    ms3[1] += dev_event_elapsed_ms(be, 1, 2);
+    ms3[2] += dev_event_elapsed_ms(be, 2, 3);
+  }
+  for (int k = 0; k < 3; ++k) ms3[k] /= reps;
 }
 
 // ------------------------------------------------------------------------------------------------ Davidson (A.4)
@@ -967,7 +985,7 @@ void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, cons
     for (int qa = 0; qa < nq; ++qa)
       for (int ql = 0; ql < nq; ++ql) {
         const int64_t M = xM[qa * nq + ql], N = A.lay.ncols(ql), K = Dl.dim[ql];
-        if (M == 0 || N == 0 || K == 0) continue;
+        if (M == 0 || N == 0) continue;
         gb.begin(xoff[qa * nq + ql], M, M, N, 0);
         gb.seg(L.lay.o(qadd(ql, qa, nq), qa), M, A.lay.o(ql, 0), K, K);
         gb.end();
@@ -1080,7 +1098,7 @@ void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, con
           const int qr = qadd(qm, qs, nq), qrp = qadd(qr, qa2, nq);
           const size_t id = ((size_t)qa2 * nq + qm) * nq + qs;
           const int64_t M = xM[id], N = Dm.dim[qm] * ds.dim[qs], K = Dr.dim[qr];
-          if (M == 0 || N == 0 || K == 0) continue;
+          if (M == 0 || N == 0) continue;
           gb.begin(xoff[id], M, M, N, 0);
           gb.seg(R.lay.o(qrp, qa2), M, B.lay.o(qm, qs), N, K);   // B^T: element (k=r, n=(m,s)) at n + N*k
           gb.end();

@@ -172,6 +172,8 @@ struct Bond {
   double weight = 0;
   void plan();
   void apply(const void* x, void* y);   // y = H_eff x (+ penalty)
+  // per-stage device times (ms, CUDA events on the launching stream), averaged over reps: [gemm1, mix, gemm2]
+  void stage_times(const void* x, void* y, int reps, double* ms3);
 };
 
 struct DavidsonResult { double eigenvalue; int nmatvec; };

@@ -152,6 +152,7 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
   // producer cursor
   int ps = 0, pk = 0;
   auto issue_load = [&](int stage) {
+    while (sg[ps].K <= 0) ++ps;   // empty segments own no k-tile
     const GemmSeg s = sg[ps];
     char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
     char* sb = sa + (size_t)Cfg::A_ELEMS * ES;

@@ -126,6 +126,8 @@ double cb200_bond_matvec_flops(const cb200_bond* b); /* F_alg of SURVEY 8(d): bl
 int cb200_bond_apply(cb200_bond* b, const void* phi, void* out);
 /* same product, device-resident, repeated `reps` times; returns mean milliseconds (CUDA events) */
 int cb200_bond_apply_timed(cb200_bond* b, const void* phi, int32_t reps, int32_t warmup, double* ms_mean);
+/* per-stage device time of the product (ms, mean of reps) and algorithmic flops: [0] L-stage GEMM, [1] W (x) W mix, [2] R-stage GEMM */
+int cb200_bond_stage_times(cb200_bond* b, const void* phi, int32_t reps, double* ms3, double* flops3);
 /* itensor::davidson (MaxIter = niter): phi in/out (host), eigenvalue out */
 int cb200_bond_davidson(cb200_bond* b, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec);
 /* MPS::svdBond: phi (host) -> A [Dl,d,m], B [m,d,Dr]; call with A=B=NULL first to get m and charges_mid

@@ -35,7 +35,7 @@ def test_gemm_conj_accumulate_offsets_segments(gpu_ctx, cplx):
     M, N = 150, 77
     Ks = [33, 0, 129, 5]
     lda, ldb, ldc = 161, 140, 157           # odd leading dimensions + odd offsets: exercises the unaligned (8-byte) load path
-    A = _rand(rng, lda * 140 + 50, cplx)
+    A = _rand(rng, lda * (M + 8), cplx)
     B = _rand(rng, ldb * N + 50, cplx)
     C0 = _rand(rng, ldc * N + 9, cplx)
     a_off, b_off = [3, 0, 11, 1000], [1, 0, 7, 2]
@@ -106,7 +106,7 @@ def test_block_jacobi_svd(gpu_ctx, rows, cols, cplx):
     s = np.linalg.svd(X, compute_uv=False)
     k = min(rows, cols)
     assert np.abs(w[:k] - s ** 2).max() <= 1e-11 * max(1.0, s[0] ** 2)
-    assert np.abs(v.conj().T @ v - np.eye(cols)).max() <= 1e-12
+    assert np.abs(v.conj().T @ v - np.eye(cols)).max() <= 1e-11
     assert np.abs(X @ v - xv).max() <= 1e-12 * max(1.0, s[0])
     g = xv.conj().T @ xv
     assert np.abs(g - np.diag(np.diag(g))).max() <= 1e-11 * max(1.0, s[0] ** 2)

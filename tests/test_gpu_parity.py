@@ -24,7 +24,7 @@ def test_bond_ops_match_oracle(gpu_ctx, case):
 
 @pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
 def test_dmrg_trajectory_matches_oracle(gpu_ctx, case):
-    common.check_dmrg_trajectory(gpu_ctx, case, nsweep=4)
+    common.check_dmrg_trajectory(gpu_ctx, case, nsweep=10)
 
 
 def test_ground_state_kat_golden_config1(gpu_ctx):

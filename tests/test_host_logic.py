@@ -15,7 +15,7 @@ def test_bond_ops_match_oracle(emu_ctx, case):
 
 @pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
 def test_dmrg_trajectory_matches_oracle(emu_ctx, case):
-    common.check_dmrg_trajectory(emu_ctx, case, nsweep=3)
+    common.check_dmrg_trajectory(emu_ctx, case, nsweep=8)
 
 
 def test_task_list_gemm_segments_and_split(emu_ctx):
