@@ -41,9 +41,10 @@ int gemm_tile_m(bool cplx);
 int gemm_tile_n(bool cplx, bool narrow);
 
 // Sparse MPO "mix" between the GEMM stages.
-void launch_mix(Backend*, bool cplx, const void* in, void* out, const MixPanel* d_panels, int npanels,
-                const MixOut* d_outs, const MixEntry* d_entries, int total_blocks);
-int mix_rows_per_block();
+// max_in = largest in_count of any panel (decides whether the inputs of a row chunk fit in shared memory).
+void launch_mix(Backend*, bool cplx, const void* in, void* out, const MixPanel* d_panels, int npanels, const MixIn* d_ins,
+                const MixOut* d_outs, const MixEntry* d_entries, int total_blocks, int max_in);
+int mix_rows_per_block(bool cplx, int max_in);
 
 // Strided 3-D copies (permutes, gathers, conj-transposes).
 void launch_copy(Backend*, bool cplx, const void* src, void* dst, const CopyTask* d_tasks, int ntasks, int total_blocks);

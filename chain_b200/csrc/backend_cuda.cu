@@ -160,12 +160,77 @@ void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const voi
 }
 
 // ------------------------------------------------------------------------------------------------ mix
-static constexpr int MIX_ROWS = 128;
-int mix_rows_per_block() { return MIX_ROWS; }
+// out[row, oslot, r] = sum_e coef[e] * in[row, islot(e), r].  Two kernels:
+//   mix_smem_kernel: a CTA stages ALL input slots of (row chunk, r) in shared memory once (coalesced, read exactly once
+//                    from HBM) and then forms every output slot from shared memory -> HBM traffic = read T1 + write T2;
+//   mix_kernel     : generic fallback when the panel's inputs do not fit in shared memory (inputs re-read through L1/L2).
+static constexpr int MIX_ROWS = 128;          // fallback kernel: rows per CTA
+static constexpr int MIX_THREADS = 128;
+static constexpr int MIX_SMEM_MAX = 200 * 1024;
+static int mix_rb(bool cplx) { return cplx ? 16 : 32; }     // 256-byte row segments either way
+int mix_rows_per_block(bool cplx, int max_in) {
+  const size_t need = (size_t)max_in * mix_rb(cplx) * (cplx ? 16 : 8);
+  return need <= (size_t)MIX_SMEM_MAX ? mix_rb(cplx) : MIX_ROWS;
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(MIX_THREADS) mix_smem_kernel(const void* __restrict__ in_, void* __restrict__ out_,
+                                                               const MixPanel* __restrict__ panels, int npanels,
+                                                               const MixIn* __restrict__ ins, const MixOut* __restrict__ outs,
+                                                               const MixEntry* __restrict__ ents) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int RB = CPLX ? 16 : 32;
+  constexpr int G = MIX_THREADS / RB;
+  extern __shared__ __align__(16) char msm[];
+  T* sm = reinterpret_cast<T*>(msm);
+  int lo = 0, hi = npanels - 1;
+  const int blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (panels[mid].blk_begin <= blk) lo = mid; else hi = mid - 1;
+  }
+  const MixPanel p = panels[lo];
+  const int local = blk - p.blk_begin;
+  const int row0 = (local % p.row_chunks) * RB;
+  const int64_t r = local / p.row_chunks;
+  const int lrow = threadIdx.x % RB, grp = threadIdx.x / RB;
+  const bool row_ok = row0 + lrow < p.rows;
+  const T* in = reinterpret_cast<const T*>(in_);
+  // stage the inputs: slot-major, RB consecutive rows per slot
+  for (int s = grp; s < p.in_count; s += G) {
+    const MixIn mi = ins[p.in_begin + s];
+    T v;
+    if constexpr (CPLX) v = make_double2(0.0, 0.0); else v = 0.0;
+    if (row_ok) v = in[mi.off + r * mi.rstride + row0 + lrow];
+    sm[s * RB + lrow] = v;
+  }
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(out_);
+  for (int o = p.out_begin + grp; o < p.out_end; o += G) {
+    const MixOut mo = outs[o];
+    if constexpr (!CPLX) {
+      double acc = 0.0;
+      for (int e = mo.e_begin; e < mo.e_end; ++e) {
+        const MixEntry me = ents[e];
+        acc = fma(me.cre, sm[me.slot * RB + lrow], acc);
+      }
+      if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = acc;
+    } else {
+      double ar = 0.0, ai = 0.0;
+      for (int e = mo.e_begin; e < mo.e_end; ++e) {
+        const MixEntry me = ents[e];
+        const double2 v = sm[me.slot * RB + lrow];
+        ar = fma(me.cre, v.x, ar); ar = fma(-me.cim, v.y, ar);
+        ai = fma(me.cre, v.y, ai); ai = fma(me.cim, v.x, ai);
+      }
+      if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = make_double2(ar, ai);
+    }
+  }
+}
 
 template <bool CPLX>
 __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ in_, void* __restrict__ out_,
-                                                       const MixPanel* __restrict__ panels, int npanels,
+                                                       const MixPanel* __restrict__ panels, int npanels, const MixIn* __restrict__ ins,
                                                        const MixOut* __restrict__ outs, const MixEntry* __restrict__ ents) {
   int lo = 0, hi = npanels - 1;
   const int blk = blockIdx.x;
@@ -185,7 +250,8 @@ __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ 
       double acc = 0.0;
       for (int e = mo.e_begin; e < mo.e_end; ++e) {
         const MixEntry me = ents[e];
-        acc = fma(me.cre, __ldg(in + me.in_off + r * me.in_rstride + row), acc);
+        const MixIn mi = ins[p.in_begin + me.slot];
+        acc = fma(me.cre, __ldg(in + mi.off + r * mi.rstride + row), acc);
       }
       ((double*)out_)[mo.off + r * mo.rstride + row] = acc;
     } else {
@@ -193,7 +259,8 @@ __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ 
       double ar = 0.0, ai = 0.0;
       for (int e = mo.e_begin; e < mo.e_end; ++e) {
         const MixEntry me = ents[e];
-        const double2 v = __ldg(in + me.in_off + r * me.in_rstride + row);
+        const MixIn mi = ins[p.in_begin + me.slot];
+        const double2 v = __ldg(in + mi.off + r * mi.rstride + row);
         ar = fma(me.cre, v.x, ar); ar = fma(-me.cim, v.y, ar);
         ai = fma(me.cre, v.y, ai); ai = fma(me.cim, v.x, ai);
       }
@@ -202,12 +269,25 @@ __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ 
   }
 }
 
-void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixOut* o, const MixEntry* e,
-                int blocks) {
+void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o,
+                const MixEntry* e, int blocks, int max_in) {
   if (blocks <= 0) return;
-  if (cplx) mix_kernel<true><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, o, e);
-  else mix_kernel<false><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, o, e);
-  CB_LAUNCH_CHECK(b, "mix_kernel");
+  const size_t need = (size_t)max_in * mix_rb(cplx) * (cplx ? 16 : 8);
+  if (need <= (size_t)MIX_SMEM_MAX) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(mix_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX);
+      cudaFuncSetAttribute(mix_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX);
+      attr_done = true;
+    }
+    if (cplx) mix_smem_kernel<true><<<blocks, MIX_THREADS, need, b->stream>>>(in, out, p, np, mi, o, e);
+    else mix_smem_kernel<false><<<blocks, MIX_THREADS, need, b->stream>>>(in, out, p, np, mi, o, e);
+    CB_LAUNCH_CHECK(b, "mix_smem_kernel");
+  } else {
+    if (cplx) mix_kernel<true><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, mi, o, e);
+    else mix_kernel<false><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, mi, o, e);
+    CB_LAUNCH_CHECK(b, "mix_kernel");
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ copy

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <random>
 
@@ -206,8 +207,10 @@ void run_gemm(Ctx* c, bool cplx, const GemmPlan& p, const void* A, const void* B
 
 struct MixBuilder {
   std::vector<MixPanel> panels;
+  std::vector<MixIn> ins;
   std::vector<MixOut> outs;
   std::vector<MixEntry> ents;
+  std::map<std::pair<int64_t, int64_t>, int> slot_of;   // (off, rstride) -> slot of the current panel
   double flops = 0;
   bool cplx;
   explicit MixBuilder(bool c) : cplx(c) {}
@@ -215,7 +218,9 @@ struct MixBuilder {
     MixPanel p{};
     p.rows = (int32_t)rows; p.nr = (int32_t)nr;
     p.out_begin = (int32_t)outs.size();
+    p.in_begin = (int32_t)ins.size();
     panels.push_back(p);
+    slot_of.clear();
   }
   void begin_out(int64_t off, int64_t rstride) {
     MixOut o{};
@@ -223,25 +228,38 @@ struct MixBuilder {
     outs.push_back(o);
   }
   void entry(int64_t in_off, int64_t in_rstride, cplx_t coef) {
+    auto key = std::make_pair(in_off, in_rstride);
+    auto it = slot_of.find(key);
+    int slot;
+    if (it == slot_of.end()) {
+      slot = (int)ins.size() - panels.back().in_begin;
+      slot_of[key] = slot;
+      ins.push_back(MixIn{in_off, in_rstride});
+    } else slot = it->second;
     MixEntry e{};
-    e.in_off = in_off; e.in_rstride = in_rstride; e.cre = coef.real(); e.cim = coef.imag();
+    e.slot = slot; e.cre = coef.real(); e.cim = coef.imag();
     ents.push_back(e);
   }
   void end_out() { outs.back().e_end = (int32_t)ents.size(); }
   void end_panel() {
     MixPanel& p = panels.back();
     p.out_end = (int32_t)outs.size();
+    p.in_count = (int32_t)ins.size() - p.in_begin;
     int64_t ne = 0;
     for (int o = p.out_begin; o < p.out_end; ++o) ne += outs[o].e_end - outs[o].e_begin;
-    flops += 2.0 * (double)ne * p.rows * p.nr;
     if (p.rows <= 0 || p.nr <= 0 || p.out_end == p.out_begin) {
       outs.resize(p.out_begin);
+      ins.resize(p.in_begin);
       // entries of dropped outs are simply left unused
       panels.pop_back();
+      return;
     }
+    flops += 2.0 * (double)ne * p.rows * p.nr;
   }
   void finish(Backend* be, MixPlan& mp) {
-    const int rpb = mix_rows_per_block();
+    int max_in = 0;
+    for (auto& p : panels) max_in = std::max(max_in, (int)p.in_count);
+    const int rpb = mix_rows_per_block(cplx, max_in);
     int blocks = 0;
     for (auto& p : panels) {
       p.blk_begin = blocks;
@@ -249,15 +267,17 @@ struct MixBuilder {
       blocks += p.row_chunks * p.nr;
     }
     mp.panels.upload(be, panels);
+    mp.ins.upload(be, ins);
     mp.outs.upload(be, outs);
     mp.ents.upload(be, ents);
     mp.blocks = blocks;
+    mp.max_in = max_in;
     mp.flops = flops * (cplx ? 4.0 : 1.0);
   }
 };
 
 void run_mix(Ctx* c, bool cplx, const MixPlan& p, const void* in, void* out) {
-  launch_mix(c->be, cplx, in, out, p.panels.ptr(), p.panels.n, p.outs.ptr(), p.ents.ptr(), p.blocks);
+  launch_mix(c->be, cplx, in, out, p.panels.ptr(), p.panels.n, p.ins.ptr(), p.outs.ptr(), p.ents.ptr(), p.blocks, p.max_in);
 }
 
 struct CopyBuilder {

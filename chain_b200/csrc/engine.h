@@ -128,9 +128,10 @@ struct GemmPlan {
 };
 struct MixPlan {
   DevList<MixPanel> panels;
+  DevList<MixIn> ins;
   DevList<MixOut> outs;
   DevList<MixEntry> ents;
-  int blocks = 0;
+  int blocks = 0, max_in = 0;
   double flops = 0;
 };
 struct CopyPlan {

@@ -31,6 +31,33 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- mbarrier helpers (full/empty pipeline: no CTA-wide barrier inside the k loop) -------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      " mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+      " @p bra WAIT_DONE;\n"
+      " bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// all cp.async issued so far by this thread arrive on `bar` when they have landed (does not change the expected count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -55,6 +82,7 @@ struct GemmCfg {
   static constexpr int B_ELEMS = (BK * (BN + PAD_MN) > BN * LDK) ? BK * (BN + PAD_MN) : BN * LDK;
   static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * ES;
   static constexpr int STAGES = 4;
+  static constexpr int AHEAD = STAGES - 2;            // k-tiles in flight; one stage of slack decouples the warps
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES;
   static constexpr int THREADS = 256;
 };
@@ -179,19 +207,31 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
       if constexpr (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
     }
 
-  int issued = 0;
+  // full[s]: the k-tile in stage s has landed (every thread's cp.async arrives on it);
+  // empty[s]: every thread has finished reading stage s.  Waiting on empty happens AHEAD+1 iterations after the
+  // consumption it guards, so warps drift freely and the DMMA pipe is fed by whichever warp has data.
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (issued < total_kt) { issue_load(s); ++issued; }
-    cp_async_commit();
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], Cfg::THREADS); mbar_init(&empty_bar[s], Cfg::THREADS); }
   }
+  __syncthreads();
+  auto produce = [&](int itl) {
+    const int stage = itl % STAGES, use = itl / STAGES;
+    if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
+    issue_load(stage);
+    cp_async_arrive(&full_bar[stage]);
+  };
+  constexpr int AHEAD = Cfg::AHEAD;
+#pragma unroll
+  for (int s = 0; s < AHEAD; ++s)
+    if (s < total_kt) produce(s);
 
   const bool conjA = (t.flags & GEMM_CONJ_A) != 0;
   for (int it = 0; it < total_kt; ++it) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (issued < total_kt) { issue_load((it + STAGES - 1) % STAGES); ++issued; }
-    cp_async_commit();
+    if (it + AHEAD < total_kt) produce(it + AHEAD);
+    mbar_wait(&full_bar[it % STAGES], (unsigned)((it / STAGES) & 1));
 
     const char* sa = smem + (size_t)(it % STAGES) * Cfg::STAGE_BYTES;
     const char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
@@ -236,8 +276,8 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
           }
       }
     }
+    mbar_arrive(&empty_bar[it % STAGES]);
   }
-  cp_async_wait<0>();
 
   // epilogue: direct stores from the accumulator fragments
   const bool accum = (t.flags & GEMM_ACCUM) != 0;

@@ -42,13 +42,18 @@ struct MixOut {
   int64_t off, rstride;   // element address = out_base + off + r*rstride + row
   int32_t e_begin, e_end; // range into the entry list
 };
+struct MixIn {
+  int64_t off, rstride;         // element address = in_base + off + r*rstride + row
+};
 struct MixEntry {
-  int64_t in_off, in_rstride;   // element address = in_base + in_off + r*in_rstride + row
+  int32_t slot;                 // index into the panel's MixIn table (in_begin + slot)
+  int32_t pad_;
   double cre, cim;
 };
 struct MixPanel {
   int32_t rows, nr;
   int32_t out_begin, out_end;   // range into the MixOut list
+  int32_t in_begin, in_count;   // the distinct input slots of this panel (staged in shared memory)
   int32_t blk_begin;            // first CTA of this panel in the flattened grid
   int32_t row_chunks;           // CTAs along rows
 };

@@ -133,7 +133,7 @@ DMRG_CASES = [
     ("golden", "p", 6, [-1.0], 0, 3, True),
     ("golden", "o", 7, [-1.0], 0, 1, True),
     ("haagerup", "p", 6, [0.0, -1.0, 0.0], 0, 1, True),
-    ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 1, 2, False),
+    ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 1, 1, False),   # real, charged sector
     ("haagerupq", "p", 6, [0.0, -1.0, 0.0], 0, 1, False),   # complex128 block-sparse (README example model)
 ]
 
@@ -172,6 +172,30 @@ def check_dmrg_trajectory(ctx, case, nsweep=10):
         done_o.append(po)
         done_g.append(pg)
     return done_g
+
+
+def check_excited_qn(ctx, nsweep=12):
+    """Penalised state in a Z3 sector (haagerupq K-only, q=0, second level -3.4971 non-degenerate).  Its sweep converges
+    slowly (1e-10 needs ~50 sweeps, in the oracle too) and is chaotic in the transient, so only a loose agreement is
+    asserted here; the exact checks of the penalty machinery are check_bond_ops (one bond) and the golden 3-state run."""
+    st, bc, n, cp, q = "haagerupq", "p", 6, [-1.0, 0.0, 0.0], 0
+    site, W, qk = build_model(st, bc, n, cp)
+    H = cb.MPO(W, qk, site.charges, nq=site.nq)
+    done_o, done_g, out = [], [], []
+    for s in range(2):
+        psi0 = warm_start(site, W, n, q, seed=7 + s)
+        sw = ([10, 20, 40, 80], [1e-5, 1e-6, 1e-7, 1e-8])
+        eo, po = od.dmrg(W, done_o, psi0, od.Sweeps(nsweep, *sw), weight=1000.0)
+        eg, pg = cb.dmrg(H, done_g, to_cb(psi0), cb.Sweeps(nsweep, *sw), weight=1000.0, ctx=ctx)
+        assert abs(eo - eg) <= (1e-10 if s == 0 else 2e-5) * abs(eo)
+        assert abs(eg - ed_level(st, bc, n, cp, q)[s]) <= (1e-8 if s == 0 else 2e-3)
+        pgo = to_oracle(pg, site)
+        for prev in done_g:
+            assert abs(od.overlap(to_oracle(prev, site), pgo)) <= 1e-3       # Weight = 1000 keeps it orthogonal
+        done_o.append(po)
+        done_g.append(pg)
+        out.append(eg)
+    return out
 
 
 def check_ground_state_kat(ctx, st, bc, n, cp, q, tol, nrep=12, seed=1):

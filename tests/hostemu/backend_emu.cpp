@@ -38,7 +38,7 @@ void dev_event_record(Backend*, int) {}
 float dev_event_elapsed_ms(Backend*, int, int) { return 0.f; }
 int gemm_tile_m(bool cplx) { return cplx ? 64 : 128; }
 int gemm_tile_n(bool, bool narrow) { return narrow ? 64 : 128; }
-int mix_rows_per_block() { return 128; }
+int mix_rows_per_block(bool, int) { return 128; }
 int copy_elems_per_block() { return 2048; }
 
 template <class T>
@@ -80,7 +80,7 @@ void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool, const void* A, c
 }
 
 template <class T>
-static void mix_t(const T* in, T* out, const MixPanel* panels, int np, const MixOut* outs, const MixEntry* ents) {
+static void mix_t(const T* in, T* out, const MixPanel* panels, int np, const MixIn* ins, const MixOut* outs, const MixEntry* ents) {
   for (int pi = 0; pi < np; ++pi) {
     const MixPanel& p = panels[pi];
     for (int64_t r = 0; r < p.nr; ++r)
@@ -92,7 +92,8 @@ static void mix_t(const T* in, T* out, const MixPanel* panels, int np, const Mix
             const MixEntry& me = ents[e];
             T c;
             if constexpr (std::is_same<T, cd>::value) c = cd(me.cre, me.cim); else c = me.cre;
-            acc += c * in[me.in_off + r * me.in_rstride + row];
+            const MixIn& mi = ins[p.in_begin + me.slot];
+            acc += c * in[mi.off + r * mi.rstride + row];
           }
           out[mo.off + r * mo.rstride + row] = acc;
         }
@@ -100,10 +101,10 @@ static void mix_t(const T* in, T* out, const MixPanel* panels, int np, const Mix
   }
 }
 
-void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixOut* o, const MixEntry* e, int blocks) {
+void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o, const MixEntry* e, int blocks, int) {
   if (blocks <= 0) return;
   b->launches++;
-  if (cplx) mix_t<cd>((const cd*)in, (cd*)out, p, np, o, e); else mix_t<double>((const double*)in, (double*)out, p, np, o, e);
+  if (cplx) mix_t<cd>((const cd*)in, (cd*)out, p, np, mi, o, e); else mix_t<double>((const double*)in, (double*)out, p, np, mi, o, e);
 }
 
 template <class T>

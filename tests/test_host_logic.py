@@ -48,3 +48,7 @@ def test_block_jacobi_svd_driver(emu_ctx, rows, cols, cplx):
 
 def test_ground_state_kat_golden(emu_ctx):
     common.check_ground_state_kat(emu_ctx, "golden", "p", 6, [-1.0], 0, tol=2e-9)
+
+
+def test_excited_state_in_charge_sector(emu_ctx):
+    common.check_excited_qn(emu_ctx)
