@@ -165,21 +165,21 @@ void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const voi
 //                    from HBM) and then forms every output slot from shared memory -> HBM traffic = read T1 + write T2;
 //   mix_kernel     : generic fallback when the panel's inputs do not fit in shared memory (inputs re-read through L1/L2).
 static constexpr int MIX_ROWS = 128;          // fallback kernel: rows per CTA
-static constexpr int MIX_THREADS = 128;
-static constexpr int MIX_SMEM_MAX = 200 * 1024;
-static int mix_rb(bool cplx) { return cplx ? 16 : 32; }     // 256-byte row segments either way
+static constexpr int MIX_THREADS = 512;       // 16 warps; each warp owns 32 rows x (every 16th output slot)
+static constexpr int MIX_RB = 32;
+static constexpr int MIX_SMEM_MAX = 208 * 1024;
 int mix_rows_per_block(bool cplx, int max_in) {
-  const size_t need = (size_t)max_in * mix_rb(cplx) * (cplx ? 16 : 8);
-  return need <= (size_t)MIX_SMEM_MAX ? mix_rb(cplx) : MIX_ROWS;
+  const size_t need = (size_t)max_in * MIX_RB * (cplx ? 16 : 8);
+  return need <= (size_t)MIX_SMEM_MAX ? MIX_RB : MIX_ROWS;
 }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(MIX_THREADS) mix_smem_kernel(const void* __restrict__ in_, void* __restrict__ out_,
-                                                               const MixPanel* __restrict__ panels, int npanels,
-                                                               const MixIn* __restrict__ ins, const MixOut* __restrict__ outs,
-                                                               const MixEntry* __restrict__ ents) {
+__global__ void __launch_bounds__(MIX_THREADS, 1) mix_smem_kernel(const void* __restrict__ in_, void* __restrict__ out_,
+                                                                  const MixPanel* __restrict__ panels, int npanels,
+                                                                  const MixIn* __restrict__ ins, const MixOut* __restrict__ outs,
+                                                                  const MixEntry* __restrict__ ents) {
   using T = typename std::conditional<CPLX, double2, double>::type;
-  constexpr int RB = CPLX ? 16 : 32;
+  constexpr int RB = MIX_RB;
   constexpr int G = MIX_THREADS / RB;
   extern __shared__ __align__(16) char msm[];
   T* sm = reinterpret_cast<T*>(msm);
@@ -196,36 +196,43 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_smem_kernel(const void* __res
   const int lrow = threadIdx.x % RB, grp = threadIdx.x / RB;
   const bool row_ok = row0 + lrow < p.rows;
   const T* in = reinterpret_cast<const T*>(in_);
-  // stage the inputs: slot-major, RB consecutive rows per slot
+  // stage every input slot of this (row chunk, r) once: fire-and-forget async copies (zero-filled past the last row)
   for (int s = grp; s < p.in_count; s += G) {
     const MixIn mi = ins[p.in_begin + s];
-    T v;
-    if constexpr (CPLX) v = make_double2(0.0, 0.0); else v = 0.0;
-    if (row_ok) v = in[mi.off + r * mi.rstride + row0 + lrow];
-    sm[s * RB + lrow] = v;
+    const T* src = row_ok ? (in + mi.off + r * mi.rstride + row0 + lrow) : in;
+    if constexpr (CPLX) cp_async16(sm + s * RB + lrow, src, row_ok ? 16 : 0);
+    else cp_async8(sm + s * RB + lrow, src, row_ok ? 8 : 0);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   T* out = reinterpret_cast<T*>(out_);
+  const double4* e4 = reinterpret_cast<const double4*>(ents);
   for (int o = p.out_begin + grp; o < p.out_end; o += G) {
     const MixOut mo = outs[o];
     if constexpr (!CPLX) {
       double acc = 0.0;
+#pragma unroll 4
       for (int e = mo.e_begin; e < mo.e_end; ++e) {
-        const MixEntry me = ents[e];
-        acc = fma(me.cre, sm[me.slot * RB + lrow], acc);
+        const double cre = __ldg(&ents[e].cre);
+        const int slot = __ldg(&ents[e].slot);
+        acc = fma(cre, sm[slot * RB + lrow], acc);
       }
       if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = acc;
     } else {
       double ar = 0.0, ai = 0.0;
+#pragma unroll 4
       for (int e = mo.e_begin; e < mo.e_end; ++e) {
-        const MixEntry me = ents[e];
-        const double2 v = sm[me.slot * RB + lrow];
-        ar = fma(me.cre, v.x, ar); ar = fma(-me.cim, v.y, ar);
-        ai = fma(me.cre, v.y, ai); ai = fma(me.cim, v.x, ai);
+        const double2 c = __ldg(reinterpret_cast<const double2*>(&ents[e].cre));
+        const int slot = __ldg(&ents[e].slot);
+        const double2 v = sm[slot * RB + lrow];
+        ar = fma(c.x, v.x, ar); ar = fma(-c.y, v.y, ar);
+        ai = fma(c.x, v.y, ai); ai = fma(c.y, v.x, ai);
       }
       if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = make_double2(ar, ai);
     }
   }
+  (void)e4;
 }
 
 template <bool CPLX>
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ 
 void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o,
                 const MixEntry* e, int blocks, int max_in) {
   if (blocks <= 0) return;
-  const size_t need = (size_t)max_in * mix_rb(cplx) * (cplx ? 16 : 8);
+  const size_t need = (size_t)max_in * MIX_RB * (cplx ? 16 : 8);
   if (need <= (size_t)MIX_SMEM_MAX) {
     static bool attr_done = false;
     if (!attr_done) {

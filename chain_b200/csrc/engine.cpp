@@ -234,7 +234,9 @@ struct MixBuilder {
     if (it == slot_of.end()) {
       slot = (int)ins.size() - panels.back().in_begin;
       slot_of[key] = slot;
-      ins.push_back(MixIn{in_off, in_rstride});
+      MixIn mi{};
+      mi.off = in_off; mi.rstride = in_rstride;
+      ins.push_back(mi);
     } else slot = it->second;
     MixEntry e{};
     e.slot = slot; e.cre = coef.real(); e.cim = coef.imag();
@@ -449,21 +451,36 @@ void Bond::plan() {
     mb.finish(be, mix);
   }
   // ---- GEMM2: out(ql', qr') [ (l',srow') x r' ] = sum_{qa''} T2(ql',qa'',qr'-qa'') [ . x (a'',r) ] * R(qr',qa'')^T
+  // The tile is BM x BN with BM != BN for complex data, so the planner may swap the operand roles (computing the
+  // transposed product and storing it with GEMM_TRANS_C) when that wastes fewer tile slots on the ragged sector sizes.
   {
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, false);
+    auto padded = [&](int64_t M, int64_t N) { return ((M + tm - 1) / tm) * tm * (((N + tn - 1) / tn) * tn); };
+    int64_t cost_n = 0, cost_s = 0;
+    for (int qlp = 0; qlp < nq; ++qlp)
+      for (int qrp = 0; qrp < nq; ++qrp) {
+        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
+        cost_n += padded(M, N);
+        cost_s += padded(N, M);
+      }
+    const bool swap = cost_s < cost_n;
     GemmBuilder gb(cplx);
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qrp = 0; qrp < nq; ++qrp) {
         const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
         if (M == 0 || N == 0) continue;
-        gb.begin(philay.o(qlp, qrp), M, M, N, 0);
+        if (!swap) gb.begin(philay.o(qlp, qrp), M, M, N, 0);
+        else gb.begin(philay.o(qlp, qrp), M, N, M, GEMM_TRANS_C);
         for (int qa2 = 0; qa2 < nq; ++qa2) {
           const int qr = qsub(qrp, qa2, nq);
           const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
-          gb.seg(t2off[id2], M, Rlay.o(qrp, qa2), Dr.dim[qrp], Kr.dim[qa2] * Dr.dim[qr]);
+          if (!swap) gb.seg(t2off[id2], M, Rlay.o(qrp, qa2), Dr.dim[qrp], Kr.dim[qa2] * Dr.dim[qr]);
+          else gb.seg(Rlay.o(qrp, qa2), Dr.dim[qrp], t2off[id2], M, Kr.dim[qa2] * Dr.dim[qr]);
         }
         gb.end();
       }
     gb.finish(be, g2, false, true);
+    g2_swapped = swap;
   }
   flops_alg = g1.flops + g2.flops + mix.flops;
   check_dev(ctx);
@@ -472,7 +489,7 @@ void Bond::plan() {
 void Bond::apply(const void* x, void* y) {
   run_gemm(ctx, cplx, g1, L, x, T1.p);
   run_mix(ctx, cplx, mix, T1.p, T2.p);
-  run_gemm(ctx, cplx, g2, T2.p, R, y);
+  if (g2_swapped) run_gemm(ctx, cplx, g2, R, T2.p, y); else run_gemm(ctx, cplx, g2, T2.p, R, y);
   if (!pen.empty() && weight != 0.0) {
     // LocalMPO_MPS::product: y += weight * sum_j <o_j|x> o_j
     const int np = (int)pen.size();
@@ -497,7 +514,7 @@ void Bond::stage_times(const void* x, void* y, int reps, double* ms3) {
     dev_event_record(be, 1);
     run_mix(ctx, cplx, mix, T1.p, T2.p);
     dev_event_record(be, 2);
-    run_gemm(ctx, cplx, g2, T2.p, R, y);
+    if (g2_swapped) run_gemm(ctx, cplx, g2, R, T2.p, y); else run_gemm(ctx, cplx, g2, T2.p, R, y);
     dev_event_record(be, 3);
     ms3[0] += dev_event_elapsed_ms(be, 0, 1);
     ms3[1] += dev_event_elapsed_ms(be, 1, 2);

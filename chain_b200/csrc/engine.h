@@ -164,6 +164,7 @@ struct Bond {
   const HostW* W2 = nullptr;
   // matvec plan
   GemmPlan g1, g2;
+  bool g2_swapped = false;   // R-stage computed as the transposed product (see Bond::plan)
   MixPlan mix;
   Buf T1, T2;
   int64_t t1_elems = 0, t2_elems = 0;

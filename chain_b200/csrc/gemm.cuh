@@ -282,6 +282,7 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
   // epilogue: direct stores from the accumulator fragments
   const bool accum = (t.flags & GEMM_ACCUM) != 0;
   const bool conj_out = (t.flags & GEMM_CONJ_OUT) != 0;
+  const bool trans_c = (t.flags & GEMM_TRANS_C) != 0;
   char* Cp = Cbase + t.c_off * ES;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
@@ -293,8 +294,9 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
       for (int e = 0; e < 2; ++e) {
         const int n = n0 + wn0 + j * 8 + tq * 2 + e;
         if (n >= t.N) continue;
-        const int64_t off = (n < t.n_split) ? ((int64_t)m + (int64_t)n * t.ldc)
-                                            : ((t.c_off2 - t.c_off) + (int64_t)m + (int64_t)(n - t.n_split) * t.ldc);
+        const int64_t off = trans_c ? ((int64_t)n + (int64_t)m * t.ldc)
+                            : (n < t.n_split) ? ((int64_t)m + (int64_t)n * t.ldc)
+                                              : ((t.c_off2 - t.c_off) + (int64_t)m + (int64_t)(n - t.n_split) * t.ldc);
         if constexpr (!CPLX) {
           double* p = reinterpret_cast<double*>(Cp) + off;
           double v = acc_re[i][j][e];

@@ -12,6 +12,7 @@ enum : uint32_t {
   GEMM_CONJ_A  = 4u,   // complex only: use conj(A)
   GEMM_ACCUM   = 8u,   // C += result (otherwise C = result)
   GEMM_CONJ_OUT = 16u, // complex only: store conj(result)
+  GEMM_TRANS_C = 32u,  // store element (m,n) at C[n + m*ldc] (lets the planner pick the operand roles that waste fewer tile slots)
 };
 
 // One K-segment of a task: C += op(A_seg) * op(B_seg).  Offsets are in elements from the base pointers
@@ -45,10 +46,10 @@ struct MixOut {
 struct MixIn {
   int64_t off, rstride;         // element address = in_base + off + r*rstride + row
 };
-struct MixEntry {
-  int32_t slot;                 // index into the panel's MixIn table (in_begin + slot)
-  int32_t pad_;
+struct MixEntry {                // 32 bytes: fetched as two 16-byte uniform loads
   double cre, cim;
+  int32_t slot;                 // index into the panel's MixIn table (in_begin + slot)
+  int32_t pad_[3];
 };
 struct MixPanel {
   int32_t rows, nr;

@@ -65,7 +65,8 @@ static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTas
       for (int m = 0; m < t.M; ++m) {
         T v = tmp[(size_t)m + (size_t)n * t.M];
         if constexpr (std::is_same<T, cd>::value) { if (conjOut) v = std::conj(v); }
-        T* p = (n < t.n_split) ? &C[t.c_off + m + (int64_t)n * t.ldc] : &C[t.c_off2 + m + (int64_t)(n - t.n_split) * t.ldc];
+        T* p = (t.flags & GEMM_TRANS_C) ? &C[t.c_off + n + (int64_t)m * t.ldc]
+               : (n < t.n_split) ? &C[t.c_off + m + (int64_t)n * t.ldc] : &C[t.c_off2 + m + (int64_t)(n - t.n_split) * t.ldc];
         *p = acc ? *p + v : v;
       }
   }
