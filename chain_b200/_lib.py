@@ -68,6 +68,7 @@ SYMBOLS = [
     ("cb200_bond_apply", C.c_int, [vp, vp, vp]),
     ("cb200_bond_apply_timed", C.c_int, [vp, vp, i32, i32, C.POINTER(dbl)]),
     ("cb200_bond_stage_times", C.c_int, [vp, vp, i32, C.POINTER(dbl), C.POINTER(dbl)]),
+    ("cb200_bond_update_timed", C.c_int, [vp, vp, i32, i32, dbl, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)]),
     ("cb200_bond_davidson", C.c_int, [vp, vp, i32, C.POINTER(dbl), C.POINTER(i32)]),
     ("cb200_bond_truncate", C.c_int, [vp, vp, i32, i32, i32, dbl, C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl),
                                       C.POINTER(dbl), vp, vp]),

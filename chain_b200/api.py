@@ -289,6 +289,15 @@ class Bond:
         self.ctx.check(self.ctx.lib.cb200_bond_stage_times(self.h, ptr(x), reps, ms, fl))
         return list(ms), list(fl)
 
+    def update_timed(self, phi, direction="left", maxdim=2 ** 30, cutoff=1e-8, niter=2):
+        """One full bond update on the device; returns dict(energy, m, jacobi_sweeps, matvec, level1, trunc, env) [seconds]."""
+        x = self._phi(phi)
+        en, m, js = C.c_double(), C.c_int32(), C.c_int32()
+        t = (C.c_double * 4)()
+        self.ctx.check(self.ctx.lib.cb200_bond_update_timed(self.h, ptr(x), 0 if direction == "left" else 1, int(min(maxdim, 2 ** 31 - 1)),
+                                                            float(cutoff), niter, C.byref(en), C.byref(m), C.byref(js), t))
+        return dict(energy=en.value, m=m.value, jacobi_sweeps=js.value, matvec=t[0], level1=t[1], trunc=t[2], env=t[3])
+
     def davidson(self, phi, niter=2):
         x = self._phi(phi).copy(order="F")
         ev, nmv = C.c_double(), C.c_int32()

@@ -207,32 +207,39 @@ __global__ void __launch_bounds__(MIX_THREADS, 1) mix_smem_kernel(const void* __
   cp_async_wait<0>();
   __syncthreads();
   T* out = reinterpret_cast<T*>(out_);
-  const double4* e4 = reinterpret_cast<const double4*>(ents);
+  // One warp per output slot: the warp reads 32 entries with one coalesced load and broadcasts them lane by lane
+  // with shuffles, so the inner loop has no global-memory latency: LDS (the row's input) + 4 DFMA per entry.
+  const int lane = threadIdx.x & 31;
   for (int o = p.out_begin + grp; o < p.out_end; o += G) {
     const MixOut mo = outs[o];
-    if constexpr (!CPLX) {
-      double acc = 0.0;
-#pragma unroll 4
-      for (int e = mo.e_begin; e < mo.e_end; ++e) {
-        const double cre = __ldg(&ents[e].cre);
-        const int slot = __ldg(&ents[e].slot);
-        acc = fma(cre, sm[slot * RB + lrow], acc);
+    double ar = 0.0, ai = 0.0;
+    for (int base = mo.e_begin; base < mo.e_end; base += 32) {
+      const int cnt = min(32, mo.e_end - base);
+      double cre = 0.0, cim = 0.0;
+      int slot = 0;
+      if (lane < cnt) {
+        const double2 c = __ldg(reinterpret_cast<const double2*>(&ents[base + lane].cre));
+        cre = c.x; cim = c.y;
+        slot = __ldg(&ents[base + lane].slot);
       }
-      if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = acc;
-    } else {
-      double ar = 0.0, ai = 0.0;
-#pragma unroll 4
-      for (int e = mo.e_begin; e < mo.e_end; ++e) {
-        const double2 c = __ldg(reinterpret_cast<const double2*>(&ents[e].cre));
-        const int slot = __ldg(&ents[e].slot);
-        const double2 v = sm[slot * RB + lrow];
-        ar = fma(c.x, v.x, ar); ar = fma(-c.y, v.y, ar);
-        ai = fma(c.x, v.y, ai); ai = fma(c.y, v.x, ai);
+      for (int j = 0; j < cnt; ++j) {
+        const double cr = __shfl_sync(0xffffffffu, cre, j);
+        const int sl = __shfl_sync(0xffffffffu, slot, j);
+        if constexpr (!CPLX) {
+          ar = fma(cr, sm[sl * RB + lrow], ar);
+        } else {
+          const double ci = __shfl_sync(0xffffffffu, cim, j);
+          const double2 v = sm[sl * RB + lrow];
+          ar = fma(cr, v.x, ar); ar = fma(-ci, v.y, ar);
+          ai = fma(cr, v.y, ai); ai = fma(ci, v.x, ai);
+        }
       }
-      if (row_ok) out[mo.off + r * mo.rstride + row0 + lrow] = make_double2(ar, ai);
+    }
+    if (row_ok) {
+      if constexpr (!CPLX) out[mo.off + r * mo.rstride + row0 + lrow] = ar;
+      else out[mo.off + r * mo.rstride + row0 + lrow] = make_double2(ar, ai);
     }
   }
-  (void)e4;
 }
 
 template <bool CPLX>

@@ -1,6 +1,7 @@
 // extern "C" boundary (include/chain_b200.h).  Marshals plain pointers into the engine and turns C++ exceptions
 // into status codes; nothing here touches the CPU for arithmetic.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -255,6 +256,39 @@ int cb200_bond_stage_times(cb200_bond* B, const void* phi, int32_t reps, double*
     dev_sync(c->be);
     B->b.stage_times(x.p, y.p, reps, ms3);
     if (flops3) { flops3[0] = B->b.g1.flops; flops3[1] = B->b.mix.flops; flops3[2] = B->b.g2.flops; }
+  });
+}
+
+int cb200_bond_update_timed(cb200_bond* B, const void* phi, int32_t dir, int32_t maxdim, double cutoff, int32_t niter,
+                            double* energy, int32_t* m_out, int32_t* jacobi_sweeps, double* seconds4) {
+  if (!B || !phi || !seconds4) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n, true);
+    import_phi(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi, x.p);
+    dev_sync(c->be);
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    c->tm = Timers{};
+    double t0 = now();
+    DavidsonResult dr = davidson(B->b, x.p, niter);
+    dev_sync(c->be);
+    const double t_dav = now() - t0;
+    t0 = now();
+    SplitResult sr = split_bond(c, B->cplx, &B->S, B->b.philay, x.p, dir, maxdim, 1, cutoff);
+    dev_sync(c->be);
+    const double t_trunc = now() - t0;
+    t0 = now();
+    DevEnv E;
+    if (dir == 0) env_update_left(c, B->cplx, &B->S, B->L, sr.A, B->W1, E);
+    else env_update_right(c, B->cplx, &B->S, B->R, sr.B, B->W2, E);
+    dev_sync(c->be);
+    const double t_env = now() - t0;
+    seconds4[0] = c->tm.matvec; seconds4[1] = t_dav - c->tm.matvec; seconds4[2] = t_trunc; seconds4[3] = t_env;
+    if (energy) *energy = dr.eigenvalue;
+    if (m_out) *m_out = (int32_t)sr.mid.total();
+    if (jacobi_sweeps) *jacobi_sweeps = sr.sweeps;
   });
 }
 

@@ -128,6 +128,10 @@ int cb200_bond_apply(cb200_bond* b, const void* phi, void* out);
 int cb200_bond_apply_timed(cb200_bond* b, const void* phi, int32_t reps, int32_t warmup, double* ms_mean);
 /* per-stage device time of the product (ms, mean of reps) and algorithmic flops: [0] L-stage GEMM, [1] W (x) W mix, [2] R-stage GEMM */
 int cb200_bond_stage_times(cb200_bond* b, const void* phi, int32_t reps, double* ms3, double* flops3);
+/* one complete bond update resident on the device (davidson -> svdBond -> makeL/makeR), phase wall times in seconds:
+ * [0] H_eff matvecs, [1] Davidson level-1, [2] truncation, [3] environment update */
+int cb200_bond_update_timed(cb200_bond* b, const void* phi, int32_t dir, int32_t maxdim, double cutoff, int32_t niter,
+                            double* energy, int32_t* m, int32_t* jacobi_sweeps, double* seconds4);
 /* itensor::davidson (MaxIter = niter): phi in/out (host), eigenvalue out */
 int cb200_bond_davidson(cb200_bond* b, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec);
 /* MPS::svdBond: phi (host) -> A [Dl,d,m], B [m,d,Dr]; call with A=B=NULL first to get m and charges_mid
