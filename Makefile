@@ -4,7 +4,7 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := $(ARCH) -I/usr/include -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Wno-sign-compare
 SRC       := chain_b200/csrc
 OBJ       := build

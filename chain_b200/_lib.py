@@ -48,6 +48,9 @@ SYMBOLS = [
     ("cb200_last_error", C.c_char_p, [vp]),
     ("cb200_backend_name", C.c_char_p, []),
     ("cb200_launch_count", C.c_uint64, [vp]),
+    ("cb200_nccl_unique_id", C.c_int, [vp, vp]),
+    ("cb200_shard_alloc", C.c_int, [vp, i64, vp]),
+    ("cb200_shard_setup", C.c_int, [vp, i32, i32, i32, vp, vp, i64]),
     ("cb200_dmrg", C.c_int, [vp, C.POINTER(MpoC), C.POINTER(MpsC), i32, C.POINTER(MpsC), C.POINTER(Sweep), i32, dbl,
                              C.POINTER(dbl), C.POINTER(vp)]),
     ("cb200_result_nsites", i32, [vp]),

@@ -46,6 +46,37 @@ class Context:
     def backend(self):
         return self.lib.cb200_backend_name().decode()
 
+    SHARD_MODES = {"none": 0, "nccl": 1, "p2p": 2}
+
+    def shard(self, rank, world, mode="p2p", landing_bytes=0, min_dim=1600, group=None):
+        """Row-shard every H_eff matvec of this context over `world` ranks (one process + context per GPU).
+
+        mode "none": no exchange (the caller sums the ranks' partial vectors); "nccl": ncclAllReduce of the zero-padded
+        partials inside the library; "p2p": all-gather fused into the R-stage GEMM epilogue over CUDA-IPC peer mappings.
+        The rendezvous (NCCL unique id / IPC handles) travels through torch.distributed's `group` (any backend), which is
+        plumbing only: the data path never touches torch."""
+        m = self.SHARD_MODES[mode]
+        uid, handles = None, None
+        if world > 1 and m != 0:
+            import torch.distributed as dist
+            if m == 1:
+                buf = C.create_string_buffer(128)
+                if rank == 0:
+                    self.check(self.lib.cb200_nccl_unique_id(self.h, buf))
+                box = [buf.raw if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0, group=group)
+                uid = C.create_string_buffer(box[0], 128)
+            else:
+                if landing_bytes <= 0:
+                    raise ValueError("p2p sharding needs landing_bytes >= the largest phi in bytes")
+                buf = C.create_string_buffer(64)
+                self.check(self.lib.cb200_shard_alloc(self.h, int(landing_bytes), buf))
+                allh = [None] * world
+                dist.all_gather_object(allh, buf.raw, group=group)
+                handles = C.create_string_buffer(b"".join(allh), 64 * world)
+        self.check(self.lib.cb200_shard_setup(self.h, rank, world, m, uid, handles, int(min_dim)))
+        self.shard_rank, self.shard_world, self.shard_mode = rank, world, mode
+
     @property
     def launches(self):
         return int(self.lib.cb200_launch_count(self.h))

@@ -40,6 +40,25 @@ void launch_gemm(Backend*, bool cplx, bool transA, bool transB, bool narrow, con
 int gemm_tile_m(bool cplx);
 int gemm_tile_n(bool cplx, bool narrow);
 
+// ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
+// Symmetric "landing" area: [flags | landing 0 | landing 1], allocated with cudaMalloc so that it can be exported through
+// CUDA IPC.  shard_alloc fills a 64-byte handle; shard_connect opens the world's handles (own slot included, not opened).
+constexpr int SHARD_HANDLE_BYTES = 64;
+int shard_alloc(Backend*, int64_t landing_bytes_each, void* handle_out);
+int shard_connect(Backend*, int rank, int world, const void* all_handles);
+int64_t shard_landing_bytes(Backend*);                   // capacity of one landing half (0 when not allocated)
+void* shard_landing(Backend*, int which);                // this rank's landing half
+void shard_peer_bases(Backend*, int which, PeerBases* out);   // every rank's landing half `which`, own included
+// stream-ordered barrier across the ranks: publishes this rank's peer stores and waits for everybody else's
+void shard_barrier(Backend*);
+// the R-stage GEMM (A not transposed, B transposed) with its C tiles stored to every destination in `peers`
+void launch_gemm_peer(Backend*, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* d_tasks, int ntasks,
+                      const GemmSeg* d_segs, int total_tiles);
+// NCCL, loaded at run time (libnccl.so.2): unique id for rank 0, communicator, in-place sum all-reduce on the context stream
+int nccl_unique_id(Backend*, void* out128);
+int nccl_init(Backend*, const void* uid128, int rank, int world);
+void nccl_allreduce_sum(Backend*, void* buf, int64_t n_doubles);
+
 // Sparse MPO "mix" between the GEMM stages.
 // max_in = largest in_count of any panel (decides whether the inputs of a row chunk fit in shared memory).
 void launch_mix(Backend*, bool cplx, const void* in, void* out, const MixPanel* d_panels, int npanels, const MixIn* d_ins,
@@ -60,7 +79,11 @@ void lincomb(Backend*, bool cplx, int nv, const void* const* x, const double* c_
 // Jacobi building blocks. G: npairs Hermitian (2JB x 2JB, column-major, ld 2JB) Gram matrices; on exit Q holds
 // the unitary eigenvector matrices.  *d_rot (device int64) is incremented by the number of rotations applied.
 // Columns whose squared norm (diagonal of G) is <= floor2 are treated as numerically zero and never rotated.
-void launch_jacobi_eig(Backend*, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, long long* d_rot);
+// Off-diagonal entries with |g|^2 <= abs_g2 are left alone (absolute criterion; 0 = purely relative).
+// max_sweeps caps the cyclic sweeps of the inner solver (<= 0: run to convergence); the block SVD uses a small cap because
+// its outer sweeps revisit every pair anyway.
+void launch_jacobi_eig(Backend*, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, double abs_g2,
+                       int max_sweeps, long long* d_rot);
 // colnorm2[j] = sum_i |X[i + j*ld]|^2
 void launch_colnorm2(Backend*, bool cplx, const void* X, int64_t ld, int64_t rows, int64_t cols, double* d_out);
 // X (n x n, ld) = identity

@@ -6,6 +6,8 @@
 //   * jacobi_eig_kernel            -> 2JB x 2JB Hermitian eigensolver in shared memory (block one-sided Jacobi SVD)
 // There is no CPU fallback here: every entry point launches a kernel or reports a CUDA error.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -25,7 +27,23 @@ struct Backend {
   std::string err;
   bool has_err = false;
   cudaEvent_t ev[8] = {};
+  // multi-GPU: symmetric area [flags (256 B) | landing 0 | landing 1] + the peers' mappings (CUDA IPC)
+  char* sym = nullptr;
+  int64_t landing_each = 0;
+  int rank = 0, world = 1;
+  char* peer_sym[MAX_PEERS] = {};
+  bool peer_opened[MAX_PEERS] = {};
+  uint64_t barrier_seq = 0;
+  // NCCL through dlopen: no link-time dependency, the library still loads on a CPU-only box
+  void* nccl_lib = nullptr;
+  ncclComm_t comm = nullptr;
+  ncclResult_t (*p_ncclGetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*p_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*p_ncclAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
+  const char* (*p_ncclGetErrorString)(ncclResult_t) = nullptr;
 };
+static constexpr int64_t SYM_FLAG_BYTES = 256;
 
 static constexpr int DOT_BLOCKS = 592;   // 4 x 148 SMs
 static constexpr int DOT_THREADS = 256;
@@ -75,6 +93,15 @@ Backend* backend_create(int device, char* err, size_t errlen) {
     return nullptr;
   }
   for (auto& ev : b->ev) cudaEventCreate(&ev);
+  // keep freed blocks in the stream-ordered pool across synchronisations (the default threshold of 0 hands them back to
+  // the driver at every cudaStreamSynchronize, which turns each per-bond temporary into a cudaMalloc/cudaFree pair)
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   // opt in to the large dynamic shared memory the GEMM / Jacobi kernels need
   {
     auto opt = [](const void* f, int bytes) { cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
@@ -84,6 +111,8 @@ Backend* backend_create(int device, char* err, size_t errlen) {
     CB_OPT(false, false, false) CB_OPT(false, false, true) CB_OPT(false, true, false) CB_OPT(false, true, true)
     CB_OPT(true, false, false) CB_OPT(true, false, true) CB_OPT(true, true, false) CB_OPT(true, true, true)
 #undef CB_OPT
+    opt((const void*)gemm_grouped_peer_kernel<false>, GemmCfg<false, 128>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_peer_kernel<true>, GemmCfg<true, 128>::SMEM_BYTES);
   }
   cudaGetLastError();
   return b;
@@ -94,6 +123,10 @@ void backend_destroy(Backend* b) {
   cudaSetDevice(b->device);
   cudaStreamSynchronize(b->stream);
   for (auto& ev : b->ev) cudaEventDestroy(ev);
+  if (b->comm && b->p_ncclCommDestroy) b->p_ncclCommDestroy(b->comm);
+  for (int r = 0; r < MAX_PEERS; ++r)
+    if (b->peer_opened[r]) cudaIpcCloseMemHandle(b->peer_sym[r]);
+  if (b->sym) cudaFree(b->sym);
   cudaFree(b->d_partial);
   cudaFree(b->d_dot_out);
   cudaFreeHost(b->h_dot_out);
@@ -157,6 +190,127 @@ void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const voi
   if (cplx) { if (narrow) launch_gemm_t<true, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<true, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
   else { if (narrow) launch_gemm_t<false, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<false, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
   CB_LAUNCH_CHECK(b, "gemm_grouped_kernel");
+}
+
+void launch_gemm_peer(Backend* b, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* t, int nt,
+                      const GemmSeg* s, int tiles) {
+  if (tiles <= 0 || nt <= 0) return;
+  if (cplx) gemm_grouped_peer_kernel<true><<<tiles, 256, GemmCfg<true, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  else gemm_grouped_peer_kernel<false><<<tiles, 256, GemmCfg<false, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  CB_LAUNCH_CHECK(b, "gemm_grouped_peer_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU plumbing
+int shard_alloc(Backend* b, int64_t landing_each, void* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == SHARD_HANDLE_BYTES, "IPC handle size");
+  if (b->sym) { set_err(b, "shard_alloc: already allocated", cudaErrorInvalidValue); return -1; }
+  landing_each = (landing_each + 255) / 256 * 256;
+  cudaError_t e = cudaMalloc(&b->sym, (size_t)(SYM_FLAG_BYTES + 2 * landing_each));
+  if (e != cudaSuccess) { set_err(b, "shard_alloc: cudaMalloc", e); return -1; }
+  b->landing_each = landing_each;
+  CB_CHECK(b, cudaMemset(b->sym, 0, SYM_FLAG_BYTES));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, b->sym);
+  if (e != cudaSuccess) { set_err(b, "shard_alloc: cudaIpcGetMemHandle", e); return -1; }
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int shard_connect(Backend* b, int rank, int world, const void* all_handles) {
+  if (!b->sym || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) {
+    set_err(b, "shard_connect: bad arguments or no landing area", cudaErrorInvalidValue);
+    return -1;
+  }
+  b->rank = rank; b->world = world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { b->peer_sym[r] = b->sym; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles + (size_t)r * SHARD_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_err(b, "shard_connect: cudaIpcOpenMemHandle", e); return -1; }
+    b->peer_sym[r] = (char*)p;
+    b->peer_opened[r] = true;
+  }
+  return 0;
+}
+
+int64_t shard_landing_bytes(Backend* b) { return b->sym ? b->landing_each : 0; }
+void* shard_landing(Backend* b, int which) { return b->sym + SYM_FLAG_BYTES + (int64_t)(which & 1) * b->landing_each; }
+void shard_peer_bases(Backend* b, int which, PeerBases* out) {
+  out->n = b->world;
+  for (int r = 0; r < MAX_PEERS; ++r) out->base[r] = r < b->world ? b->peer_sym[r] + SYM_FLAG_BYTES + (int64_t)(which & 1) * b->landing_each : nullptr;
+}
+
+struct PeerFlags { unsigned long long* f[MAX_PEERS]; };
+// Thread t publishes this rank's arrival in rank t's flag row and waits for rank t's arrival in ours.  The release store
+// follows a system-scope fence, so the peer stores of every kernel launched earlier on this stream (the R-stage tiles)
+// are visible to whoever observes the flag; the acquire load orders our later kernels after the peers' data.
+__global__ void shard_barrier_kernel(PeerFlags pf, int rank, int world, unsigned long long seq) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  __threadfence_system();
+  unsigned long long* dst = pf.f[t] + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(seq) : "memory");
+  const unsigned long long* src = pf.f[rank] + t;
+  unsigned long long v = 0, t0 = 0, now = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - t0 > 60000000000ull) __trap();   // a peer died: fail this launch instead of hanging the box
+  } while (v < seq);
+}
+
+void shard_barrier(Backend* b) {
+  if (b->world <= 1) return;
+  PeerFlags pf{};
+  for (int r = 0; r < b->world; ++r) pf.f[r] = reinterpret_cast<unsigned long long*>(b->peer_sym[r]);
+  shard_barrier_kernel<<<1, 32, 0, b->stream>>>(pf, b->rank, b->world, ++b->barrier_seq);
+  CB_LAUNCH_CHECK(b, "shard_barrier_kernel");
+}
+
+static bool nccl_load(Backend* b) {
+  if (b->nccl_lib) return true;
+  b->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!b->nccl_lib) b->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!b->nccl_lib) { set_err(b, "dlopen(libnccl.so.2) failed", cudaErrorUnknown); return false; }
+#define CB_SYM(name) *(void**)(&b->p_##name) = dlsym(b->nccl_lib, #name)
+  CB_SYM(ncclGetUniqueId); CB_SYM(ncclCommInitRank); CB_SYM(ncclAllReduce); CB_SYM(ncclCommDestroy); CB_SYM(ncclGetErrorString);
+#undef CB_SYM
+  if (!b->p_ncclGetUniqueId || !b->p_ncclCommInitRank || !b->p_ncclAllReduce) { set_err(b, "libnccl: missing symbols", cudaErrorUnknown); return false; }
+  return true;
+}
+static void nccl_fail(Backend* b, const char* what, ncclResult_t r) {
+  if (!b->has_err) {
+    b->err = std::string(what) + ": " + (b->p_ncclGetErrorString ? b->p_ncclGetErrorString(r) : "nccl error");
+    b->has_err = true;
+  }
+}
+int nccl_unique_id(Backend* b, void* out128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!nccl_load(b)) return -1;
+  ncclUniqueId id;
+  ncclResult_t r = b->p_ncclGetUniqueId(&id);
+  if (r != ncclSuccess) { nccl_fail(b, "ncclGetUniqueId", r); return -1; }
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+int nccl_init(Backend* b, const void* uid128, int rank, int world) {
+  if (!nccl_load(b)) return -1;
+  ncclUniqueId id;
+  memcpy(&id, uid128, sizeof(id));
+  cudaSetDevice(b->device);
+  ncclResult_t r = b->p_ncclCommInitRank(&b->comm, world, id, rank);
+  if (r != ncclSuccess) { nccl_fail(b, "ncclCommInitRank", r); return -1; }
+  b->rank = rank; b->world = world;
+  return 0;
+}
+void nccl_allreduce_sum(Backend* b, void* buf, int64_t n_doubles) {
+  if (!b->comm) { set_err(b, "nccl_allreduce_sum: no communicator", cudaErrorInvalidValue); return; }
+  ncclResult_t r = b->p_ncclAllReduce(buf, buf, (size_t)n_doubles, ncclDouble, ncclSum, b->comm, b->stream);
+  if (r != ncclSuccess) nccl_fail(b, "ncclAllReduce", r);
+  b->launches++;
 }
 
 // ------------------------------------------------------------------------------------------------ mix
@@ -486,8 +640,8 @@ static constexpr int JAC_THREADS = 256;
 static constexpr int JAC_MAX_SWEEPS = 60;
 
 template <bool CPLX>
-__global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __restrict__ G_, void* __restrict__ Q_, double tol, double floor2,
-                                                                 unsigned long long* __restrict__ rot_total) {
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __restrict__ G_, void* __restrict__ Q_, double tol, double floor2, double abs_g2,
+                                                                 int max_sweeps, unsigned long long* __restrict__ rot_total) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   extern __shared__ __align__(16) char jsm[];
   T* G = reinterpret_cast<T*>(jsm);
@@ -495,7 +649,9 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __r
   __shared__ double rc[NJ / 2], rs[NJ / 2], rer[NJ / 2], rei[NJ / 2];
   __shared__ int rp[NJ / 2], rq[NJ / 2];
   __shared__ int sweep_rot;
+  __shared__ int any_big;
   const int tid = threadIdx.x;
+  if (tid == 0) any_big = 0;
   const T* Gg = reinterpret_cast<const T*>(G_) + (size_t)blockIdx.x * NJ * NJ;
   T* Qg = reinterpret_cast<T*>(Q_) + (size_t)blockIdx.x * NJ * NJ;
 
@@ -517,8 +673,19 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __r
   __syncthreads();
 
   const double tol2 = tol * tol;
+  // a pair that is already orthogonal to working precision (the common case in the last outer sweeps) costs one scan, not a sweep
+  for (int idx = tid; idx < NJ * NJ; idx += JAC_THREADS) {
+    const int r = idx % NJ, c = idx / NJ;
+    if (r >= c) continue;
+    double gpp, gqq, g2;
+    if constexpr (CPLX) { gpp = G[r + r * LDJ].x; gqq = G[c + c * LDJ].x; const T v = G[r + c * LDJ]; g2 = v.x * v.x + v.y * v.y; }
+    else { gpp = G[r + r * LDJ]; gqq = G[c + c * LDJ]; const T v = G[r + c * LDJ]; g2 = v * v; }
+    if (g2 > tol2 * fabs(gpp * gqq) && g2 > abs_g2 && gpp > floor2 && gqq > floor2) any_big = 1;
+  }
+  __syncthreads();
+  if (!any_big) max_sweeps = 0;
   unsigned long long my_total = 0;
-  for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (tid == 0) sweep_rot = 0;
     __syncthreads();
     for (int step = 0; step < NJ - 1; ++step) {
@@ -533,7 +700,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __r
         else { gpp = G[p + p * LDJ]; gqq = G[q + q * LDJ]; gr = G[p + q * LDJ]; gi = 0.0; }
         const double g2 = gr * gr + gi * gi;
         double c = 1.0, s = 0.0, er = 1.0, ei = 0.0;
-        if (g2 > tol2 * fabs(gpp * gqq) && g2 > 0.0 && gpp > floor2 && gqq > floor2) {
+        if (g2 > tol2 * fabs(gpp * gqq) && g2 > abs_g2 && gpp > floor2 && gqq > floor2) {
           const double ag = sqrt(g2);
           er = gr / ag; ei = gi / ag;
           const double tau = (gqq - gpp) / (2.0 * ag);
@@ -611,7 +778,9 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_eig_kernel(const void* __r
   if (tid == 0 && my_total) atomicAdd(rot_total, my_total);
 }
 
-void launch_jacobi_eig(Backend* b, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, long long* d_rot) {
+void launch_jacobi_eig(Backend* b, bool cplx, const void* G, void* Q, int npairs, double tol, double floor2, double abs_g2,
+                       int max_sweeps, long long* d_rot) {
+  if (max_sweeps <= 0 || max_sweeps > JAC_MAX_SWEEPS) max_sweeps = JAC_MAX_SWEEPS;
   if (npairs <= 0) return;
   const size_t smem = (size_t)2 * NJ * LDJ * (cplx ? 16 : 8);
   static bool attr_done = false;
@@ -620,8 +789,8 @@ void launch_jacobi_eig(Backend* b, bool cplx, const void* G, void* Q, int npairs
     cudaFuncSetAttribute(jacobi_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NJ * LDJ * 8);
     attr_done = true;
   }
-  if (cplx) jacobi_eig_kernel<true><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, (unsigned long long*)d_rot);
-  else jacobi_eig_kernel<false><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, (unsigned long long*)d_rot);
+  if (cplx) jacobi_eig_kernel<true><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, abs_g2, max_sweeps, (unsigned long long*)d_rot);
+  else jacobi_eig_kernel<false><<<npairs, JAC_THREADS, smem, b->stream>>>(G, Q, tol, floor2, abs_g2, max_sweeps, (unsigned long long*)d_rot);
   CB_LAUNCH_CHECK(b, "jacobi_eig_kernel");
 }
 

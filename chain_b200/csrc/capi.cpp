@@ -71,6 +71,43 @@ const char* cb200_last_error(const cb200_ctx* ctx) { return ctx ? ctx->c.err.c_s
 const char* cb200_backend_name(void) { return backend_name(); }
 uint64_t cb200_launch_count(const cb200_ctx* ctx) { return ctx ? dev_launch_count(ctx->c.be) : 0; }
 
+// ---------------------------------------------------------------------------------------------- multi-GPU
+int cb200_nccl_unique_id(cb200_ctx* ctx, void* out128) {
+  if (!ctx || !out128) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (nccl_unique_id(ctx->c.be, out128) != 0) fail(CB200_ERR_CUDA, std::string("nccl: ") + (dev_last_error(ctx->c.be) ? dev_last_error(ctx->c.be) : "?"));
+  });
+}
+int cb200_shard_alloc(cb200_ctx* ctx, int64_t landing_bytes, void* handle_out64) {
+  if (!ctx || !handle_out64 || landing_bytes <= 0) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (shard_alloc(ctx->c.be, landing_bytes, handle_out64) != 0)
+      fail(CB200_ERR_CUDA, std::string("shard_alloc: ") + (dev_last_error(ctx->c.be) ? dev_last_error(ctx->c.be) : "?"));
+  });
+}
+int cb200_shard_setup(cb200_ctx* ctx, int32_t rank, int32_t world, int32_t mode, const void* nccl_uid128, const void* handles,
+                      int64_t min_dim) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || mode < 0 || mode > 2) fail(CB200_ERR_INVALID, "shard_setup: bad rank/world/mode");
+    if (mode == 1 && world > 1) {
+      if (!nccl_uid128) fail(CB200_ERR_INVALID, "shard_setup: mode 1 needs the NCCL unique id");
+      if (nccl_init(ctx->c.be, nccl_uid128, rank, world) != 0)
+        fail(CB200_ERR_CUDA, std::string("nccl: ") + (dev_last_error(ctx->c.be) ? dev_last_error(ctx->c.be) : "?"));
+    }
+    if (mode == 2 && world > 1) {
+      if (!handles) fail(CB200_ERR_INVALID, "shard_setup: mode 2 needs the ranks' landing handles");
+      if (shard_connect(ctx->c.be, rank, world, handles) != 0)
+        fail(CB200_ERR_CUDA, std::string("shard_connect: ") + (dev_last_error(ctx->c.be) ? dev_last_error(ctx->c.be) : "?"));
+    }
+    ctx->c.shard.rank = rank;
+    ctx->c.shard.world = world;
+    ctx->c.shard.mode = mode;
+    ctx->c.shard.flip = 0;
+    if (min_dim >= 0) ctx->c.shard.min_dim = min_dim;
+  });
+}
+
 // ---------------------------------------------------------------------------------------------- coarse: dmrg
 static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
   HostMPS h;
@@ -212,7 +249,7 @@ int cb200_bond_set_penalty(cb200_bond* B, int32_t nprev, const void* const* o, d
   });
 }
 int64_t cb200_bond_phi_elems(const cb200_bond* B) { return B ? B->l.g.total() * B->S.d * B->S.d * B->r.g.total() : 0; }
-double cb200_bond_matvec_flops(const cb200_bond* B) { return B ? B->b.flops_alg : 0; }
+double cb200_bond_matvec_flops(const cb200_bond* B) { return B ? B->b.flops_alg_full : 0; }
 
 int cb200_bond_apply(cb200_bond* B, const void* phi, void* out) {
   if (!B || !phi || !out) return CB200_ERR_INVALID;
@@ -393,7 +430,7 @@ int cb200_k_jacobi_eig(cb200_ctx* ctx, int32_t dtype, int32_t npairs, const void
     const size_t bytes = (size_t)(cx ? 16 : 8) * 4 * JB * JB * npairs;
     Buf dG(c->be, (int64_t)bytes), dQ(c->be, (int64_t)bytes), rot(c->be, 8, true);
     dev_h2d(c->be, dG.p, G, bytes);
-    launch_jacobi_eig(c->be, cx, dG.p, dQ.p, npairs, tol, 0.0, (long long*)rot.p);
+    launch_jacobi_eig(c->be, cx, dG.p, dQ.p, npairs, tol, 0.0, 0.0, 0, (long long*)rot.p);
     dev_d2h(c->be, Q, dQ.p, bytes);
     long long r = 0;
     dev_d2h(c->be, &r, rot.p, 8);

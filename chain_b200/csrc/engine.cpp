@@ -158,10 +158,12 @@ struct GemmBuilder {
   std::vector<GemmTask> tasks;
   std::vector<GemmSeg> segs;
   bool cplx, narrow;
-  double flops = 0;
+  double flops = 0, flops_full = 0;
+  double ratio = 1.0;      // full rows / local rows of the task being built (row-sharded plans)
   GemmTask cur{};
   bool open = false;
   GemmBuilder(bool cplx_, bool narrow_ = false) : cplx(cplx_), narrow(narrow_) {}
+  void chunk(int64_t rows, int64_t stride) { cur.chunk = (int32_t)std::max<int64_t>(rows, 1); cur.chunk_stride = stride; }
   void begin(int64_t c_off, int64_t ldc, int64_t M, int64_t N, uint32_t flags) {
     cur = GemmTask{};
     cur.c_off = c_off; cur.ldc = ldc; cur.c_off2 = c_off;
@@ -178,6 +180,7 @@ struct GemmBuilder {
     s.a_off = a_off; s.b_off = b_off; s.lda = lda; s.ldb = ldb; s.K = (int32_t)K;
     segs.push_back(s);
     flops += 2.0 * cur.M * cur.N * (double)K;
+    flops_full += 2.0 * cur.M * cur.N * (double)K * ratio;
   }
   void end() {
     open = false;
@@ -211,7 +214,8 @@ struct MixBuilder {
   std::vector<MixOut> outs;
   std::vector<MixEntry> ents;
   std::map<std::pair<int64_t, int64_t>, int> slot_of;   // (off, rstride) -> slot of the current panel
-  double flops = 0;
+  double flops = 0, flops_full = 0;
+  double ratio = 1.0;
   bool cplx;
   explicit MixBuilder(bool c) : cplx(c) {}
   void begin_panel(int64_t rows, int64_t nr) {
@@ -257,6 +261,7 @@ struct MixBuilder {
       return;
     }
     flops += 2.0 * (double)ne * p.rows * p.nr;
+    flops_full += 2.0 * (double)ne * p.rows * p.nr * ratio;
   }
   void finish(Backend* be, MixPlan& mp) {
     int max_in = 0;
@@ -334,13 +339,44 @@ void Bond::plan() {
   Llay.build(Dl, Kl);
   Rlay.build(Dr, Kr);
   philay.build(Dl, Dr, S);
+  // ---- row shard: this rank's bra rows l' of every left-link sector
+  const ShardState& sh = ctx->shard;
+  sharded = sh.world > 1 && Dl.total() >= sh.min_dim;
+  Dlo = Dl;
+  row_lo.assign(nq, 0);
+  std::vector<double> ratio(nq, 1.0);
+  if (sharded) {
+    for (int q = 0; q < nq; ++q) {
+      const int64_t lo = Dl.dim[q] * sh.rank / sh.world, hi = Dl.dim[q] * (sh.rank + 1) / sh.world;
+      row_lo[q] = lo;
+      Dlo.dim[q] = hi - lo;
+      ratio[q] = Dlo.dim[q] > 0 ? (double)Dl.dim[q] / (double)Dlo.dim[q] : 0.0;
+    }
+  }
+  // local copy of this rank's rows of L: block (ql', qa) as [l'_local + nloc*(a + k*l)]
+  std::vector<int64_t> lloc_off((size_t)nq * nq, 0);
+  if (sharded) {
+    int64_t lt = 0;
+    CopyBuilder cb;
+    for (int qlp = 0; qlp < nq; ++qlp)
+      for (int qa = 0; qa < nq; ++qa) {
+        const int ql = qsub(qlp, qa, nq);
+        lloc_off[qlp * nq + qa] = lt;
+        const int64_t cols = Kl.dim[qa] * Dl.dim[ql];
+        cb.add(Llay.o(qlp, qa) + row_lo[qlp], lt, Dlo.dim[qlp], 1, 1, cols, Dl.dim[qlp], Dlo.dim[qlp]);
+        lt += Dlo.dim[qlp] * cols;
+      }
+    Lloc = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(lt, 1));
+    cb.run(ctx, cplx, L, Lloc.p);
+  }
+  auto l_off = [&](int qlp, int qa) { return sharded ? lloc_off[qlp * nq + qa] : Llay.o(qlp, qa); };
   // ---- T1 layout: block (qa, ql): rows (l', a), cols = phi columns of left sector ql
   std::vector<int64_t> t1off((size_t)nq * nq, 0), t1M((size_t)nq * nq, 0);
   int64_t t1 = 0;
   for (int qa = 0; qa < nq; ++qa)
     for (int ql = 0; ql < nq; ++ql) {
       const int qlp = qadd(ql, qa, nq);
-      const int64_t M = Dl.dim[qlp] * Kl.dim[qa];
+      const int64_t M = Dlo.dim[qlp] * Kl.dim[qa];
       t1off[qa * nq + ql] = t1;
       t1M[qa * nq + ql] = M;
       if (Dl.dim[ql] > 0) t1 += M * philay.ncols(ql);
@@ -353,7 +389,7 @@ void Bond::plan() {
     for (int qa2 = 0; qa2 < nq; ++qa2)
       for (int qr = 0; qr < nq; ++qr) {
         const int qrp = qadd(qr, qa2, nq);
-        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp);
+        const int64_t M = Dlo.dim[qlp] * philay.ns(qlp, qrp);
         const size_t id = ((size_t)qlp * nq + qa2) * nq + qr;
         t2off[id] = t2;
         t2M[id] = M;
@@ -371,11 +407,13 @@ void Bond::plan() {
         const int qlp = qadd(ql, qa, nq);
         const int64_t M = t1M[qa * nq + ql], N = philay.ncols(ql), K = Dl.dim[ql];
         if (M == 0 || N == 0) continue;   // K == 0 still emits the task: it zero-fills the block the mix stage reads
+        gb.ratio = ratio[qlp];
         gb.begin(t1off[qa * nq + ql], M, M, N, 0);
-        gb.seg(Llay.o(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
+        gb.seg(l_off(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
         gb.end();
       }
     gb.finish(be, g1, false, false);
+    flops_alg_full = gb.flops_full * (cplx ? 4.0 : 1.0);
   }
   // ---- Omega = W1 (x) W2 contracted over the middle MPO link, as a sparse map (a,s1,s2) -> (a'',t1,t2)
   const int64_t kl = Kl.total(), km = Km.total(), kr = Kr.total();
@@ -423,7 +461,8 @@ void Bond::plan() {
     MixBuilder mb(cplx);
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qr = 0; qr < nq; ++qr) {
-        mb.begin_panel(Dl.dim[qlp], Dr.dim[qr]);
+        mb.ratio = ratio[qlp];
+        mb.begin_panel(Dlo.dim[qlp], Dr.dim[qr]);
         for (int qa2 = 0; qa2 < nq; ++qa2) {
           const int qrp = qadd(qr, qa2, nq);
           const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
@@ -434,7 +473,7 @@ void Bond::plan() {
             for (int64_t sro = 0; sro < S->ns(qd_out); ++sro) {
               const int t1s = S->srow[qd_out][sro].first, t2s = S->srow[qd_out][sro].second;
               const int64_t out = app + kr * (t1s + (int64_t)d * t2s);
-              mb.begin_out(t2off[id2] + Dl.dim[qlp] * sro + M2 * a2l, M2 * Kr.dim[qa2]);
+              mb.begin_out(t2off[id2] + Dlo.dim[qlp] * sro + M2 * a2l, M2 * Kr.dim[qa2]);
               const cplx_t* row = &omega[(size_t)nin * out];
               for (int64_t in = 0; in < nin; ++in) {
                 if (row[in] == cplx_t(0, 0)) continue;
@@ -450,7 +489,7 @@ void Bond::plan() {
                 const int64_t M1 = t1M[qa * nq + ql];
                 const int64_t sri = S->srow_index[(size_t)s1 * d + s2];
                 const int64_t nsi = S->ns(qd_in);
-                mb.entry(t1off[qa * nq + ql] + Dl.dim[qlp] * aloc + M1 * (philay.colbase(ql, qr) + sri), M1 * nsi, row[in]);
+                mb.entry(t1off[qa * nq + ql] + Dlo.dim[qlp] * aloc + M1 * (philay.colbase(ql, qr) + sri), M1 * nsi, row[in]);
               }
               mb.end_out();
             }
@@ -459,17 +498,19 @@ void Bond::plan() {
         mb.end_panel();
       }
     mb.finish(be, mix);
+    flops_alg_full += mb.flops_full * (cplx ? 4.0 : 1.0);
   }
   // ---- GEMM2: out(ql', qr') [ (l',srow') x r' ] = sum_{qa''} T2(ql',qa'',qr'-qa'') [ . x (a'',r) ] * R(qr',qa'')^T
   // The tile is BM x BN with BM != BN for complex data, so the planner may swap the operand roles (computing the
   // transposed product and storing it with GEMM_TRANS_C) when that wastes fewer tile slots on the ragged sector sizes.
+  // Sharded: the (l'_local, srow') rows go straight to rows row_lo + l'_local of the full [l, srow, r] block (chunked C).
   {
     const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, false);
     auto padded = [&](int64_t M, int64_t N) { return ((M + tm - 1) / tm) * tm * (((N + tn - 1) / tn) * tn); };
     int64_t cost_n = 0, cost_s = 0;
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qrp = 0; qrp < nq; ++qrp) {
-        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
+        const int64_t M = Dlo.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
         cost_n += padded(M, N);
         cost_s += padded(N, M);
       }
@@ -477,10 +518,13 @@ void Bond::plan() {
     GemmBuilder gb(cplx);
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qrp = 0; qrp < nq; ++qrp) {
-        const int64_t M = Dl.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
+        const int64_t M = Dlo.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
         if (M == 0 || N == 0) continue;
-        if (!swap) gb.begin(philay.o(qlp, qrp), M, M, N, 0);
-        else gb.begin(philay.o(qlp, qrp), M, N, M, GEMM_TRANS_C);
+        const int64_t ldc = Dl.dim[qlp] * philay.ns(qlp, qrp);
+        gb.ratio = ratio[qlp];
+        if (!swap) gb.begin(philay.o(qlp, qrp) + row_lo[qlp], ldc, M, N, 0);
+        else gb.begin(philay.o(qlp, qrp) + row_lo[qlp], ldc, N, M, GEMM_TRANS_C);
+        if (sharded) gb.chunk(Dlo.dim[qlp], Dl.dim[qlp]);
         for (int qa2 = 0; qa2 < nq; ++qa2) {
           const int qr = qsub(qrp, qa2, nq);
           const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
@@ -491,16 +535,38 @@ void Bond::plan() {
       }
     gb.finish(be, g2, false, true);
     g2_swapped = swap;
+    flops_alg_full += gb.flops_full * (cplx ? 4.0 : 1.0);
   }
   flops_alg = g1.flops + g2.flops + mix.flops;
+  if (sharded && sh.mode == 2 && (int64_t)esz(cplx) * philay.total > shard_landing_bytes(be))
+    fail(-2, "sharded matvec: the landing area is smaller than phi (cb200_shard_alloc)");
   check_dev(ctx);
 }
 
 void Bond::apply(const void* x, void* y) {
-  run_gemm(ctx, cplx, g1, L, x, T1.p);
+  Backend* be = ctx->be;
+  const void* Lp = sharded ? Lloc.p : L;
+  run_gemm(ctx, cplx, g1, Lp, x, T1.p);
   run_mix(ctx, cplx, mix, T1.p, T2.p);
-  if (g2_swapped) run_gemm(ctx, cplx, g2, R, T2.p, y); else run_gemm(ctx, cplx, g2, T2.p, R, y);
-  if (!pen.empty() && weight != 0.0) {
+  const void* A2 = g2_swapped ? R : T2.p;
+  const void* B2 = g2_swapped ? T2.p : R;
+  if (!sharded) {
+    run_gemm(ctx, cplx, g2, A2, B2, y);
+  } else if (ctx->shard.mode == 2) {
+    // all-gather fused into the R-stage epilogue: tiles land in every rank's landing half; the barrier publishes them
+    PeerBases pb;
+    shard_peer_bases(be, ctx->shard.flip, &pb);
+    launch_gemm_peer(be, cplx, A2, B2, pb, g2.tasks.ptr(), g2.tasks.n, g2.segs.ptr(), g2.tiles);
+    shard_barrier(be);
+    dev_d2d(be, y, shard_landing(be, ctx->shard.flip), esz(cplx) * (size_t)philay.total);
+    ctx->shard.flip ^= 1;
+  } else {
+    dev_memset0(be, y, esz(cplx) * (size_t)philay.total);
+    run_gemm(ctx, cplx, g2, A2, B2, y);
+    if (ctx->shard.mode == 1) nccl_allreduce_sum(be, y, philay.total * (cplx ? 2 : 1));
+  }
+  // (exchange-free shard mode: the caller sums the ranks' vectors, so only rank 0 adds the replicated penalty term)
+  if (!pen.empty() && weight != 0.0 && !(sharded && ctx->shard.mode == 0 && ctx->shard.rank != 0)) {
     // LocalMPO_MPS::product: y += weight * sum_j <o_j|x> o_j
     const int np = (int)pen.size();
     for (int j0 = 0; j0 < np; j0 += MAX_LC) {
@@ -512,15 +578,16 @@ void Bond::apply(const void* x, void* y) {
     }
   }
   ctx->tm.nmatvec += 1;
-  ctx->tm.matvec_flops += flops_alg;
+  ctx->tm.matvec_flops += flops_alg_full;
 }
 
 void Bond::stage_times(const void* x, void* y, int reps, double* ms3) {
   Backend* be = ctx->be;
   ms3[0] = ms3[1] = ms3[2] = 0;
+  const void* Lp = sharded ? Lloc.p : L;
   for (int i = 0; i < reps; ++i) {
     dev_event_record(be, 0);
-    run_gemm(ctx, cplx, g1, L, x, T1.p);
+    run_gemm(ctx, cplx, g1, Lp, x, T1.p);
     dev_event_record(be, 1);
     run_mix(ctx, cplx, mix, T1.p, T2.p);
     dev_event_record(be, 2);
@@ -758,6 +825,23 @@ void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, doub
 }
 
 // ------------------------------------------------------------------------------------------------ block Jacobi SVD
+// Inner-solver sweep cap (CB200_JACOBI_INNER overrides; 0 = to convergence).
+static int jacobi_inner_sweeps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB200_JACOBI_INNER");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static double jacobi_abs_tol() {
+  static double v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB200_JACOBI_ABS");
+    v = e ? atof(e) : 1e-17;
+  }
+  return v;
+}
 JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) {
   Backend* be = c->be;
   const size_t es = esz(cplx);
@@ -816,7 +900,7 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
   Buf rot(be, 8, true);
   const double tol = std::max(1e-14, 8.0 * 1.1e-16 * std::sqrt((double)rows));
   // columns with norm^2 below 1e-26 ||X||_F^2 are numerically zero (rank-deficient rho): never rotated, always truncated
-  double floor2 = 0;
+  double floor2 = 0, abs_g2 = 0;
   {
     Buf wd0(be, 8 * npad);
     launch_colnorm2(be, cplx, Xa.p, ldx, rows, npad, (double*)wd0.p);
@@ -825,6 +909,10 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
     double tot = 0;
     for (double x : w0) tot += x;
     floor2 = 1e-26 * tot;
+    // ITensor diagonalises rho = phi phi^H with LAPACK, i.e. to an ABSOLUTE accuracy of eps * ||rho||; rotating pairs whose
+    // coupling is already below that only polishes the relative accuracy of the (discarded) tiny eigenvalues.
+    const double ga = jacobi_abs_tol() * tot;
+    abs_g2 = ga * ga;
   }
   void* xc = Xa.p; void* xn = Xb.p; void* vc = Va.p; void* vn = Vb.p;
   const int max_sweeps = 60;
@@ -834,7 +922,7 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
     dev_memset0(be, rot.p, 8);
     for (int64_t round = 0; round < std::max<int64_t>(nb - 1, 1); ++round) {
       run_gemm(c, cplx, gram, xc, xc, G.p);
-      launch_jacobi_eig(be, cplx, G.p, Q.p, (int)npairs, tol, floor2, (long long*)rot.p);
+      launch_jacobi_eig(be, cplx, G.p, Q.p, (int)npairs, tol, floor2, abs_g2, jacobi_inner_sweeps(), (long long*)rot.p);
       run_gemm(c, cplx, appX, xc, Q.p, xn);
       run_gemm(c, cplx, appV, vc, Q.p, vn);
       std::swap(xc, xn);

@@ -143,10 +143,24 @@ struct Timers {
   double env = 0, matvec = 0, level1 = 0, trunc = 0, other = 0, nmatvec = 0, matvec_flops = 0;
 };
 
+// Row sharding of the H_eff matvec over the GPUs of one box (one process per GPU).  Rank g owns a contiguous
+// range of the bra rows l' inside every charge sector of the left link; it runs the L-stage, the mix and the R-stage for
+// those rows only (1/world of the flops, perfectly balanced) and the ranks then exchange their output rows:
+//   mode 0  no exchange: rows not owned are zero; the caller sums the partial vectors (used by the gloo CPU tests)
+//   mode 1  ncclAllReduce(sum) of the zero-padded partial vectors on the context stream
+//   mode 2  all-gather fused into the R-stage epilogue: every C tile is stored straight into every rank's landing buffer
+//           through CUDA-IPC peer mappings (NVLink), followed by a stream-ordered flag barrier
+struct ShardState {
+  int rank = 0, world = 1, mode = 0;
+  int64_t min_dim = 1600;    // north_star: only bonds with D >= 1600 are partitioned, smaller ones stay on one GPU
+  int flip = 0;              // landing half used by the next matvec (mode 2)
+};
+
 struct Ctx {
   Backend* be = nullptr;
   std::string err;
   Timers tm;
+  ShardState shard;
 };
 
 // One two-site problem with everything resident on the device.
@@ -156,6 +170,12 @@ struct Bond {
   int nq = 1;
   const SiteInfo* S = nullptr;
   Grading Dl, Dr, Kl, Km, Kr;
+  // row shard of this bond: local bra rows per charge sector (Dlo) starting at row_lo[q]; Dlo == Dl when not sharded
+  bool sharded = false;
+  Grading Dlo;
+  std::vector<int64_t> row_lo;
+  Buf Lloc;                  // this rank's rows of L, re-laid out as [l'_local, a, l] per block (sharded only)
+  double flops_alg_full = 0; // F_alg of the whole (unsharded) product
   EnvLayout Llay, Rlay;
   PhiLayout philay;
   const void* L = nullptr;   // not owned

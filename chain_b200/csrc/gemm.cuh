@@ -142,10 +142,10 @@ __device__ __forceinline__ void load_operand_tile(char* smem, const char* g, int
   }
 }
 
-template <bool CPLX, bool TA, bool TB, int BN_ = 128>
-__global__ void __launch_bounds__(256, 1)
-gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
-                    const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs) {
+template <bool CPLX, bool TA, bool TB, int BN_, bool PEER>
+__device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
+                                                  const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs,
+                                                  const PeerBases& peers) {
   using Cfg = GemmCfg<CPLX, BN_>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, MT = Cfg::MT, NT = Cfg::NT, ES = Cfg::ES, STAGES = Cfg::STAGES;
   // smem strides (elements) of the fragment reads
@@ -288,15 +288,26 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
   for (int i = 0; i < MT; ++i) {
     const int m = m0 + wm0 + i * 8 + g;
     if (m >= t.M) continue;
+    const int64_t mc = (int64_t)(m % t.chunk) + (int64_t)(m / t.chunk) * t.chunk_stride;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int n = n0 + wn0 + j * 8 + tq * 2 + e;
         if (n >= t.N) continue;
-        const int64_t off = trans_c ? ((int64_t)n + (int64_t)m * t.ldc)
-                            : (n < t.n_split) ? ((int64_t)m + (int64_t)n * t.ldc)
-                                              : ((t.c_off2 - t.c_off) + (int64_t)m + (int64_t)(n - t.n_split) * t.ldc);
+        const int64_t off = trans_c ? ((int64_t)(n % t.chunk) + (int64_t)(n / t.chunk) * t.chunk_stride + (int64_t)m * t.ldc)
+                            : (n < t.n_split) ? (mc + (int64_t)n * t.ldc)
+                                              : ((t.c_off2 - t.c_off) + mc + (int64_t)(n - t.n_split) * t.ldc);
+        if constexpr (PEER) {
+          // all-gather fused into the epilogue: the tile goes to every rank's landing buffer over NVLink (plain stores;
+          // the cross-GPU barrier that follows the launch publishes them)
+          for (int pr = 0; pr < peers.n; ++pr) {
+            char* Pp = peers.base[pr] + t.c_off * ES;
+            if constexpr (!CPLX) reinterpret_cast<double*>(Pp)[off] = acc_re[i][j][e];
+            else reinterpret_cast<double2*>(Pp)[off] = make_double2(acc_re[i][j][e], conj_out ? -acc_im[i][j][e] : acc_im[i][j][e]);
+          }
+          continue;
+        }
         if constexpr (!CPLX) {
           double* p = reinterpret_cast<double*>(Cp) + off;
           double v = acc_re[i][j][e];
@@ -311,6 +322,23 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
       }
     }
   }
+}
+
+template <bool CPLX, bool TA, bool TB, int BN_ = 128>
+__global__ void __launch_bounds__(256, 1)
+gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
+                    const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs) {
+  PeerBases none;
+  none.n = 0;
+  gemm_grouped_body<CPLX, TA, TB, BN_, false>(Abase, Bbase, Cbase, tasks, ntasks, segs, none);
+}
+
+// R-stage of the row-sharded matvec: same mainloop, C tiles stored to every rank's landing buffer
+template <bool CPLX>
+__global__ void __launch_bounds__(256, 1)
+gemm_grouped_peer_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, const GemmTask* __restrict__ tasks, int ntasks,
+                         const GemmSeg* __restrict__ segs, const __grid_constant__ PeerBases peers) {
+  gemm_grouped_body<CPLX, false, true, 128, true>(Abase, Bbase, nullptr, tasks, ntasks, segs, peers);
 }
 
 }  // namespace cb200

@@ -34,6 +34,22 @@ struct GemmTask {
   int32_t tile_begin, tiles_m;
   uint32_t flags;
   int32_t n_split;      // set to N (or larger) when unused
+  // Chunked addressing of the contiguous C index (m, or n with GEMM_TRANS_C): index i is stored at
+  // (i % chunk) + (i / chunk) * chunk_stride.  A row-sharded matvec writes its (l'_local, s) rows straight into the
+  // full [l, s, r] layout of the output vector this way (chunk = local rows, chunk_stride = full left dimension).
+  // chunk = INT32_MAX disables it.
+  int32_t chunk = 0x7fffffff;
+  int32_t pad_ = 0;
+  int64_t chunk_stride = 0;
+};
+
+// Destinations of a GEMM launched with peer stores: the same C tile goes to every base pointer (own landing buffer and the
+// peers' buffers mapped through CUDA IPC) -- the all-gather of the row-sharded matvec, fused into the R-stage epilogue.
+constexpr int MAX_PEERS = 8;
+struct PeerBases {
+  char* base[MAX_PEERS];
+  int32_t n;
+  int32_t pad_;
 };
 
 // "Mix": the bandwidth-bound application of the (sparse) MPO tensors between the two GEMM stages.

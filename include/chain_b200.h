@@ -47,6 +47,22 @@ const char* cb200_backend_name(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t cb200_launch_count(const cb200_ctx* ctx);
 
+/* ---- multi-GPU: the H_eff matvec row-sharded over the GPUs of one box (one process and one context per GPU) ------
+ * Rank g applies H_eff for its own slice of the bra rows l' of every charge sector (1/world of the work) and the ranks
+ * exchange output rows; everything else of a bond update is replicated and stays bit-identical across ranks.
+ *   mode 0: no exchange -- rows a rank does not own come back as zeros, the caller sums the vectors (CPU/gloo tests);
+ *   mode 1: ncclAllReduce(sum, ncclDouble) of the zero-padded partial vectors (libnccl.so.2 is dlopen'ed on first use);
+ *   mode 2: all-gather fused into the R-stage GEMM epilogue: tiles are stored into every rank's landing buffer through
+ *           CUDA-IPC peer mappings over NVLink, then a stream-ordered flag barrier.
+ * Only bonds whose left link has dimension >= min_dim are sharded (default 1600, BASELINE north_star); pass -1 to keep it.
+ * Setup: every rank calls cb200_shard_alloc (mode 2; landing_bytes >= the largest phi in bytes) and the host side
+ * all-gathers the 64-byte handles; rank 0 calls cb200_nccl_unique_id (mode 1) and broadcasts the 128 bytes; then every
+ * rank calls cb200_shard_setup. */
+int cb200_nccl_unique_id(cb200_ctx* ctx, void* out128);
+int cb200_shard_alloc(cb200_ctx* ctx, int64_t landing_bytes, void* handle_out64);
+int cb200_shard_setup(cb200_ctx* ctx, int32_t rank, int32_t world, int32_t mode, const void* nccl_uid128 /* mode 1 */,
+                      const void* handles /* mode 2: world x 64 bytes */, int64_t min_dim);
+
 /* ---- problem description -------------------------------------------------------------------------------------- */
 typedef struct cb200_index {
   int64_t dim;

@@ -65,8 +65,10 @@ static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTas
       for (int m = 0; m < t.M; ++m) {
         T v = tmp[(size_t)m + (size_t)n * t.M];
         if constexpr (std::is_same<T, cd>::value) { if (conjOut) v = std::conj(v); }
-        T* p = (t.flags & GEMM_TRANS_C) ? &C[t.c_off + n + (int64_t)m * t.ldc]
-               : (n < t.n_split) ? &C[t.c_off + m + (int64_t)n * t.ldc] : &C[t.c_off2 + m + (int64_t)(n - t.n_split) * t.ldc];
+        const int64_t mc = (int64_t)(m % t.chunk) + (int64_t)(m / t.chunk) * t.chunk_stride;
+        const int64_t nc = (int64_t)(n % t.chunk) + (int64_t)(n / t.chunk) * t.chunk_stride;
+        T* p = (t.flags & GEMM_TRANS_C) ? &C[t.c_off + nc + (int64_t)m * t.ldc]
+               : (n < t.n_split) ? &C[t.c_off + mc + (int64_t)n * t.ldc] : &C[t.c_off2 + mc + (int64_t)(n - t.n_split) * t.ldc];
         *p = acc ? *p + v : v;
       }
   }
@@ -159,15 +161,16 @@ void lincomb(Backend* b, bool cplx, int nv, const void* const* x, const double* 
 }
 
 // serial cyclic Jacobi on one NJ x NJ Hermitian matrix
-static long long jacobi_one(int n, std::vector<cd>& G, std::vector<cd>& Q, double tol, double floor2) {
+static long long jacobi_one(int n, std::vector<cd>& G, std::vector<cd>& Q, double tol, double floor2, double abs_g2, int max_sweeps) {
   long long total = 0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  if (max_sweeps <= 0 || max_sweeps > 60) max_sweeps = 60;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     long long nrot = 0;
     for (int p = 0; p < n; ++p)
       for (int q = p + 1; q < n; ++q) {
         const cd g = G[p + (size_t)q * n];
         const double g2 = std::norm(g), gpp = G[p + (size_t)p * n].real(), gqq = G[q + (size_t)q * n].real();
-        if (!(g2 > tol * tol * std::fabs(gpp * gqq)) || g2 == 0.0 || !(gpp > floor2) || !(gqq > floor2)) continue;
+        if (!(g2 > tol * tol * std::fabs(gpp * gqq)) || !(g2 > abs_g2) || !(gpp > floor2) || !(gqq > floor2)) continue;
         ++nrot;
         const double ag = std::sqrt(g2);
         const cd e = g / ag;
@@ -195,7 +198,8 @@ static long long jacobi_one(int n, std::vector<cd>& G, std::vector<cd>& Q, doubl
   return total;
 }
 
-void launch_jacobi_eig(Backend* b, bool cplx, const void* G_, void* Q_, int npairs, double tol, double floor2, long long* d_rot) {
+void launch_jacobi_eig(Backend* b, bool cplx, const void* G_, void* Q_, int npairs, double tol, double floor2, double abs_g2,
+                       int max_sweeps, long long* d_rot) {
   b->launches++;
   const int n = 2 * JB;
   for (int pi = 0; pi < npairs; ++pi) {
@@ -209,7 +213,7 @@ void launch_jacobi_eig(Backend* b, bool cplx, const void* G_, void* Q_, int npai
         G[r + (size_t)c * n] = v;
       }
     for (int i = 0; i < n; ++i) Q[i + (size_t)i * n] = 1;
-    *d_rot += jacobi_one(n, G, Q, tol, floor2);
+    *d_rot += jacobi_one(n, G, Q, tol, floor2, abs_g2, max_sweeps);
     for (size_t i = 0; i < (size_t)n * n; ++i) {
       if (cplx) ((cd*)Q_)[(size_t)pi * n * n + i] = Q[i]; else ((double*)Q_)[(size_t)pi * n * n + i] = Q[i].real();
     }
@@ -234,5 +238,17 @@ void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) 
 }
 
 double fp64_pipe_peak(Backend*, int, int) { return 0.0; }
+
+// multi-GPU plumbing does not exist on the host emulation: only the exchange-free shard mode (0) is testable here
+int shard_alloc(Backend*, int64_t, void*) { return -1; }
+int shard_connect(Backend*, int, int, const void*) { return -1; }
+int64_t shard_landing_bytes(Backend*) { return 0; }
+void* shard_landing(Backend*, int) { return nullptr; }
+void shard_peer_bases(Backend*, int, PeerBases* out) { out->n = 0; }
+void shard_barrier(Backend*) {}
+void launch_gemm_peer(Backend*, bool, const void*, const void*, const PeerBases&, const GemmTask*, int, const GemmSeg*, int) {}
+int nccl_unique_id(Backend*, void*) { return -1; }
+int nccl_init(Backend*, const void*, int, int) { return -1; }
+void nccl_allreduce_sum(Backend*, void*, int64_t) {}
 
 }  // namespace cb200

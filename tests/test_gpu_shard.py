@@ -1,0 +1,83 @@
+"""-m gpu: the row-sharded H_eff matvec with its real exchanges, two processes.
+  * p2p : all-gather fused into the R-stage epilogue through CUDA-IPC peer mappings + the flag barrier.  Runs on ONE GPU as
+          well (both ranks on cuda:0, time-sliced), so the plumbing is covered on the single-GPU box;
+  * nccl: ncclAllReduce of the zero-padded partials; needs two GPUs (NCCL refuses two ranks on one device).
+Both are compared with the unsharded product on the same inputs, then a short sharded DMRG run with the unsharded one."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PRODUCT_LIB, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, mode, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import chain_b200 as cb
+    import common
+    from oracle import dmrg as od
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev = rank % torch.cuda.device_count()
+        out = {}
+        for case in (common.BOND_CASES[2], common.BOND_CASES[4]):           # dense real, complex Z3 block-sparse
+            st, bc, n, cp, ch, bond = case
+            site, W, qk, c = common.capture_bond(st, bc, n, cp, ch, bond)
+            ref = cb.Context(device=dev, lib_path=PRODUCT_LIB)
+            want = common.make_bond(ref, site, qk, c).apply(c["phi"])
+            ctx = cb.Context(device=dev, lib_path=PRODUCT_LIB)
+            ctx.shard(rank, world, mode=mode, landing_bytes=16 * c["phi"].size, min_dim=0)
+            B = common.make_bond(ctx, site, qk, c)
+            for rep in range(3):                                              # both landing halves + reuse
+                got = B.apply(c["phi"] * (rep + 1))
+                out["%s rep%d" % (st, rep)] = (float(np.abs(got - (rep + 1) * want).max()), float(np.abs(want).max()))
+            ev, x, nmv = B.davidson(c["phi"], 2)
+            evr, xr, _ = common.make_bond(ref, site, qk, c).davidson(c["phi"], 2)
+            out["%s davidson" % st] = (abs(ev - evr), abs(evr))
+            B.close()
+        # a short sharded DMRG run (every rank drives the same sweep in lockstep; min_dim=0 shards every bond)
+        site, W, qk = common.build_model("golden", "p", 6, [-1.0])
+        H = cb.MPO(W, qk, site.charges, nq=1)
+        psi0 = common.to_cb(od.product_mps(site, 6, 0, np.random.default_rng(0)))
+        sw = cb.Sweeps(4, [10, 20, 40, 80], [1e-5, 1e-6, 1e-7, 1e-8])
+        e1, _ = cb.dmrg(H, [], psi0, sw, ctx=ref)
+        e2, _ = cb.dmrg(H, [], psi0, sw, ctx=ctx)
+        out["dmrg"] = (abs(e1 - e2), abs(e1))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(mode):
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [mpc.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        for k, (err, scale) in out.items():
+            assert err <= 1e-11 * max(1.0, scale), (rank, k, err, scale)
+
+
+def test_p2p_fused_allgather_two_ranks():
+    _run("p2p")
+
+
+def test_nccl_allreduce_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("ncclAllReduce needs two GPUs (two ranks cannot share one device)")
+    _run("nccl")
