@@ -89,6 +89,23 @@ void launch_colnorm2(Backend*, bool cplx, const void* X, int64_t ld, int64_t row
 // X (n x n, ld) = identity
 void launch_set_identity(Backend*, bool cplx, void* X, int64_t ld, int64_t n);
 
+// ---- Hermitian eigensolver of the bond truncation: rho -> tridiagonal -> eigenvalues -> kept eigenvectors ---------------
+// (1) Householder tridiagonalisation of the Hermitian n x n matrix A (column-major, ld = n, BOTH triangles valid), in place:
+//     d[n], e[n-1] (real) is the tridiagonal T = Q^H A Q; reflector j is H_j = I - tau[j] v v^H with v = [1; A[j+2.., j] * scl[j]]
+//     acting on rows j+1.. (LAPACK zhetd2 'L' convention; the unscaled column stays in A).  tau/scl have A's element type.
+//     p_work: n elements of A's type.  Returns false when the backend has no such kernel (the engine then uses block Jacobi).
+bool launch_tridiag(Backend*, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p_work);
+// (2) all n eigenvalues of T by Sturm bisection, ascending
+void launch_bisect(Backend*, const double* d, const double* e, int64_t n, double* w);
+// (3) inverse iteration for m given eigenvalues (one thread per eigenvalue); Zt[i*m + j] = component i of eigenvector j, unit
+//     2-norm; work: 6*n*m doubles
+void launch_invit(Backend*, const double* d, const double* e, int64_t n, const double* lam, int64_t m, double* Zt, double* work);
+// (4) Newton-Schulz orthonormalisation step: C = alpha*(1.5 I - 0.5 alpha^2 G) for the m x m Gram matrix G;
+//     stats[0] = max |G - I|, stats[1] = max row sum of |G|  (device doubles, overwritten)
+void launch_ns_coeff(Backend*, const double* G, int64_t m, double alpha, double* Cout, double* stats);
+// (5) V[:, c] = H_0 H_1 ... H_{n-2} z_c for the m columns z_c = Zt[. * m + c]; V is n x m column-major of A's type
+void launch_backtransform(Backend*, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V);
+
 // FP64 issue-rate calibration (0 = DMMA.8x8x4, 1 = DFMA); TFLOP/s.  Device-only, used by bench.py for the roofline denominator.
 double fp64_pipe_peak(Backend*, int which, int iters);
 

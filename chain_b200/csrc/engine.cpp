@@ -947,6 +947,86 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
   return out;
 }
 
+// ------------------------------------------------------------------------------------------------ Hermitian eigensolver
+bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
+  Backend* be = c->be;
+  const size_t es = esz(cplx);
+  h.n = n; h.cplx = cplx;
+  h.A = std::move(A);
+  h.d = Buf(be, 8 * std::max<int64_t>(n, 1));
+  h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
+  h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
+  h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
+  Buf p(be, (int64_t)es * std::max<int64_t>(n, 1));
+  if (!launch_tridiag(be, cplx, h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, p.p)) return false;
+  Buf w(be, 8 * std::max<int64_t>(n, 1));
+  launch_bisect(be, (const double*)h.d.p, (const double*)h.e.p, n, (double*)w.p);
+  h.w.resize(n);
+  dev_d2h(be, h.w.data(), w.p, 8 * (size_t)n);
+  std::reverse(h.w.begin(), h.w.end());
+  check_dev(c);
+  return true;
+}
+
+Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
+  Backend* be = c->be;
+  const int64_t n = h.n;
+  const size_t es = esz(h.cplx);
+  if (m <= 0 || m > n) fail(-2, "heig_vectors: bad vector count");
+  // shifts: the m largest eigenvalues, forced apart by a few ulps of ||T|| so that members of a degenerate multiplet
+  // get different (random-start) vectors that span the multiplet; the orthonormalisation below does the rest
+  double tn = 0;
+  for (double x : h.w) tn = std::max(tn, std::fabs(x));
+  const double sep = 10.0 * 2.3e-16 * std::max(tn, 1e-300);
+  std::vector<double> lam(h.w.begin(), h.w.begin() + m);
+  for (int64_t k = 1; k < m; ++k)
+    if (lam[k - 1] - lam[k] < sep) lam[k] = lam[k - 1] - sep;
+  Buf dlam(be, 8 * m);
+  dev_h2d(be, dlam.p, lam.data(), 8 * (size_t)m);
+  Buf Za(be, 8 * n * m), Zb(be, 8 * n * m);
+  {
+    Buf work(be, 8 * 6 * n * m);
+    launch_invit(be, (const double*)h.d.p, (const double*)h.e.p, n, (const double*)dlam.p, m, (double*)Za.p, (double*)work.p);
+  }
+  // Newton-Schulz: Z <- Z (1.5 I - 0.5 Z^T Z) until Z^T Z = I to working precision (all GEMM; quadratic convergence)
+  GemmPlan gram, apply;
+  {
+    GemmBuilder gb(false);
+    gb.begin(0, m, m, m, 0);
+    gb.seg(0, m, 0, m, n);
+    gb.end();
+    gb.finish(be, gram, false, true);
+    GemmBuilder ga(false);
+    ga.begin(0, m, m, n, 0);
+    ga.seg(0, m, 0, m, m);
+    ga.end();
+    ga.finish(be, apply, false, false);
+  }
+  Buf G(be, 8 * m * m), C(be, 8 * m * m), st(be, 16);
+  void* zc = Za.p; void* zn = Zb.p;
+  double prev = 1e300;
+  int it = 0;
+  for (;; ++it) {
+    run_gemm(c, false, gram, zc, zc, G.p);
+    launch_ns_coeff(be, (const double*)G.p, m, 1.0, (double*)C.p, (double*)st.p);
+    double s2[2];
+    dev_d2h(be, s2, st.p, 16);
+    const double dev = s2[0];
+    if (!(dev == dev)) fail(-5, "heig_vectors: non-finite Gram matrix");
+    if (dev <= 1e-14 || (it >= 2 && dev < 1e-12 && dev >= 0.5 * prev)) break;
+    if (it >= 60) fail(-5, "heig_vectors: Newton-Schulz orthonormalisation did not converge");
+    if (s2[1] > 2.5) launch_ns_coeff(be, (const double*)G.p, m, std::sqrt(1.5 / s2[1]), (double*)C.p, (double*)st.p);
+    run_gemm(c, false, apply, C.p, zc, zn);
+    std::swap(zc, zn);
+    prev = dev;
+  }
+  h.ns_iters = it;
+  Buf V(be, (int64_t)es * n * m);
+  launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
+  check_dev(c);
+  return V;
+}
+
 // ------------------------------------------------------------------------------------------------ svdBond
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
                        int64_t mindim, double cutoff) {

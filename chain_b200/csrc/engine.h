@@ -236,6 +236,19 @@ struct JacobiOut {
 };
 JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n);
 
+// Hermitian eigensolver of the truncation (tridiagonalisation -> bisection -> inverse iteration -> back-transformation):
+// what replaces LAPACK dsyev/zheev inside ITensor's diagHermitian(rho).  Two phases, because the number of vectors wanted
+// is only known after the eigenvalues of all charge blocks have been pooled.
+struct Heig {
+  int64_t n = 0;
+  bool cplx = false;
+  Buf A, d, e, tau, scl;
+  std::vector<double> w;      // all eigenvalues, descending
+  int ns_iters = 0;
+};
+bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h);   // false: backend has no tridiagonalisation kernel
+Buf heig_vectors(Ctx* c, Heig& h, int64_t m);                       // n x m column-major, orthonormal, spans the top-m eigenspace
+
 // ITensor truncate() on a descending spectrum
 void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, double cutoff, int64_t* m, double* truncerr, double* docut);
 

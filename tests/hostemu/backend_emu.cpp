@@ -239,6 +239,181 @@ void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) 
 
 double fp64_pipe_peak(Backend*, int, int) { return 0.0; }
 
+// ---- Hermitian eigensolver building blocks: serial restatement of the device kernels (same conventions, see backend.h) ----
+template <class T> static inline T cj(const T& x) { return x; }
+template <> inline cd cj<cd>(const cd& x) { return std::conj(x); }
+template <class T> static inline double re_(const T& x) { return x; }
+template <> inline double re_<cd>(const cd& x) { return x.real(); }
+template <class T> static inline double im_(const T&) { return 0.0; }
+template <> inline double im_<cd>(const cd& x) { return x.imag(); }
+template <class T> static inline T mk(double r, double i) { return r; }
+template <> inline cd mk<cd>(double r, double i) { return cd(r, i); }
+
+template <class T>
+static void tridiag_t(T* A, int64_t n, double* d, double* e, T* tau, T* scl, T* p) {
+  for (int64_t j = 0; j + 1 < n; ++j) {
+    const int64_t m = n - j - 1;
+    T* x = A + (j + 1) + j * n;
+    const T alpha = x[0];
+    double sigma = 0;
+    for (int64_t i = 1; i < m; ++i) sigma += std::norm(cd(re_(x[i]), im_(x[i])));
+    const double ar = re_(alpha), ai = im_(alpha);
+    d[j] = re_(A[j + j * n]);
+    if (sigma == 0.0 && ai == 0.0) { tau[j] = T(0); scl[j] = T(0); e[j] = ar; continue; }
+    const double beta = -std::copysign(std::sqrt(ar * ar + ai * ai + sigma), ar);
+    const T tj = mk<T>((beta - ar) / beta, -ai / beta);
+    const T sc = T(1) / (alpha - T(beta));
+    auto v = [&](int64_t i) { return i == 0 ? T(1) : x[i] * sc; };
+    T* A22 = A + (j + 1) + (j + 1) * n;
+    for (int64_t c = 0; c < m; ++c) {
+      T acc(0);
+      for (int64_t r = 0; r < m; ++r) acc += cj(A22[r + c * n]) * v(r);
+      p[c] = tj * acc;
+    }
+    T s(0);
+    for (int64_t i = 0; i < m; ++i) s += cj(p[i]) * v(i);
+    const T a2 = T(-0.5) * tj * s;
+    for (int64_t i = 0; i < m; ++i) p[i] += a2 * v(i);     // w
+    for (int64_t c = 0; c < m; ++c)
+      for (int64_t r = 0; r < m; ++r) A22[r + c * n] -= v(r) * cj(p[c]) + p[r] * cj(v(c));
+    e[j] = beta; tau[j] = tj; scl[j] = sc;
+  }
+  d[n - 1] = re_(A[(n - 1) + (n - 1) * n]);
+}
+
+bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p) {
+  b->launches++;
+  if (cplx) tridiag_t<cd>((cd*)A, n, d, e, (cd*)tau, (cd*)scl, (cd*)p); else tridiag_t<double>((double*)A, n, d, e, (double*)tau, (double*)scl, (double*)p);
+  return true;
+}
+
+void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, double* w) {
+  b->launches++;
+  double gl = d[0], gu = d[0], emax2 = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(e[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[i]) : 0.0);
+    gl = std::min(gl, d[i] - r); gu = std::max(gu, d[i] + r);
+    if (i + 1 < n) emax2 = std::max(emax2, e[i] * e[i]);
+  }
+  const double pivmin = 2.2250738585072014e-308 * std::max(1.0, emax2);
+  const double span = std::max(gu - gl, 1e-300);
+  gl -= 2.0 * span * 2.3e-16 * n + 2 * pivmin; gu += 2.0 * span * 2.3e-16 * n + 2 * pivmin;
+  for (int64_t k = 0; k < n; ++k) {
+    double lo = gl, hi = gu;
+    for (int it = 0; it < 200; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (mid <= lo || mid >= hi) break;
+      int64_t cnt = 0;
+      double q = d[0] - mid;
+      if (std::fabs(q) < pivmin) q = -pivmin;
+      if (q < 0) ++cnt;
+      for (int64_t i = 1; i < n; ++i) {
+        q = d[i] - mid - e[i - 1] * e[i - 1] / q;
+        if (std::fabs(q) < pivmin) q = -pivmin;
+        if (q < 0) ++cnt;
+      }
+      if (cnt > k) hi = mid; else lo = mid;
+    }
+    w[k] = 0.5 * (lo + hi);
+  }
+}
+
+static inline double hash_unit(uint64_t i, uint64_t j) {   // deterministic start vector in (-1, 1)
+  uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull ^ (j + 1) * 0xC2B2AE3D27D4EB4Full;
+  z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29; z *= 0x94D049BB133111EBull; z ^= z >> 32;
+  return ((double)(z >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+}
+
+void launch_invit(Backend* b, const double* d, const double* e, int64_t n, const double* lam, int64_t m, double* Zt, double* work) {
+  b->launches++;
+  double tnorm = 0;
+  for (int64_t i = 0; i < n; ++i) tnorm = std::max(tnorm, std::fabs(d[i]) + (i > 0 ? std::fabs(e[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[i]) : 0.0));
+  const double tol = std::max(2.3e-16 * tnorm, 1e-300);
+  double* u0 = work; double* u1 = work + n * m; double* u2 = work + 2 * n * m; double* lm = work + 3 * n * m; double* sw = work + 4 * n * m;
+  for (int64_t j = 0; j < m; ++j) {
+    auto at = [&](double* a, int64_t i) -> double& { return a[i * m + j]; };
+    const double l = lam[j];
+    double p0 = d[0] - l, p1 = n > 1 ? e[0] : 0.0;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+      const double r0 = e[i], r1 = d[i + 1] - l, r2 = (i + 2 < n) ? e[i + 1] : 0.0;
+      if (std::fabs(p0) >= std::fabs(r0)) {
+        if (std::fabs(p0) < tol) p0 = p0 < 0 ? -tol : tol;
+        const double mult = r0 / p0;
+        at(sw, i) = 0; at(lm, i) = mult; at(u0, i) = p0; at(u1, i) = p1; at(u2, i) = 0;
+        p0 = r1 - mult * p1; p1 = r2;
+      } else {
+        const double mult = p0 / r0;
+        at(sw, i) = 1; at(lm, i) = mult; at(u0, i) = r0; at(u1, i) = r1; at(u2, i) = r2;
+        p0 = p1 - mult * r1; p1 = -mult * r2;
+      }
+    }
+    if (std::fabs(p0) < tol) p0 = p0 < 0 ? -tol : tol;
+    at(u0, n - 1) = p0; at(u1, n - 1) = 0; at(u2, n - 1) = 0;
+    for (int64_t i = 0; i < n; ++i) at(Zt, i) = hash_unit(i, j);
+    for (int it = 0; it < 3; ++it) {
+      for (int64_t i = 0; i + 1 < n; ++i) {
+        if (at(sw, i) != 0) std::swap(at(Zt, i), at(Zt, i + 1));
+        at(Zt, i + 1) -= at(lm, i) * at(Zt, i);
+      }
+      double mx = 0;
+      for (int64_t i = n - 1; i >= 0; --i) {
+        double y = at(Zt, i);
+        if (i + 1 < n) y -= at(u1, i) * at(Zt, i + 1);
+        if (i + 2 < n) y -= at(u2, i) * at(Zt, i + 2);
+        y /= at(u0, i);
+        at(Zt, i) = y;
+        mx = std::max(mx, std::fabs(y));
+      }
+      const double sc = mx > 0 ? 1.0 / mx : 1.0;
+      for (int64_t i = 0; i < n; ++i) at(Zt, i) *= sc;
+    }
+    double nn = 0;
+    for (int64_t i = 0; i < n; ++i) nn += at(Zt, i) * at(Zt, i);
+    nn = 1.0 / std::sqrt(nn);
+    for (int64_t i = 0; i < n; ++i) at(Zt, i) *= nn;
+  }
+}
+
+void launch_ns_coeff(Backend* b, const double* G, int64_t m, double alpha, double* Cout, double* stats) {
+  b->launches++;
+  double dev = 0, rs = 0;
+  for (int64_t r = 0; r < m; ++r) {
+    double s = 0;
+    for (int64_t c = 0; c < m; ++c) {
+      const double g = G[r + c * m];
+      dev = std::max(dev, std::fabs(g - (r == c ? 1.0 : 0.0)));
+      s += std::fabs(g);
+      Cout[r + c * m] = alpha * ((r == c ? 1.5 : 0.0) - 0.5 * alpha * alpha * g);
+    }
+    rs = std::max(rs, s);
+  }
+  stats[0] = dev; stats[1] = rs;
+}
+
+template <class T>
+static void backtransform_t(const T* A, int64_t n, const T* tau, const T* scl, const double* Zt, int64_t m, T* V) {
+  for (int64_t c = 0; c < m; ++c) {
+    T* z = V + c * n;
+    for (int64_t i = 0; i < n; ++i) z[i] = T(Zt[i * m + c]);
+    for (int64_t j = n - 2; j >= 0; --j) {
+      if (tau[j] == T(0)) continue;
+      const T* x = A + (j + 1) + j * n;
+      const int64_t len = n - j - 1;
+      auto v = [&](int64_t i) { return i == 0 ? T(1) : x[i] * scl[j]; };
+      T t(0);
+      for (int64_t i = 0; i < len; ++i) t += cj(v(i)) * z[j + 1 + i];
+      t *= tau[j];
+      for (int64_t i = 0; i < len; ++i) z[j + 1 + i] -= t * v(i);
+    }
+  }
+}
+
+void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V) {
+  b->launches++;
+  if (cplx) backtransform_t<cd>((const cd*)A, n, (const cd*)tau, (const cd*)scl, Zt, m, (cd*)V);
+  else backtransform_t<double>((const double*)A, n, (const double*)tau, (const double*)scl, Zt, m, (double*)V);
+}
+
 // multi-GPU plumbing does not exist on the host emulation: only the exchange-free shard mode (0) is testable here
 int shard_alloc(Backend*, int64_t, void*) { return -1; }
 int shard_connect(Backend*, int, int, const void*) { return -1; }
