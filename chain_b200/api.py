@@ -408,6 +408,20 @@ def k_svd(X, ctx=None):
     return x, v, w, sw.value
 
 
+def k_heig(A, m, ctx=None):
+    """Eigenvalues (descending) of the Hermitian matrix A and an orthonormal basis of its top-m invariant subspace."""
+    ctx = ctx or default_context()
+    cplx = np.iscomplexobj(A)
+    dt = np.complex128 if cplx else np.float64
+    n = A.shape[0]
+    a = _lib.fcol(A, dt)
+    w = np.zeros(n)
+    v = np.zeros((n, max(m, 1)), dtype=dt, order="F")
+    it = C.c_int32()
+    ctx.check(ctx.lib.cb200_k_heig(ctx.h, 1 if cplx else 0, n, ptr(a), m, w.ctypes.data_as(C.POINTER(C.c_double)), ptr(v), C.byref(it)))
+    return w, v[:, :m], it.value
+
+
 def k_dots(xs, y, ctx=None):
     ctx = ctx or default_context()
     cplx = np.iscomplexobj(xs) or np.iscomplexobj(y)

@@ -9,11 +9,13 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <type_traits>
 #include "backend.h"
 #include "gemm.cuh"
+#include "heig.cuh"
 
 namespace cb200 {
 
@@ -27,6 +29,7 @@ struct Backend {
   std::string err;
   bool has_err = false;
   cudaEvent_t ev[8] = {};
+  double* d_bounds = nullptr;     // eigensolver scratch (Gershgorin bounds, pivmin, ||T||)
   // multi-GPU: symmetric area [flags (256 B) | landing 0 | landing 1] + the peers' mappings (CUDA IPC)
   char* sym = nullptr;
   int64_t landing_each = 0;
@@ -127,6 +130,7 @@ void backend_destroy(Backend* b) {
   for (int r = 0; r < MAX_PEERS; ++r)
     if (b->peer_opened[r]) cudaIpcCloseMemHandle(b->peer_sym[r]);
   if (b->sym) cudaFree(b->sym);
+  if (b->d_bounds) cudaFree(b->d_bounds);
   cudaFree(b->d_partial);
   cudaFree(b->d_dot_out);
   cudaFreeHost(b->h_dot_out);
@@ -840,6 +844,74 @@ void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) 
   if (cplx) set_identity_kernel<true><<<(unsigned)blocks, 256, 0, b->stream>>>(X, ld, n);
   else set_identity_kernel<false><<<(unsigned)blocks, 256, 0, b->stream>>>(X, ld, n);
   CB_LAUNCH_CHECK(b, "set_identity_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ Hermitian eigensolver
+bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p) {
+  if (n <= 0) return true;
+  static int grid_blocks[2] = {0, 0};
+  const void* fn = cplx ? (const void*)tridiag_kernel<true> : (const void*)tridiag_kernel<false>;
+  if (!grid_blocks[cplx]) {
+    int per_sm = 0, sms = 0;
+    CB_CHECK(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TRI_THREADS, 0));
+    CB_CHECK(b, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    grid_blocks[cplx] = std::max(1, per_sm) * std::max(1, sms);
+  }
+  // no more CTAs than there are columns to own (one warp per column): fewer CTAs = cheaper grid barriers on small problems
+  int blocks = (int)std::min<int64_t>(grid_blocks[cplx], std::max<int64_t>(1, (n + TRI_WARPS - 1) / TRI_WARPS));
+  long long nn = n;
+  void* args[] = {&A, &nn, &d, &e, &tau, &scl, &p};
+  CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(TRI_THREADS), args, 0, b->stream));
+  CB_LAUNCH_CHECK(b, "tridiag_kernel");
+  return true;
+}
+
+static double* tri_bounds(Backend* b, const double* d, const double* e, int64_t n) {
+  if (!b->d_bounds) CB_CHECK(b, cudaMalloc(&b->d_bounds, 8 * sizeof(double)));
+  tri_bounds_kernel<<<1, 256, 0, b->stream>>>(d, e, (long long)n, b->d_bounds);
+  CB_LAUNCH_CHECK(b, "tri_bounds_kernel");
+  return b->d_bounds;
+}
+
+void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, double* w) {
+  if (n <= 0) return;
+  double* bounds = tri_bounds(b, d, e, n);
+  bisect_kernel<<<(unsigned)((n + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, bounds, w);
+  CB_LAUNCH_CHECK(b, "bisect_kernel");
+}
+
+void launch_invit(Backend* b, const double* d, const double* e, int64_t n, const double* lam, int64_t m, double* Zt, double* work) {
+  if (n <= 0 || m <= 0) return;
+  double* bounds = tri_bounds(b, d, e, n);
+  invit_kernel<<<(unsigned)((m + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, lam, (long long)m, bounds, Zt, work);
+  CB_LAUNCH_CHECK(b, "invit_kernel");
+}
+
+void launch_ns_coeff(Backend* b, const double* G, int64_t m, double alpha, double* Cout, double* stats) {
+  if (m <= 0) return;
+  CB_CHECK(b, cudaMemsetAsync(stats, 0, 16, b->stream));
+  ns_coeff_kernel<<<(unsigned)m, 256, 0, b->stream>>>(G, (long long)m, alpha, Cout, (unsigned long long*)stats);
+  CB_LAUNCH_CHECK(b, "ns_coeff_kernel");
+}
+
+void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V) {
+  if (n <= 0 || m <= 0) return;
+  const size_t col_bytes = (size_t)n * (cplx ? 16 : 8);
+  const size_t budget = 200 * 1024;
+  int cpc = (int)std::min<size_t>(16, budget / col_bytes);
+  const int use_smem = cpc >= 1;
+  if (!use_smem) cpc = 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(backtransform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    cudaFuncSetAttribute(backtransform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    attr_done = true;
+  }
+  const unsigned blocks = (unsigned)((m + cpc - 1) / cpc);
+  const size_t smem = use_smem ? (size_t)cpc * col_bytes : 0;
+  if (cplx) backtransform_kernel<true><<<blocks, 32 * cpc, smem, b->stream>>>(A, (long long)n, tau, scl, Zt, (long long)m, V, use_smem);
+  else backtransform_kernel<false><<<blocks, 32 * cpc, smem, b->stream>>>(A, (long long)n, tau, scl, Zt, (long long)m, V, use_smem);
+  CB_LAUNCH_CHECK(b, "backtransform_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 pipe calibration

@@ -464,6 +464,26 @@ int cb200_k_svd(cb200_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, void*
   });
 }
 
+int cb200_k_heig(cb200_ctx* ctx, int32_t dtype, int64_t n, const void* A, int64_t m, double* w, void* V, int32_t* ns_iters) {
+  if (!ctx) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    if (n < 1 || m < 0 || m > n) fail(CB200_ERR_INVALID, "k_heig: bad sizes");
+    Buf dA(c->be, (int64_t)es * n * n);
+    dev_h2d(c->be, dA.p, A, es * (size_t)n * n);
+    Heig h;
+    if (!heig_values(c, cx, std::move(dA), n, h)) fail(CB200_ERR_INVALID, "k_heig: this backend has no tridiagonalisation kernel");
+    for (int64_t i = 0; i < n; ++i) w[i] = h.w[i];
+    if (m > 0) {
+      Buf dV = heig_vectors(c, h, m);
+      dev_d2h(c->be, V, dV.p, es * (size_t)n * m);
+    }
+    if (ns_iters) *ns_iters = h.ns_iters;
+  });
+}
+
 int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out) {
   if (!ctx) return CB200_ERR_INVALID;
   return guard(ctx, [&] {

@@ -1029,7 +1029,7 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
 
 // ------------------------------------------------------------------------------------------------ svdBond
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
-                       int64_t mindim, double cutoff) {
+                       int64_t mindim, double cutoff, bool exact_rank) {
   Backend* be = c->be;
   const int nq = pl.L.nq, d = S->d;
   const Grading& Dl = pl.L;
@@ -1039,10 +1039,17 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   struct Blk {
     int64_t rows = 0, n = 0;
     std::vector<int64_t> rowbase, colbase;   // indexed by q2 / ql (dir 0) or ql / q2 (dir 1)
-    JacobiOut jo;
-    std::vector<int64_t> order;              // slots sorted by descending w
+    JacobiOut jo;                            // block-Jacobi path (CB200_TRUNC=jacobi)
+    std::vector<int64_t> order;              // Jacobi slots sorted by descending w
+    Buf X;                                   // tridiagonal path: the gathered matrix, needed again for X * V_kept
+    Heig h;
+    std::vector<double> wd;                  // eigenvalues of rho, descending
     int64_t keep = 0;
   };
+  static const bool force_jacobi = [] { const char* e = getenv("CB200_TRUNC"); return e && std::string(e) == "jacobi"; }();
+  // exact_rank: the one-sided Jacobi SVD resolves exactly-zero singular values (rank of a product state) that an
+  // eigensolver working on rho = X^H X can only see as +-eps*||rho||; used for the untruncated canonicalisation of the input.
+  bool tri = !force_jacobi && !exact_rank;
   std::vector<Blk> blk(nq);
   // sizes: dir 0 orthogonalises (l,s1) [columns], long index (s2,r) [rows]; dir 1 the other way round
   for (int qm = 0; qm < nq; ++qm) {
@@ -1085,12 +1092,35 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
         }
     }
     cb.run(c, cplx, phi, X.p);
-    b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n);
-    const int64_t npad = (int64_t)b.jo.w.size();
-    b.order.resize(npad);
-    std::iota(b.order.begin(), b.order.end(), 0);
-    std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
-    for (int64_t k = 0; k < b.n; ++k) pooled.push_back(b.jo.w[b.order[k]]);
+    if (tri) {
+      // rho = X^H X (what ITensor's denmatDecomp forms), then its eigenvalues through the tridiagonal form
+      Buf rho(be, (int64_t)es * b.n * b.n);
+      GemmBuilder gb(cplx);
+      gb.begin(0, b.n, b.n, b.n, GEMM_TRANS_A | GEMM_CONJ_A);
+      gb.seg(0, ld, 0, ld, b.rows);
+      gb.end();
+      GemmPlan gp;
+      gb.finish(be, gp, true, false);
+      run_gemm(c, cplx, gp, X.p, X.p, rho.p);
+      if (heig_values(c, cplx, std::move(rho), b.n, b.h)) {
+        b.wd = b.h.w;
+        for (int64_t k = std::min(b.rows, b.n); k < b.n; ++k) b.wd[k] = 0.0;   // rank(X^H X) <= rows: the rest is rounding noise
+        b.X = std::move(X);
+      } else {
+        if (qm != 0 && !pooled.empty()) fail(-3, "split_bond: eigensolver became unavailable mid-way");
+        tri = false;
+      }
+    }
+    if (!tri) {
+      b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n);
+      const int64_t npad = (int64_t)b.jo.w.size();
+      b.order.resize(npad);
+      std::iota(b.order.begin(), b.order.end(), 0);
+      std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
+      b.wd.resize(b.n);
+      for (int64_t k = 0; k < b.n; ++k) b.wd[k] = b.jo.w[b.order[k]];
+    }
+    for (int64_t k = 0; k < b.n; ++k) pooled.push_back(b.wd[k]);
   }
   std::sort(pooled.begin(), pooled.end(), std::greater<double>());
   int64_t m = 0;
@@ -1104,21 +1134,20 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   for (int qm = 0; qm < nq; ++qm) {
     Blk& b = blk[qm];
     int64_t keep = 0;
-    while (keep < b.n && b.jo.w[b.order[keep]] > docut) ++keep;
+    while (keep < b.n && b.wd[keep] > docut) ++keep;
     b.keep = keep;
     total_keep += keep;
   }
   if (total_keep == 0) {   // keep the single largest state
     int best = -1;
     for (int qm = 0; qm < nq; ++qm)
-      if (blk[qm].n > 0 && (best < 0 || blk[qm].jo.w[blk[qm].order[0]] > blk[best].jo.w[blk[best].order[0]])) best = qm;
+      if (blk[qm].n > 0 && (best < 0 || blk[qm].wd[0] > blk[best].wd[0])) best = qm;
     blk[best].keep = 1;
   }
-  double kept_w = 0;
   for (int qm = 0; qm < nq; ++qm) {
     res.mid.dim[qm] = blk[qm].keep;
-    for (int64_t k = 0; k < blk[qm].keep; ++k) { kept_w += blk[qm].jo.w[blk[qm].order[k]]; res.spectrum.push_back(blk[qm].jo.w[blk[qm].order[k]]); }
-    res.sweeps = std::max(res.sweeps, blk[qm].jo.sweeps);
+    for (int64_t k = 0; k < blk[qm].keep; ++k) res.spectrum.push_back(blk[qm].wd[k]);
+    res.sweeps = std::max(res.sweeps, tri ? blk[qm].h.ns_iters : blk[qm].jo.sweeps);
   }
   std::sort(res.spectrum.begin(), res.spectrum.end(), std::greater<double>());
   res.A.lay.build(Dl, res.mid, S);
@@ -1131,8 +1160,19 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     const int64_t keep = b.keep;
     if (keep == 0) continue;
     const int64_t ldxk = std::max<int64_t>(b.rows, 1), ldvk = b.n;
-    Buf Xk(be, (int64_t)es * ldxk * keep), Vk(be, (int64_t)es * ldvk * keep);
-    {
+    Buf Xk(be, (int64_t)es * ldxk * keep), Vk;
+    if (tri) {
+      Vk = heig_vectors(c, b.h, keep);                         // n x keep, orthonormal
+      GemmBuilder gb(cplx);
+      gb.begin(0, ldxk, b.rows, keep, 0);
+      gb.seg(0, ldxk, 0, ldvk, b.n);
+      gb.end();
+      GemmPlan gp;
+      gb.finish(be, gp, false, false);
+      run_gemm(c, cplx, gp, b.X.p, Vk.p, Xk.p);                // the weight-carrying factor X V_kept
+      res.sweeps = std::max(res.sweeps, b.h.ns_iters);
+    } else {
+      Vk = Buf(be, (int64_t)es * ldvk * keep);
       CopyBuilder cx_, cv_;
       for (int64_t k = 0; k < keep; ++k) {
         cx_.add(b.order[k] * b.jo.ldx, k * ldxk, b.rows, 1, 1);
@@ -1161,11 +1201,11 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     toB_V.run(c, cplx, Vk.p, res.B.buf.p);
     toB_X.run(c, cplx, Xk.p, res.B.buf.p);
   }
-  // DoNormalize: the weight-carrying tensor has squared norm = sum of kept eigenvalues
-  if (kept_w > 0) {
-    const double s = 1.0 / std::sqrt(kept_w);
-    if (dir == 0) scale_inplace(c, cplx, res.B.buf.p, res.B.lay.total, s);
-    else scale_inplace(c, cplx, res.A.buf.p, res.A.lay.total, s);
+  // DoNormalize: newoc /= norm(newoc) (its squared norm is the sum of the kept eigenvalues)
+  {
+    DevSite3& oc = dir == 0 ? res.B : res.A;
+    const double nn = norm2_dev(c, cplx, oc.buf.p, oc.lay.total);
+    if (nn > 0) scale_inplace(c, cplx, oc.buf.p, oc.lay.total, 1.0 / std::sqrt(nn));
   }
   dev_sync(be);
   check_dev(c);

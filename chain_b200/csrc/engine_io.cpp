@@ -406,7 +406,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
       PhiLayout pl; Buf phi;
       phi_of(i, pl, phi);
       // tiny relative cutoff: drops only the numerically-zero directions, so a product state keeps bond dimension 1
-      SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 1, INT64_MAX / 4, 1, 1e-20);
+      SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 1, INT64_MAX / 4, 1, 1e-20, true);
       A[i] = std::move(sr.A);
       A[i + 1] = std::move(sr.B);
     }

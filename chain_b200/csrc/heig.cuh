@@ -1,0 +1,316 @@
+// Hermitian eigensolver kernels of the bond truncation (MPS::svdBond -> denmatDecomp -> diagHermitian in ITensor, reached from
+// /root/reference/src/dmrg.h:544,563,596):  rho --Householder--> T (real tridiagonal) --Sturm bisection--> eigenvalues
+// --inverse iteration--> eigenvectors of T --(Newton-Schulz, GEMM)--> orthonormal --back-transformation--> eigenvectors of rho.
+// Conventions are those of backend.h / LAPACK zhetd2('L').  Everything here is HBM/L2-bandwidth or latency bound; the O(n^3)
+// GEMM parts (rho = X^H X, Newton-Schulz, X V) run on the DMMA kernel of gemm.cuh.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <type_traits>
+
+namespace cb200 {
+namespace cg = cooperative_groups;
+
+// ---- scalar helpers: T = double or double2 (complex) ----------------------------------------------------------------
+__device__ __forceinline__ double t_zero(double) { return 0.0; }
+__device__ __forceinline__ double2 t_zero(double2) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double t_one(double) { return 1.0; }
+__device__ __forceinline__ double2 t_one(double2) { return make_double2(1.0, 0.0); }
+__device__ __forceinline__ double t_conj(double a) { return a; }
+__device__ __forceinline__ double2 t_conj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double t_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double2 t_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double t_add(double a, double b) { return a + b; }
+__device__ __forceinline__ double2 t_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double t_sub(double a, double b) { return a - b; }
+__device__ __forceinline__ double2 t_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double t_scale(double a, double s) { return a * s; }
+__device__ __forceinline__ double2 t_scale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double t_norm2(double a) { return a * a; }
+__device__ __forceinline__ double t_norm2(double2 a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ double t_re(double a) { return a; }
+__device__ __forceinline__ double t_re(double2 a) { return a.x; }
+__device__ __forceinline__ double t_im(double) { return 0.0; }
+__device__ __forceinline__ double t_im(double2 a) { return a.y; }
+__device__ __forceinline__ bool t_is_zero(double a) { return a == 0.0; }
+__device__ __forceinline__ bool t_is_zero(double2 a) { return a.x == 0.0 && a.y == 0.0; }
+__device__ __forceinline__ double t_make(double r, double, double) { return r; }
+__device__ __forceinline__ double2 t_make(double r, double i, double2) { return make_double2(r, i); }
+__device__ __forceinline__ double t_inv(double a) { return 1.0 / a; }
+__device__ __forceinline__ double2 t_inv(double2 a) { const double q = 1.0 / (a.x * a.x + a.y * a.y); return make_double2(a.x * q, -a.y * q); }
+__device__ __forceinline__ double t_shfl_down(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ double2 t_shfl_down(double2 v, int o) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, o), __shfl_down_sync(0xffffffffu, v.y, o));
+}
+__device__ __forceinline__ double t_shfl(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ double2 t_shfl(double2 v, int l) { return make_double2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l)); }
+template <class T>
+__device__ __forceinline__ T t_warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = t_add(v, t_shfl_down(v, o));
+  return t_shfl(v, 0);
+}
+
+constexpr int TRI_THREADS = 512;
+constexpr int TRI_WARPS = TRI_THREADS / 32;
+
+// block-wide sum, identical summation order in every CTA (all CTAs compute the Householder scalars redundantly and must agree bitwise)
+template <class T>
+__device__ __forceinline__ T tri_block_sum(T v, T* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = t_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  T s = t_zero(v);
+#pragma unroll
+  for (int k = 0; k < TRI_WARPS; ++k) s = t_add(s, red[k]);
+  return s;
+}
+
+// One persistent cooperative kernel for the whole reduction: two grid barriers per Householder step.
+//   phase B  p = tau * A22 * v      one warp per column (A22 is Hermitian and stored in full, so row c = conj(column c): coalesced)
+//   phase C  w = p - (tau/2)(p^H v) v ;  A22 -= v w^H + w v^H     the same warp updates the same column
+template <bool CPLX>
+__global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(void* __restrict__ A_, long long n, double* __restrict__ d, double* __restrict__ e,
+                                                              void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  cg::grid_group grid = cg::this_grid();
+  T* A = reinterpret_cast<T*>(A_);
+  T* tau = reinterpret_cast<T*>(tau_);
+  T* scl = reinterpret_cast<T*>(scl_);
+  T* p = reinterpret_cast<T*>(p_);
+  __shared__ T red[TRI_WARPS];
+  __shared__ double redd[TRI_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * TRI_WARPS + warp, GW = (long long)gridDim.x * TRI_WARPS;
+  for (long long j = 0; j + 1 < n; ++j) {
+    const long long m = n - j - 1;
+    const T* x = A + (j + 1) + j * n;
+    // ---- phase A: Householder scalars (zlarfg), redundantly per CTA
+    double part = 0.0;
+    for (long long i = 1 + threadIdx.x; i < m; i += TRI_THREADS) part += t_norm2(x[i]);
+    const double sigma = tri_block_sum(part, redd);
+    const T alpha = x[0];
+    const double ar = t_re(alpha), ai = t_im(alpha);
+    if (blockIdx.x == 0 && threadIdx.x == 0) d[j] = t_re(A[j + j * n]);
+    if (sigma == 0.0 && ai == 0.0) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) { tau[j] = t_zero(alpha); scl[j] = t_zero(alpha); e[j] = ar; }
+      continue;   // H = I; every CTA takes this branch together (same inputs, same arithmetic)
+    }
+    const double beta = -copysign(sqrt(ar * ar + ai * ai + sigma), ar);
+    const T tj = t_make((beta - ar) / beta, -ai / beta, alpha);
+    const T sc = t_inv(t_sub(alpha, t_make(beta, 0.0, alpha)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tau[j] = tj; scl[j] = sc; e[j] = beta; }
+    T* A22 = A + (j + 1) + (j + 1) * n;
+    // ---- phase B
+    for (long long c = gw; c < m; c += GW) {
+      const T* col = A22 + c * n;
+      T acc = t_zero(alpha);
+      for (long long r = lane; r < m; r += 32) {
+        const T vr = r == 0 ? t_one(alpha) : t_mul(x[r], sc);
+        acc = t_add(acc, t_mul(t_conj(col[r]), vr));
+      }
+      acc = t_warp_sum(acc);
+      if (lane == 0) p[c] = t_mul(tj, acc);
+    }
+    grid.sync();
+    // ---- phase C
+    T sp = t_zero(alpha);
+    for (long long i = threadIdx.x; i < m; i += TRI_THREADS) {
+      const T vi = i == 0 ? t_one(alpha) : t_mul(x[i], sc);
+      sp = t_add(sp, t_mul(t_conj(p[i]), vi));
+    }
+    const T s = tri_block_sum(sp, red);
+    const T a2 = t_scale(t_mul(tj, s), -0.5);
+    for (long long c = gw; c < m; c += GW) {
+      T* col = A22 + c * n;
+      const T vc = c == 0 ? t_one(alpha) : t_mul(x[c], sc);
+      const T wc = t_add(p[c], t_mul(a2, vc));
+      const T cvc = t_conj(vc), cwc = t_conj(wc);
+      for (long long r = lane; r < m; r += 32) {
+        const T vr = r == 0 ? t_one(alpha) : t_mul(x[r], sc);
+        const T wr = t_add(p[r], t_mul(a2, vr));
+        col[r] = t_sub(col[r], t_add(t_mul(vr, cwc), t_mul(wr, cvc)));
+      }
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
+}
+
+// bounds[0..3] = Gershgorin lower / upper bound (widened), pivmin, ||T||_1
+__global__ void __launch_bounds__(256) tri_bounds_kernel(const double* __restrict__ d, const double* __restrict__ e, long long n, double* __restrict__ bounds) {
+  double gl = 1e300, gu = -1e300, em = 0.0, tn = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i + 1 < n ? fabs(e[i]) : 0.0);
+    gl = fmin(gl, d[i] - r); gu = fmax(gu, d[i] + r);
+    tn = fmax(tn, fabs(d[i]) + r);
+    if (i + 1 < n) em = fmax(em, e[i] * e[i]);
+  }
+  __shared__ double s[4][256];
+  s[0][threadIdx.x] = gl; s[1][threadIdx.x] = gu; s[2][threadIdx.x] = em; s[3][threadIdx.x] = tn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 256; ++k) { gl = fmin(gl, s[0][k]); gu = fmax(gu, s[1][k]); em = fmax(em, s[2][k]); tn = fmax(tn, s[3][k]); }
+    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, em);
+    const double span = fmax(gu - gl, 1e-300);
+    const double pad = 2.0 * span * 2.3e-16 * (double)n + 2.0 * pivmin;
+    bounds[0] = gl - pad; bounds[1] = gu + pad; bounds[2] = pivmin; bounds[3] = tn;
+  }
+}
+
+// thread k -> k-th smallest eigenvalue of T (Sturm count bisection; every lane walks the same d/e stream: broadcast loads)
+__global__ void __launch_bounds__(128) bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, long long n,
+                                                     const double* __restrict__ bounds, double* __restrict__ w) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double lo = bounds[0], hi = bounds[1];
+  const double pivmin = bounds[2];
+  const double atol = 5.6e-17 * bounds[3];     // eps/4 * ||T||: the absolute accuracy a backward-stable solver delivers on rho
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi || hi - lo <= atol) break;
+    long long cnt = 0;
+    double q = __ldg(d) - mid;
+    if (fabs(q) < pivmin) q = -pivmin;
+    if (q < 0.0) ++cnt;
+    for (long long i = 1; i < n; ++i) {
+      const double ee = __ldg(e + i - 1);
+      q = __ldg(d + i) - mid - ee * ee / q;
+      if (fabs(q) < pivmin) q = -pivmin;
+      if (q < 0.0) ++cnt;
+    }
+    if (cnt > k) hi = mid; else lo = mid;
+  }
+  w[k] = 0.5 * (lo + hi);
+}
+
+__device__ __forceinline__ double hash_unit(unsigned long long i, unsigned long long j) {
+  unsigned long long z = (i + 1ull) * 0x9E3779B97F4A7C15ull ^ (j + 1ull) * 0xC2B2AE3D27D4EB4Full;
+  z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29; z *= 0x94D049BB133111EBull; z ^= z >> 32;
+  return ((double)(z >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+}
+
+// thread j -> eigenvector of T for the shift lam[j]: LU with partial pivoting of T - lam (two super-diagonals), three inverse
+// iterations from a hashed start vector.  All per-vector arrays are interleaved [i*m + j] so that a warp's accesses coalesce.
+__global__ void __launch_bounds__(128) invit_kernel(const double* __restrict__ d, const double* __restrict__ e, long long n,
+                                                    const double* __restrict__ lam, long long m, const double* __restrict__ bounds,
+                                                    double* __restrict__ Zt, double* __restrict__ work) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double tol = fmax(2.3e-16 * bounds[3], 1e-300);
+  double* u0 = work + j; double* u1 = u0 + n * m; double* u2 = u1 + n * m; double* lm = u2 + n * m; double* sw = lm + n * m;
+  double* z = Zt + j;
+  const double l = lam[j];
+  double p0 = __ldg(d) - l, p1 = n > 1 ? __ldg(e) : 0.0;
+  for (long long i = 0; i + 1 < n; ++i) {
+    const double r0 = __ldg(e + i), r1 = __ldg(d + i + 1) - l, r2 = (i + 2 < n) ? __ldg(e + i + 1) : 0.0;
+    if (fabs(p0) >= fabs(r0)) {
+      if (fabs(p0) < tol) p0 = p0 < 0.0 ? -tol : tol;
+      const double mult = r0 / p0;
+      sw[i * m] = 0.0; lm[i * m] = mult; u0[i * m] = p0; u1[i * m] = p1; u2[i * m] = 0.0;
+      p0 = r1 - mult * p1; p1 = r2;
+    } else {
+      const double mult = p0 / r0;
+      sw[i * m] = 1.0; lm[i * m] = mult; u0[i * m] = r0; u1[i * m] = r1; u2[i * m] = r2;
+      p0 = p1 - mult * r1; p1 = -mult * r2;
+    }
+  }
+  if (fabs(p0) < tol) p0 = p0 < 0.0 ? -tol : tol;
+  u0[(n - 1) * m] = p0; u1[(n - 1) * m] = 0.0; u2[(n - 1) * m] = 0.0;
+  for (long long i = 0; i < n; ++i) z[i * m] = hash_unit((unsigned long long)i, (unsigned long long)j);
+  for (int it = 0; it < 3; ++it) {
+    double cur = z[0];
+    for (long long i = 0; i + 1 < n; ++i) {
+      double nxt = z[(i + 1) * m];
+      if (sw[i * m] != 0.0) { const double t = cur; cur = nxt; nxt = t; }
+      z[i * m] = cur;
+      cur = nxt - lm[i * m] * cur;
+    }
+    z[(n - 1) * m] = cur;
+    double mx = 0.0, x1 = 0.0, x2 = 0.0;
+    for (long long i = n - 1; i >= 0; --i) {
+      double y = z[i * m] - u1[i * m] * x1 - u2[i * m] * x2;
+      y /= u0[i * m];
+      z[i * m] = y;
+      x2 = x1; x1 = y;
+      mx = fmax(mx, fabs(y));
+    }
+    const double sc = mx > 0.0 ? 1.0 / mx : 1.0;
+    for (long long i = 0; i < n; ++i) z[i * m] *= sc;
+  }
+  double nn = 0.0;
+  for (long long i = 0; i < n; ++i) nn = fma(z[i * m], z[i * m], nn);
+  nn = 1.0 / sqrt(nn);
+  for (long long i = 0; i < n; ++i) z[i * m] *= nn;
+}
+
+// Newton-Schulz coefficient matrix C = alpha (1.5 I - 0.5 alpha^2 G), one block per column; stats (as ordered uint64 bit patterns
+// of non-negative doubles): [0] max |G - I|, [1] max column sum of |G|
+__global__ void __launch_bounds__(256) ns_coeff_kernel(const double* __restrict__ G, long long m, double alpha, double* __restrict__ Cout,
+                                                       unsigned long long* __restrict__ stats) {
+  const long long c = blockIdx.x;
+  double dev = 0.0, cs = 0.0;
+  for (long long r = threadIdx.x; r < m; r += 256) {
+    const double g = G[r + c * m];
+    dev = fmax(dev, fabs(g - (r == c ? 1.0 : 0.0)));
+    cs += fabs(g);
+    Cout[r + c * m] = alpha * ((r == c ? 1.5 : 0.0) - 0.5 * alpha * alpha * g);
+  }
+  __shared__ double sd[256], ss[256];
+  sd[threadIdx.x] = dev; ss[threadIdx.x] = cs;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sd[threadIdx.x] = fmax(sd[threadIdx.x], sd[threadIdx.x + o]); ss[threadIdx.x] += ss[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (!(sd[0] == sd[0])) sd[0] = 1e300;   // NaN -> reported as a huge deviation
+    atomicMax(stats, (unsigned long long)__double_as_longlong(sd[0]));
+    atomicMax(stats + 1, (unsigned long long)__double_as_longlong(ss[0]));
+  }
+}
+
+// V[:, c] = H_0 H_1 ... H_{n-2} z_c: one warp per column, the column lives in shared memory (or in V itself when it does not fit)
+template <bool CPLX>
+__global__ void backtransform_kernel(const void* __restrict__ A_, long long n, const void* __restrict__ tau_, const void* __restrict__ scl_,
+                                     const double* __restrict__ Zt, long long m, void* __restrict__ V_, int use_smem) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  extern __shared__ __align__(16) char bsm[];
+  const T* A = reinterpret_cast<const T*>(A_);
+  const T* tau = reinterpret_cast<const T*>(tau_);
+  const T* scl = reinterpret_cast<const T*>(scl_);
+  T* V = reinterpret_cast<T*>(V_);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long c = (long long)blockIdx.x * nw + warp;
+  if (c >= m) return;
+  T* z = use_smem ? reinterpret_cast<T*>(bsm) + (size_t)warp * n : V + c * n;
+  const T one = t_one(T());
+  for (long long i = lane; i < n; i += 32) z[i] = t_scale(one, Zt[i * m + c]);
+  __syncwarp();
+  for (long long j = n - 2; j >= 0; --j) {
+    const T tj = tau[j];
+    if (t_is_zero(tj)) continue;
+    const T sc = scl[j];
+    const T* x = A + (j + 1) + j * n;
+    const long long len = n - j - 1;
+    T* zz = z + j + 1;
+    T t = t_zero(one);
+    for (long long i = lane; i < len; i += 32) {
+      const T vi = i == 0 ? one : t_mul(x[i], sc);
+      t = t_add(t, t_mul(t_conj(vi), zz[i]));
+    }
+    t = t_mul(tj, t_warp_sum(t));
+    for (long long i = lane; i < len; i += 32) {
+      const T vi = i == 0 ? one : t_mul(x[i], sc);
+      zz[i] = t_sub(zz[i], t_mul(t, vi));
+    }
+    __syncwarp();
+  }
+  if (use_smem)
+    for (long long i = lane; i < n; i += 32) V[c * n + i] = z[i];
+}
+
+}  // namespace cb200

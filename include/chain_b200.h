@@ -169,6 +169,11 @@ int cb200_k_gemm(cb200_ctx* ctx, int32_t dtype, int32_t trans_a, int32_t trans_b
 int cb200_k_jacobi_eig(cb200_ctx* ctx, int32_t dtype, int32_t npairs, const void* G, void* Q, double tol, int64_t* rotations);
 /* full one-sided block-Jacobi SVD of X [rows x cols]: X <- X V (columns orthogonal), V [cols x cols], w[cols] = column norms^2 */
 int cb200_k_svd(cb200_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, void* X, void* V, double* w, int32_t* sweeps);
+/* Hermitian eigensolver of the truncation (Householder tridiagonalisation, Sturm bisection, inverse iteration, Newton-Schulz
+ * orthonormalisation, back-transformation): A [n x n] Hermitian (both triangles) -> w[n] all eigenvalues, descending, and
+ * V [n x m] an orthonormal basis of the invariant subspace of the m largest.  Replaces LAPACK dsyev/zheev inside
+ * ITensor's diagHermitian(rho). */
+int cb200_k_heig(cb200_ctx* ctx, int32_t dtype, int64_t n, const void* A, int64_t m, double* w, void* V, int32_t* ns_iters);
 /* out[j] = <x_j | y>, dst = beta*dst + sum c_j x_j */
 int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out_re_im);
 int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const double* c_re_im, double beta_re,

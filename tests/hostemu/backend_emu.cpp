@@ -289,9 +289,10 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
 
 void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, double* w) {
   b->launches++;
-  double gl = d[0], gu = d[0], emax2 = 0;
+  double gl = d[0], gu = d[0], emax2 = 0, tn = 0;
   for (int64_t i = 0; i < n; ++i) {
     const double r = (i > 0 ? std::fabs(e[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(e[i]) : 0.0);
+    tn = std::max(tn, std::fabs(d[i]) + r);
     gl = std::min(gl, d[i] - r); gu = std::max(gu, d[i] + r);
     if (i + 1 < n) emax2 = std::max(emax2, e[i] * e[i]);
   }
@@ -302,7 +303,7 @@ void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, doub
     double lo = gl, hi = gu;
     for (int it = 0; it < 200; ++it) {
       const double mid = 0.5 * (lo + hi);
-      if (mid <= lo || mid >= hi) break;
+      if (mid <= lo || mid >= hi || hi - lo <= 5.6e-17 * tn) break;
       int64_t cnt = 0;
       double q = d[0] - mid;
       if (std::fabs(q) < pivmin) q = -pivmin;

@@ -110,3 +110,28 @@ def test_block_jacobi_svd(gpu_ctx, rows, cols, cplx):
     assert np.abs(X @ v - xv).max() <= 1e-12 * max(1.0, s[0])
     g = xv.conj().T @ xv
     assert np.abs(g - np.diag(np.diag(g))).max() <= 1e-11 * max(1.0, s[0] ** 2)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n,m,decay", [(1, 1, 0.0), (2, 1, 0.5), (3, 3, 0.3), (37, 20, 0.4), (200, 200, 0.0), (333, 100, 0.08), (1000, 300, 0.03)])
+def test_hermitian_eigensolver(gpu_ctx, cplx, n, m, decay):
+    """rho -> tridiagonal -> bisection -> inverse iteration -> Newton-Schulz -> back-transformation, against numpy.eigh."""
+    rng = np.random.default_rng(n * 10 + m + cplx)
+    X = _rand(rng, (n + 5, n), cplx) * (10.0 ** (-decay * np.arange(n)))      # graded spectrum like a DMRG rho
+    if n > 30:
+        X[:, 7] = X[:, 3]                                                      # an exactly rank-deficient direction
+        X[:, 11] = 1j * X[:, 4] if cplx else -X[:, 4]
+    A = X.conj().T @ X
+    A /= np.trace(A).real
+    w, V, it = cb.k_heig(A, m, ctx=gpu_ctx)
+    ev, evec = np.linalg.eigh(A)
+    assert np.abs(w - ev[::-1]).max() <= 1e-14 * np.sqrt(n)
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
+    # V spans an invariant subspace: residual of the Rayleigh-Ritz pair at the eps*||A|| level
+    R = A @ V - V @ (V.conj().T @ A @ V)
+    assert np.abs(R).max() <= 2e-14 * np.sqrt(n)
+    # and it is the TOP-m one wherever that is well defined (gap at the cut well above the noise)
+    if m < n and ev[::-1][m - 1] - ev[::-1][m] > 1e-9:
+        P = evec[:, n - m:] @ evec[:, n - m:].conj().T
+        assert np.abs(V @ V.conj().T - P).max() <= 1e-5
+    assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[::-1][:m]).max() <= 1e-14 * np.sqrt(n)

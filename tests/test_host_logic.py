@@ -52,3 +52,20 @@ def test_ground_state_kat_golden(emu_ctx):
 
 def test_excited_state_in_charge_sector(emu_ctx):
     common.check_excited_qn(emu_ctx)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n,m,decay", [(1, 1, 0.0), (2, 1, 0.5), (3, 3, 0.3), (37, 20, 0.4), (90, 90, 0.0), (120, 40, 0.1)])
+def test_hermitian_eigensolver_driver(emu_ctx, cplx, n, m, decay):
+    rng = np.random.default_rng(n * 10 + m + cplx)
+    X = (rng.standard_normal((n + 5, n)) + (1j * rng.standard_normal((n + 5, n)) if cplx else 0)) * (10.0 ** (-decay * np.arange(n)))
+    if n > 30:
+        X[:, 7] = X[:, 3]
+    A = X.conj().T @ X
+    A /= np.trace(A).real
+    w, V, it = cb.k_heig(A, m, ctx=emu_ctx)
+    ev = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(w - ev).max() <= 1e-14 * np.sqrt(n)
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
+    assert np.abs(A @ V - V @ (V.conj().T @ A @ V)).max() <= 2e-14 * np.sqrt(n)
+    assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[:m]).max() <= 1e-14 * np.sqrt(n)
