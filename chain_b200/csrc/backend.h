@@ -106,6 +106,13 @@ void launch_ns_coeff(Backend*, const double* G, int64_t m, double alpha, double*
 // (5) V[:, c] = H_0 H_1 ... H_{n-2} z_c for the m columns z_c = Zt[. * m + c]; V is n x m column-major of A's type
 void launch_backtransform(Backend*, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V);
 
+// (5') blocked back-transformation on the GEMM kernel (compact WY, LAPACK dlarft/dlarfb 'Forward','Columnwise'):
+//     zt_to_v: V[i + c*n] = Zt[i*m + c];  form_y: Y (len x nbk, ld = len, len = n-j0-1) = the reflectors j0..j0+nbk-1 as explicit
+//     columns over rows j0+1..n-1;  wy_t: Tneg = -T with H_j0 ... H_{j0+nbk-1} = I - Y T Y^H, from S = Y^H Y (nbk x nbk) and tau.
+void launch_zt_to_v(Backend*, bool cplx, const double* Zt, int64_t n, int64_t m, void* V);
+void launch_form_y(Backend*, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, int64_t j0, int nbk, void* Y);
+void launch_wy_t(Backend*, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg);
+
 // FP64 issue-rate calibration (0 = DMMA.8x8x4, 1 = DFMA); TFLOP/s.  Device-only, used by bench.py for the roofline denominator.
 double fp64_pipe_peak(Backend*, int which, int iters);
 

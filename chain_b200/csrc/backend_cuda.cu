@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <type_traits>
+#include <vector>
 #include "backend.h"
 #include "gemm.cuh"
 #include "heig.cuh"
@@ -847,8 +848,7 @@ void launch_set_identity(Backend* b, bool cplx, void* X, int64_t ld, int64_t n) 
 }
 
 // ------------------------------------------------------------------------------------------------ Hermitian eigensolver
-bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p) {
-  if (n <= 0) return true;
+static bool tridiag_unblocked(Backend* b, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p) {
   static int grid_blocks[2] = {0, 0};
   const void* fn = cplx ? (const void*)tridiag_kernel<true> : (const void*)tridiag_kernel<false>;
   if (!grid_blocks[cplx]) {
@@ -866,6 +866,73 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   return true;
 }
 
+bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p) {
+  if (n <= 0) return true;
+  static const bool unblocked = [] { const char* v = getenv("CB200_TRIDIAG"); return v && std::string(v) == "unblocked"; }();
+  if (unblocked || n < 3) return tridiag_unblocked(b, cplx, A, n, d, e, tau, scl, p);
+  // ---- blocked: one cooperative launch per panel of <= 64 reflectors + one GEMM launch for the deferred rank-2nb update
+  const int NB = 64;
+  const size_t es = cplx ? 16 : 8;
+  static int grid_blocks[2] = {0, 0};
+  const void* fn = cplx ? (const void*)tridiag_panel_kernel<true> : (const void*)tridiag_panel_kernel<false>;
+  if (!grid_blocks[cplx]) {
+    int per_sm = 0, sms = 0;
+    CB_CHECK(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TRI_THREADS, 0));
+    CB_CHECK(b, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    const char* v = getenv("CB200_TRI_CTAS_PER_SM");
+    if (v && atoi(v) > 0) per_sm = std::min(per_sm, atoi(v));
+    grid_blocks[cplx] = std::max(1, per_sm) * std::max(1, sms);
+  }
+  const int blocks = (int)std::min<int64_t>(grid_blocks[cplx], std::max<int64_t>(1, (n + TRI_WARPS - 1) / TRI_WARPS));
+  const int64_t nref = n - 1;
+  const int npanel = (int)((nref + NB - 1) / NB);
+  char* pan = (char*)dev_alloc(b, 4 * es * (size_t)n * NB);          // Vp | W | Vn | Wn, each n x NB (ld n)
+  char* gbuf = (char*)dev_alloc(b, es * 128);
+  double* partial = (double*)dev_alloc(b, sizeof(double) * (size_t)blocks);
+  GemmTask* d_tasks = (GemmTask*)dev_alloc(b, sizeof(GemmTask) * (size_t)npanel);
+  GemmSeg* d_segs = (GemmSeg*)dev_alloc(b, sizeof(GemmSeg) * 2 * (size_t)npanel);
+  if (!pan || !gbuf || !partial || !d_tasks || !d_segs) return true;   // the allocation error is already recorded
+  void* Vp = pan; void* W = pan + es * (size_t)n * NB; void* Vn = pan + 2 * es * (size_t)n * NB; void* Wn = pan + 3 * es * (size_t)n * NB;
+  // task list of the rank-2nb updates: A[t0:, t0:] += conj( conj(Vn) W^T + conj(Wn) Vp^T ) = -(V W^H + W V^H)
+  std::vector<GemmTask> tasks(npanel);
+  std::vector<GemmSeg> segs(2 * (size_t)npanel);
+  std::vector<int> tiles(npanel, 0);
+  const int bm = gemm_tile_m(cplx), bn = gemm_tile_n(cplx, false);
+  for (int pi = 0; pi < npanel; ++pi) {
+    const int64_t j0 = (int64_t)pi * NB;
+    const int nbk = (int)std::min<int64_t>(NB, nref - j0);
+    const int64_t t0 = j0 + nbk, mt = n - t0;
+    GemmTask t{};
+    t.c_off = t0 + t0 * n; t.c_off2 = t.c_off; t.ldc = n;
+    t.M = (int32_t)mt; t.N = (int32_t)mt; t.n_split = (int32_t)mt;
+    t.seg_begin = 2 * pi; t.seg_count = 2;
+    t.tile_begin = 0; t.tiles_m = (int32_t)((mt + bm - 1) / bm);
+    t.flags = GEMM_ACCUM | (cplx ? (GEMM_CONJ_A | GEMM_CONJ_OUT) : 0u);
+    tiles[pi] = t.tiles_m * (int)((mt + bn - 1) / bn);
+    tasks[pi] = t;
+    GemmSeg s1{}, s2{};
+    // A-operands are addressed from Vn (the panel base handed to the launch); Wn sits 1 panel further, W / Vp are the B-operands
+    s1.a_off = t0; s1.lda = n; s1.b_off = t0; s1.ldb = n; s1.K = nbk;                       // conj(Vn) * W^T
+    s2.a_off = t0 + (int64_t)n * NB; s2.lda = n; s2.b_off = t0 - (int64_t)n * NB; s2.ldb = n; s2.K = nbk;   // conj(Wn) * Vp^T
+    segs[2 * pi] = s1; segs[2 * pi + 1] = s2;
+  }
+  dev_h2d(b, d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size());
+  dev_h2d(b, d_segs, segs.data(), sizeof(GemmSeg) * segs.size());
+  long long nn = n;
+  for (int pi = 0; pi < npanel; ++pi) {
+    long long j0 = (long long)pi * NB;
+    int nbk = (int)std::min<int64_t>(NB, nref - j0);
+    void* args[] = {&A, &nn, &j0, &nbk, &d, &e, &tau, &scl, &p, &gbuf, &partial, &Vp, &W, &Vn, &Wn};
+    CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(TRI_THREADS), args, 0, b->stream));
+    CB_LAUNCH_CHECK(b, "tridiag_panel_kernel");
+    const int64_t t0 = j0 + nbk;
+    if (t0 < n - 1 && tiles[pi] > 0)    // (the last panel updates the final diagonal element itself)
+      launch_gemm(b, cplx, false, true, false, Vn, W, A, d_tasks + pi, 1, d_segs, tiles[pi]);
+  }
+  dev_free(b, pan); dev_free(b, gbuf); dev_free(b, partial); dev_free(b, d_tasks); dev_free(b, d_segs);
+  return true;
+}
+
 static double* tri_bounds(Backend* b, const double* d, const double* e, int64_t n) {
   if (!b->d_bounds) CB_CHECK(b, cudaMalloc(&b->d_bounds, 8 * sizeof(double)));
   tri_bounds_kernel<<<1, 256, 0, b->stream>>>(d, e, (long long)n, b->d_bounds);
@@ -876,7 +943,7 @@ static double* tri_bounds(Backend* b, const double* d, const double* e, int64_t 
 void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, double* w) {
   if (n <= 0) return;
   double* bounds = tri_bounds(b, d, e, n);
-  bisect_kernel<<<(unsigned)((n + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, bounds, w);
+  bisect_kernel<<<(unsigned)((n + 3) / 4), 128, 0, b->stream>>>(d, e, (long long)n, bounds, w);
   CB_LAUNCH_CHECK(b, "bisect_kernel");
 }
 
@@ -912,6 +979,37 @@ void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const
   if (cplx) backtransform_kernel<true><<<blocks, 32 * cpc, smem, b->stream>>>(A, (long long)n, tau, scl, Zt, (long long)m, V, use_smem);
   else backtransform_kernel<false><<<blocks, 32 * cpc, smem, b->stream>>>(A, (long long)n, tau, scl, Zt, (long long)m, V, use_smem);
   CB_LAUNCH_CHECK(b, "backtransform_kernel");
+}
+
+void launch_zt_to_v(Backend* b, bool cplx, const double* Zt, int64_t n, int64_t m, void* V) {
+  if (n <= 0 || m <= 0) return;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32));
+  if (cplx) zt_to_v_kernel<true><<<grid, 256, 0, b->stream>>>(Zt, (long long)n, (long long)m, V);
+  else zt_to_v_kernel<false><<<grid, 256, 0, b->stream>>>(Zt, (long long)n, (long long)m, V);
+  CB_LAUNCH_CHECK(b, "zt_to_v_kernel");
+}
+
+void launch_form_y(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, int64_t j0, int nbk, void* Y) {
+  const int64_t len = n - j0 - 1;
+  if (len <= 0 || nbk <= 0) return;
+  dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)nbk);
+  if (cplx) form_y_kernel<true><<<grid, 256, 0, b->stream>>>(A, (long long)n, tau, scl, (long long)j0, nbk, Y);
+  else form_y_kernel<false><<<grid, 256, 0, b->stream>>>(A, (long long)n, tau, scl, (long long)j0, nbk, Y);
+  CB_LAUNCH_CHECK(b, "form_y_kernel");
+}
+
+void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg) {
+  if (nbk <= 0 || nbk > 64) { set_err(b, "launch_wy_t: block size out of range", cudaErrorInvalidValue); return; }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wy_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 16);
+    cudaFuncSetAttribute(wy_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 8);
+    attr_done = true;
+  }
+  const size_t smem = (size_t)nbk * nbk * (cplx ? 16 : 8);
+  if (cplx) wy_t_kernel<true><<<1, 64, smem, b->stream>>>(S, tau_j0, nbk, Tneg);
+  else wy_t_kernel<false><<<1, 64, smem, b->stream>>>(S, tau_j0, nbk, Tneg);
+  CB_LAUNCH_CHECK(b, "wy_t_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 pipe calibration

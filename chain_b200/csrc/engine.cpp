@@ -834,6 +834,14 @@ static int jacobi_inner_sweeps() {
   }
   return v;
 }
+static int64_t wy_min_n() {   // below this the per-column kernel wins (CB200_WY_MIN_N overrides)
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB200_WY_MIN_N");
+    v = e ? atoll(e) : 192;
+  }
+  return v;
+}
 static double jacobi_abs_tol() {
   static double v = -1;
   if (v < 0) {
@@ -1022,7 +1030,33 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
   }
   h.ns_iters = it;
   Buf V(be, (int64_t)es * n * m);
-  launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
+  if (n < wy_min_n()) {
+    launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
+  } else {
+    // Q Z = B_0 (B_1 (... (B_last Z))) with B_k = H_j0 ... H_{j0+nb-1} = I - Y T Y^H (compact WY): four GEMMs per block of 64
+    // reflectors on the DMMA kernel instead of 64 memory-bound rank-1 updates
+    const bool cx = h.cplx;
+    launch_zt_to_v(be, cx, (const double*)zc, n, m, V.p);
+    const int NB = 64;
+    const int64_t nref = n - 1;
+    Buf Y(be, (int64_t)es * n * NB), S(be, (int64_t)es * NB * NB), Tn(be, (int64_t)es * NB * NB);
+    Buf W1(be, (int64_t)es * NB * m), W2(be, (int64_t)es * NB * m);
+    for (int64_t j0 = ((nref - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
+      const int nbk = (int)std::min<int64_t>(NB, nref - j0);
+      const int64_t r0 = j0 + 1, len = n - r0;
+      launch_form_y(be, cx, h.A.p, n, h.tau.p, h.scl.p, j0, nbk, Y.p);
+      GemmPlan ps, pw1, pw2, pz;
+      { GemmBuilder g(cx); g.begin(0, nbk, nbk, nbk, GEMM_TRANS_A | GEMM_CONJ_A); g.seg(0, len, 0, len, len); g.end(); g.finish(be, ps, true, false); }
+      { GemmBuilder g(cx); g.begin(0, nbk, nbk, m, GEMM_TRANS_A | GEMM_CONJ_A); g.seg(0, len, r0, n, len); g.end(); g.finish(be, pw1, true, false); }
+      { GemmBuilder g(cx); g.begin(0, nbk, nbk, m, 0); g.seg(0, nbk, 0, nbk, nbk); g.end(); g.finish(be, pw2, false, false); }
+      { GemmBuilder g(cx); g.begin(r0, n, len, m, GEMM_ACCUM); g.seg(0, len, 0, nbk, nbk); g.end(); g.finish(be, pz, false, false); }
+      run_gemm(c, cx, ps, Y.p, Y.p, S.p);
+      launch_wy_t(be, cx, S.p, (const char*)h.tau.p + es * (size_t)j0, nbk, Tn.p);
+      run_gemm(c, cx, pw1, Y.p, V.p, W1.p);
+      run_gemm(c, cx, pw2, Tn.p, W1.p, W2.p);
+      run_gemm(c, cx, pz, Y.p, W2.p, V.p);
+    }
+  }
   check_dev(c);
   return V;
 }

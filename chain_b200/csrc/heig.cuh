@@ -73,7 +73,7 @@ __device__ __forceinline__ T tri_block_sum(T v, T* red) {
 //   phase B  p = tau * A22 * v      one warp per column (A22 is Hermitian and stored in full, so row c = conj(column c): coalesced)
 //   phase C  w = p - (tau/2)(p^H v) v ;  A22 -= v w^H + w v^H     the same warp updates the same column
 template <bool CPLX>
-__global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(void* __restrict__ A_, long long n, double* __restrict__ d, double* __restrict__ e,
+__global__ void __launch_bounds__(TRI_THREADS, 2) tridiag_kernel(void* __restrict__ A_, long long n, double* __restrict__ d, double* __restrict__ e,
                                                               void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   cg::grid_group grid = cg::this_grid();
@@ -104,15 +104,21 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(void* __restrict__
     const T sc = t_inv(t_sub(alpha, t_make(beta, 0.0, alpha)));
     if (blockIdx.x == 0 && threadIdx.x == 0) { tau[j] = tj; scl[j] = sc; e[j] = beta; }
     T* A22 = A + (j + 1) + (j + 1) * n;
-    // ---- phase B
+    // ---- phase B (4 independent loads per lane in flight: the column walk is latency-bound otherwise)
     for (long long c = gw; c < m; c += GW) {
       const T* col = A22 + c * n;
-      T acc = t_zero(alpha);
-      for (long long r = lane; r < m; r += 32) {
-        const T vr = r == 0 ? t_one(alpha) : t_mul(x[r], sc);
-        acc = t_add(acc, t_mul(t_conj(col[r]), vr));
+      T acc0 = t_zero(alpha), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+      long long r = lane;
+      for (; r + 96 < m; r += 128) {
+        const T a0 = col[r], a1 = col[r + 32], a2_ = col[r + 64], a3 = col[r + 96];
+        const T x0 = x[r], x1 = x[r + 32], x2 = x[r + 64], x3 = x[r + 96];
+        acc0 = t_add(acc0, t_mul(t_conj(a0), r == 0 ? t_one(alpha) : t_mul(x0, sc)));
+        acc1 = t_add(acc1, t_mul(t_conj(a1), t_mul(x1, sc)));
+        acc2 = t_add(acc2, t_mul(t_conj(a2_), t_mul(x2, sc)));
+        acc3 = t_add(acc3, t_mul(t_conj(a3), t_mul(x3, sc)));
       }
-      acc = t_warp_sum(acc);
+      for (; r < m; r += 32) acc0 = t_add(acc0, t_mul(t_conj(col[r]), r == 0 ? t_one(alpha) : t_mul(x[r], sc)));
+      const T acc = t_warp_sum(t_add(t_add(acc0, acc1), t_add(acc2, acc3)));
       if (lane == 0) p[c] = t_mul(tj, acc);
     }
     grid.sync();
@@ -129,7 +135,19 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(void* __restrict__
       const T vc = c == 0 ? t_one(alpha) : t_mul(x[c], sc);
       const T wc = t_add(p[c], t_mul(a2, vc));
       const T cvc = t_conj(vc), cwc = t_conj(wc);
-      for (long long r = lane; r < m; r += 32) {
+      long long r = lane;
+      for (; r + 96 < m; r += 128) {
+        T a[4], xv[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = col[r + 32 * u]; xv[u] = x[r + 32 * u]; pv[u] = p[r + 32 * u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T vr = (r + 32 * u) == 0 ? t_one(alpha) : t_mul(xv[u], sc);
+          const T wr = t_add(pv[u], t_mul(a2, vr));
+          col[r + 32 * u] = t_sub(a[u], t_add(t_mul(vr, cwc), t_mul(wr, cvc)));
+        }
+      }
+      for (; r < m; r += 32) {
         const T vr = r == 0 ? t_one(alpha) : t_mul(x[r], sc);
         const T wr = t_add(p[r], t_mul(a2, vr));
         col[r] = t_sub(col[r], t_add(t_mul(vr, cwc), t_mul(wr, cvc)));
@@ -138,6 +156,150 @@ __global__ void __launch_bounds__(TRI_THREADS) tridiag_kernel(void* __restrict__
     grid.sync();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
+}
+
+// Blocked variant (LAPACK zlatrd 'L' restated for one persistent kernel per panel of <= 64 reflectors): the trailing matrix is
+// NOT updated inside a panel -- the matrix-vector product is corrected with the panel's V and W columns instead -- so a step
+// makes ONE pass over the trailing block (the unblocked kernel makes three) and the rank-2nb update after the panel is a GEMM
+// on the DMMA kernel.  Still two grid barriers per step:
+//   S2+S3  Householder scalars (redundant per CTA, fixed-order sums); one warp per column: p = A22^H-column dot v for the trailing
+//          columns, g1 = W^H v, g2 = V^H v for the panel columns
+//   S4+S1' one thread per row: w = tau (p - V g1 - W g2) + alpha v (column i of W), then the deferred update of the NEXT column
+//          of A with all panel reflectors so far, and the partial norms the next step's Householder vector needs
+template <bool CPLX>
+__global__ void __launch_bounds__(TRI_THREADS, 2)
+tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
+                     void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
+                     double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  cg::grid_group grid = cg::this_grid();
+  T* A = reinterpret_cast<T*>(A_);
+  T* tau = reinterpret_cast<T*>(tau_);
+  T* scl = reinterpret_cast<T*>(scl_);
+  T* p = reinterpret_cast<T*>(p_);
+  T* g = reinterpret_cast<T*>(g_);
+  T* Vp = reinterpret_cast<T*>(Vp_);
+  T* W = reinterpret_cast<T*>(W_);
+  T* Vn = reinterpret_cast<T*>(Vn_);
+  T* Wn = reinterpret_cast<T*>(Wn_);
+  __shared__ T red[TRI_WARPS];
+  __shared__ double redd[TRI_WARPS];
+  __shared__ T sg1[64], sg2[64], swp[64], svp[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * TRI_WARPS + warp, GW = (long long)gridDim.x * TRI_WARPS;
+  const long long gtid = (long long)blockIdx.x * TRI_THREADS + threadIdx.x, GT = (long long)gridDim.x * TRI_THREADS;
+  const int G = gridDim.x;
+  const T zero = t_zero(T()), one = t_one(T());
+  {   // prologue: the first column of the panel is up to date (rank-2nb GEMM of the previous panel); its partial norms are not
+    double part = 0.0;
+    for (long long r = j0 + 2 + gtid; r < n; r += GT) part += t_norm2(A[r + j0 * n]);
+    const double sblk = tri_block_sum(part, redd);
+    if (threadIdx.x == 0) partial[blockIdx.x] = sblk;
+  }
+  grid.sync();
+  for (int i = 0; i < nbk; ++i) {
+    const long long j = j0 + i, m = n - j - 1;
+    const T* x = A + (j + 1) + j * n;
+    // ---- S2
+    double ps = 0.0;
+    for (int b = threadIdx.x; b < G; b += TRI_THREADS) ps += partial[b];
+    const double sigma = tri_block_sum(ps, redd);
+    const T alpha = x[0];
+    const double ar = t_re(alpha), ai = t_im(alpha);
+    const bool off = (sigma == 0.0 && ai == 0.0);
+    double beta = ar;
+    T tj = zero, sc = zero;
+    if (!off) {
+      beta = -copysign(sqrt(ar * ar + ai * ai + sigma), ar);
+      tj = t_make((beta - ar) / beta, -ai / beta, alpha);
+      sc = t_inv(t_sub(alpha, t_make(beta, 0.0, alpha)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { d[j] = t_re(A[j + j * n]); e[j] = beta; tau[j] = tj; scl[j] = sc; }
+    // ---- S3
+    if (!off) {
+      const long long ncol = m + 2 * i;
+      for (long long cc = gw; cc < ncol; cc += GW) {
+        const T* col = cc < m ? A + (j + 1) + (j + 1 + cc) * n : (cc < m + i ? W + (j + 1) + (cc - m) * n : Vp + (j + 1) + (cc - m - i) * n);
+        T acc0 = zero, acc1 = zero, acc2 = zero, acc3 = zero;
+        long long r = lane;
+        for (; r + 96 < m; r += 128) {
+          const T a0 = col[r], a1 = col[r + 32], a2_ = col[r + 64], a3 = col[r + 96];
+          const T x0 = x[r], x1 = x[r + 32], x2 = x[r + 64], x3 = x[r + 96];
+          acc0 = t_add(acc0, t_mul(t_conj(a0), r == 0 ? one : t_mul(x0, sc)));
+          acc1 = t_add(acc1, t_mul(t_conj(a1), t_mul(x1, sc)));
+          acc2 = t_add(acc2, t_mul(t_conj(a2_), t_mul(x2, sc)));
+          acc3 = t_add(acc3, t_mul(t_conj(a3), t_mul(x3, sc)));
+        }
+        for (; r < m; r += 32) acc0 = t_add(acc0, t_mul(t_conj(col[r]), r == 0 ? one : t_mul(x[r], sc)));
+        const T acc = t_warp_sum(t_add(t_add(acc0, acc1), t_add(acc2, acc3)));
+        if (lane == 0) {
+          if (cc < m) p[cc] = acc;
+          else if (cc < m + i) g[cc - m] = acc;              // g1 = W^H v
+          else g[64 + (cc - m - i)] = acc;                    // g2 = V^H v
+        }
+      }
+    }
+    grid.sync();
+    // ---- S4 + S1'
+    T sp = zero;
+    if (!off)
+      for (long long q = threadIdx.x; q < m; q += TRI_THREADS) sp = t_add(sp, t_mul(t_conj(p[q]), q == 0 ? one : t_mul(x[q], sc)));
+    const T s0 = tri_block_sum(sp, red);
+    if (threadIdx.x < i) {
+      sg1[threadIdx.x] = off ? zero : g[threadIdx.x];
+      sg2[threadIdx.x] = off ? zero : g[64 + threadIdx.x];
+      swp[threadIdx.x] = t_conj(W[(j + 1) + (long long)threadIdx.x * n]);
+      svp[threadIdx.x] = t_conj(Vp[(j + 1) + (long long)threadIdx.x * n]);
+    }
+    __syncthreads();
+    T cross = zero;
+    for (int k = 0; k < i; ++k) cross = t_add(cross, t_add(t_mul(t_conj(sg1[k]), sg2[k]), t_mul(t_conj(sg2[k]), sg1[k])));
+    const T a2 = t_scale(t_sub(s0, cross), -0.5 * t_norm2(tj));
+    if (threadIdx.x == 0) {   // row j+1 of the new W column (every CTA needs it for the next column's update)
+      T pt = off ? zero : p[0];
+      for (int k = 0; k < i; ++k) pt = t_sub(pt, t_add(t_mul(t_conj(svp[k]), sg1[k]), t_mul(t_conj(swp[k]), sg2[k])));
+      const T wf0 = off ? zero : t_add(t_mul(tj, pt), a2);
+      swp[i] = t_conj(wf0);
+      svp[i] = one;
+    }
+    __syncthreads();
+    const bool next = (j + 1 <= n - 1) && (i + 1 < nbk || j + 1 == n - 1);
+    double part = 0.0;
+    for (long long r = (j + 1) + gtid; r < n; r += GT) {
+      const long long rr = r - (j + 1);
+      T pt = off ? zero : p[rr];
+      T an = next ? A[r + (j + 1) * n] : zero;
+      int k = 0;
+      for (; k + 8 <= i; k += 8) {      // 16 independent loads in flight per thread (the panel columns are L2-resident)
+        T vk[8], wk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { vk[u] = Vp[r + (long long)(k + u) * n]; wk[u] = W[r + (long long)(k + u) * n]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          pt = t_sub(pt, t_add(t_mul(vk[u], sg1[k + u]), t_mul(wk[u], sg2[k + u])));
+          an = t_sub(an, t_add(t_mul(vk[u], swp[k + u]), t_mul(wk[u], svp[k + u])));
+        }
+      }
+      for (; k < i; ++k) {
+        const T vk = Vp[r + (long long)k * n], wk = W[r + (long long)k * n];
+        pt = t_sub(pt, t_add(t_mul(vk, sg1[k]), t_mul(wk, sg2[k])));
+        an = t_sub(an, t_add(t_mul(vk, swp[k]), t_mul(wk, svp[k])));
+      }
+      const T vr = rr == 0 ? one : t_mul(x[rr], sc);
+      const T wf = off ? zero : t_add(t_mul(tj, pt), t_mul(a2, vr));
+      W[r + (long long)i * n] = wf; Wn[r + (long long)i * n] = t_scale(wf, -1.0);
+      Vp[r + (long long)i * n] = vr; Vn[r + (long long)i * n] = t_scale(vr, -1.0);
+      if (next) {
+        an = t_sub(an, t_add(t_mul(vr, swp[i]), t_mul(wf, svp[i])));
+        A[r + (j + 1) * n] = an;
+        if (r >= j + 3) part += t_norm2(an);
+      }
+    }
+    const double sblk = tri_block_sum(part, redd);
+    if (threadIdx.x == 0) partial[blockIdx.x] = sblk;
+    grid.sync();
+  }
+  if (j0 + nbk == n - 1 && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
 }
 
 // bounds[0..3] = Gershgorin lower / upper bound (widened), pivmin, ||T||_1
@@ -161,30 +323,39 @@ __global__ void __launch_bounds__(256) tri_bounds_kernel(const double* __restric
   }
 }
 
-// thread k -> k-th smallest eigenvalue of T (Sturm count bisection; every lane walks the same d/e stream: broadcast loads)
+// warp k -> k-th smallest eigenvalue of T by 32-way multisection on the Sturm count: every round the lanes evaluate the count
+// at 32 interior points of [lo, hi] and the interval shrinks 33x, so ~11 sequential passes over (d, e) reach eps/4 * ||T||
+// (plain bisection needs ~55; the pass is a division-latency-bound recurrence, so passes are what cost).
 __global__ void __launch_bounds__(128) bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, long long n,
                                                      const double* __restrict__ bounds, double* __restrict__ w) {
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (k >= n) return;
   double lo = bounds[0], hi = bounds[1];
   const double pivmin = bounds[2];
   const double atol = 5.6e-17 * bounds[3];     // eps/4 * ||T||: the absolute accuracy a backward-stable solver delivers on rho
-  for (int it = 0; it < 200; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (mid <= lo || mid >= hi || hi - lo <= atol) break;
+  for (int it = 0; it < 64; ++it) {
+    if (hi - lo <= atol) break;
+    const double step = (hi - lo) * (1.0 / 33.0);
+    const double x = lo + step * (double)(lane + 1);
+    if (!(step > 0.0) || !(lo + step > lo)) break;
     long long cnt = 0;
-    double q = __ldg(d) - mid;
+    double q = __ldg(d) - x;
     if (fabs(q) < pivmin) q = -pivmin;
     if (q < 0.0) ++cnt;
     for (long long i = 1; i < n; ++i) {
       const double ee = __ldg(e + i - 1);
-      q = __ldg(d + i) - mid - ee * ee / q;
+      q = __ldg(d + i) - x - ee * ee / q;
       if (fabs(q) < pivmin) q = -pivmin;
       if (q < 0.0) ++cnt;
     }
-    if (cnt > k) hi = mid; else lo = mid;
+    // counts are monotone in x: lanes 0..t-1 still have at most k eigenvalues below their point
+    const int t = __popc(__ballot_sync(0xffffffffu, cnt <= k));
+    const double nlo = t == 0 ? lo : lo + step * (double)t;
+    const double nhi = t == 32 ? hi : lo + step * (double)(t + 1);
+    lo = nlo; hi = nhi;
   }
-  w[k] = 0.5 * (lo + hi);
+  if (lane == 0) w[k] = 0.5 * (lo + hi);
 }
 
 __device__ __forceinline__ double hash_unit(unsigned long long i, unsigned long long j) {
@@ -311,6 +482,75 @@ __global__ void backtransform_kernel(const void* __restrict__ A_, long long n, c
   }
   if (use_smem)
     for (long long i = lane; i < n; i += 32) V[c * n + i] = z[i];
+}
+
+// ---- blocked back-transformation helpers (the O(n^2 m) work itself runs on the DMMA GEMM) ----------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) zt_to_v_kernel(const double* __restrict__ Zt, long long n, long long m, void* __restrict__ V_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  T* V = reinterpret_cast<T*>(V_);
+  // 32 x 32 tiles through shared memory so that both the read ([i*m + c], c fastest) and the write ([i + c*n], i fastest) coalesce
+  __shared__ double tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long i = i0 + r, c = c0 + tx;
+    tile[r][tx] = (i < n && c < m) ? Zt[i * m + c] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const long long c = c0 + r, i = i0 + tx;
+    if (i < n && c < m) V[i + c * n] = t_scale(t_one(T()), tile[tx][r]);
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) form_y_kernel(const void* __restrict__ A_, long long n, const void* __restrict__ tau_,
+                                                     const void* __restrict__ scl_, long long j0, int nbk, void* __restrict__ Y_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const T* A = reinterpret_cast<const T*>(A_);
+  const T* tau = reinterpret_cast<const T*>(tau_);
+  const T* scl = reinterpret_cast<const T*>(scl_);
+  T* Y = reinterpret_cast<T*>(Y_);
+  const long long r0 = j0 + 1, len = n - r0;
+  const int i = blockIdx.y;                 // reflector j0 + i
+  const long long j = j0 + i;
+  const T sc = scl[j];
+  const bool off = t_is_zero(tau[j]);
+  for (long long rr = (long long)blockIdx.x * 256 + threadIdx.x; rr < len; rr += (long long)gridDim.x * 256) {
+    const long long r = r0 + rr;
+    T y = t_zero(T());
+    if (!off) {
+      if (r == j + 1) y = t_one(T());
+      else if (r > j + 1) y = t_mul(A[r + j * n], sc);
+    }
+    Y[rr + (long long)i * len] = y;
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(64) wy_t_kernel(const void* __restrict__ S_, const void* __restrict__ tau_, int nb, void* __restrict__ Tn_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const T* S = reinterpret_cast<const T*>(S_);
+  const T* tau = reinterpret_cast<const T*>(tau_);
+  T* Tn = reinterpret_cast<T*>(Tn_);
+  extern __shared__ __align__(16) char wsm[];
+  T* Ts = reinterpret_cast<T*>(wsm);
+  const int r = threadIdx.x;
+  for (int k = r; k < nb * nb; k += 64) Ts[k] = t_zero(T());
+  __syncthreads();
+  for (int i = 0; i < nb; ++i) {
+    const T ti = tau[i];
+    if (r < i) {
+      T tmp = t_zero(T());
+      for (int c = r; c < i; ++c) tmp = t_add(tmp, t_mul(Ts[r + c * nb], S[c + i * nb]));
+      Ts[r + i * nb] = t_scale(t_mul(ti, tmp), -1.0);
+    } else if (r == i) {
+      Ts[i + i * nb] = ti;
+    }
+    __syncthreads();
+  }
+  for (int k = r; k < nb * nb; k += 64) Tn[k] = t_scale(Ts[k], -1.0);
 }
 
 }  // namespace cb200

@@ -409,6 +409,54 @@ static void backtransform_t(const T* A, int64_t n, const T* tau, const T* scl, c
   }
 }
 
+template <class T>
+static void zt_to_v_t(const double* Zt, int64_t n, int64_t m, T* V) {
+  for (int64_t c = 0; c < m; ++c)
+    for (int64_t i = 0; i < n; ++i) V[i + c * n] = T(Zt[i * m + c]);
+}
+void launch_zt_to_v(Backend* b, bool cplx, const double* Zt, int64_t n, int64_t m, void* V) {
+  b->launches++;
+  if (cplx) zt_to_v_t<cd>(Zt, n, m, (cd*)V); else zt_to_v_t<double>(Zt, n, m, (double*)V);
+}
+template <class T>
+static void form_y_t(const T* A, int64_t n, const T* tau, const T* scl, int64_t j0, int nbk, T* Y) {
+  const int64_t r0 = j0 + 1, len = n - r0;
+  for (int i = 0; i < nbk; ++i) {
+    const int64_t j = j0 + i;
+    for (int64_t rr = 0; rr < len; ++rr) {
+      const int64_t r = r0 + rr;
+      T y(0);
+      if (!(tau[j] == T(0))) {
+        if (r == j + 1) y = T(1);
+        else if (r > j + 1) y = A[r + j * n] * scl[j];
+      }
+      Y[rr + (int64_t)i * len] = y;
+    }
+  }
+}
+void launch_form_y(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, int64_t j0, int nbk, void* Y) {
+  b->launches++;
+  if (cplx) form_y_t<cd>((const cd*)A, n, (const cd*)tau, (const cd*)scl, j0, nbk, (cd*)Y);
+  else form_y_t<double>((const double*)A, n, (const double*)tau, (const double*)scl, j0, nbk, (double*)Y);
+}
+template <class T>
+static void wy_t_t(const T* S, const T* tau, int nb, T* Tn) {
+  std::vector<T> Ts((size_t)nb * nb, T(0));
+  for (int i = 0; i < nb; ++i) {
+    for (int r = 0; r < i; ++r) {
+      T tmp(0);
+      for (int c = r; c < i; ++c) tmp += Ts[r + (size_t)c * nb] * S[c + (size_t)i * nb];
+      Ts[r + (size_t)i * nb] = -tau[i] * tmp;
+    }
+    Ts[i + (size_t)i * nb] = tau[i];
+  }
+  for (size_t k = 0; k < Ts.size(); ++k) Tn[k] = -Ts[k];
+}
+void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg) {
+  b->launches++;
+  if (cplx) wy_t_t<cd>((const cd*)S, (const cd*)tau_j0, nbk, (cd*)Tneg); else wy_t_t<double>((const double*)S, (const double*)tau_j0, nbk, (double*)Tneg);
+}
+
 void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V) {
   b->launches++;
   if (cplx) backtransform_t<cd>((const cd*)A, n, (const cd*)tau, (const cd*)scl, Zt, m, (cd*)V);
