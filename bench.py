@@ -253,6 +253,31 @@ def main():
     e2e_v = falg * args.steps / float(e2e_t.item()) / 1e12
     nbytes = int(phi.size * phi.itemsize)
 
+    # ---- one complete bond update resident on the device (davidson -> svdBond -> makeL): the unit a DMRG sweep is made of
+    bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)           # warm-up (grows the memory pool)
+    barrier()
+    bu = bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)
+    barrier()
+    bu_tot = bu["matvec"] + bu["level1"] + bu["trunc"] + bu["env"]
+    bu_t = torch.tensor([bu_tot], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(bu_t, op=dist.ReduceOp.MAX)
+    L_chain = WORKLOADS[args.workload][2]
+    bond_update = {"matvec_s": bu["matvec"], "davidson_level1_s": bu["level1"], "truncation_s": bu["trunc"], "env_update_s": bu["env"],
+                   "total_s": float(bu_t.item()), "kept_states": bu["m"], "matvecs": 3,
+                   "sweep_s_if_all_bonds_at_D": 2 * (L_chain - 1) * float(bu_t.item()),
+                   "note": "one two-site bond update (3 matvecs, Gram-Schmidt, truncation to maxdim=D, environment update) with everything "
+                           "resident in HBM; the sweep figure is 2(L-1) such updates, an upper bound since the edge bonds are smaller"}
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_%s_summary.json" % args.workload)) as f:
+            traffic = json.load(f).get("dram_bytes_per_matvec_gemm_launches")
+    except Exception:
+        pass
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum of the L-stage + R-stage launches, ncu --set full (profiles/)" if traffic else None
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -268,7 +293,7 @@ def main():
                            "parallelism": "single GPU" if world == 1 else "matvec row-sharded x%d, exchange=%s" % (world, args.exchange)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "wall_s_timed_region": wall}
         print(json.dumps(line), flush=True)
     bond.close()
     if world > 1:

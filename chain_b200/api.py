@@ -251,6 +251,18 @@ def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
     return energy.value, MPS(sites, charges, nq=H.nq, center=1)
 
 
+def calc_ee(psi, site_charges=None, ctx=None):
+    """CalcEE of /root/reference/src/utility.cpp:5-27 on the device: entropy of every cut (p > 1e-12 rule, natural log)."""
+    ctx = ctx or default_context()
+    keep = []
+    pc = psi._to_c(keep)
+    d = psi.sites[0].shape[1]
+    sq = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
+    out = np.zeros(psi.n - 1)
+    ctx.check(ctx.lib.cb200_mps_entropies(ctx.h, C.byref(pc), d, i32ptr(sq), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out.tolist()
+
+
 class Bond:
     """One two-site problem resident on the device (cb200_bond): LocalMPO::product, davidson, svdBond, makeL/makeR."""
 

@@ -166,6 +166,16 @@ int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_
   });
 }
 
+int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double* out) {
+  if (!ctx || !psi || !out) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    bool cx = false;
+    HostMPS h = to_host_mps(psi, psi->nq, d, &cx);
+    std::vector<double> ee = mps_entropies(&ctx->c, psi->nq, d, site_charge, h, cx);
+    for (size_t i = 0; i < ee.size(); ++i) out[i] = ee[i];
+  });
+}
+
 int32_t cb200_result_nsites(const cb200_result* r) { return r ? r->r->psi.n : 0; }
 int32_t cb200_result_dtype(const cb200_result* r) { return r && r->r->cplx ? 1 : 0; }
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link) {

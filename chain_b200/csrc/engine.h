@@ -291,4 +291,7 @@ struct MpoIn {
 std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<HostMPS>& prev, const std::vector<bool>& prev_cplx,
                                      const HostMPS& psi0, bool psi0_cplx, const std::vector<SweepParams>& sweeps, double weight);
 
+// CalcEE (src/utility.cpp:5-27) on the device truncation path
+std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx);
+
 }  // namespace cb200

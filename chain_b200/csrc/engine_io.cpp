@@ -542,4 +542,44 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   return res;
 }
 
+// ------------------------------------------------------------------------------------------------ CalcEE
+// Entanglement entropy of every cut, as /root/reference/src/utility.cpp:5-27 computes it: move the orthogonality centre along
+// the chain, take the Schmidt spectrum p = sigma^2 of each cut, S = -sum_{p > 1e-12} p ln p.  The spectrum comes from the same
+// device truncation path as the sweep (rho eigenvalues; cutoff 1e-15 only drops numerically-zero directions).
+std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx) {
+  const int n = psi.n;
+  if (n < 2) fail(-2, "entropies need at least 2 sites");
+  SiteInfo S = SiteInfo::make(nq, d, site_charge);
+  std::vector<DevSite3> A(n);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j].data(), A[j]);
+  auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
+    pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
+    phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
+    two_site(c, cplx, A[i], A[i + 1], pl, phi.p);
+  };
+  if (psi.center != 1) {
+    for (int i = n - 2; i >= 0; --i) {
+      PhiLayout pl; Buf phi;
+      phi_of(i, pl, phi);
+      SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 1, INT64_MAX / 4, 1, 1e-20, true);
+      A[i] = std::move(sr.A);
+      A[i + 1] = std::move(sr.B);
+    }
+  }
+  std::vector<double> out;
+  for (int i = 0; i + 1 < n; ++i) {
+    PhiLayout pl; Buf phi;
+    phi_of(i, pl, phi);
+    SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 0, INT64_MAX / 4, 1, 1e-15);
+    double sv = 0;
+    for (double p : sr.spectrum)
+      if (p > 1e-12) sv += -p * std::log(p);
+    out.push_back(sv);
+    A[i] = std::move(sr.A);
+    A[i + 1] = std::move(sr.B);
+  }
+  check_dev(c);
+  return out;
+}
+
 }  // namespace cb200

@@ -110,6 +110,9 @@ typedef struct cb200_result cb200_result;   /* owns the optimised MPS until cb20
 
 int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_t nprev, const cb200_mps* psi0,
                const cb200_sweep* sweeps, int32_t nsweep, double weight, double* energy, cb200_result** out);
+/* CalcEE of /root/reference/src/utility.cpp:5-27: von Neumann entropy of every cut b = 1..n-1 (p > 1e-12 rule, natural log),
+ * Schmidt spectra from the device truncation path; out has n-1 entries */
+int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double* out);
 int32_t cb200_result_nsites(const cb200_result* r);
 int32_t cb200_result_dtype(const cb200_result* r);                                  /* 0 f64, 1 c128 */
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link);                 /* link in [0, n] */

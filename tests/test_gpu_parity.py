@@ -133,3 +133,18 @@ def test_truncation_roundtrip_large(gpu_ctx):
         s = np.linalg.svd(phi.reshape(D * d, d * D), compute_uv=False)[:r]
         assert np.allclose(np.sort(spec)[::-1], s ** 2, atol=1e-13)
     B.close()
+
+
+def test_driver_config1_on_gpu(gpu_ctx, tmp_path):
+    # BASELINE config 1 end to end through the stand-in driver: schedule of src/dmrg.h:527-653, .en/.ee writers, CalcEE on the device
+    import test_driver
+    sim, states = test_driver.run_config1(gpu_ctx, tmp_path)
+    assert gpu_ctx.launches > 0
+
+
+def test_calc_ee_on_gpu_matches_oracle(gpu_ctx):
+    st, bc, n, cp, q, nst, product = common.DMRG_CASES[4]
+    site, W, qk = common.build_model(st, bc, n, cp)
+    psi0 = common.warm_start(site, W, n, q, seed=7)
+    eo, po = od.dmrg(W, [], psi0, od.Sweeps(4, [10, 20, 40, 80], [1e-5, 1e-6, 1e-7, 1e-8]))
+    assert np.abs(np.array(od.calc_ee(po)) - np.array(cb.calc_ee(common.to_cb(po), site.charges, ctx=gpu_ctx))).max() <= 1e-10
