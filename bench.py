@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_emit = None
+
 WORKLOADS = {
     # name: (site, bc, L, couplings, D, description)
     "cfg2": ("haagerupq", "p", 8, [0.0, -1.0, 0.0], 1600, "haagerupq p j=(0,-1,0) synthetic D=1600 Z3(534,533,533) k=26(10,8,8) c128 (BASELINE configs[1])"),
@@ -133,7 +135,7 @@ def run_reference(args, rank):
             "config": {"workload": desc, "note": "each step = a bounded sample of the matvec's block-pair GEMMs on the host cores"},
             "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": cbz.host_threads(), "kind": "port", "sample": sample + " per step"},
             "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def build_dims_only(name):
@@ -149,6 +151,14 @@ def build_dims_only(name):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print there (e.g. "NCCL version ...") is sent to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    global _emit
+    _emit = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -294,7 +304,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "wall_s_timed_region": wall}
-        print(json.dumps(line), flush=True)
+        emit(line)
     bond.close()
     if world > 1:
         dist.destroy_process_group()

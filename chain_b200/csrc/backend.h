@@ -54,6 +54,10 @@ void shard_barrier(Backend*);
 // the R-stage GEMM (A not transposed, B transposed) with its C tiles stored to every destination in `peers`
 void launch_gemm_peer(Backend*, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* d_tasks, int ntasks,
                       const GemmSeg* d_segs, int total_tiles);
+// broadcast `bytes` of device memory from rank `root` to every rank (in place): peer stores into the landing half `which` + the flag
+// barrier (bytes must fit one landing half; the engine chunks), or ncclBroadcast
+void shard_bcast_p2p(Backend*, void* buf, int64_t bytes, int root, int which);
+void nccl_bcast(Backend*, void* buf, int64_t bytes, int root);
 // NCCL, loaded at run time (libnccl.so.2): unique id for rank 0, communicator, in-place sum all-reduce on the context stream
 int nccl_unique_id(Backend*, void* out128);
 int nccl_init(Backend*, const void* uid128, int rank, int world);

@@ -44,6 +44,7 @@ struct Backend {
   ncclResult_t (*p_ncclGetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*p_ncclCommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*p_ncclAllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclBroadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
   const char* (*p_ncclGetErrorString)(ncclResult_t) = nullptr;
 };
@@ -275,13 +276,45 @@ void shard_barrier(Backend* b) {
   CB_LAUNCH_CHECK(b, "shard_barrier_kernel");
 }
 
+static void nccl_fail(Backend* b, const char* what, ncclResult_t r);
+// 16-byte grid-stride copy of one source buffer into every destination (the root's broadcast over NVLink)
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerBases dst, const uint4* __restrict__ src, long long n16) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256) {
+    const uint4 v = src[i];
+    for (int r = 0; r < dst.n; ++r) reinterpret_cast<uint4*>(dst.base[r])[i] = v;
+  }
+}
+
+void shard_bcast_p2p(Backend* b, void* buf, int64_t bytes, int root, int which) {
+  if (b->world <= 1 || bytes <= 0) return;
+  if (bytes > b->landing_each) { set_err(b, "shard_bcast_p2p: message larger than the landing area", cudaErrorInvalidValue); return; }
+  const int64_t padded = (bytes + 15) / 16 * 16;     // buffers come from the pool allocator: at least 16-byte granular
+  if (b->rank == root) {
+    PeerBases pb;
+    shard_peer_bases(b, which, &pb);
+    const long long n16 = padded / 16;
+    const int blocks = (int)std::min<long long>((n16 + 255) / 256, 148 * 8);
+    peer_push_kernel<<<blocks, 256, 0, b->stream>>>(pb, (const uint4*)buf, n16);
+    CB_LAUNCH_CHECK(b, "peer_push_kernel");
+  }
+  shard_barrier(b);
+  if (b->rank != root) CB_CHECK(b, cudaMemcpyAsync(buf, shard_landing(b, which), (size_t)bytes, cudaMemcpyDeviceToDevice, b->stream));
+}
+
+void nccl_bcast(Backend* b, void* buf, int64_t bytes, int root) {
+  if (!b->comm || !b->p_ncclBroadcast) { set_err(b, "nccl_bcast: no communicator", cudaErrorInvalidValue); return; }
+  ncclResult_t r = b->p_ncclBroadcast(buf, buf, (size_t)bytes, ncclChar, root, b->comm, b->stream);
+  if (r != ncclSuccess) nccl_fail(b, "ncclBroadcast", r);
+  b->launches++;
+}
+
 static bool nccl_load(Backend* b) {
   if (b->nccl_lib) return true;
   b->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!b->nccl_lib) b->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!b->nccl_lib) { set_err(b, "dlopen(libnccl.so.2) failed", cudaErrorUnknown); return false; }
 #define CB_SYM(name) *(void**)(&b->p_##name) = dlsym(b->nccl_lib, #name)
-  CB_SYM(ncclGetUniqueId); CB_SYM(ncclCommInitRank); CB_SYM(ncclAllReduce); CB_SYM(ncclCommDestroy); CB_SYM(ncclGetErrorString);
+  CB_SYM(ncclGetUniqueId); CB_SYM(ncclCommInitRank); CB_SYM(ncclAllReduce); CB_SYM(ncclBroadcast); CB_SYM(ncclCommDestroy); CB_SYM(ncclGetErrorString);
 #undef CB_SYM
   if (!b->p_ncclGetUniqueId || !b->p_ncclCommInitRank || !b->p_ncclAllReduce) { set_err(b, "libnccl: missing symbols", cudaErrorUnknown); return false; }
   return true;
@@ -886,13 +919,14 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   const int blocks = (int)std::min<int64_t>(grid_blocks[cplx], std::max<int64_t>(1, (n + TRI_WARPS - 1) / TRI_WARPS));
   const int64_t nref = n - 1;
   const int npanel = (int)((nref + NB - 1) / NB);
-  char* pan = (char*)dev_alloc(b, 4 * es * (size_t)n * NB);          // Vp | W | Vn | Wn, each n x NB (ld n)
+  char* pan = (char*)dev_alloc(b, 6 * es * (size_t)n * NB);          // Vp | W | Vn | Wn (n x NB, ld n) | Vt | Wt (NB x n, ld NB)
   char* gbuf = (char*)dev_alloc(b, es * 128);
   double* partial = (double*)dev_alloc(b, sizeof(double) * (size_t)blocks);
   GemmTask* d_tasks = (GemmTask*)dev_alloc(b, sizeof(GemmTask) * (size_t)npanel);
   GemmSeg* d_segs = (GemmSeg*)dev_alloc(b, sizeof(GemmSeg) * 2 * (size_t)npanel);
   if (!pan || !gbuf || !partial || !d_tasks || !d_segs) return true;   // the allocation error is already recorded
   void* Vp = pan; void* W = pan + es * (size_t)n * NB; void* Vn = pan + 2 * es * (size_t)n * NB; void* Wn = pan + 3 * es * (size_t)n * NB;
+  void* Vt = pan + 4 * es * (size_t)n * NB; void* Wt = pan + 5 * es * (size_t)n * NB;
   // task list of the rank-2nb updates: A[t0:, t0:] += conj( conj(Vn) W^T + conj(Wn) Vp^T ) = -(V W^H + W V^H)
   std::vector<GemmTask> tasks(npanel);
   std::vector<GemmSeg> segs(2 * (size_t)npanel);
@@ -922,7 +956,7 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   for (int pi = 0; pi < npanel; ++pi) {
     long long j0 = (long long)pi * NB;
     int nbk = (int)std::min<int64_t>(NB, nref - j0);
-    void* args[] = {&A, &nn, &j0, &nbk, &d, &e, &tau, &scl, &p, &gbuf, &partial, &Vp, &W, &Vn, &Wn};
+    void* args[] = {&A, &nn, &j0, &nbk, &d, &e, &tau, &scl, &p, &gbuf, &partial, &Vp, &W, &Vn, &Wn, &Vt, &Wt};
     CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(TRI_THREADS), args, 0, b->stream));
     CB_LAUNCH_CHECK(b, "tridiag_panel_kernel");
     const int64_t t0 = j0 + nbk;

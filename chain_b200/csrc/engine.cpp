@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -213,35 +214,33 @@ struct MixBuilder {
   std::vector<MixIn> ins;
   std::vector<MixOut> outs;
   std::vector<MixEntry> ents;
-  std::map<std::pair<int64_t, int64_t>, int> slot_of;   // (off, rstride) -> slot of the current panel
+  std::vector<int> slot_of;   // input key (dense index chosen by the caller, < nkeys) -> slot of the current panel
   double flops = 0, flops_full = 0;
   double ratio = 1.0;
   bool cplx;
   explicit MixBuilder(bool c) : cplx(c) {}
-  void begin_panel(int64_t rows, int64_t nr) {
+  void begin_panel(int64_t rows, int64_t nr, int64_t nkeys) {
     MixPanel p{};
     p.rows = (int32_t)rows; p.nr = (int32_t)nr;
     p.out_begin = (int32_t)outs.size();
     p.in_begin = (int32_t)ins.size();
     panels.push_back(p);
-    slot_of.clear();
+    slot_of.assign((size_t)nkeys, -1);
   }
   void begin_out(int64_t off, int64_t rstride) {
     MixOut o{};
     o.off = off; o.rstride = rstride; o.e_begin = (int32_t)ents.size();
     outs.push_back(o);
   }
-  void entry(int64_t in_off, int64_t in_rstride, cplx_t coef) {
-    auto key = std::make_pair(in_off, in_rstride);
-    auto it = slot_of.find(key);
-    int slot;
-    if (it == slot_of.end()) {
+  void entry(int64_t key, int64_t in_off, int64_t in_rstride, cplx_t coef) {
+    int slot = slot_of[(size_t)key];
+    if (slot < 0) {
       slot = (int)ins.size() - panels.back().in_begin;
-      slot_of[key] = slot;
+      slot_of[(size_t)key] = slot;
       MixIn mi{};
       mi.off = in_off; mi.rstride = in_rstride;
       ins.push_back(mi);
-    } else slot = it->second;
+    }
     MixEntry e{};
     e.slot = slot; e.cre = coef.real(); e.cim = coef.imag();
     ents.push_back(e);
@@ -333,8 +332,87 @@ double norm2_dev(Ctx* c, bool cplx, const void* v, int64_t n) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ H_eff matvec
+OmegaMap build_omega(const HostW& W1, const HostW& W2) {
+  const int d = W1.d;
+  static const bool ptimes = getenv("CB200_PLAN_TIMES") != nullptr;
+  double pt0 = now_s();
+  auto lap = [&](const char* what) { if (ptimes) { double t = now_s(); fprintf(stderr, "  omega %s %.3f ms\n", what, (t - pt0) * 1e3); pt0 = t; } };
+  const int64_t kl = W1.KL.total(), km = W1.KR.total(), kr = W2.KR.total();
+  const int64_t nin = kl * d * d, nout = kr * d * d;
+  // dense scratch omega[in + nin*out], kept between calls (a fresh 14 MB vector costs more in page faults than the arithmetic)
+  static thread_local std::vector<cplx_t> omega;
+  omega.assign((size_t)nin * nout, cplx_t(0, 0));
+  struct E1 { int64_t a; int t, s; cplx_t v; };
+  struct E2 { int t, s; int64_t app; cplx_t v; };
+  std::vector<std::vector<E1>> n1(km);
+  std::vector<std::vector<E2>> n2(km);
+  {   // W[a + kl*(t + d*(s + d*a'))] walked in storage order
+    const cplx_t* w1 = W1.w.data();
+    for (int64_t ap = 0; ap < km; ++ap)
+      for (int s = 0; s < d; ++s)
+        for (int t = 0; t < d; ++t)
+          for (int64_t a = 0; a < kl; ++a, ++w1)
+            if (*w1 != cplx_t(0, 0)) n1[ap].push_back({a, t, s, *w1});
+    const cplx_t* w2 = W2.w.data();
+    for (int64_t app = 0; app < kr; ++app)
+      for (int s = 0; s < d; ++s)
+        for (int t = 0; t < d; ++t)
+          for (int64_t ap = 0; ap < km; ++ap, ++w2)
+            if (*w2 != cplx_t(0, 0)) n2[ap].push_back({t, s, app, *w2});
+  }
+  lap("nonzeros");
+  if (ptimes) { size_t a = 0, b = 0; for (auto& v : n1) a += v.size(); for (auto& v : n2) b += v.size(); fprintf(stderr, "  nnz W1 %zu W2 %zu\n", a, b); }
+  // y outermost: for a fixed W2 entry the updates fall into d rows of omega and one kl*d-long column segment (cache-resident)
+  for (int64_t ap = 0; ap < km; ++ap)
+    for (const auto& y : n2[ap])
+      for (const auto& x : n1[ap]) {
+        const int64_t in = x.a + kl * (x.s + (int64_t)d * y.s);
+        const int64_t out = y.app + kr * (x.t + (int64_t)d * y.t);
+        omega[(size_t)in + (size_t)nin * out] += x.v * y.v;
+      }
+  lap("products");
+  // Contracting the (dense, SVD-mixed) MPO channel index restores the sparse operator-string structure, but only up
+  // to rounding: entries below 1e-14 of the largest one are exact zeros of the Hamiltonian and are dropped (8x fewer
+  // multiply-adds for the Haagerup MPOs).
+  double omax2 = 0;
+  for (const auto& v : omega) omax2 = std::max(omax2, std::norm(v));
+  const double thr2 = 1e-28 * omax2;
+  OmegaMap om;
+  om.nin = nin; om.nout = nout;
+  om.rows.resize((size_t)nout);
+  for (int64_t out = 0; out < nout; ++out) {
+    const cplx_t* row = &omega[(size_t)nin * out];
+    for (int64_t in = 0; in < nin; ++in)
+      if (std::norm(row[in]) > thr2) om.rows[(size_t)out].push_back({in, row[in]});
+  }
+  lap("compress");
+  return om;
+}
+
+std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2) {
+  auto mix = [](uint64_t h, const void* p, size_t bytes) {   // FNV-1a over 8-byte words
+    const uint64_t* w = (const uint64_t*)p;
+    for (size_t i = 0; i < bytes / 8; ++i) { h ^= w[i]; h *= 0x100000001b3ull; }
+    return h;
+  };
+  uint64_t h = 0xcbf29ce484222325ull;
+  h = mix(h, W1.w.data(), W1.w.size() * sizeof(cplx_t));
+  h = mix(h, W2.w.data(), W2.w.size() * sizeof(cplx_t));
+  const uint64_t dims[4] = {(uint64_t)W1.KL.total(), (uint64_t)W1.KR.total(), (uint64_t)W2.KR.total(), (uint64_t)W1.d};
+  h = mix(h, dims, sizeof(dims));
+  auto it = c->omega_cache.find(h);
+  if (it != c->omega_cache.end()) return it->second;
+  if (c->omega_cache.size() > 512) c->omega_cache.clear();
+  auto om = std::make_shared<OmegaMap>(build_omega(W1, W2));
+  c->omega_cache[h] = om;
+  return om;
+}
+
 void Bond::plan() {
   Backend* be = ctx->be;
+  static const bool ptimes = getenv("CB200_PLAN_TIMES") != nullptr;
+  double pt0 = now_s();
+  auto lap = [&](const char* what) { if (ptimes) { double t = now_s(); fprintf(stderr, "plan %s %.3f ms\n", what, (t - pt0) * 1e3); pt0 = t; } };
   const int d = S->d;
   Llay.build(Dl, Kl);
   Rlay.build(Dr, Kr);
@@ -415,54 +493,21 @@ void Bond::plan() {
     gb.finish(be, g1, false, false);
     flops_alg_full = gb.flops_full * (cplx ? 4.0 : 1.0);
   }
-  // ---- Omega = W1 (x) W2 contracted over the middle MPO link, as a sparse map (a,s1,s2) -> (a'',t1,t2)
-  const int64_t kl = Kl.total(), km = Km.total(), kr = Kr.total();
-  const int64_t nin = kl * d * d, nout = kr * d * d;
-  std::vector<cplx_t> omega((size_t)nin * nout, cplx_t(0, 0));   // omega[in + nin*out]
-  {
-    struct E1 { int64_t a; int t, s; cplx_t v; };
-    struct E2 { int t, s; int64_t app; cplx_t v; };
-    std::vector<std::vector<E1>> n1(km);
-    std::vector<std::vector<E2>> n2(km);
-    for (int64_t ap = 0; ap < km; ++ap)
-      for (int s = 0; s < d; ++s)
-        for (int t = 0; t < d; ++t)
-          for (int64_t a = 0; a < kl; ++a) {
-            cplx_t v = W1->at(a, t, s, ap);
-            if (v != cplx_t(0, 0)) n1[ap].push_back({a, t, s, v});
-          }
-    for (int64_t app = 0; app < kr; ++app)
-      for (int s = 0; s < d; ++s)
-        for (int t = 0; t < d; ++t)
-          for (int64_t ap = 0; ap < km; ++ap) {
-            cplx_t v = W2->at(ap, t, s, app);
-            if (v != cplx_t(0, 0)) n2[ap].push_back({t, s, app, v});
-          }
-    for (int64_t ap = 0; ap < km; ++ap)
-      for (const auto& x : n1[ap])
-        for (const auto& y : n2[ap]) {
-          const int64_t in = x.a + kl * (x.s + (int64_t)d * y.s);
-          const int64_t out = y.app + kr * (x.t + (int64_t)d * y.t);
-          omega[(size_t)in + (size_t)nin * out] += x.v * y.v;
-        }
-  }
-  // Contracting the (dense, SVD-mixed) MPO channel index restores the sparse operator-string structure, but only up
-  // to rounding: entries below 1e-14 of the largest one are exact zeros of the Hamiltonian and are dropped (8x fewer
-  // multiply-adds for the Haagerup MPOs).
-  {
-    double omax = 0;
-    for (const auto& v : omega) omax = std::max(omax, std::abs(v));
-    const double thr = 1e-14 * omax;
-    for (auto& v : omega)
-      if (std::abs(v) <= thr) v = cplx_t(0, 0);
-  }
+  // ---- Omega = W1 (x) W2 contracted over the middle MPO link, as a sparse map (a,s1,s2) -> (a'',t1,t2); it depends on the MPO
+  // only, so the sweep driver computes it once per site pair and hands it in (omega_cache)
+  const int64_t kl = Kl.total(), kr = Kr.total();
+  const int64_t nin = kl * d * d;
+  OmegaMap own_omega;
+  if (!omega_cache) own_omega = build_omega(*W1, *W2);
+  const OmegaMap& om = omega_cache ? *omega_cache : own_omega;
+  lap("omega");
   // ---- mix panels (ql', qr)
   {
     MixBuilder mb(cplx);
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qr = 0; qr < nq; ++qr) {
         mb.ratio = ratio[qlp];
-        mb.begin_panel(Dlo.dim[qlp], Dr.dim[qr]);
+        mb.begin_panel(Dlo.dim[qlp], Dr.dim[qr], nin);
         for (int qa2 = 0; qa2 < nq; ++qa2) {
           const int qrp = qadd(qr, qa2, nq);
           const size_t id2 = ((size_t)qlp * nq + qa2) * nq + qr;
@@ -474,9 +519,8 @@ void Bond::plan() {
               const int t1s = S->srow[qd_out][sro].first, t2s = S->srow[qd_out][sro].second;
               const int64_t out = app + kr * (t1s + (int64_t)d * t2s);
               mb.begin_out(t2off[id2] + Dlo.dim[qlp] * sro + M2 * a2l, M2 * Kr.dim[qa2]);
-              const cplx_t* row = &omega[(size_t)nin * out];
-              for (int64_t in = 0; in < nin; ++in) {
-                if (row[in] == cplx_t(0, 0)) continue;
+              for (const auto& ent : om.rows[out]) {
+                const int64_t in = ent.first;
                 const int64_t a = in % kl;
                 const int s1 = (int)((in / kl) % d), s2 = (int)(in / (kl * d));
                 // internal MPO link value a -> (qa, a_loc)
@@ -489,7 +533,7 @@ void Bond::plan() {
                 const int64_t M1 = t1M[qa * nq + ql];
                 const int64_t sri = S->srow_index[(size_t)s1 * d + s2];
                 const int64_t nsi = S->ns(qd_in);
-                mb.entry(t1off[qa * nq + ql] + Dlo.dim[qlp] * aloc + M1 * (philay.colbase(ql, qr) + sri), M1 * nsi, row[in]);
+                mb.entry(in, t1off[qa * nq + ql] + Dlo.dim[qlp] * aloc + M1 * (philay.colbase(ql, qr) + sri), M1 * nsi, ent.second);
               }
               mb.end_out();
             }
@@ -497,8 +541,10 @@ void Bond::plan() {
         }
         mb.end_panel();
       }
+    lap("mix build");
     mb.finish(be, mix);
     flops_alg_full += mb.flops_full * (cplx ? 4.0 : 1.0);
+    lap("mix upload");
   }
   // ---- GEMM2: out(ql', qr') [ (l',srow') x r' ] = sum_{qa''} T2(ql',qa'',qr'-qa'') [ . x (a'',r) ] * R(qr',qa'')^T
   // The tile is BM x BN with BM != BN for complex data, so the planner may swap the operand roles (computing the
@@ -537,6 +583,7 @@ void Bond::plan() {
     g2_swapped = swap;
     flops_alg_full += gb.flops_full * (cplx ? 4.0 : 1.0);
   }
+  lap("gemm2");
   flops_alg = g1.flops + g2.flops + mix.flops;
   if (sharded && sh.mode == 2 && (int64_t)esz(cplx) * philay.total > shard_landing_bytes(be))
     fail(-2, "sharded matvec: the landing area is smaller than phi (cb200_shard_alloc)");
@@ -1062,6 +1109,18 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
 }
 
 // ------------------------------------------------------------------------------------------------ svdBond
+// in-place broadcast of device memory from `root` over the context's shard exchange (chunked to the landing size for p2p)
+static void shard_broadcast(Ctx* c, void* buf, int64_t bytes, int root) {
+  if (c->shard.world <= 1 || bytes <= 0) return;
+  if (c->shard.mode == 1) { nccl_bcast(c->be, buf, bytes, root); return; }
+  const int64_t cap = shard_landing_bytes(c->be) / 16 * 16;
+  if (cap <= 0) fail(-2, "shard_broadcast: no landing area");
+  for (int64_t off = 0; off < bytes; off += cap) {
+    shard_bcast_p2p(c->be, (char*)buf + off, std::min(cap, bytes - off), root, c->shard.flip);
+    c->shard.flip ^= 1;
+  }
+}
+
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
                        int64_t mindim, double cutoff, bool exact_rank) {
   Backend* be = c->be;
@@ -1078,12 +1137,19 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     Buf X;                                   // tridiagonal path: the gathered matrix, needed again for X * V_kept
     Heig h;
     std::vector<double> wd;                  // eigenvalues of rho, descending
+    Buf Xk, Vk;                              // kept columns: X V_kept (rows x keep) and V_kept (n x keep)
     int64_t keep = 0;
   };
   static const bool force_jacobi = [] { const char* e = getenv("CB200_TRUNC"); return e && std::string(e) == "jacobi"; }();
   // exact_rank: the one-sided Jacobi SVD resolves exactly-zero singular values (rank of a product state) that an
   // eigensolver working on rho = X^H X can only see as +-eps*||rho||; used for the untruncated canonicalisation of the input.
   bool tri = !force_jacobi && !exact_rank;
+  // Multi-GPU: the charge blocks of the middle link are independent eigenproblems; with an exchange available (modes 1, 2) block
+  // qm is solved by rank qm % world only and its eigenvalues / kept vectors are broadcast (bit-identical data on every rank, so
+  // the replicated truncation decision stays in lockstep).  Small bonds are not worth the barriers.
+  const ShardState& sh = c->shard;
+  const bool spread = tri && sh.world > 1 && sh.mode != 0 && nq > 1 && Dl.total() >= sh.min_dim;
+  auto owner = [&](int qm) { return spread ? qm % sh.world : sh.rank; };
   std::vector<Blk> blk(nq);
   // sizes: dir 0 orthogonalises (l,s1) [columns], long index (s2,r) [rows]; dir 1 the other way round
   for (int qm = 0; qm < nq; ++qm) {
@@ -1126,6 +1192,10 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
         }
     }
     cb.run(c, cplx, phi, X.p);
+    if (spread && owner(qm) != sh.rank) {   // another rank solves this block; keep X for the scatter-free bookkeeping only
+      b.wd.assign(b.n, 0.0);
+      continue;
+    }
     if (tri) {
       // rho = X^H X (what ITensor's denmatDecomp forms), then its eigenvalues through the tridiagonal form
       Buf rho(be, (int64_t)es * b.n * b.n);
@@ -1154,8 +1224,19 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       b.wd.resize(b.n);
       for (int64_t k = 0; k < b.n; ++k) b.wd[k] = b.jo.w[b.order[k]];
     }
-    for (int64_t k = 0; k < b.n; ++k) pooled.push_back(b.wd[k]);
   }
+  if (spread) {   // eigenvalues of every block to every rank
+    for (int qm = 0; qm < nq; ++qm) {
+      Blk& b = blk[qm];
+      if (b.n == 0) continue;
+      Buf w(be, 8 * b.n);
+      if (owner(qm) == sh.rank) dev_h2d(be, w.p, b.wd.data(), 8 * (size_t)b.n);
+      shard_broadcast(c, w.p, 8 * b.n, owner(qm));
+      dev_d2h(be, b.wd.data(), w.p, 8 * (size_t)b.n);
+    }
+  }
+  for (int qm = 0; qm < nq; ++qm)
+    for (int64_t k = 0; k < blk[qm].n; ++k) pooled.push_back(blk[qm].wd[k]);
   std::sort(pooled.begin(), pooled.end(), std::greater<double>());
   int64_t m = 0;
   double terr = 0, docut = 0;
@@ -1188,33 +1269,51 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   res.B.lay.build(res.mid, Dr, S);
   res.A.buf = Buf(be, (int64_t)es * std::max<int64_t>(res.A.lay.total, 1), true);
   res.B.buf = Buf(be, (int64_t)es * std::max<int64_t>(res.B.lay.total, 1), true);
-  // ---- compaction of the kept columns (sorted by weight) and scatter into the two site tensors
+  // ---- kept columns of every block: X V_kept and V_kept (by the block's owner when the blocks are spread over the ranks)
   for (int qm = 0; qm < nq; ++qm) {
     Blk& b = blk[qm];
     const int64_t keep = b.keep;
     if (keep == 0) continue;
     const int64_t ldxk = std::max<int64_t>(b.rows, 1), ldvk = b.n;
-    Buf Xk(be, (int64_t)es * ldxk * keep), Vk;
-    if (tri) {
-      Vk = heig_vectors(c, b.h, keep);                         // n x keep, orthonormal
+    b.Xk = Buf(be, (int64_t)es * ldxk * keep);
+    if (tri && owner(qm) != sh.rank) {
+      b.Vk = Buf(be, (int64_t)es * ldvk * keep);               // filled by the broadcast below
+    } else if (tri) {
+      b.Vk = heig_vectors(c, b.h, keep);                       // n x keep, orthonormal
       GemmBuilder gb(cplx);
       gb.begin(0, ldxk, b.rows, keep, 0);
       gb.seg(0, ldxk, 0, ldvk, b.n);
       gb.end();
       GemmPlan gp;
       gb.finish(be, gp, false, false);
-      run_gemm(c, cplx, gp, b.X.p, Vk.p, Xk.p);                // the weight-carrying factor X V_kept
+      run_gemm(c, cplx, gp, b.X.p, b.Vk.p, b.Xk.p);            // the weight-carrying factor X V_kept
       res.sweeps = std::max(res.sweeps, b.h.ns_iters);
     } else {
-      Vk = Buf(be, (int64_t)es * ldvk * keep);
+      b.Vk = Buf(be, (int64_t)es * ldvk * keep);
       CopyBuilder cx_, cv_;
       for (int64_t k = 0; k < keep; ++k) {
         cx_.add(b.order[k] * b.jo.ldx, k * ldxk, b.rows, 1, 1);
         cv_.add(b.order[k] * b.jo.ldv, k * ldvk, b.n, 1, 1);
       }
-      cx_.run(c, cplx, b.jo.XV.p, Xk.p);
-      cv_.run(c, cplx, b.jo.V.p, Vk.p);
+      cx_.run(c, cplx, b.jo.XV.p, b.Xk.p);
+      cv_.run(c, cplx, b.jo.V.p, b.Vk.p);
     }
+  }
+  if (spread)
+    for (int qm = 0; qm < nq; ++qm) {
+      Blk& b = blk[qm];
+      if (b.keep == 0) continue;
+      shard_broadcast(c, b.Vk.p, (int64_t)es * b.n * b.keep, owner(qm));
+      shard_broadcast(c, b.Xk.p, (int64_t)es * std::max<int64_t>(b.rows, 1) * b.keep, owner(qm));
+    }
+  // ---- scatter into the two site tensors
+  for (int qm = 0; qm < nq; ++qm) {
+    Blk& b = blk[qm];
+    const int64_t keep = b.keep;
+    if (keep == 0) continue;
+    const int64_t ldxk = std::max<int64_t>(b.rows, 1), ldvk = b.n;
+    Buf& Xk = b.Xk;
+    Buf& Vk = b.Vk;
     // isometry from V (columns = orthogonalised index), weight tensor from X V (rows = long index)
     CopyBuilder toA_V, toA_X, toB_V, toB_X;
     for (int ql = 0; ql < nq; ++ql) {
@@ -1298,7 +1397,7 @@ void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, cons
     const int64_t kl = Kl.total();
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qm = 0; qm < nq; ++qm) {
-        mb.begin_panel(Dl.dim[qlp], Dm.dim[qm]);
+        mb.begin_panel(Dl.dim[qlp], Dm.dim[qm], kl * d);
         for (int qsp = 0; qsp < nq; ++qsp) {
           const int qap = qsub(qadd(qlp, qsp, nq), qm, nq);
           const int64_t MY = Dl.dim[qlp] * ds.dim[qsp];
@@ -1320,7 +1419,7 @@ void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, cons
                   const int64_t M = xM[qa * nq + ql];
                   // column of A's right-form matrix: cb(ql,qs) + s_loc + ds*m
                   const int64_t cb = (A.lay.o(ql, qs) - A.lay.o(ql, 0)) / std::max<int64_t>(Dl.dim[ql], 1);
-                  mb.entry(xoff[qa * nq + ql] + Dl.dim[qlp] * aloc + M * (cb + S->loc_int[s]), M * ds.dim[qs], v);
+                  mb.entry(a + kl * s, xoff[qa * nq + ql] + Dl.dim[qlp] * aloc + M * (cb + S->loc_int[s]), M * ds.dim[qs], v);
                 }
               mb.end_out();
             }
@@ -1411,7 +1510,7 @@ void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, con
     const int64_t kr = Kr.total();
     for (int qrp = 0; qrp < nq; ++qrp)
       for (int qm = 0; qm < nq; ++qm) {
-        mb.begin_panel(Dr.dim[qrp], Dm.dim[qm]);
+        mb.begin_panel(Dr.dim[qrp], Dm.dim[qm], kr * d);
         for (int qsp = 0; qsp < nq; ++qsp) {
           const int qa = qsub(qsub(qrp, qsp, nq), qm, nq);
           const int64_t yo = yoff[((size_t)qrp * nq + qsp) * nq + qa];
@@ -1432,7 +1531,7 @@ void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, con
                   if (qadd(qm, qs, nq) != qr) fail(-2, "MPO tensor does not conserve the Z_N charge (env update)");
                   const size_t id = ((size_t)qa2 * nq + qm) * nq + qs;
                   const int64_t M = xM[id];
-                  mb.entry(xoff[id] + Dr.dim[qrp] * a2loc + M * Dm.dim[qm] * S->loc_int[s], M, v);
+                  mb.entry(a2 + kr * s, xoff[id] + Dr.dim[qrp] * a2loc + M * Dm.dim[qm] * S->loc_int[s], M, v);
                 }
               mb.end_out();
             }

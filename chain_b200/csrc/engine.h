@@ -5,6 +5,7 @@
 #pragma once
 #include <complex>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -143,6 +144,14 @@ struct Timers {
   double env = 0, matvec = 0, level1 = 0, trunc = 0, other = 0, nmatvec = 0, matvec_flops = 0;
 };
 
+// W_b (x) W_{b+1} contracted over the middle MPO bond, as a sparse map: rows[out] = list of (in, coefficient) with
+// in = a + kl*(s1 + d*s2), out = a'' + kr*(t1 + d*t2) (internal index orders).  Depends on the MPO only.
+struct OmegaMap {
+  int64_t nin = 0, nout = 0;
+  std::vector<std::vector<std::pair<int64_t, cplx_t>>> rows;
+};
+OmegaMap build_omega(const HostW& W1, const HostW& W2);
+
 // Row sharding of the H_eff matvec over the GPUs of one box (one process per GPU).  Rank g owns a contiguous
 // range of the bra rows l' inside every charge sector of the left link; it runs the L-stage, the mix and the R-stage for
 // those rows only (1/world of the flops, perfectly balanced) and the ranks then exchange their output rows:
@@ -161,7 +170,11 @@ struct Ctx {
   std::string err;
   Timers tm;
   ShardState shard;
+  // Omega maps of MPO site pairs seen by this context, keyed by a hash of the two tensors: the reference calls dmrg() once per
+  // sweep with the same H (src/dmrg.h:596), so the planner's only O(k^2 d^4) host step is paid once per run, not per sweep
+  std::map<uint64_t, std::shared_ptr<OmegaMap>> omega_cache;
 };
+std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2);
 
 // One two-site problem with everything resident on the device.
 struct Bond {
@@ -182,6 +195,7 @@ struct Bond {
   const void* R = nullptr;
   const HostW* W1 = nullptr;
   const HostW* W2 = nullptr;
+  const OmegaMap* omega_cache = nullptr;   // optional: Omega of (W1, W2) computed by the caller (constant over the sweeps)
   // matvec plan
   GemmPlan g1, g2;
   bool g2_swapped = false;   // R-stage computed as the transposed product (see Bond::plan)

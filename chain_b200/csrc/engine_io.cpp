@@ -462,6 +462,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   auto res = std::make_unique<DmrgResult>();
   res->cplx = cplx;
   double energy = 0;
+  std::vector<std::shared_ptr<OmegaMap>> omega(n - 1);   // W_i (x) W_{i+1} per site pair (context-level cache: reused across calls)
   for (int sw = 0; sw < (int)sweeps.size(); ++sw) {
     const SweepParams& sp = sweeps[sw];
     if (sp.noise != 0.0) fail(-2, "noise != 0 is not supported (Chain always runs with noise 0, src/dmrg.h:350)");
@@ -479,6 +480,8 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
         bond.Kl = W[i].KL; bond.Km = W[i].KR; bond.Kr = W[i + 1].KR;
         bond.L = LE[b - 1].buf.p; bond.R = RE[b + 1].buf.p;
         bond.W1 = &W[i]; bond.W2 = &W[i + 1];
+        if (!omega[i]) omega[i] = cached_omega(c, W[i], W[i + 1]);
+        bond.omega_cache = omega[i].get();
         bond.plan();
         // penalty vectors o_j = FL . Psi_b . Psi_{b+1} . FR^T (built once per bond, LocalMPO_MPS)
         std::vector<Buf> pen(np);

@@ -170,7 +170,8 @@ template <bool CPLX>
 __global__ void __launch_bounds__(TRI_THREADS, 2)
 tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
                      void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
-                     double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_) {
+                     double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_,
+                     void* __restrict__ Vt_, void* __restrict__ Wt_) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   cg::grid_group grid = cg::this_grid();
   T* A = reinterpret_cast<T*>(A_);
@@ -178,6 +179,8 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
   T* scl = reinterpret_cast<T*>(scl_);
   T* p = reinterpret_cast<T*>(p_);
   T* g = reinterpret_cast<T*>(g_);
+  T* Vt = reinterpret_cast<T*>(Vt_);   // transposed copies of the panel, [k + 64*r]
+  T* Wt = reinterpret_cast<T*>(Wt_);
   T* Vp = reinterpret_cast<T*>(Vp_);
   T* W = reinterpret_cast<T*>(W_);
   T* Vn = reinterpret_cast<T*>(Vn_);
@@ -185,6 +188,7 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
   __shared__ T red[TRI_WARPS];
   __shared__ double redd[TRI_WARPS];
   __shared__ T sg1[64], sg2[64], swp[64], svp[64];
+  __shared__ T sa2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * TRI_WARPS + warp, GW = (long long)gridDim.x * TRI_WARPS;
   const long long gtid = (long long)blockIdx.x * TRI_THREADS + threadIdx.x, GT = (long long)gridDim.x * TRI_THREADS;
@@ -245,54 +249,61 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
     if (!off)
       for (long long q = threadIdx.x; q < m; q += TRI_THREADS) sp = t_add(sp, t_mul(t_conj(p[q]), q == 0 ? one : t_mul(x[q], sc)));
     const T s0 = tri_block_sum(sp, red);
-    if (threadIdx.x < i) {
+    if (threadIdx.x < i) {   // row j+1 of the panel (transposed copies: contiguous) and the g vectors
       sg1[threadIdx.x] = off ? zero : g[threadIdx.x];
       sg2[threadIdx.x] = off ? zero : g[64 + threadIdx.x];
-      swp[threadIdx.x] = t_conj(W[(j + 1) + (long long)threadIdx.x * n]);
-      svp[threadIdx.x] = t_conj(Vp[(j + 1) + (long long)threadIdx.x * n]);
+      swp[threadIdx.x] = t_conj(Wt[threadIdx.x + (j + 1) * 64]);
+      svp[threadIdx.x] = t_conj(Vt[threadIdx.x + (j + 1) * 64]);
     }
     __syncthreads();
-    T cross = zero;
-    for (int k = 0; k < i; ++k) cross = t_add(cross, t_add(t_mul(t_conj(sg1[k]), sg2[k]), t_mul(t_conj(sg2[k]), sg1[k])));
-    const T a2 = t_scale(t_sub(s0, cross), -0.5 * t_norm2(tj));
-    if (threadIdx.x == 0) {   // row j+1 of the new W column (every CTA needs it for the next column's update)
-      T pt = off ? zero : p[0];
-      for (int k = 0; k < i; ++k) pt = t_sub(pt, t_add(t_mul(t_conj(svp[k]), sg1[k]), t_mul(t_conj(swp[k]), sg2[k])));
-      const T wf0 = off ? zero : t_add(t_mul(tj, pt), a2);
-      swp[i] = t_conj(wf0);
-      svp[i] = one;
+    if (warp == 0) {   // alpha' and row j+1 of the new W column (every CTA needs both), lanes over the panel index
+      T cross = zero, ptc = zero;
+      for (int k = lane; k < i; k += 32) {
+        cross = t_add(cross, t_add(t_mul(t_conj(sg1[k]), sg2[k]), t_mul(t_conj(sg2[k]), sg1[k])));
+        ptc = t_add(ptc, t_add(t_mul(t_conj(svp[k]), sg1[k]), t_mul(t_conj(swp[k]), sg2[k])));
+      }
+      cross = t_warp_sum(cross);
+      ptc = t_warp_sum(ptc);
+      if (lane == 0) {
+        const T a2w = t_scale(t_sub(s0, cross), -0.5 * t_norm2(tj));
+        const T wf0 = off ? zero : t_add(t_mul(tj, t_sub(p[0], ptc)), a2w);
+        sa2 = a2w;
+        swp[i] = t_conj(wf0);
+        svp[i] = one;
+      }
     }
     __syncthreads();
+    const T a2 = sa2;
     const bool next = (j + 1 <= n - 1) && (i + 1 < nbk || j + 1 == n - 1);
     double part = 0.0;
-    for (long long r = (j + 1) + gtid; r < n; r += GT) {
+    // one warp per row: the lanes split the panel index (rows of the transposed panel copies are contiguous -> one round trip)
+    for (long long r = (j + 1) + gw; r < n; r += GW) {
       const long long rr = r - (j + 1);
-      T pt = off ? zero : p[rr];
-      T an = next ? A[r + (j + 1) * n] : zero;
-      int k = 0;
-      for (; k + 8 <= i; k += 8) {      // 16 independent loads in flight per thread (the panel columns are L2-resident)
-        T vk[8], wk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { vk[u] = Vp[r + (long long)(k + u) * n]; wk[u] = W[r + (long long)(k + u) * n]; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          pt = t_sub(pt, t_add(t_mul(vk[u], sg1[k + u]), t_mul(wk[u], sg2[k + u])));
-          an = t_sub(an, t_add(t_mul(vk[u], swp[k + u]), t_mul(wk[u], svp[k + u])));
+      T pt = zero, an = zero;
+      for (int k = lane; k < i; k += 32) {
+        const T vk = Vt[k + r * 64], wk = Wt[k + r * 64];
+        pt = t_add(pt, t_add(t_mul(vk, sg1[k]), t_mul(wk, sg2[k])));
+        an = t_add(an, t_add(t_mul(vk, swp[k]), t_mul(wk, svp[k])));
+      }
+      T p_r = zero, x_r = zero, a_r = zero;
+      if (lane == 0) {
+        if (!off) p_r = p[rr];
+        if (rr != 0) x_r = x[rr];
+        if (next) a_r = A[r + (j + 1) * n];
+      }
+      pt = t_warp_sum(pt);
+      an = t_warp_sum(an);
+      if (lane == 0) {
+        const T vr = rr == 0 ? one : t_mul(x_r, sc);
+        const T wf = off ? zero : t_add(t_mul(tj, t_sub(p_r, pt)), t_mul(a2, vr));
+        W[r + (long long)i * n] = wf; Wn[r + (long long)i * n] = t_scale(wf, -1.0);
+        Vp[r + (long long)i * n] = vr; Vn[r + (long long)i * n] = t_scale(vr, -1.0);
+        Wt[i + r * 64] = wf; Vt[i + r * 64] = vr;
+        if (next) {
+          const T anew = t_sub(t_sub(a_r, an), t_add(t_mul(vr, swp[i]), t_mul(wf, svp[i])));
+          A[r + (j + 1) * n] = anew;
+          if (r >= j + 3) part += t_norm2(anew);
         }
-      }
-      for (; k < i; ++k) {
-        const T vk = Vp[r + (long long)k * n], wk = W[r + (long long)k * n];
-        pt = t_sub(pt, t_add(t_mul(vk, sg1[k]), t_mul(wk, sg2[k])));
-        an = t_sub(an, t_add(t_mul(vk, swp[k]), t_mul(wk, svp[k])));
-      }
-      const T vr = rr == 0 ? one : t_mul(x[rr], sc);
-      const T wf = off ? zero : t_add(t_mul(tj, pt), t_mul(a2, vr));
-      W[r + (long long)i * n] = wf; Wn[r + (long long)i * n] = t_scale(wf, -1.0);
-      Vp[r + (long long)i * n] = vr; Vn[r + (long long)i * n] = t_scale(vr, -1.0);
-      if (next) {
-        an = t_sub(an, t_add(t_mul(vr, swp[i]), t_mul(wf, svp[i])));
-        A[r + (j + 1) * n] = an;
-        if (r >= j + 3) part += t_norm2(an);
       }
     }
     const double sblk = tri_block_sum(part, redd);

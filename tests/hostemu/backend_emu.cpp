@@ -474,5 +474,7 @@ void launch_gemm_peer(Backend*, bool, const void*, const void*, const PeerBases&
 int nccl_unique_id(Backend*, void*) { return -1; }
 int nccl_init(Backend*, const void*, int, int) { return -1; }
 void nccl_allreduce_sum(Backend*, void*, int64_t) {}
+void shard_bcast_p2p(Backend*, void*, int64_t, int, int) {}
+void nccl_bcast(Backend*, void*, int64_t, int) {}
 
 }  // namespace cb200
