@@ -41,6 +41,16 @@ def _worker(rank, world, port, mode, q):
             ev, x, nmv = B.davidson(c["phi"], 2)
             evr, xr, _ = common.make_bond(ref, site, qk, c).davidson(c["phi"], 2)
             out["%s davidson" % st] = (abs(ev - evr), abs(evr))
+            # svdBond: with Z_N blocks the eigenproblems are spread over the ranks and broadcast (nq > 1), else replicated
+            Br = common.make_bond(ref, site, qk, c)
+            for d in ("left", "right"):
+                A1, B1, qm1, sp1, te1 = B.truncate(xr, d, 40, 1e-8)
+                A2, B2, qm2, sp2, te2 = Br.truncate(xr, d, 40, 1e-8)
+                out["%s trunc %s m" % (st, d)] = (float(abs(A1.shape[2] - A2.shape[2])), 0.0)
+                out["%s trunc %s spec" % (st, d)] = (float(np.abs(np.sort(sp1) - np.sort(sp2)).max()), 1.0)
+                r1 = np.tensordot(A1, B1, axes=([2], [0]))
+                r2 = np.tensordot(A2, B2, axes=([2], [0]))
+                out["%s trunc %s rec" % (st, d)] = (float(np.abs(r1 - r2).max()) * 1e-3, 1.0)     # eigenvectors near the cut: 1e-8 abs
             B.close()
         # a short sharded DMRG run (every rank drives the same sweep in lockstep; min_dim=0 shards every bond)
         site, W, qk = common.build_model("golden", "p", 6, [-1.0])
@@ -50,6 +60,14 @@ def _worker(rank, world, port, mode, q):
         e1, _ = cb.dmrg(H, [], psi0, sw, ctx=ref)
         e2, _ = cb.dmrg(H, [], psi0, sw, ctx=ctx)
         out["dmrg"] = (abs(e1 - e2), abs(e1))
+        # the same with Z3 blocks (complex128): sharded matvec + spread truncation + replicated rest must track the 1-GPU run
+        site, W, qk = common.build_model("haagerupq", "p", 6, [0.0, -1.0, 0.0])
+        H = cb.MPO(W, qk, site.charges, nq=site.nq)
+        psi0 = common.to_cb(common.warm_start(site, W, 6, 0, seed=7))
+        sw = cb.Sweeps(3, [10, 20, 40], [1e-5, 1e-6, 1e-7])
+        e1, _ = cb.dmrg(H, [], psi0, sw, ctx=ref)
+        e2, _ = cb.dmrg(H, [], psi0, sw, ctx=ctx)
+        out["dmrg z3"] = (abs(e1 - e2), abs(e1) * 10)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
