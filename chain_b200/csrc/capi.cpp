@@ -64,7 +64,9 @@ int cb200_create(cb200_ctx** out, int device) {
 }
 void cb200_destroy(cb200_ctx* ctx) {
   if (!ctx) return;
+  ctx->c.ws.clear();                 // device buffers go before the backend (stream, pool) they belong to
   backend_destroy(ctx->c.be);
+  ctx->c.be = nullptr;
   delete ctx;
 }
 const char* cb200_last_error(const cb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }

@@ -104,6 +104,16 @@ void Buf::reset() {
   bytes = 0;
 }
 
+void* workspace(Ctx* c, int slot, int64_t bytes) {
+  if ((int)c->ws.size() < WS_COUNT) c->ws.resize(WS_COUNT);
+  Buf& b = c->ws[slot];
+  if (b.bytes < bytes || !b.p) {
+    b.reset();                                            // stream-ordered: kernels still using the old block finish first
+    b = Buf(c->be, bytes + bytes / 8);                    // a little head-room so slowly growing bonds do not reallocate every time
+  }
+  return b.p;
+}
+
 // ------------------------------------------------------------------------------------------------ layouts
 void Site3Layout::build(const Grading& x, const Grading& y, const SiteInfo* s) {
   X = x; Y = y; S = s;
@@ -474,8 +484,6 @@ void Bond::plan() {
         t2 += M * Kr.dim[qa2] * Dr.dim[qr];
       }
   t2_elems = t2;
-  T1 = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(t1_elems, 1));
-  T2 = Buf(be, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
 
   // ---- GEMM1: T1(qa,ql) = L(ql+qa, qa) [ (l',a) x l ] * Phi_ql [ l x cols ]
   {
@@ -593,10 +601,12 @@ void Bond::plan() {
 void Bond::apply(const void* x, void* y) {
   Backend* be = ctx->be;
   const void* Lp = sharded ? Lloc.p : L;
-  run_gemm(ctx, cplx, g1, Lp, x, T1.p);
-  run_mix(ctx, cplx, mix, T1.p, T2.p);
-  const void* A2 = g2_swapped ? R : T2.p;
-  const void* B2 = g2_swapped ? T2.p : R;
+  void* t1 = workspace(ctx, WS_T1, (int64_t)esz(cplx) * std::max<int64_t>(t1_elems, 1));
+  void* t2 = workspace(ctx, WS_T2, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
+  run_gemm(ctx, cplx, g1, Lp, x, t1);
+  run_mix(ctx, cplx, mix, t1, t2);
+  const void* A2 = g2_swapped ? R : t2;
+  const void* B2 = g2_swapped ? t2 : R;
   if (!sharded) {
     run_gemm(ctx, cplx, g2, A2, B2, y);
   } else if (ctx->shard.mode == 2) {
@@ -632,13 +642,15 @@ void Bond::stage_times(const void* x, void* y, int reps, double* ms3) {
   Backend* be = ctx->be;
   ms3[0] = ms3[1] = ms3[2] = 0;
   const void* Lp = sharded ? Lloc.p : L;
+  void* t1 = workspace(ctx, WS_T1, (int64_t)esz(cplx) * std::max<int64_t>(t1_elems, 1));
+  void* t2 = workspace(ctx, WS_T2, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
   for (int i = 0; i < reps; ++i) {
     dev_event_record(be, 0);
-    run_gemm(ctx, cplx, g1, Lp, x, T1.p);
+    run_gemm(ctx, cplx, g1, Lp, x, t1);
     dev_event_record(be, 1);
-    run_mix(ctx, cplx, mix, T1.p, T2.p);
+    run_mix(ctx, cplx, mix, t1, t2);
     dev_event_record(be, 2);
-    if (g2_swapped) run_gemm(ctx, cplx, g2, R, T2.p, y); else run_gemm(ctx, cplx, g2, T2.p, R, y);
+    if (g2_swapped) run_gemm(ctx, cplx, g2, R, t2, y); else run_gemm(ctx, cplx, g2, t2, R, y);
     dev_event_record(be, 3);
     ms3[0] += dev_event_elapsed_ms(be, 0, 1);
     ms3[1] += dev_event_elapsed_ms(be, 1, 2);
@@ -713,9 +725,15 @@ DavidsonResult davidson(Bond& b, void* phi, int niter) {
   double t0 = now_s();
   double nrm2 = norm2_dev(c, cx, phi, n);
   if (nrm2 == 0.0) fail(-2, "davidson: zero initial vector");
-  std::vector<Buf> V, AV;
-  V.emplace_back(be, nbytes);
-  AV.emplace_back(be, nbytes);
+  // Krylov basis V[k], A V[k] and the residual q live in the context workspace (resident in HBM for the whole bond)
+  struct Slot { void* p; };
+  std::vector<Slot> V, AV;
+  auto grow = [&]() {
+    const int k = (int)V.size();
+    V.push_back({workspace(c, WS_V + k, nbytes)});
+    AV.push_back({workspace(c, WS_AV + k, nbytes)});
+  };
+  grow();
   {
     const void* xs[1] = {phi};
     double co[2] = {1.0 / std::sqrt(nrm2), 0.0};
@@ -740,7 +758,7 @@ DavidsonResult davidson(Bond& b, void* phi, int niter) {
     lam = out[0];
     M[0] = lam;
   }
-  Buf q(be, nbytes);
+  struct { void* p; } q{workspace(c, WS_Q, nbytes)};
   double last_lam = 1000.0;
   int nmv = 1;
   for (int ii = 0; ii <= actual_maxiter; ++ii) {
@@ -794,8 +812,7 @@ DavidsonResult davidson(Bond& b, void* phi, int niter) {
       qn = std::sqrt(std::max(0.0, norm2_dev(c, cx, q.p, n)));
       ++passes;
     }
-    V.emplace_back(be, nbytes);
-    AV.emplace_back(be, nbytes);
+    grow();
     {
       const void* qs[1] = {q.p};
       double cs[2] = {1.0 / qn, 0.0};

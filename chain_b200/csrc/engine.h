@@ -173,7 +173,12 @@ struct Ctx {
   // Omega maps of MPO site pairs seen by this context, keyed by a hash of the two tensors: the reference calls dmrg() once per
   // sweep with the same H (src/dmrg.h:596), so the planner's only O(k^2 d^4) host step is paid once per run, not per sweep
   std::map<uint64_t, std::shared_ptr<OmegaMap>> omega_cache;
+  // persistent scratch (matvec intermediates, Krylov basis): one buffer per slot, grown to the largest request and kept, so
+  // a sweep does not churn multi-GB temporaries through the allocator at every bond
+  std::vector<Buf> ws;
 };
+enum { WS_T1 = 0, WS_T2 = 1, WS_V = 2, WS_AV = 2 + MAX_LC, WS_Q = 2 + 2 * MAX_LC, WS_COUNT = 3 + 2 * MAX_LC };
+void* workspace(Ctx* c, int slot, int64_t bytes);
 std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2);
 
 // One two-site problem with everything resident on the device.
@@ -200,8 +205,7 @@ struct Bond {
   GemmPlan g1, g2;
   bool g2_swapped = false;   // R-stage computed as the transposed product (see Bond::plan)
   MixPlan mix;
-  Buf T1, T2;
-  int64_t t1_elems = 0, t2_elems = 0;
+  int64_t t1_elems = 0, t2_elems = 0;   // intermediates live in the context workspace (WS_T1, WS_T2)
   double flops_alg = 0;      // SURVEY 8(d) F_alg
   // penalty
   std::vector<const void*> pen;   // device phi-layout vectors (not owned)
