@@ -67,10 +67,25 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <bool CPLX, int BN_ = 128>
 struct GemmCfg {
   // real:    CTA 128x128x16, 8 warps as 2(m) x 4(n), warp tile 64x32  -> 8x4 DMMA tiles
-  // complex: CTA  64x128x8,  8 warps as 2(m) x 4(n), warp tile 32x32  -> 4x4 complex tiles (4 DMMA each)
+  // complex: CTA  64x128x16, 8 warps as 2(m) x 4(n), warp tile 32x32  -> 4x4 complex tiles (4 DMMA each)
   static constexpr int BM = CPLX ? 64 : 128;
   static constexpr int BN = BN_;                     // 128 (default) or 64 (narrow outputs: Jacobi rotations, Gram blocks)
-  static constexpr int BK = CPLX ? 8 : 16;
+  // k-tile depth / pipeline stages.  Measured on cfg2 (c128): BK 8 x 4 stages -> 0.84 of the cuBLAS DGEMM rate, BK 16 x 3 stages ->
+  // 0.90: the per-k-tile producer code (addressing + cp.async issue, ~300 instructions) is amortised over twice the DMMAs.
+  // The real kernel is insensitive (BK 16 x 4 and BK 32 x 3 both 0.87).  Overridable for A/B builds.
+#ifndef CB200_BK_CPLX
+#define CB200_BK_CPLX 16
+#endif
+#ifndef CB200_BK_REAL
+#define CB200_BK_REAL 16
+#endif
+#ifndef CB200_STAGES_CPLX
+#define CB200_STAGES_CPLX 3
+#endif
+#ifndef CB200_STAGES_REAL
+#define CB200_STAGES_REAL 4
+#endif
+  static constexpr int BK = CPLX ? CB200_BK_CPLX : CB200_BK_REAL;
   static constexpr int WM = CPLX ? 32 : 64;
   static constexpr int WN = BN_ / 4;
   static constexpr int MT = WM / 8;
@@ -81,7 +96,7 @@ struct GemmCfg {
   static constexpr int A_ELEMS = (BK * (BM + PAD_MN) > BM * LDK) ? BK * (BM + PAD_MN) : BM * LDK;
   static constexpr int B_ELEMS = (BK * (BN + PAD_MN) > BN * LDK) ? BK * (BN + PAD_MN) : BN * LDK;
   static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * ES;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = CPLX ? CB200_STAGES_CPLX : CB200_STAGES_REAL;
   static constexpr int AHEAD = STAGES - 2;            // k-tiles in flight; one stage of slack decouples the warps
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES;
   static constexpr int THREADS = 256;
