@@ -184,10 +184,10 @@ static void launch_gemm_t(Backend* b, bool ta, bool tb, const void* A, const voi
   const char* a = (const char*)A;
   const char* bb = (const char*)B;
   char* c = (char*)C;
-  if (!ta && !tb) gemm_grouped_kernel<CPLX, false, false, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else if (!ta && tb) gemm_grouped_kernel<CPLX, false, true, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else if (ta && !tb) gemm_grouped_kernel<CPLX, true, false, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else gemm_grouped_kernel<CPLX, true, true, BN_><<<tiles, 256, smem, b->stream>>>(a, bb, c, t, nt, s);
+  if (!ta && !tb) gemm_grouped_kernel<CPLX, false, false, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (!ta && tb) gemm_grouped_kernel<CPLX, false, true, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (ta && !tb) gemm_grouped_kernel<CPLX, true, false, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else gemm_grouped_kernel<CPLX, true, true, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
 }
 
 void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const void* A, const void* B, void* C, const GemmTask* t,
@@ -201,8 +201,8 @@ void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const voi
 void launch_gemm_peer(Backend* b, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* t, int nt,
                       const GemmSeg* s, int tiles) {
   if (tiles <= 0 || nt <= 0) return;
-  if (cplx) gemm_grouped_peer_kernel<true><<<tiles, 256, GemmCfg<true, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
-  else gemm_grouped_peer_kernel<false><<<tiles, 256, GemmCfg<false, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  if (cplx) gemm_grouped_peer_kernel<true><<<tiles, GemmCfg<true, 128>::THREADS, GemmCfg<true, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  else gemm_grouped_peer_kernel<false><<<tiles, GemmCfg<false, 128>::THREADS, GemmCfg<false, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
   CB_LAUNCH_CHECK(b, "gemm_grouped_peer_kernel");
 }
 

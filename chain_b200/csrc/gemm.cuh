@@ -99,7 +99,15 @@ struct GemmCfg {
   static constexpr int STAGES = CPLX ? CB200_STAGES_CPLX : CB200_STAGES_REAL;
   static constexpr int AHEAD = STAGES - 2;            // k-tiles in flight; one stage of slack decouples the warps
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES;
-  static constexpr int THREADS = 256;
+  static constexpr int CONSUMERS = 256;             // 8 DMMA warps
+  static constexpr int PRODUCERS = 128;             // 1 warpgroup that only issues the cp.async tile loads (warp specialisation)
+  // setmaxnreg budgets.  The CTA's register pool is fixed at launch: 168 registers (what __launch_bounds__(384,1) yields) x 384
+  // threads; setmaxnreg.inc BLOCKS until the pool can serve it, so the two budgets must add up to no more than the pool.
+  static constexpr int LAUNCH_REGS = 168;
+  static constexpr int PRODUCER_REGS = 40;
+  static constexpr int CONSUMER_REGS = 232;
+  static_assert(CONSUMER_REGS * CONSUMERS + PRODUCER_REGS * PRODUCERS <= LAUNCH_REGS * (CONSUMERS + PRODUCERS), "setmaxnreg budgets exceed the CTA register pool (deadlock)");
+  static constexpr int THREADS = CONSUMERS + PRODUCERS;
 };
 
 // Load one operand tile (BMN x BK elements) into shared memory.
@@ -116,8 +124,8 @@ __device__ __forceinline__ void load_operand_tile(char* smem, const char* g, int
   if constexpr (CPLX) {
     // one 16-byte element per copy
     constexpr int TOTAL = BMN * BK;
-#pragma unroll
-    for (int c = tid; c < TOTAL; c += Cfg::THREADS) {
+#pragma unroll 4
+    for (int c = tid; c < TOTAL; c += Cfg::PRODUCERS) {
       int mn, k;
       if constexpr (MN_CONTIG) { k = c / BMN; mn = c % BMN; } else { mn = c / BK; k = c % BK; }
       const bool ok = (mn0 + mn < MN) && (k0 + k < K);
@@ -128,8 +136,8 @@ __device__ __forceinline__ void load_operand_tile(char* smem, const char* g, int
   } else {
     // two doubles per 16-byte copy along the contiguous direction
     constexpr int TOTAL = BMN * BK / 2;
-#pragma unroll
-    for (int c = tid; c < TOTAL; c += Cfg::THREADS) {
+#pragma unroll 4
+    for (int c = tid; c < TOTAL; c += Cfg::PRODUCERS) {
       int mn, k, rem;
       int64_t goff;
       int soff;
@@ -192,26 +200,49 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   int total_kt = 0;
   for (int s = 0; s < t.seg_count; ++s) total_kt += (sg[s].K + BK - 1) / BK;
 
-  // producer cursor
-  int ps = 0, pk = 0;
-  auto issue_load = [&](int stage) {
-    while (sg[ps].K <= 0) ++ps;   // empty segments own no k-tile
-    const GemmSeg s = sg[ps];
-    char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-    char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
-    const char* ga = Abase + s.a_off * ES;
-    const char* gb = Bbase + s.b_off * ES;
-    bool va = true, vb = true;
-    if constexpr (!CPLX) {
-      va = ((((uintptr_t)ga) & 15) == 0) && ((s.lda & 1) == 0);
-      vb = ((((uintptr_t)gb) & 15) == 0) && ((s.ldb & 1) == 0);
-    }
-    load_operand_tile<CPLX, BN_, BM, !TA>(sa, ga, s.lda, m0, t.M, pk, s.K, va, tid);
-    load_operand_tile<CPLX, BN_, BN, TB>(sb, gb, s.ldb, n0, t.N, pk, s.K, vb, tid);
-    pk += BK;
-    if (pk >= s.K) { pk = 0; ++ps; }
-  };
+  // full[s]: the k-tile in stage s has landed (the producer lanes' cp.async arrive on it);
+  // empty[s]: every consumer warp has finished reading stage s.
+  // Warp specialisation: warps 8-11 do nothing but address arithmetic + cp.async for the whole CTA, run up to STAGES k-tiles
+  // ahead and hand their registers to the DMMA warps (setmaxnreg); warps 0-7 never execute producer code, so the DMMA pipe is
+  // fed by whichever of them has a landed tile.
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], Cfg::PRODUCERS); mbar_init(&empty_bar[s], Cfg::CONSUMERS / 32); }
+  }
+  __syncthreads();
 
+  if (warp >= Cfg::CONSUMERS / 32) {
+    // ---------------------------------------------------------------- producer warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
+    const int ptid = tid - Cfg::CONSUMERS;
+    int ps = 0, pk = 0;
+    for (int itl = 0; itl < total_kt; ++itl) {
+      const int stage = itl % STAGES, use = itl / STAGES;
+      if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
+      while (sg[ps].K <= 0) ++ps;   // empty segments own no k-tile
+      const GemmSeg s = sg[ps];
+      char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+      char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
+      const char* ga = Abase + s.a_off * ES;
+      const char* gb = Bbase + s.b_off * ES;
+      bool va = true, vb = true;
+      if constexpr (!CPLX) {
+        va = ((((uintptr_t)ga) & 15) == 0) && ((s.lda & 1) == 0);
+        vb = ((((uintptr_t)gb) & 15) == 0) && ((s.ldb & 1) == 0);
+      }
+      load_operand_tile<CPLX, BN_, BM, !TA>(sa, ga, s.lda, m0, t.M, pk, s.K, va, ptid);
+      load_operand_tile<CPLX, BN_, BN, TB>(sb, gb, s.ldb, n0, t.N, pk, s.K, vb, ptid);
+      cp_async_arrive(&full_bar[stage]);
+      pk += BK;
+      if (pk >= s.K) { pk = 0; ++ps; }
+    }
+    return;   // the producer has no part in the epilogue (its cp.async have all been waited on by the consumers' full barriers)
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
   double acc_re[MT][NT][2];
   double acc_im[CPLX ? MT : 1][CPLX ? NT : 1][2];
 #pragma unroll
@@ -222,30 +253,8 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
       if constexpr (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
     }
 
-  // full[s]: the k-tile in stage s has landed (every thread's cp.async arrives on it);
-  // empty[s]: every thread has finished reading stage s.  Waiting on empty happens AHEAD+1 iterations after the
-  // consumption it guards, so warps drift freely and the DMMA pipe is fed by whichever warp has data.
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], Cfg::THREADS); mbar_init(&empty_bar[s], Cfg::THREADS); }
-  }
-  __syncthreads();
-  auto produce = [&](int itl) {
-    const int stage = itl % STAGES, use = itl / STAGES;
-    if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
-    issue_load(stage);
-    cp_async_arrive(&full_bar[stage]);
-  };
-  constexpr int AHEAD = Cfg::AHEAD;
-#pragma unroll
-  for (int s = 0; s < AHEAD; ++s)
-    if (s < total_kt) produce(s);
-
   const bool conjA = (t.flags & GEMM_CONJ_A) != 0;
   for (int it = 0; it < total_kt; ++it) {
-    if (it + AHEAD < total_kt) produce(it + AHEAD);
     mbar_wait(&full_bar[it % STAGES], (unsigned)((it / STAGES) & 1));
 
     const char* sa = smem + (size_t)(it % STAGES) * Cfg::STAGE_BYTES;
@@ -291,7 +300,8 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
           }
       }
     }
-    mbar_arrive(&empty_bar[it % STAGES]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[it % STAGES]);
   }
 
   // epilogue: direct stores from the accumulator fragments
@@ -340,7 +350,7 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
 }
 
 template <bool CPLX, bool TA, bool TB, int BN_ = 128>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<CPLX, BN_>::THREADS, 1)
 gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
                     const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs) {
   PeerBases none;
@@ -350,7 +360,7 @@ gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bba
 
 // R-stage of the row-sharded matvec: same mainloop, C tiles stored to every rank's landing buffer
 template <bool CPLX>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmCfg<CPLX, 128>::THREADS, 1)
 gemm_grouped_peer_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, const GemmTask* __restrict__ tasks, int ntasks,
                          const GemmSeg* __restrict__ segs, const __grid_constant__ PeerBases peers) {
   gemm_grouped_body<CPLX, false, true, 128, true>(Abase, Bbase, nullptr, tasks, ntasks, segs, peers);
