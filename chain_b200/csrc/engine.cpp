@@ -467,7 +467,7 @@ void Bond::plan() {
       const int64_t M = Dlo.dim[qlp] * Kl.dim[qa];
       t1off[qa * nq + ql] = t1;
       t1M[qa * nq + ql] = M;
-      if (Dl.dim[ql] > 0) t1 += M * philay.ncols(ql);
+      t1 += M * philay.ncols(ql);   // also when Dl[ql] = 0: the K = 0 task zero-fills this block and the mix stage reads it
     }
   t1_elems = t1;
   // ---- T2 layout: block (ql', qa'', qr): rows (l', srow'), cols (a'', r)

@@ -148,3 +148,14 @@ def test_calc_ee_on_gpu_matches_oracle(gpu_ctx):
     psi0 = common.warm_start(site, W, n, q, seed=7)
     eo, po = od.dmrg(W, [], psi0, od.Sweeps(4, [10, 20, 40, 80], [1e-5, 1e-6, 1e-7, 1e-8]))
     assert np.abs(np.array(od.calc_ee(po)) - np.array(cb.calc_ee(common.to_cb(po), site.charges, ctx=gpu_ctx))).max() <= 1e-10
+
+
+def test_edge_cases_on_gpu(gpu_ctx):
+    # the host-logic edge cases (tests/test_edge_cases.py) through the CUDA kernels: empty / ragged charge sectors, bond dimension 1,
+    # sine-squared and Dirichlet boundary terms
+    import test_edge_cases as te
+    te.test_ragged_and_empty_sectors(gpu_ctx)
+    te.test_bond_dimension_one(gpu_ctx)
+    te.test_boundary_conditions_track_the_oracle(gpu_ctx, "golden", "s", 7, [-1.0])
+    te.test_boundary_conditions_track_the_oracle(gpu_ctx, "haagerupq", "s", 6, [-1.0, 0.0, 0.0])
+    te.test_invalid_inputs_give_status_codes(gpu_ctx)
