@@ -206,6 +206,52 @@ class DmrgInfo:
         self.timers = {}
 
 
+def _unpack_result(ctx, res, d):
+    lib = ctx.lib
+    n = lib.cb200_result_nsites(res)
+    dt = np.complex128 if lib.cb200_result_dtype(res) == 1 else np.float64
+    dims = [int(lib.cb200_result_link_dim(res, j)) for j in range(n + 1)]
+    charges = []
+    for j in range(n + 1):
+        q = np.zeros(dims[j], np.int32)
+        ctx.check(lib.cb200_result_link_charges(res, j, i32ptr(q)))
+        charges.append(q)
+    sites = []
+    for j in range(n):
+        a = np.zeros((dims[j], d, dims[j + 1]), dtype=dt, order="F")
+        ctx.check(lib.cb200_result_site(res, j, ptr(a)))
+        sites.append(a)
+    return sites, charges
+
+
+def translate(psi, site_charges=None, cutoff=1e-5, ctx=None):
+    """One-site translation by L-1 swap gates + truncated SVDs, as Measure("translation") applies it (src/dmrg.h:855-858)."""
+    ctx = ctx or default_context()
+    keep = []
+    pc = psi._to_c(keep)
+    d = psi.sites[0].shape[1]
+    sq = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
+    res = C.c_void_p()
+    ctx.check(ctx.lib.cb200_mps_translate(ctx.h, C.byref(pc), d, i32ptr(sq), float(cutoff), C.byref(res)))
+    try:
+        sites, charges = _unpack_result(ctx, res, d)
+    finally:
+        ctx.lib.cb200_result_free(res)
+    return MPS(sites, charges, nq=psi.nq, center=psi.n)
+
+
+def overlap(a, b, site_charges=None, ctx=None):
+    """innerC(a, b) = <a|b>."""
+    ctx = ctx or default_context()
+    keep = []
+    ac, bc = a._to_c(keep), b._to_c(keep)
+    d = a.sites[0].shape[1]
+    sq = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
+    z = (C.c_double * 2)()
+    ctx.check(ctx.lib.cb200_mps_overlap(ctx.h, C.byref(ac), C.byref(bc), d, i32ptr(sq), z))
+    return complex(z[0], z[1])
+
+
 def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
     """(energy, psi) = dmrg(H, psis, psi0, sweeps, {"Weight": weight}) -- same meaning as itensor::dmrg at
     src/dmrg.h:544: `psis` are the previously found states to be penalised with `weight`."""
@@ -223,20 +269,7 @@ def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
     ctx.check(lib.cb200_dmrg(ctx.h, C.byref(Hc), prev, len(psis), C.byref(p0), sw, sweeps.nsweep, float(weight),
                              C.byref(energy), C.byref(res)))
     try:
-        n = lib.cb200_result_nsites(res)
-        cplx = lib.cb200_result_dtype(res) == 1
-        dt = np.complex128 if cplx else np.float64
-        dims = [int(lib.cb200_result_link_dim(res, j)) for j in range(n + 1)]
-        charges = []
-        for j in range(n + 1):
-            q = np.zeros(dims[j], np.int32)
-            ctx.check(lib.cb200_result_link_charges(res, j, i32ptr(q)))
-            charges.append(q)
-        sites = []
-        for j in range(n):
-            a = np.zeros((dims[j], H.d, dims[j + 1]), dtype=dt, order="F")
-            ctx.check(lib.cb200_result_site(res, j, ptr(a)))
-            sites.append(a)
+        sites, charges = _unpack_result(ctx, res, H.d)
         if info is not None:
             ns = lib.cb200_result_nstats(res)
             arr = (BondStat * max(ns, 1))()

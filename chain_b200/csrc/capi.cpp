@@ -178,6 +178,29 @@ int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const i
   });
 }
 
+int cb200_mps_translate(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double cutoff, cb200_result** out) {
+  if (!ctx || !psi || !out) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    bool cx = false;
+    HostMPS h = to_host_mps(psi, psi->nq, d, &cx);
+    auto r = mps_translate(&ctx->c, psi->nq, d, site_charge, h, cx, cutoff);
+    cb200_result* res = new cb200_result();
+    res->r = std::move(r);
+    *out = res;
+  });
+}
+
+int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, int32_t d, const int32_t* site_charge, double* re_im) {
+  if (!ctx || !a || !b || !re_im) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (a->nq != b->nq) fail(CB200_ERR_INVALID, "overlap: the two states use different symmetry groups");
+    bool ca = false, cbb = false;
+    HostMPS ha = to_host_mps(a, a->nq, d, &ca), hb = to_host_mps(b, b->nq, d, &cbb);
+    const cplx_t z = mps_overlap(&ctx->c, a->nq, d, site_charge, ha, ca, hb, cbb);
+    re_im[0] = z.real(); re_im[1] = z.imag();
+  });
+}
+
 int32_t cb200_result_nsites(const cb200_result* r) { return r ? r->r->psi.n : 0; }
 int32_t cb200_result_dtype(const cb200_result* r) { return r && r->r->cplx ? 1 : 0; }
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link) {

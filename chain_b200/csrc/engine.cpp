@@ -1139,7 +1139,7 @@ static void shard_broadcast(Ctx* c, void* buf, int64_t bytes, int root) {
 }
 
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
-                       int64_t mindim, double cutoff, bool exact_rank) {
+                       int64_t mindim, double cutoff, bool exact_rank, bool normalize) {
   Backend* be = c->be;
   const int nq = pl.L.nq, d = S->d;
   const Grading& Dl = pl.L;
@@ -1351,8 +1351,8 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     toB_V.run(c, cplx, Vk.p, res.B.buf.p);
     toB_X.run(c, cplx, Xk.p, res.B.buf.p);
   }
-  // DoNormalize: newoc /= norm(newoc) (its squared norm is the sum of the kept eigenvalues)
-  {
+  // DoNormalize: newoc /= norm(newoc) (its squared norm is the sum of the kept eigenvalues); a plain svd() (Swap) does not
+  if (normalize) {
     DevSite3& oc = dir == 0 ? res.B : res.A;
     const double nn = norm2_dev(c, cplx, oc.buf.p, oc.lay.total);
     if (nn > 0) scale_inplace(c, cplx, oc.buf.p, oc.lay.total, 1.0 / std::sqrt(nn));

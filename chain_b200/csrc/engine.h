@@ -240,7 +240,7 @@ struct SplitResult {
 };
 // MPS::svdBond. dir 0: Fromleft (A isometry), 1: Fromright (B isometry). The weight-carrying tensor is normalised.
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
-                       int64_t mindim, double cutoff, bool exact_rank = false);
+                       int64_t mindim, double cutoff, bool exact_rank = false, bool normalize = true);
 
 void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, const DevSite3& A, const HostW& W, DevEnv& out);
 void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, const DevSite3& B, const HostW& W, DevEnv& out);
@@ -309,6 +309,11 @@ struct MpoIn {
 std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<HostMPS>& prev, const std::vector<bool>& prev_cplx,
                                      const HostMPS& psi0, bool psi0_cplx, const std::vector<SweepParams>& sweeps, double weight);
 
+// Translation by one site as L-1 consecutive swap gates with an SVD of relative cutoff `cutoff` each (Swap, src/chain.cpp:486-507,
+// applied as in Measure("translation"), src/dmrg.h:855-858); the result carries the translated MPS
+std::unique_ptr<DmrgResult> mps_translate(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx, double cutoff);
+// innerC(a, b) = <a|b>
+cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& a, bool a_cplx, const HostMPS& b, bool b_cplx);
 // CalcEE (src/utility.cpp:5-27) on the device truncation path
 std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx);
 

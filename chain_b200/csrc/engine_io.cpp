@@ -585,4 +585,108 @@ std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_cha
   return out;
 }
 
+// ------------------------------------------------------------------------------------------------ translation / overlap
+namespace {
+void export_mps(Ctx* c, bool cplx, const SiteInfo& S, std::vector<DevSite3>& A, DmrgResult& res) {
+  const int n = (int)A.size();
+  res.cplx = cplx;
+  res.psi.n = n;
+  res.psi.link.resize(n + 1);
+  res.psi.site.resize(n);
+  for (int j = 0; j <= n; ++j) res.psi.link[j] = IndexMap::from_grading(j == 0 ? A[0].lay.X : A[j - 1].lay.Y);
+  for (int j = 0; j < n; ++j) {
+    const int64_t tot = A[j].lay.X.total() * S.d * A[j].lay.Y.total();
+    res.psi.site[j].assign(esz(cplx) * (size_t)tot, 0);
+    export_site3(c, cplx, S, res.psi.link[j], res.psi.link[j + 1], A[j], res.psi.site[j].data());
+  }
+}
+}  // namespace
+
+std::unique_ptr<DmrgResult> mps_translate(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx, double cutoff) {
+  const int n = psi.n;
+  if (n < 2) fail(-2, "translation needs at least 2 sites");
+  SiteInfo S = SiteInfo::make(nq, d, site_charge);
+  std::vector<DevSite3> A(n);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j].data(), A[j]);
+  auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
+    pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
+    phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
+    two_site(c, cplx, A[i], A[i + 1], pl, phi.p);
+  };
+  if (psi.center != 1) {   // Swap starts with psi.position(b); bring an uncanonical input to site 1 once, exactly
+    for (int i = n - 2; i >= 0; --i) {
+      PhiLayout pl; Buf phi;
+      phi_of(i, pl, phi);
+      SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 1, INT64_MAX / 4, 1, 1e-20, true);
+      A[i] = std::move(sr.A);
+      A[i + 1] = std::move(sr.B);
+    }
+  }
+  auto res = std::make_unique<DmrgResult>();
+  for (int i = 0; i + 1 < n; ++i) {
+    PhiLayout pl; Buf phi;
+    phi_of(i, pl, phi);
+    // wf[l, s1 = u, s2 = v, r] = phi[l, v, u, r]: a permutation of the fused site-pair index inside every charge block
+    Buf sw(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
+    std::vector<CopyTask> tasks;
+    for (int ql = 0; ql < nq; ++ql)
+      for (int qr = 0; qr < nq; ++qr) {
+        const int64_t Dl = pl.L.dim[ql], Dr = pl.R.dim[qr], ns = pl.ns(ql, qr);
+        if (Dl == 0 || Dr == 0) continue;
+        const int qd = qsub(qr, ql, nq);
+        for (int64_t sr = 0; sr < ns; ++sr) {
+          const int u = S.srow[qd][sr].first, v = S.srow[qd][sr].second;
+          const int64_t src_sr = S.srow_index[(size_t)v * d + u];
+          CopyTask t{};
+          t.src_off = pl.o(ql, qr) + Dl * src_sr; t.dst_off = pl.o(ql, qr) + Dl * sr;
+          t.n0 = (int32_t)Dl; t.n1 = (int32_t)Dr; t.n2 = 1;
+          t.ss0 = 1; t.ds0 = 1; t.ss1 = Dl * ns; t.ds1 = Dl * ns; t.ss2 = 0; t.ds2 = 0;
+          tasks.push_back(t);
+        }
+      }
+    run_copy_tasks(c, cplx, tasks, phi.p, sw.p);
+    // svd(wf, inds(psi(b)), {"Cutoff", cutoff}): U -> site b, S V -> site b+1 (not normalised)
+    SplitResult sr = split_bond(c, cplx, &S, pl, sw.p, 0, INT64_MAX / 4, 1, cutoff, false, false);
+    res->stats.push_back({0, i + 1, 0, (int)sr.mid.total(), 0.0, sr.truncerr});
+    A[i] = std::move(sr.A);
+    A[i + 1] = std::move(sr.B);
+  }
+  export_mps(c, cplx, S, A, *res);
+  res->psi.center = n;
+  check_dev(c);
+  return res;
+}
+
+cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& a, bool a_cplx, const HostMPS& b, bool b_cplx) {
+  const int n = a.n;
+  if (b.n != n || n < 1) fail(-2, "overlap: length mismatch");
+  const bool cplx = a_cplx || b_cplx;
+  SiteInfo S = SiteInfo::make(nq, d, site_charge);
+  DevMat F;
+  {
+    DevSite3 A0, B0;
+    import_site3_t(c, cplx, a_cplx, S, a.link[0], a.link[1], a.site[0].data(), A0);
+    import_site3_t(c, cplx, b_cplx, S, b.link[0], b.link[1], b.site[0].data(), B0);
+    if (A0.lay.X.total() != 1 || B0.lay.X.total() != 1) fail(-2, "overlap: outer links must have dimension 1");
+    if (!(A0.lay.X == B0.lay.X)) return cplx_t(0, 0);          // different total charge
+    site3H_times_site3(c, cplx, &S, A0, B0, F);                 // F[m, n] = sum_{l,s} conj(A[l,s,m]) B[l,s,n]
+  }
+  for (int j = 1; j < n; ++j) {
+    DevSite3 Aj, Bj, X;
+    import_site3_t(c, cplx, a_cplx, S, a.link[j], a.link[j + 1], a.site[j].data(), Aj);
+    import_site3_t(c, cplx, b_cplx, S, b.link[j], b.link[j + 1], b.site[j].data(), Bj);
+    // X[m, s, n'] = sum_n F[m, n] B[n, s, n'] ; F'[m', n'] = sum_{m,s} conj(A[m,s,m']) X[m,s,n']
+    mat_times_site3(c, cplx, &S, F, Bj, X);
+    DevMat Fn;
+    site3H_times_site3(c, cplx, &S, Aj, X, Fn);
+    F = std::move(Fn);
+  }
+  if (F.total == 0) return cplx_t(0, 0);                        // right boundary links carry different charges
+  if (F.total != 1) fail(-2, "overlap: right boundary is not 1x1");
+  std::vector<char> h(esz(cplx), 0);
+  dev_d2h(c->be, h.data(), F.buf.p, h.size());
+  check_dev(c);
+  return rd(h.data(), cplx, 0);
+}
+
 }  // namespace cb200

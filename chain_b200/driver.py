@@ -10,8 +10,9 @@ Nothing here does tensor arithmetic: Hamiltonians come from chain_b200.models (h
 
 Differences from the reference, all deliberate: output goes under --out (the reference compiles the parent of the cwd in,
 src/path_template.h:8); --seed makes the random product start reproducible (the reference never seeds); there is no
-pgs/ checkpoint (ITensor's private binary format); modes other than 0 print what is missing
-(mode 1/5 measurements are SURVEY 8f row f2).
+pgs/ checkpoint (ITensor's private binary format); mode 5 runs the simulation and then the energy /
+translation measurements and the {energy, momentum} table (AnalyzeWithoutRho); the rho-defect column of mode 1/5 is the one
+part of SURVEY 8f row f2 that is not built.
 """
 import argparse
 import os
@@ -53,6 +54,42 @@ def dump_ee(path, n, svns):
         f.write("},\n")
 
 
+def dump_matrix(path, rows):
+    """DumpMatrix, src/utility.cpp:81-113 (.an, overwritten)."""
+    with open(path, "w") as f:
+        f.write("{\n")
+        f.write(",\n".join("{" + ",".join("%.10f" % v for v in r) + "}" for r in rows))
+        f.write("\n}\n")
+
+
+def dump_mathematica(path, name, M):
+    """DumpMathematicaSingle, src/utility.cpp:56-78 (.m, appended)."""
+    M = np.asarray(M, dtype=complex)
+    n = M.shape[0]
+    with open(path, "a") as f:
+        f.write("%s = {\n" % name)
+        for i in range(n):
+            f.write("{" + ",  ".join("%.10f + I * %.10f" % (M[i, j].real, M[i, j].imag) for j in range(n)))
+            f.write("},\n" if i != n - 1 else "}\n};\n\n")
+
+
+def analyze_without_rho(energies, T, n):
+    """AnalyzeWithoutRho, src/dmrg.h:1177-1218: m = E/L + T; eigen(m); rotate E and T into its eigenbasis;
+    momentum_i = round(Re(log(T_ii) / (2 pi i) * L) * 1e5) / 1e5 with -L/2 -> L/2; rows {energy, momentum} sorted by energy.
+    (Host-side post-processing of an n_states x n_states matrix, as in the reference.)"""
+    E = np.diag(np.asarray(energies, dtype=complex))
+    w, U = np.linalg.eig(E / n + np.asarray(T, dtype=complex))
+    Ui = np.linalg.inv(U)
+    Er, Tr = Ui @ E @ U, Ui @ T @ U
+    rows = []
+    for i in range(len(energies)):
+        mom = np.round((np.log(Tr[i, i]) / (2j * np.pi) * n).real * 1e5) / 1e5
+        if mom == -(n // 2):
+            mom = n // 2
+        rows.append((float(Er[i, i].real), float(mom)))
+    return sorted(rows)
+
+
 def state_name(k):
     return {0: "1st state", 1: "2nd state", 2: "3rd state"}.get(k, "%dth state" % (k + 1))
 
@@ -81,10 +118,12 @@ class Simulation:
         self.log = log
         stem = file_stem(site, bc, n, self.max_bond_dim, self.svd_cutoff, self.precision, coupling_str, self.u, charge)
         self.stem = stem
-        for sub in ("ee", "en"):
+        for sub in ("ee", "en", "m", "an"):
             os.makedirs(os.path.join(out, sub), exist_ok=True)
         self.ee_path = os.path.join(out, "ee", stem + ".ee")
         self.en_path = os.path.join(out, "en", stem + ".en")
+        self.m_path = os.path.join(out, "m", stem + ".m")
+        self.an_path = os.path.join(out, "an", stem + ".an")
         self.energies, self.states, self.sweep_log = [], [], []
 
     def hamiltonian(self, bc):
@@ -158,6 +197,38 @@ class Simulation:
         return self.energies, self.states
 
 
+def analyze(sim, log=print):
+    """What mode 5 runs after the simulation (src/dmrg.h:637-648): Measure("energy") rewrites .en with 1-based state numbers
+    (:752-755) and dumps the energy matrix to .m; for periodic / Dirichlet chains Measure("translation") (L-1 swaps per state on
+    the device, kCutoff = 1e-5) + T_ij = innerC(psi_i, T psi_j) + AnalyzeWithoutRho give the {energy, momentum} table in .an.
+    The rho-defect column of the charge-0 Analyze (RhoOp / applyMPO, src/chain.cpp:65-214) is not built: charge-0 runs get the
+    AnalyzeWithoutRho table too, and that is said on stdout."""
+    n, ens, states = sim.n, sim.energies, sim.states
+    if os.path.exists(sim.en_path):
+        os.remove(sim.en_path)
+    for i, e in enumerate(ens):
+        dump_energy(sim.en_path, i + 1, e)
+    if os.path.exists(sim.m_path):
+        os.remove(sim.m_path)
+    dump_mathematica(sim.m_path, "energy", np.diag(np.asarray(ens, dtype=complex)))
+    if sim.bc not in ("p", "d", "sp"):
+        rows = [(e,) for e in ens]                               # Energies(), src/dmrg.h:1221-1244
+        dump_matrix(sim.an_path, rows)
+        return rows
+    sq = sim.sites.charges
+    acted = [cb.translate(p, sq, 1e-5, ctx=sim.ctx) for p in states]
+    T = np.array([[cb.overlap(a, t, sq, ctx=sim.ctx) for t in acted] for a in states])
+    dump_mathematica(sim.m_path, "translation", T)
+    rows = analyze_without_rho(ens, T, n)
+    dump_matrix(sim.an_path, rows)
+    if sim.charge == 0:
+        log("> note: charge 0: the reference's Analyze() adds a rho-defect column (not built, SURVEY 8f row f2); {energy, momentum} written")
+    log("\nSpectrum:  {energy, momentum}")
+    for r in rows:
+        log("{%s}" % ",".join("%.10f" % v for v in r))
+    return rows
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="chain_b200.driver", description="Simulates DMRG on anyon chains (stand-in for ./Chain).", add_help=False)
     ap.add_argument("-s", "--site", required=True, choices=["golden", "haagerup", "haagerupq"])
@@ -194,8 +265,8 @@ def main(argv=None):
         ", ".join("%.10f" % e for e in ens)))
     print("> wrote %s and %s (wall %.2f s)" % (sim.en_path, sim.ee_path, wall))
     if a.mode == 5:
-        print("> mode 5: the DMRG part is done; translation / rho measurements (Analyze, src/dmrg.h:1118-1174) are not part of the hot path "
-              "and not built yet (SURVEY 8f row f2)")
+        analyze(sim)
+        print("> wrote %s and %s" % (sim.m_path, sim.an_path))
     return 0
 
 

@@ -113,6 +113,12 @@ int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_
 /* CalcEE of /root/reference/src/utility.cpp:5-27: von Neumann entropy of every cut b = 1..n-1 (p > 1e-12 rule, natural log),
  * Schmidt spectra from the device truncation path; out has n-1 entries */
 int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double* out);
+/* Translation by one site as the reference measures it (Measure("translation"), /root/reference/src/dmrg.h:855-858): L-1 swap
+ * gates (Swap, src/chain.cpp:486-507), each followed by an SVD with relative cutoff `cutoff` (kCutoff = 1e-5 there); the
+ * translated MPS comes back as a cb200_result (read with cb200_result_site / _link_dim / _link_charges) */
+int cb200_mps_translate(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double cutoff, cb200_result** out);
+/* innerC(a, b) = <a|b> (src/dmrg.h:1063); re_im[2] */
+int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, int32_t d, const int32_t* site_charge, double* re_im);
 int32_t cb200_result_nsites(const cb200_result* r);
 int32_t cb200_result_dtype(const cb200_result* r);                                  /* 0 f64, 1 c128 */
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link);                 /* link in [0, n] */

@@ -192,7 +192,7 @@ def truncate_probs(P, maxdim, mindim, cutoff):
     return m, truncerr, docut
 
 
-def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff, use_svd=False):
+def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff, use_svd=False, normalize=True):
     """svdBond of A.5. phi[l,s1,s2,r]; returns (A_b, A_{b+1}, qmid, spectrum, truncerr).
     direction 'left'  (Fromleft):  A_b is the isometry, A_{b+1} carries the weight (normalised).
     direction 'right' (Fromright): A_{b+1} is the isometry, A_b carries the weight."""
@@ -242,7 +242,8 @@ def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff,
     mm = U.shape[1]
     qmid = np.array(qmid, dtype=np.int64)
     oc = U.conj().T @ Mx                     # (m, cols)
-    oc = oc / np.linalg.norm(oc)             # DoNormalize
+    if normalize:
+        oc = oc / np.linalg.norm(oc)         # DoNormalize (svdBond); a plain svd() as in Swap keeps S*V as it is
     if direction == "left":
         A1 = U.reshape(Dl, d, mm)
         A2 = oc.reshape(mm, d, Dr)
@@ -250,7 +251,8 @@ def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff,
         A2 = U.T.reshape(mm, d, Dr)          # B[m,(s2,r)] = U[(s2,r),m] (no conj: phi ~ oc^T-part * B)
         # phi[(l,s1),(s2,r)] = sum_m A1[(l,s1),m] B[m,(s2,r)] with B rows orthonormal => A1 = phi B^H
         A1 = (phi.reshape(Dl * d, d * Dr) @ A2.reshape(mm, d * Dr).conj().T)
-        A1 = A1 / np.linalg.norm(A1)
+        if normalize:
+            A1 = A1 / np.linalg.norm(A1)
         A1 = A1.reshape(Dl, d, mm)
     return A1, A2, qmid, np.concatenate(kept), truncerr
 
@@ -376,6 +378,42 @@ def overlap(a, b):
     for x, y in zip(a.A, b.A):
         E = np.tensordot(np.tensordot(E, x.conj(), axes=([0], [0])), y, axes=([0, 1], [0, 1]))
     return E[0, 0]
+
+
+def swap_translate(psi, cutoff=1e-5):
+    """Measure("translation") of src/dmrg.h:855-858: Swap(psi, j) for j = 1..L-1 (src/chain.cpp:486-507), each a two-site swap
+    gate followed by svd(wf, inds(psi(b)), {"Cutoff", kCutoff}) with U -> site b and S*V -> site b+1 (no renormalisation)."""
+    psi = psi.copy()
+    orthogonalize_to_first(psi)
+    n = psi.n
+    for b in range(n - 1):
+        A, B = psi.A[b], psi.A[b + 1]
+        wf = np.tensordot(A, B, axes=([2], [0])).transpose(0, 2, 1, 3)      # wf[l, s1, s2, r] = phi[l, s2, s1, r]
+        Dl, d, _, Dr = wf.shape
+        ql, qr = psi.q[b], psi.q[b + 2]
+        A1, B1, qm, spec, terr = split_bond(np.ascontiguousarray(wf), ql, qr, psi.site_charges, psi.nq, "left", 10 ** 9, 1, cutoff,
+                                            use_svd=True, normalize=False)
+        psi.A[b], psi.A[b + 1] = A1, B1
+        psi.q[b + 1] = np.asarray(qm)
+    psi.center = n
+    return psi
+
+
+def momentum_analysis(energies, T, n):
+    """AnalyzeWithoutRho, src/dmrg.h:1177-1218: m = E/L + T, eigen(m), rotate E and T, momentum_i = round(Re(log(T_ii)/(2 pi i) L) 1e5)/1e5
+    (with -L/2 -> L/2), rows sorted by energy."""
+    E = np.diag(np.asarray(energies, dtype=complex))
+    m = E / n + T
+    w, U = np.linalg.eig(m)
+    Ui = np.linalg.inv(U)
+    Er, Tr = Ui @ E @ U, Ui @ T @ U
+    out = []
+    for i in range(len(energies)):
+        mom = np.round((np.log(Tr[i, i]) / (2j * np.pi) * n).real * 1e5) / 1e5
+        if mom == -(n // 2):
+            mom = n // 2
+        out.append((Er[i, i].real, float(mom)))
+    return sorted(out)
 
 
 def expect_mpo(psi, W):

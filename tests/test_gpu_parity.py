@@ -159,3 +159,10 @@ def test_edge_cases_on_gpu(gpu_ctx):
     te.test_boundary_conditions_track_the_oracle(gpu_ctx, "golden", "s", 7, [-1.0])
     te.test_boundary_conditions_track_the_oracle(gpu_ctx, "haagerupq", "s", 6, [-1.0, 0.0, 0.0])
     te.test_invalid_inputs_give_status_codes(gpu_ctx)
+
+
+def test_translation_and_momentum_on_gpu(gpu_ctx, tmp_path):
+    # mode-5 momentum assignment through the CUDA path (swap gates + truncated SVDs + overlaps), against the oracle restatement
+    import test_translation as tt
+    tt.test_translate_and_overlap_match_oracle(gpu_ctx, "haagerupq", 6, [-1.0, 0.0, 0.0], 1)
+    tt.test_momentum_assignment_golden(gpu_ctx, tmp_path)
