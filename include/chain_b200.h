@@ -115,7 +115,7 @@ int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_
 int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double* out);
 /* Translation by one site as the reference measures it (Measure("translation"), /root/reference/src/dmrg.h:855-858): L-1 swap
  * gates (Swap, src/chain.cpp:486-507), each followed by an SVD with relative cutoff `cutoff` (kCutoff = 1e-5 there); the
- * translated MPS comes back as a cb200_result (read with cb200_result_site / _link_dim / _link_charges) */
+ * translated MPS comes back in a result object: read it with cb200_result_site, cb200_result_link_dim, cb200_result_link_charges */
 int cb200_mps_translate(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double cutoff, cb200_result** out);
 /* innerC(a, b) = <a|b> (src/dmrg.h:1063); re_im[2] */
 int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, int32_t d, const int32_t* site_charge, double* re_im);
