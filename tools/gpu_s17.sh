@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s17_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/s17_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 300 python -m chain_b200.driver -s haagerupq -b p -l 6 -d 1600 -c 1e-8 -p 1e-2 -j 0,-1,0 -u 2 -q 0 -n 2 -m 5 --out gpurun_out/drv_readme --seed 1 2>&1 | tail -12
+cat gpurun_out/drv_readme/an/*.an
