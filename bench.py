@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg5": ("haagerupq", "p", 8, [-1.0, 0.0, 0.0], 4000, "haagerupq p j=(-1,0,0) synthetic D=4000 Z3(1334,1333,1333) k=26(10,8,8) f64 (BASELINE configs[4])"),
     "cfg3": ("golden", "p", 24, [-1.0], 800, "golden p synthetic D=800 k=10 f64 dense (BASELINE configs[2])"),
     "cfg4": ("haagerup", "o", 12, [0.0, -1.0, 0.0], 3000, "haagerup o synthetic D=3000 k=14 f64 dense (BASELINE configs[3])"),
+    "cfg4s": ("haagerup", "o", 12, [0.0, -1.0, 0.0], 1500, "haagerup o synthetic D=1500 k=14 f64 dense (half-size BASELINE configs[3])"),
     "tiny": ("haagerupq", "p", 8, [0.0, -1.0, 0.0], 96, "haagerupq p j=(0,-1,0) synthetic D=96 (smoke size)"),
 }
 
@@ -193,8 +194,16 @@ def main():
 
     w = build_workload(args.workload, seed=2000)          # every rank holds the same bond problem
     ctx = cb.Context(device=local_rank)
+    exchange = args.exchange
     if world > 1:
-        ctx.shard(rank, world, mode=args.exchange, landing_bytes=w["phi"].size * (16 if w["dims"]["cplx"] else 8), min_dim=0)
+        try:
+            ctx.shard(rank, world, mode=exchange, landing_bytes=w["phi"].size * (16 if w["dims"]["cplx"] else 8), min_dim=0)
+        except cb.ChainB200Error as err:
+            if exchange != "p2p":
+                raise
+            print("bench: %s -- falling back to --exchange nccl" % err, file=sys.stderr)   # same decision on every rank (see Context.shard)
+            exchange = "nccl"
+            ctx.shard(rank, world, mode=exchange, min_dim=0)
     bond = cb.Bond(w["L"], w["W1"], w["W2"], w["R"], ql=w["ql"], qr=w["qr"], qkl=w["qkl"], qkm=w["qkm"], qkr=w["qkr"],
                    site_charges=w["sq"], nq=w["nq"], ctx=ctx)
     falg = bond.matvec_flops
@@ -300,7 +309,7 @@ def main():
                 "dtype": "c128" if w["dims"]["cplx"] else "f64", "data": "synthetic",
                 "config": {"workload": w["desc"], "dims": w["dims"], "f_alg_per_matvec": falg,
                            "l2": "inputs larger than L2 (phi + environments + intermediates >> 126 MB)",
-                           "parallelism": "single GPU" if world == 1 else "matvec row-sharded x%d, exchange=%s" % (world, args.exchange)},
+                           "parallelism": "single GPU" if world == 1 else "matvec row-sharded x%d, exchange=%s" % (world, exchange)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "wall_s_timed_region": wall}

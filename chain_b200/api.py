@@ -69,11 +69,23 @@ class Context:
             else:
                 if landing_bytes <= 0:
                     raise ValueError("p2p sharding needs landing_bytes >= the largest phi in bytes")
+                # every rank takes part in both exchanges even when its own step failed, so that a CUDA-IPC problem on one rank
+                # surfaces as the same exception everywhere instead of a hang
                 buf = C.create_string_buffer(64)
-                self.check(self.lib.cb200_shard_alloc(self.h, int(landing_bytes), buf))
+                rc = self.lib.cb200_shard_alloc(self.h, int(landing_bytes), buf)
                 allh = [None] * world
-                dist.all_gather_object(allh, buf.raw, group=group)
+                dist.all_gather_object(allh, buf.raw if rc == 0 else None, group=group)
+                if any(h is None for h in allh):
+                    raise ChainB200Error(-3, "p2p sharding unavailable: cb200_shard_alloc failed on rank(s) %s" % [i for i, h in enumerate(allh) if h is None])
                 handles = C.create_string_buffer(b"".join(allh), 64 * world)
+                rc = self.lib.cb200_shard_setup(self.h, rank, world, m, uid, handles, int(min_dim))
+                rcs = [None] * world
+                dist.all_gather_object(rcs, int(rc), group=group)
+                if any(r != 0 for r in rcs):
+                    self.lib.cb200_shard_setup(self.h, 0, 1, 0, None, None, int(min_dim))      # back to unsharded
+                    raise ChainB200Error(-3, "p2p sharding unavailable: peer mapping failed on rank(s) %s" % [i for i, r in enumerate(rcs) if r != 0])
+                self.shard_rank, self.shard_world, self.shard_mode = rank, world, mode
+                return
         self.check(self.lib.cb200_shard_setup(self.h, rank, world, m, uid, handles, int(min_dim)))
         self.shard_rank, self.shard_world, self.shard_mode = rank, world, mode
 

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <type_traits>
 #include <vector>
 #include "backend.h"
@@ -30,6 +32,13 @@ struct Backend {
   std::string err;
   bool has_err = false;
   cudaEvent_t ev[8] = {};
+  // Exact-size block cache in front of the stream-ordered pool.  A sweep asks for the same multi-GB temporaries bond after bond;
+  // the pool sub-allocates and fragments, so large requests kept falling through to new physical allocations (seconds per
+  // bond at D = 3000).  Freed blocks >= 32 MiB are parked here and handed back to the next request of (nearly) the same size; all work is
+  // on one stream, so reuse is ordered.  Bounded: the largest parked blocks are released when the cache exceeds its cap.
+  std::unordered_map<void*, size_t> live_size;
+  std::multimap<size_t, void*> parked;
+  size_t parked_bytes = 0, parked_cap = (size_t)48 << 30;
   double* d_bounds = nullptr;     // eigensolver scratch (Gershgorin bounds, pivmin, ||T||)
   // multi-GPU: symmetric area [flags (256 B) | landing 0 | landing 1] + the peers' mappings (CUDA IPC)
   char* sym = nullptr;
@@ -131,6 +140,9 @@ void backend_destroy(Backend* b) {
   if (b->comm && b->p_ncclCommDestroy) b->p_ncclCommDestroy(b->comm);
   for (int r = 0; r < MAX_PEERS; ++r)
     if (b->peer_opened[r]) cudaIpcCloseMemHandle(b->peer_sym[r]);
+  for (auto& kv : b->parked) cudaFreeAsync(kv.second, b->stream);
+  b->parked.clear();
+  cudaStreamSynchronize(b->stream);
   if (b->sym) cudaFree(b->sym);
   if (b->d_bounds) cudaFree(b->d_bounds);
   cudaFree(b->d_partial);
@@ -140,14 +152,50 @@ void backend_destroy(Backend* b) {
   delete b;
 }
 
+static constexpr size_t PARK_MIN = (size_t)32 << 20;   // smaller blocks are the pool's business (it recycles them well)
+
 void* dev_alloc(Backend* b, size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
+  if (bytes >= PARK_MIN) {
+    auto it = b->parked.lower_bound(bytes);           // smallest parked block that fits, if it wastes < 1/8
+    if (it != b->parked.end() && it->first <= bytes + bytes / 8) {
+      p = it->second;
+      const size_t got = it->first;
+      b->parked.erase(it);
+      b->parked_bytes -= got;
+      b->live_size[p] = got;
+      return p;
+    }
+  }
   cudaError_t e = cudaMallocAsync(&p, bytes, b->stream);
+  if (e != cudaSuccess && !b->parked.empty()) {       // out of memory with blocks parked: release them and retry once
+    cudaGetLastError();
+    for (auto& kv : b->parked) cudaFreeAsync(kv.second, b->stream);
+    b->parked.clear();
+    b->parked_bytes = 0;
+    cudaStreamSynchronize(b->stream);
+    e = cudaMallocAsync(&p, bytes, b->stream);
+  }
   if (e != cudaSuccess) { set_err(b, "cudaMallocAsync", e); return nullptr; }
+  if (bytes >= PARK_MIN) b->live_size[p] = bytes;
   return p;
 }
-void dev_free(Backend* b, void* p) { if (p) CB_CHECK(b, cudaFreeAsync(p, b->stream)); }
+void dev_free(Backend* b, void* p) {
+  if (!p) return;
+  auto it = b->live_size.find(p);
+  if (it == b->live_size.end()) { CB_CHECK(b, cudaFreeAsync(p, b->stream)); return; }
+  const size_t bytes = it->second;
+  b->live_size.erase(it);
+  b->parked.emplace(bytes, p);
+  b->parked_bytes += bytes;
+  while (b->parked_bytes > b->parked_cap && !b->parked.empty()) {   // over the cap: let the largest parked blocks go
+    auto big = std::prev(b->parked.end());
+    b->parked_bytes -= big->first;
+    CB_CHECK(b, cudaFreeAsync(big->second, b->stream));
+    b->parked.erase(big);
+  }
+}
 void dev_memset0(Backend* b, void* p, size_t bytes) { if (bytes) CB_CHECK(b, cudaMemsetAsync(p, 0, bytes, b->stream)); }
 void dev_h2d(Backend* b, void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
