@@ -166,3 +166,17 @@ def test_translation_and_momentum_on_gpu(gpu_ctx, tmp_path):
     import test_translation as tt
     tt.test_translate_and_overlap_match_oracle(gpu_ctx, "haagerupq", 6, [-1.0, 0.0, 0.0], 1)
     tt.test_momentum_assignment_golden(gpu_ctx, tmp_path)
+
+
+def test_random_structures_on_gpu(gpu_ctx):
+    import test_random_structures as tr
+    for seed in (0, 1, 5):
+        rng = np.random.default_rng(100 + seed)
+        dims_l, dims_r = rng.integers(0, 6, 3), rng.integers(0, 6, 3)
+        if dims_l.sum() == 0: dims_l[0] = 2
+        if dims_r.sum() == 0: dims_r[0] = 2
+        cp = [[-1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [-0.5, 0.3, 0.2]][seed % 4]
+        b = tr.random_bond(rng, "haagerupq", cp, dims_l.tolist(), dims_r.tolist(), cplx_data=(seed % 2 == 1))
+        if np.any(b["phi"]):
+            tr.check(gpu_ctx, b)
+    tr.check(gpu_ctx, tr.random_bond(np.random.default_rng(3), "haagerup", [0.0, -1.0, 0.0], [3], [5]))
