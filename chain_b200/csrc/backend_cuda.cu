@@ -964,7 +964,11 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
     if (v && atoi(v) > 0) per_sm = std::min(per_sm, atoi(v));
     grid_blocks[cplx] = std::max(1, per_sm) * std::max(1, sms);
   }
-  const int blocks = (int)std::min<int64_t>(grid_blocks[cplx], std::max<int64_t>(1, (n + TRI_WARPS - 1) / TRI_WARPS));
+  int blocks = (int)std::min<int64_t>(grid_blocks[cplx], std::max<int64_t>(1, (n + TRI_WARPS - 1) / TRI_WARPS));
+  {
+    static const int cap = [] { const char* v = getenv("CB200_TRI_MAX_CTAS"); return v ? atoi(v) : 0; }();
+    if (cap > 0) blocks = std::min(blocks, cap);
+  }
   const int64_t nref = n - 1;
   const int npanel = (int)((nref + NB - 1) / NB);
   char* pan = (char*)dev_alloc(b, 6 * es * (size_t)n * NB);          // Vp | W | Vn | Wn (n x NB, ld n) | Vt | Wt (NB x n, ld NB)

@@ -227,6 +227,28 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
       // (only for columns long enough to be bandwidth-bound: the two extra CTA barriers cost more than they save on short ones)
       if (m * (long long)sizeof(T) >= 16384)
         while (f < TRI_WARPS && ncol * (2 * f) <= GW) f *= 2;
+      if (f == 1) {   // the common (latency-bound) case: one warp per column, no CTA barriers
+        for (long long cc = gw; cc < ncol; cc += GW) {
+          const T* col = cc < m ? A + (j + 1) + (j + 1 + cc) * n : (cc < m + i ? W + (j + 1) + (cc - m) * n : Vp + (j + 1) + (cc - m - i) * n);
+          T acc0 = zero, acc1 = zero, acc2 = zero, acc3 = zero;
+          long long r = lane;
+          for (; r + 96 < m; r += 128) {
+            const T a0 = col[r], a1 = col[r + 32], a2_ = col[r + 64], a3 = col[r + 96];
+            const T x0 = x[r], x1 = x[r + 32], x2 = x[r + 64], x3 = x[r + 96];
+            acc0 = t_add(acc0, t_mul(t_conj(a0), r == 0 ? one : t_mul(x0, sc)));
+            acc1 = t_add(acc1, t_mul(t_conj(a1), t_mul(x1, sc)));
+            acc2 = t_add(acc2, t_mul(t_conj(a2_), t_mul(x2, sc)));
+            acc3 = t_add(acc3, t_mul(t_conj(a3), t_mul(x3, sc)));
+          }
+          for (; r < m; r += 32) acc0 = t_add(acc0, t_mul(t_conj(col[r]), r == 0 ? one : t_mul(x[r], sc)));
+          const T acc = t_warp_sum(t_add(t_add(acc0, acc1), t_add(acc2, acc3)));
+          if (lane == 0) {
+            if (cc < m) p[cc] = acc;
+            else if (cc < m + i) g[cc - m] = acc;
+            else g[64 + (cc - m - i)] = acc;
+          }
+        }
+      } else {
       const long long cstride = GW / f;
       const int part = warp & (f - 1);
       const long long seg = ((m + f - 1) / f + 31) / 32 * 32;          // rows per part, multiple of 32
@@ -264,6 +286,7 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
           else if (cc < m + i) g[cc - m] = acc;              // g1 = W^H v
           else g[64 + (cc - m - i)] = acc;                    // g2 = V^H v
         }
+      }
       }
     }
     grid.sync();
