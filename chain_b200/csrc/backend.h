@@ -117,6 +117,12 @@ void launch_zt_to_v(Backend*, bool cplx, const double* Zt, int64_t n, int64_t m,
 void launch_form_y(Backend*, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, int64_t j0, int nbk, void* Y);
 void launch_wy_t(Backend*, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg);
 
+// ITensor's truncate() evaluated on the device: pooled[n] (device, any order) is rank-sorted descending into sorted[n], then ONE
+// thread applies the rule of SURVEY App. A.5 verbatim (negative tail zeroed, maxdim, relative cutoff on the discarded weight,
+// degeneracy guard on docut).  out3 (device): [0] = m, [1] = truncerr, [2] = docut.
+void launch_truncate_select(Backend*, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* sorted,
+                            double* out3);
+
 // FP64 issue-rate calibration (0 = DMMA.8x8x4, 1 = DFMA); TFLOP/s.  Device-only, used by bench.py for the roofline denominator.
 double fp64_pipe_peak(Backend*, int which, int iters);
 

@@ -1098,6 +1098,15 @@ void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int n
   CB_LAUNCH_CHECK(b, "wy_t_kernel");
 }
 
+void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* sorted,
+                            double* out3) {
+  if (n <= 0) return;
+  rank_sort_desc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(pooled, (long long)n, sorted);
+  CB_LAUNCH_CHECK(b, "rank_sort_desc_kernel");
+  truncate_rule_kernel<<<1, 32, 0, b->stream>>>(sorted, (long long)n, (long long)maxdim, (long long)mindim, cutoff, out3);
+  CB_LAUNCH_CHECK(b, "truncate_rule_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ FP64 pipe calibration
 // Pure issue-rate loops (no memory traffic): the roofline denominators for the DMMA GEMM (MEASURED_PEAKS.json has no FP64 entry).
 __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {

@@ -1031,10 +1031,10 @@ bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
   Buf p(be, (int64_t)es * std::max<int64_t>(n, 1));
   if (!launch_tridiag(be, cplx, h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, p.p)) return false;
-  Buf w(be, 8 * std::max<int64_t>(n, 1));
-  launch_bisect(be, (const double*)h.d.p, (const double*)h.e.p, n, (double*)w.p);
+  h.wdev = Buf(be, 8 * std::max<int64_t>(n, 1));
+  launch_bisect(be, (const double*)h.d.p, (const double*)h.e.p, n, (double*)h.wdev.p);
   h.w.resize(n);
-  dev_d2h(be, h.w.data(), w.p, 8 * (size_t)n);
+  dev_d2h(be, h.w.data(), h.wdev.p, 8 * (size_t)n);
   std::reverse(h.w.begin(), h.w.end());
   check_dev(c);
   return true;
@@ -1179,7 +1179,6 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     else { b.n = nr; b.rows = nl; b.colbase = rbase; b.rowbase = lbase; }
   }
   // ---- gather + Jacobi per middle-charge block
-  std::vector<double> pooled;
   for (int qm = 0; qm < nq; ++qm) {
     Blk& b = blk[qm];
     if (b.n == 0) continue;
@@ -1225,10 +1224,13 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       run_gemm(c, cplx, gp, X.p, X.p, rho.p);
       if (heig_values(c, cplx, std::move(rho), b.n, b.h)) {
         b.wd = b.h.w;
-        for (int64_t k = std::min(b.rows, b.n); k < b.n; ++k) b.wd[k] = 0.0;   // rank(X^H X) <= rows: the rest is rounding noise
+        if (b.rows < b.n) {   // rank(X^H X) <= rows: the n - rows smallest eigenvalues are rounding noise (device copy is ascending)
+          for (int64_t k = b.rows; k < b.n; ++k) b.wd[k] = 0.0;
+          dev_memset0(be, b.h.wdev.p, 8 * (size_t)(b.n - b.rows));
+        }
         b.X = std::move(X);
       } else {
-        if (qm != 0 && !pooled.empty()) fail(-3, "split_bond: eigensolver became unavailable mid-way");
+        if (qm != 0) fail(-3, "split_bond: eigensolver became unavailable mid-way");
         tri = false;
       }
     }
@@ -1246,19 +1248,37 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     for (int qm = 0; qm < nq; ++qm) {
       Blk& b = blk[qm];
       if (b.n == 0) continue;
-      Buf w(be, 8 * b.n);
-      if (owner(qm) == sh.rank) dev_h2d(be, w.p, b.wd.data(), 8 * (size_t)b.n);
-      shard_broadcast(c, w.p, 8 * b.n, owner(qm));
-      dev_d2h(be, b.wd.data(), w.p, 8 * (size_t)b.n);
+      if (owner(qm) != sh.rank) b.h.wdev = Buf(be, 8 * b.n);
+      shard_broadcast(c, b.h.wdev.p, 8 * b.n, owner(qm));
+      if (owner(qm) != sh.rank) {
+        dev_d2h(be, b.wd.data(), b.h.wdev.p, 8 * (size_t)b.n);
+        std::reverse(b.wd.begin(), b.wd.end());
+      }
     }
   }
-  for (int qm = 0; qm < nq; ++qm)
-    for (int64_t k = 0; k < blk[qm].n; ++k) pooled.push_back(blk[qm].wd[k]);
-  std::sort(pooled.begin(), pooled.end(), std::greater<double>());
+  // ---- cutoff / maxdim selection ON THE DEVICE: the blocks' eigenvalues are pooled device-to-device, rank-sorted, and ITensor's
+  // truncate() rule is applied by one thread; only (m, truncerr, docut) come back
+  int64_t npool = 0;
+  for (int qm = 0; qm < nq; ++qm) npool += blk[qm].n;
+  if (npool == 0) fail(-2, "split_bond: empty bond");
   int64_t m = 0;
   double terr = 0, docut = 0;
-  if (pooled.empty()) fail(-2, "split_bond: empty bond");
-  truncate_probs(pooled, maxdim, mindim, cutoff, &m, &terr, &docut);
+  {
+    Buf pool(be, 8 * npool), sorted(be, 8 * npool), out3(be, 24);
+    int64_t off = 0;
+    for (int qm = 0; qm < nq; ++qm) {
+      Blk& b = blk[qm];
+      if (b.n == 0) continue;
+      if (tri) dev_d2d(be, (char*)pool.p + 8 * off, b.h.wdev.p, 8 * (size_t)b.n);
+      else dev_h2d(be, (char*)pool.p + 8 * off, b.wd.data(), 8 * (size_t)b.n);     // block-Jacobi path: column norms live on the host
+      off += b.n;
+    }
+    launch_truncate_select(be, (const double*)pool.p, npool, maxdim, mindim, cutoff, (double*)sorted.p, (double*)out3.p);
+    double o3[3];
+    dev_d2h(be, o3, out3.p, 24);
+    m = (int64_t)o3[0]; terr = o3[1]; docut = o3[2];
+  }
+  (void)m;
   SplitResult res;
   res.truncerr = terr;
   res.mid = Grading(nq);

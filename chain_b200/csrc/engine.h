@@ -261,7 +261,8 @@ struct Heig {
   int64_t n = 0;
   bool cplx = false;
   Buf A, d, e, tau, scl;
-  std::vector<double> w;      // all eigenvalues, descending
+  Buf wdev;                   // all eigenvalues on the device, ASCENDING (bisection order)
+  std::vector<double> w;      // all eigenvalues, descending (host copy: shifts of the inverse iteration, spectrum output)
   int ns_iters = 0;
 };
 bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h);   // false: backend has no tridiagonalisation kernel

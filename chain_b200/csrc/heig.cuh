@@ -610,4 +610,47 @@ __global__ void __launch_bounds__(64) wy_t_kernel(const void* __restrict__ S_, c
   for (int k = r; k < nb * nb; k += 64) Tn[k] = t_scale(Ts[k], -1.0);
 }
 
+// ---- cutoff / maxdim selection on the device (ITensor truncate()) ------------------------------------------
+// rank sort: position of pooled[i] in descending order (ties broken by index, so the result is a permutation)
+__global__ void __launch_bounds__(256) rank_sort_desc_kernel(const double* __restrict__ in, long long n, double* __restrict__ out) {
+  __shared__ double tile[256];
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const double mine = i < n ? in[i] : 0.0;
+  long long rank = 0;
+  for (long long j0 = 0; j0 < n; j0 += 256) {
+    __syncthreads();
+    tile[threadIdx.x] = (j0 + threadIdx.x < n) ? in[j0 + threadIdx.x] : -1e308;
+    __syncthreads();
+    const int lim = (int)((n - j0) < 256 ? (n - j0) : 256);
+    for (int t = 0; t < lim; ++t) {
+      const double v = tile[t];
+      rank += (v > mine) || (v == mine && (j0 + t) < i);
+    }
+  }
+  if (i < n) out[rank] = mine;
+}
+
+__global__ void truncate_rule_kernel(double* __restrict__ P, long long origm, long long maxdim, long long mindim, double cutoff,
+                                     double* __restrict__ out3) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long n = origm - 1;
+  for (long long zn = n; zn >= 0 && P[zn] < 0.0; --zn) P[zn] = 0.0;
+  if (origm == 1) { out3[0] = 1.0; out3[1] = 0.0; out3[2] = P[0] / 2.0; return; }
+  double truncerr = 0.0;
+  while (n >= maxdim) { truncerr += P[n]; --n; }
+  double scale = 0.0;
+  for (long long k = 0; k < origm; ++k) scale += P[k];
+  if (scale == 0.0) scale = 1.0;
+  while (n >= mindim && n >= 0 && truncerr + P[n] < cutoff * scale) { truncerr += P[n]; --n; }
+  truncerr /= scale;
+  if (n < 0) n = 0;
+  const long long m = n + 1;
+  double docut = 0.0;
+  if (m < origm) {
+    docut = (P[m - 1] + P[m]) / 2.0;
+    if (fabs(P[m - 1] - P[m]) < 1e-3 * P[m - 1]) docut += 1e-3 * P[m - 1];
+  }
+  out3[0] = (double)m; out3[1] = truncerr; out3[2] = docut;
+}
+
 }  // namespace cb200

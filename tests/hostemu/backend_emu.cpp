@@ -4,6 +4,7 @@
 // in the GPU-less container.  Each function executes the same task lists the CUDA kernels execute, with the
 // simplest possible loops; it makes no attempt to mirror the kernels' arithmetic order.
 #include <cmath>
+#include <algorithm>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -455,6 +456,34 @@ static void wy_t_t(const T* S, const T* tau, int nb, T* Tn) {
 void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg) {
   b->launches++;
   if (cplx) wy_t_t<cd>((const cd*)S, (const cd*)tau_j0, nbk, (cd*)Tneg); else wy_t_t<double>((const double*)S, (const double*)tau_j0, nbk, (double*)Tneg);
+}
+
+void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* P,
+                            double* out3) {
+  b->launches++;
+  if (n <= 0) return;
+  std::vector<double> v(pooled, pooled + n);
+  std::stable_sort(v.begin(), v.end(), [](double x, double y) { return x > y; });
+  for (int64_t i = 0; i < n; ++i) P[i] = v[i];
+  const int64_t origm = n;
+  int64_t nn = origm - 1;
+  for (int64_t zn = nn; zn >= 0 && P[zn] < 0; --zn) P[zn] = 0;
+  if (origm == 1) { out3[0] = 1; out3[1] = 0; out3[2] = P[0] / 2.0; return; }
+  double truncerr = 0;
+  while (nn >= maxdim) { truncerr += P[nn]; --nn; }
+  double scale = 0;
+  for (int64_t k = 0; k < origm; ++k) scale += P[k];
+  if (scale == 0) scale = 1.0;
+  while (nn >= mindim && nn >= 0 && truncerr + P[nn] < cutoff * scale) { truncerr += P[nn]; --nn; }
+  truncerr /= scale;
+  if (nn < 0) nn = 0;
+  const int64_t m = nn + 1;
+  double docut = 0;
+  if (m < origm) {
+    docut = (P[m - 1] + P[m]) / 2.0;
+    if (std::fabs(P[m - 1] - P[m]) < 1e-3 * P[m - 1]) docut += 1e-3 * P[m - 1];
+  }
+  out3[0] = (double)m; out3[1] = truncerr; out3[2] = docut;
 }
 
 void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, const double* Zt, int64_t m, void* V) {
