@@ -864,30 +864,6 @@ void two_site(Ctx* c, bool cplx, const DevSite3& A, const DevSite3& B, const Phi
   run_gemm(c, cplx, p, A.buf.p, B.buf.p, phi);
 }
 
-// ------------------------------------------------------------------------------------------------ truncation rule (A.5)
-void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, double cutoff, int64_t* m_out, double* terr_out,
-                    double* docut_out) {
-  const int64_t origm = (int64_t)P.size();
-  int64_t n = origm - 1;
-  for (int64_t zn = n; zn >= 0 && P[zn] < 0; --zn) P[zn] = 0;
-  if (origm == 1) { *m_out = 1; *terr_out = 0; *docut_out = P[0] / 2.0; return; }
-  double truncerr = 0;
-  while (n >= maxdim) { truncerr += P[n]; --n; }
-  double scale = 0;
-  for (double x : P) scale += x;
-  if (scale == 0) scale = 1.0;
-  while (n >= mindim && n >= 0 && truncerr + P[n] < cutoff * scale) { truncerr += P[n]; --n; }
-  truncerr /= scale;
-  if (n < 0) n = 0;
-  const int64_t m = n + 1;
-  double docut = 0;
-  if (m < origm) {
-    docut = (P[m - 1] + P[m]) / 2.0;
-    if (std::fabs(P[m - 1] - P[m]) < 1e-3 * P[m - 1]) docut += 1e-3 * P[m - 1];
-  }
-  *m_out = m; *terr_out = truncerr; *docut_out = docut;
-}
-
 // ------------------------------------------------------------------------------------------------ block Jacobi SVD
 // Inner-solver sweep cap (CB200_JACOBI_INNER overrides; 0 = to convergence).
 static int jacobi_inner_sweeps() {

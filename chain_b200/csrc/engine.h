@@ -268,8 +268,6 @@ struct Heig {
 bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h);   // false: backend has no tridiagonalisation kernel
 Buf heig_vectors(Ctx* c, Heig& h, int64_t m);                       // n x m column-major, orthonormal, spans the top-m eigenspace
 
-// ITensor truncate() on a descending spectrum
-void truncate_probs(std::vector<double>& P, int64_t maxdim, int64_t mindim, double cutoff, int64_t* m, double* truncerr, double* docut);
 
 // ---- import / export ---------------------------------------------------------------------------------------------
 HostW import_w(int nq, int d, const SiteInfo& S, const IndexMap& kl, const IndexMap& kr, bool cplx, const void* data);
