@@ -99,7 +99,16 @@ def main():
     t0 = time.perf_counter()
     psi, dims = random_right_canonical(ss, n, D, H.is_complex(), seed=0)
     t_gen = time.perf_counter() - t0
-    ctx = cb.Context(0)
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = cb.Context(local)
+    if world > 1:        # torchrun: every rank drives the same sweep; matvecs of bonds with D >= 1600 are row-sharded, Z_N truncations spread
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        big = max(int(a.sum()) for a in dims)
+        ctx.shard(rank, world, mode="p2p", landing_bytes=big * big * ss.d * ss.d * (16 if H.is_complex() else 8) // max(ss.nq, 1) + (1 << 20),
+                  min_dim=int(os.environ.get("CB200_SHARD_MIN_DIM", "1600")))
     out = []
     for sw in range(nsweep):                             # sweep 0 also pays the first-touch growth of the memory pool
         info = cb.DmrgInfo()
@@ -111,7 +120,9 @@ def main():
         out.append(dict(sweep=sw, wall_s=wall, energy=en, bond_updates=len(info.stats), max_m=max(s["m"] for s in info.stats),
                         env_s=t["env"], matvec_s=t["matvec"], level1_s=t["level1"], trunc_s=t["trunc"], other_s=t["other"],
                         matvecs=int(t["nmatvec"]), matvec_tflops=t["matvec_flops"] / max(t["matvec"], 1e-12) / 1e12, launches=ctx.launches - l0))
-    print(json.dumps(dict(workload="%s %s L=%d D=%d j=%s (synthetic right-canonical MPS, true MPO k=%d)" % (st, bc, n, D, sys.argv[5], max(len(q) for q in mpo.link_charges)),
+    if rank != 0:
+        return
+    print(json.dumps(dict(n_gpus=world, workload="%s %s L=%d D=%d j=%s (synthetic right-canonical MPS, true MPO k=%d)" % (st, bc, n, D, sys.argv[5], max(len(q) for q in mpo.link_charges)),
                           dtype="c128" if H.is_complex() else "f64", bond_profile=[int(x.sum()) for x in dims], host_generation_s=t_gen, sweeps=out)))
 
 
