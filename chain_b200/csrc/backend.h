@@ -34,11 +34,14 @@ void dev_event_record(Backend*, int slot);            // timing helpers (CUDA ev
 float dev_event_elapsed_ms(Backend*, int slot0, int slot1);
 
 // Grouped segment-accumulating GEMM (tasks.h). All tasks of a launch share the transpose flags.
-// narrow = true selects the 64-column tile (tasks must then be tiled with gemm_tile_n(cplx, true)).
-void launch_gemm(Backend*, bool cplx, bool transA, bool transB, bool narrow, const void* A, const void* B, void* C,
+// Tile mode (tasks must be tiled with gemm_tile_n(cplx, mode)): WIDE = 128 columns; NARROW = 64 columns (Jacobi rotations, Gram
+// blocks); NARROW_3M / MID_3M = 64 / 96 columns with the 3-multiplication complex product (complex only: 3 DMMA per complex MAC
+// instead of 4; the third accumulator set does not fit the register budget at 128 columns).
+enum { GEMM_TILE_WIDE = 0, GEMM_TILE_NARROW = 1, GEMM_TILE_NARROW_3M = 2, GEMM_TILE_MID_3M = 3 };
+void launch_gemm(Backend*, bool cplx, bool transA, bool transB, int mode, const void* A, const void* B, void* C,
                  const GemmTask* d_tasks, int ntasks, const GemmSeg* d_segs, int total_tiles);
 int gemm_tile_m(bool cplx);
-int gemm_tile_n(bool cplx, bool narrow);
+int gemm_tile_n(bool cplx, int mode);
 
 // ---- multi-GPU plumbing (one process per GPU) ---------------------------------------------------------
 // Symmetric "landing" area: [flags | landing 0 | landing 1], allocated with cudaMalloc so that it can be exported through
@@ -52,7 +55,7 @@ void shard_peer_bases(Backend*, int which, PeerBases* out);   // every rank's la
 // stream-ordered barrier across the ranks: publishes this rank's peer stores and waits for everybody else's
 void shard_barrier(Backend*);
 // the R-stage GEMM (A not transposed, B transposed) with its C tiles stored to every destination in `peers`
-void launch_gemm_peer(Backend*, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* d_tasks, int ntasks,
+void launch_gemm_peer(Backend*, bool cplx, int mode, const void* A, const void* B, const PeerBases& peers, const GemmTask* d_tasks, int ntasks,
                       const GemmSeg* d_segs, int total_tiles);
 // broadcast `bytes` of device memory from rank `root` to every rank (in place): peer stores into the landing half `which` + the flag
 // barrier (bytes must fit one landing half; the engine chunks), or ncclBroadcast

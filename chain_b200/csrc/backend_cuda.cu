@@ -127,6 +127,16 @@ Backend* backend_create(int device, char* err, size_t errlen) {
 #undef CB_OPT
     opt((const void*)gemm_grouped_peer_kernel<false>, GemmCfg<false, 128>::SMEM_BYTES);
     opt((const void*)gemm_grouped_peer_kernel<true>, GemmCfg<true, 128>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_peer_kernel<true, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_peer_kernel<true, 96, true>, GemmCfg<true, 96>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, false, false, 96, true>, GemmCfg<true, 96>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, false, true, 96, true>, GemmCfg<true, 96>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, true, false, 96, true>, GemmCfg<true, 96>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, true, true, 96, true>, GemmCfg<true, 96>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, false, false, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, false, true, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, true, false, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
+    opt((const void*)gemm_grouped_kernel<true, true, true, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
   }
   cudaGetLastError();
   return b;
@@ -223,33 +233,46 @@ float dev_event_elapsed_ms(Backend* b, int s0, int s1) {
 
 // ------------------------------------------------------------------------------------------------ GEMM
 int gemm_tile_m(bool cplx) { return cplx ? GemmCfg<true>::BM : GemmCfg<false>::BM; }
-int gemm_tile_n(bool, bool narrow) { return narrow ? 64 : 128; }
+int gemm_tile_n(bool, int mode) { return mode == GEMM_TILE_WIDE ? 128 : (mode == GEMM_TILE_MID_3M ? 96 : 64); }
 
-template <bool CPLX, int BN_>
+template <bool CPLX, int BN_, bool M3 = false>
 static void launch_gemm_t(Backend* b, bool ta, bool tb, const void* A, const void* B, void* C, const GemmTask* t, int nt,
                           const GemmSeg* s, int tiles) {
   const int smem = GemmCfg<CPLX, BN_>::SMEM_BYTES;
   const char* a = (const char*)A;
   const char* bb = (const char*)B;
   char* c = (char*)C;
-  if (!ta && !tb) gemm_grouped_kernel<CPLX, false, false, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else if (!ta && tb) gemm_grouped_kernel<CPLX, false, true, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else if (ta && !tb) gemm_grouped_kernel<CPLX, true, false, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
-  else gemm_grouped_kernel<CPLX, true, true, BN_><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  if (!ta && !tb) gemm_grouped_kernel<CPLX, false, false, BN_, M3><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (!ta && tb) gemm_grouped_kernel<CPLX, false, true, BN_, M3><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else if (ta && !tb) gemm_grouped_kernel<CPLX, true, false, BN_, M3><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
+  else gemm_grouped_kernel<CPLX, true, true, BN_, M3><<<tiles, GemmCfg<CPLX, BN_>::THREADS, smem, b->stream>>>(a, bb, c, t, nt, s);
 }
 
-void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool narrow, const void* A, const void* B, void* C, const GemmTask* t,
+void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, int mode, const void* A, const void* B, void* C, const GemmTask* t,
                  int nt, const GemmSeg* s, int tiles) {
   if (tiles <= 0 || nt <= 0) return;
-  if (cplx) { if (narrow) launch_gemm_t<true, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<true, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
-  else { if (narrow) launch_gemm_t<false, 64>(b, ta, tb, A, B, C, t, nt, s, tiles); else launch_gemm_t<false, 128>(b, ta, tb, A, B, C, t, nt, s, tiles); }
+  if (cplx) {
+    if (mode == GEMM_TILE_MID_3M) launch_gemm_t<true, 96, true>(b, ta, tb, A, B, C, t, nt, s, tiles);
+    else if (mode == GEMM_TILE_NARROW_3M) launch_gemm_t<true, 64, true>(b, ta, tb, A, B, C, t, nt, s, tiles);
+    else if (mode == GEMM_TILE_NARROW) launch_gemm_t<true, 64>(b, ta, tb, A, B, C, t, nt, s, tiles);
+    else launch_gemm_t<true, 128>(b, ta, tb, A, B, C, t, nt, s, tiles);
+  } else {
+    if (mode == GEMM_TILE_NARROW) launch_gemm_t<false, 64>(b, ta, tb, A, B, C, t, nt, s, tiles);
+    else if (mode == GEMM_TILE_WIDE) launch_gemm_t<false, 128>(b, ta, tb, A, B, C, t, nt, s, tiles);
+    else set_err(b, "launch_gemm: the 3M tile modes are complex-only", cudaErrorInvalidValue);
+  }
   CB_LAUNCH_CHECK(b, "gemm_grouped_kernel");
 }
 
-void launch_gemm_peer(Backend* b, bool cplx, const void* A, const void* B, const PeerBases& peers, const GemmTask* t, int nt,
+void launch_gemm_peer(Backend* b, bool cplx, int mode, const void* A, const void* B, const PeerBases& peers, const GemmTask* t, int nt,
                       const GemmSeg* s, int tiles) {
   if (tiles <= 0 || nt <= 0) return;
-  if (cplx) gemm_grouped_peer_kernel<true><<<tiles, GemmCfg<true, 128>::THREADS, GemmCfg<true, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  if (cplx && mode == GEMM_TILE_MID_3M)
+    gemm_grouped_peer_kernel<true, 96, true><<<tiles, GemmCfg<true, 96>::THREADS, GemmCfg<true, 96>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  else if (cplx && mode == GEMM_TILE_NARROW_3M)
+    gemm_grouped_peer_kernel<true, 64, true><<<tiles, GemmCfg<true, 64>::THREADS, GemmCfg<true, 64>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
+  else if (mode != GEMM_TILE_WIDE) set_err(b, "launch_gemm_peer: unsupported tile mode", cudaErrorInvalidValue);
+  else if (cplx) gemm_grouped_peer_kernel<true><<<tiles, GemmCfg<true, 128>::THREADS, GemmCfg<true, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
   else gemm_grouped_peer_kernel<false><<<tiles, GemmCfg<false, 128>::THREADS, GemmCfg<false, 128>::SMEM_BYTES, b->stream>>>((const char*)A, (const char*)B, t, nt, s, peers);
   CB_LAUNCH_CHECK(b, "gemm_grouped_peer_kernel");
 }
@@ -983,7 +1006,7 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   std::vector<GemmTask> tasks(npanel);
   std::vector<GemmSeg> segs(2 * (size_t)npanel);
   std::vector<int> tiles(npanel, 0);
-  const int bm = gemm_tile_m(cplx), bn = gemm_tile_n(cplx, false);
+  const int bm = gemm_tile_m(cplx), bn = gemm_tile_n(cplx, GEMM_TILE_WIDE);
   for (int pi = 0; pi < npanel; ++pi) {
     const int64_t j0 = (int64_t)pi * NB;
     const int nbk = (int)std::min<int64_t>(NB, nref - j0);
@@ -1013,7 +1036,7 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
     CB_LAUNCH_CHECK(b, "tridiag_panel_kernel");
     const int64_t t0 = j0 + nbk;
     if (t0 < n - 1 && tiles[pi] > 0)    // (the last panel updates the final diagonal element itself)
-      launch_gemm(b, cplx, false, true, false, Vn, W, A, d_tasks + pi, 1, d_segs, tiles[pi]);
+      launch_gemm(b, cplx, false, true, GEMM_TILE_WIDE, Vn, W, A, d_tasks + pi, 1, d_segs, tiles[pi]);
   }
   dev_free(b, pan); dev_free(b, gbuf); dev_free(b, partial); dev_free(b, d_tasks); dev_free(b, d_segs);
   return true;

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -440,17 +441,21 @@ int cb200_k_gemm(cb200_ctx* ctx, int32_t dtype, int32_t trans_a, int32_t trans_b
     t.c_off = c_off; t.c_off2 = c_off; t.ldc = ldc; t.M = M; t.N = N; t.n_split = N;
     t.seg_begin = 0; t.seg_count = nseg;
     t.flags = (trans_a ? GEMM_TRANS_A : 0) | (trans_b ? GEMM_TRANS_B : 0) | (conj_a ? GEMM_CONJ_A : 0) | (accumulate ? GEMM_ACCUM : 0);
-    const int tm = gemm_tile_m(cx), tn = gemm_tile_n(cx, false);
+    // tile mode of this test hook: CB200_K_GEMM_MODE = 0 wide (default), 1 narrow, 2 narrow + 3M, 3 mid (96) + 3M (3M: complex only)
+    const char* me = getenv("CB200_K_GEMM_MODE");
+    int mode = me ? atoi(me) : GEMM_TILE_WIDE;
+    if (!cx && (mode == GEMM_TILE_NARROW_3M || mode == GEMM_TILE_MID_3M)) mode = GEMM_TILE_WIDE;
+    const int tm = gemm_tile_m(cx), tn = gemm_tile_n(cx, mode);
     t.tile_begin = 0; t.tiles_m = (M + tm - 1) / tm;
     const int tiles = t.tiles_m * ((N + tn - 1) / tn);
     for (int s = 0; s < nseg; ++s) { segs[s] = GemmSeg{}; segs[s].a_off = a_off[s]; segs[s].b_off = b_off[s]; segs[s].lda = lda; segs[s].ldb = ldb; segs[s].K = K[s]; }
     DevList<GemmTask> dt; DevList<GemmSeg> dsg;
     dt.upload(c->be, tasks); dsg.upload(c->be, segs);
-    launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+    launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, mode, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
     dev_d2h(c->be, C, dC.p, es * c_elems);
     if (reps > 0 && ms_mean) {
       dev_event_record(c->be, 0);
-      for (int i = 0; i < reps; ++i) launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, false, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
+      for (int i = 0; i < reps; ++i) launch_gemm(c->be, cx, trans_a != 0, trans_b != 0, mode, dA.p, dB.p, dC.p, dt.ptr(), 1, dsg.ptr(), tiles);
       dev_event_record(c->be, 1);
       *ms_mean = dev_event_elapsed_ms(c->be, 0, 1) / reps;
     }

@@ -168,12 +168,13 @@ namespace {
 struct GemmBuilder {
   std::vector<GemmTask> tasks;
   std::vector<GemmSeg> segs;
-  bool cplx, narrow;
+  bool cplx;
+  int mode;
   double flops = 0, flops_full = 0;
   double ratio = 1.0;      // full rows / local rows of the task being built (row-sharded plans)
   GemmTask cur{};
   bool open = false;
-  GemmBuilder(bool cplx_, bool narrow_ = false) : cplx(cplx_), narrow(narrow_) {}
+  GemmBuilder(bool cplx_, int mode_ = GEMM_TILE_WIDE) : cplx(cplx_), mode(cplx_ ? mode_ : ((mode_ == GEMM_TILE_NARROW_3M || mode_ == GEMM_TILE_MID_3M) ? GEMM_TILE_WIDE : mode_)) {}
   void chunk(int64_t rows, int64_t stride) { cur.chunk = (int32_t)std::max<int64_t>(rows, 1); cur.chunk_stride = stride; }
   void begin(int64_t c_off, int64_t ldc, int64_t M, int64_t N, uint32_t flags) {
     cur = GemmTask{};
@@ -200,7 +201,7 @@ struct GemmBuilder {
     tasks.push_back(cur);
   }
   void finish(Backend* be, GemmPlan& p, bool ta, bool tb) {
-    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, narrow);
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, mode);
     int tiles = 0;
     for (auto& t : tasks) {
       t.tile_begin = tiles;
@@ -210,13 +211,20 @@ struct GemmBuilder {
     p.tasks.upload(be, tasks);
     p.segs.upload(be, segs);
     p.tiles = tiles;
-    p.ta = ta; p.tb = tb; p.narrow = narrow;
+    p.ta = ta; p.tb = tb; p.mode = mode;
     p.flops = flops * (cplx ? 4.0 : 1.0);
   }
 };
 
+// tile mode of the O(D^3) contractions (matvec stages, environment update): complex data uses the 3-multiplication kernel unless
+// CB200_CPLX_3M=0 (A/B switch; the 4-multiplication kernel with the wide tile is the fallback)
+int heavy_mode(bool cplx) {
+  static const int v = [] { const char* e = getenv("CB200_CPLX_3M"); return e ? atoi(e) : 96; }();   // 0 off, 64 / 96 = tile columns
+  return (cplx && v) ? (v == 64 ? GEMM_TILE_NARROW_3M : GEMM_TILE_MID_3M) : GEMM_TILE_WIDE;
+}
+
 void run_gemm(Ctx* c, bool cplx, const GemmPlan& p, const void* A, const void* B, void* C) {
-  launch_gemm(c->be, cplx, p.ta, p.tb, p.narrow, A, B, C, p.tasks.ptr(), p.tasks.n, p.segs.ptr(), p.tiles);
+  launch_gemm(c->be, cplx, p.ta, p.tb, p.mode, A, B, C, p.tasks.ptr(), p.tasks.n, p.segs.ptr(), p.tiles);
 }
 
 struct MixBuilder {
@@ -487,7 +495,7 @@ void Bond::plan() {
 
   // ---- GEMM1: T1(qa,ql) = L(ql+qa, qa) [ (l',a) x l ] * Phi_ql [ l x cols ]
   {
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qa = 0; qa < nq; ++qa)
       for (int ql = 0; ql < nq; ++ql) {
         const int qlp = qadd(ql, qa, nq);
@@ -559,7 +567,7 @@ void Bond::plan() {
   // transposed product and storing it with GEMM_TRANS_C) when that wastes fewer tile slots on the ragged sector sizes.
   // Sharded: the (l'_local, srow') rows go straight to rows row_lo + l'_local of the full [l, srow, r] block (chunked C).
   {
-    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, false);
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, heavy_mode(cplx));
     auto padded = [&](int64_t M, int64_t N) { return ((M + tm - 1) / tm) * tm * (((N + tn - 1) / tn) * tn); };
     int64_t cost_n = 0, cost_s = 0;
     for (int qlp = 0; qlp < nq; ++qlp)
@@ -569,7 +577,7 @@ void Bond::plan() {
         cost_s += padded(N, M);
       }
     const bool swap = cost_s < cost_n;
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qlp = 0; qlp < nq; ++qlp)
       for (int qrp = 0; qrp < nq; ++qrp) {
         const int64_t M = Dlo.dim[qlp] * philay.ns(qlp, qrp), N = Dr.dim[qrp];
@@ -613,7 +621,7 @@ void Bond::apply(const void* x, void* y) {
     // all-gather fused into the R-stage epilogue: tiles land in every rank's landing half; the barrier publishes them
     PeerBases pb;
     shard_peer_bases(be, ctx->shard.flip, &pb);
-    launch_gemm_peer(be, cplx, A2, B2, pb, g2.tasks.ptr(), g2.tasks.n, g2.segs.ptr(), g2.tiles);
+    launch_gemm_peer(be, cplx, g2.mode, A2, B2, pb, g2.tasks.ptr(), g2.tasks.n, g2.segs.ptr(), g2.tiles);
     shard_barrier(be);
     dev_d2d(be, y, shard_landing(be, ctx->shard.flip), esz(cplx) * (size_t)philay.total);
     ctx->shard.flip ^= 1;
@@ -919,7 +927,7 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
   };
   GemmPlan gram, appX, appV;
   {
-    GemmBuilder gb(cplx, true);
+    GemmBuilder gb(cplx, GEMM_TILE_NARROW);
     for (int64_t p = 0; p < npairs; ++p) {
       gb.begin(p * NJ * NJ, NJ, NJ, NJ, 0);
       gb.seg(p * NJ * ldx, ldx, p * NJ * ldx, ldx, rows);
@@ -929,7 +937,7 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
     gb.finish(be, gram, true, false);
   }
   {
-    GemmBuilder gx(cplx, true), gv(cplx, true);
+    GemmBuilder gx(cplx, GEMM_TILE_NARROW), gv(cplx, GEMM_TILE_NARROW);
     for (int64_t p = 0; p < npairs; ++p) {
       const int64_t s0 = next_slot(2 * p), s1 = next_slot(2 * p + 1);
       gx.begin(s0 * JB * ldx, ldx, rows, NJ, 0);
@@ -1382,7 +1390,7 @@ void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, cons
   Buf X(be, (int64_t)es * std::max<int64_t>(xt, 1));
   GemmPlan p1;
   {
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qa = 0; qa < nq; ++qa)
       for (int ql = 0; ql < nq; ++ql) {
         const int64_t M = xM[qa * nq + ql], N = A.lay.ncols(ql), K = Dl.dim[ql];
@@ -1443,7 +1451,7 @@ void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, cons
   }
   GemmPlan p3;
   {
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qmp = 0; qmp < nq; ++qmp)
       for (int qap = 0; qap < nq; ++qap) {
         const int qm = qsub(qmp, qap, nq);
@@ -1492,7 +1500,7 @@ void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, con
   Buf X(be, (int64_t)es * std::max<int64_t>(xt, 1));
   GemmPlan p1;
   {
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qa2 = 0; qa2 < nq; ++qa2)
       for (int qm = 0; qm < nq; ++qm)
         for (int qs = 0; qs < nq; ++qs) {
@@ -1555,7 +1563,7 @@ void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, con
   }
   GemmPlan p3;
   {
-    GemmBuilder gb(cplx);
+    GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qmp = 0; qmp < nq; ++qmp)
       for (int qa = 0; qa < nq; ++qa) {
         const int qm = qsub(qmp, qa, nq);

@@ -124,7 +124,8 @@ struct GemmPlan {
   DevList<GemmTask> tasks;
   DevList<GemmSeg> segs;
   int tiles = 0;
-  bool ta = false, tb = false, narrow = false;
+  bool ta = false, tb = false;
+  int mode = 0;       // GEMM_TILE_*
   double flops = 0;   // real flops (x4 already applied for complex by the caller of finish())
 };
 struct MixPlan {

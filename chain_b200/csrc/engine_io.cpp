@@ -269,7 +269,7 @@ struct GB {
   }
   void run(Ctx* c, bool ta, bool tb, const void* A, const void* B, void* C) {
     if (tasks.empty()) return;
-    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, false);
+    const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, GEMM_TILE_WIDE);
     int tiles = 0;
     for (auto& t : tasks) {
       t.tile_begin = tiles;
@@ -280,7 +280,7 @@ struct GB {
     DevList<GemmSeg> dsg;
     dt.upload(c->be, tasks);
     dsg.upload(c->be, segs);
-    launch_gemm(c->be, cplx, ta, tb, false, A, B, C, dt.ptr(), dt.n, dsg.ptr(), tiles);
+    launch_gemm(c->be, cplx, ta, tb, GEMM_TILE_WIDE, A, B, C, dt.ptr(), dt.n, dsg.ptr(), tiles);
   }
 };
 

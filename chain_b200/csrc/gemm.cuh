@@ -165,7 +165,7 @@ __device__ __forceinline__ void load_operand_tile(char* smem, const char* g, int
   }
 }
 
-template <bool CPLX, bool TA, bool TB, int BN_, bool PEER>
+template <bool CPLX, bool TA, bool TB, int BN_, bool PEER, bool M3>
 __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
                                                   const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs,
                                                   const PeerBases& peers) {
@@ -243,14 +243,19 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
 
   // -------------------------------------------------------------------- consumer warps
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Cfg::CONSUMER_REGS));
+  // complex, standard: acc_re = Re, acc_im = Im (4 DMMA per complex MAC).  complex, M3 (Karatsuba "3M"): acc_re = P1 = sum ar*br,
+  // acc_im = P2 = sum ai*bi, acc_p3 = P3 = sum (ar+ai)(br+bi) -- 3 DMMA per complex MAC, Re = P1 - P2, Im = P3 - P1 - P2 formed
+  // once in the epilogue (normwise backward stable; the FP64 adds of the fragment sums run on the DFMA pipe, not the DMMA pipe).
   double acc_re[MT][NT][2];
   double acc_im[CPLX ? MT : 1][CPLX ? NT : 1][2];
+  double acc_p3[(CPLX && M3) ? MT : 1][(CPLX && M3) ? NT : 1][2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       acc_re[i][j][0] = 0.0; acc_re[i][j][1] = 0.0;
       if constexpr (CPLX) { acc_im[i][j][0] = 0.0; acc_im[i][j][1] = 0.0; }
+      if constexpr (CPLX && M3) { acc_p3[i][j][0] = 0.0; acc_p3[i][j][1] = 0.0; }
     }
 
   const bool conjA = (t.flags & GEMM_CONJ_A) != 0;
@@ -285,25 +290,51 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
         for (int i = 0; i < MT; ++i) {
           a[i] = As[i * 8 * A_SM + kk * 4 * A_SK];
           if (conjA) a[i].y = -a[i].y;
-          nai[i] = -a[i].y;
+          nai[i] = M3 ? a[i].x + a[i].y : -a[i].y;          // M3: the fragment sum ar + ai
         }
 #pragma unroll
         for (int j = 0; j < NT; ++j) b[j] = Bs[j * 8 * B_SN + kk * 4 * B_SK];
+        if constexpr (M3) {
+          double bs[NT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i)
+          for (int j = 0; j < NT; ++j) bs[j] = b[j].x + b[j].y;
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
-            dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
-            dmma884(acc_re[i][j][0], acc_re[i][j][1], nai[i], b[j].y);
-            dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
-          }
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+              dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].y);
+              dmma884(acc_p3[i][j][0], acc_p3[i][j][1], nai[i], bs[j]);
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              dmma884(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+              dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
+              dmma884(acc_re[i][j][0], acc_re[i][j][1], nai[i], b[j].y);
+              dmma884(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
+            }
+        }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[it % STAGES]);
   }
 
+  if constexpr (CPLX && M3) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double p1 = acc_re[i][j][e], p2 = acc_im[i][j][e], p3 = acc_p3[i][j][e];
+          acc_re[i][j][e] = p1 - p2;
+          acc_im[i][j][e] = p3 - p1 - p2;
+        }
+  }
   // epilogue: direct stores from the accumulator fragments
   const bool accum = (t.flags & GEMM_ACCUM) != 0;
   const bool conj_out = (t.flags & GEMM_CONJ_OUT) != 0;
@@ -349,21 +380,21 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   }
 }
 
-template <bool CPLX, bool TA, bool TB, int BN_ = 128>
+template <bool CPLX, bool TA, bool TB, int BN_ = 128, bool M3 = false>
 __global__ void __launch_bounds__(GemmCfg<CPLX, BN_>::THREADS, 1)
 gemm_grouped_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, char* __restrict__ Cbase,
                     const GemmTask* __restrict__ tasks, int ntasks, const GemmSeg* __restrict__ segs) {
   PeerBases none;
   none.n = 0;
-  gemm_grouped_body<CPLX, TA, TB, BN_, false>(Abase, Bbase, Cbase, tasks, ntasks, segs, none);
+  gemm_grouped_body<CPLX, TA, TB, BN_, false, M3>(Abase, Bbase, Cbase, tasks, ntasks, segs, none);
 }
 
 // R-stage of the row-sharded matvec: same mainloop, C tiles stored to every rank's landing buffer
-template <bool CPLX>
-__global__ void __launch_bounds__(GemmCfg<CPLX, 128>::THREADS, 1)
+template <bool CPLX, int BN_ = 128, bool M3 = false>
+__global__ void __launch_bounds__(GemmCfg<CPLX, BN_>::THREADS, 1)
 gemm_grouped_peer_kernel(const char* __restrict__ Abase, const char* __restrict__ Bbase, const GemmTask* __restrict__ tasks, int ntasks,
                          const GemmSeg* __restrict__ segs, const __grid_constant__ PeerBases peers) {
-  gemm_grouped_body<CPLX, false, true, 128, true>(Abase, Bbase, nullptr, tasks, ntasks, segs, peers);
+  gemm_grouped_body<CPLX, false, true, BN_, true, M3>(Abase, Bbase, nullptr, tasks, ntasks, segs, peers);
 }
 
 }  // namespace cb200

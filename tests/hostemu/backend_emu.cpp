@@ -38,7 +38,7 @@ uint64_t dev_launch_count(Backend* b) { return b->launches; }
 void dev_event_record(Backend*, int) {}
 float dev_event_elapsed_ms(Backend*, int, int) { return 0.f; }
 int gemm_tile_m(bool cplx) { return cplx ? 64 : 128; }
-int gemm_tile_n(bool, bool narrow) { return narrow ? 64 : 128; }
+int gemm_tile_n(bool, int mode) { return mode == GEMM_TILE_WIDE ? 128 : (mode == GEMM_TILE_MID_3M ? 96 : 64); }
 int mix_rows_per_block(bool, int) { return 128; }
 int copy_elems_per_block() { return 2048; }
 
@@ -75,7 +75,7 @@ static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTas
   }
 }
 
-void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, bool, const void* A, const void* B, void* C, const GemmTask* t, int nt,
+void launch_gemm(Backend* b, bool cplx, bool ta, bool tb, int, const void* A, const void* B, void* C, const GemmTask* t, int nt,
                  const GemmSeg* s, int tiles) {
   if (tiles <= 0 || nt <= 0) return;
   b->launches++;
@@ -499,7 +499,7 @@ int64_t shard_landing_bytes(Backend*) { return 0; }
 void* shard_landing(Backend*, int) { return nullptr; }
 void shard_peer_bases(Backend*, int, PeerBases* out) { out->n = 0; }
 void shard_barrier(Backend*) {}
-void launch_gemm_peer(Backend*, bool, const void*, const void*, const PeerBases&, const GemmTask*, int, const GemmSeg*, int) {}
+void launch_gemm_peer(Backend*, bool, int, const void*, const void*, const PeerBases&, const GemmTask*, int, const GemmSeg*, int) {}
 int nccl_unique_id(Backend*, void*) { return -1; }
 int nccl_init(Backend*, const void*, int, int) { return -1; }
 void nccl_allreduce_sum(Backend*, void*, int64_t) {}

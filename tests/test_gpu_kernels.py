@@ -135,3 +135,21 @@ def test_hermitian_eigensolver(gpu_ctx, cplx, n, m, decay):
         P = evec[:, n - m:] @ evec[:, n - m:].conj().T
         assert np.abs(V @ V.conj().T - P).max() <= 1e-5
     assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[::-1][:m]).max() <= 1e-14 * np.sqrt(n)
+
+
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
+def test_gemm_narrow_and_3m_tiles(gpu_ctx, monkeypatch, mode, ta, tb):
+    """The 64-column tile and its 3-multiplication complex variant (3 DMMA per complex MAC: Re = P1 - P2, Im = P3 - P1 - P2)."""
+    monkeypatch.setenv("CB200_K_GEMM_MODE", mode)
+    rng = np.random.default_rng(int(mode) * 7 + ta + 2 * tb)
+    for cplx in (True, False):
+        for M, N, K in [(257, 131, 95), (64, 640, 33), (533, 300, 534)]:
+            A = _rand(rng, (M, K), cplx)
+            B = _rand(rng, (K, N), cplx)
+            a = (A.T if ta else A).ravel(order="F")
+            b = (B.T if tb else B).ravel(order="F")
+            c, _ = cb.k_gemm(a, b, np.zeros(M * N), M, N, [K], [0], [0], K if ta else M, N if tb else K, 0, M, trans_a=ta, trans_b=tb,
+                             conj_a=cplx and ta, ctx=gpu_ctx)
+            want = (A.conj() if (cplx and ta) else A) @ B
+            assert np.abs(c.reshape(N, M).T - want).max() <= 2e-13 * K * max(1.0, np.abs(want).max())
