@@ -25,6 +25,8 @@ CASES = [
     ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 1, 4),
     ("haagerupq", "p", 6, [0.0, 0.0, -1.0], 0, 4),
     ("haagerupq", "s", 6, [0.0, -1.0, 0.0], 0, 6),   # highly degenerate: only distinct values are meaningful
+    ("haagerupq", "p", 8, [-1.0, 0.0, 0.0], 0, 3),   # BASELINE configs[4]'s physical chain (6^8/3 states per charge, ~40 s each)
+    ("haagerupq", "p", 8, [-1.0, 0.0, 0.0], 1, 3),
 ]
 EE_CASES = [("golden", "p", 6, [-1.0], None), ("haagerupq", "p", 6, [0.0, -1.0, 0.0], 0), ("haagerupq", "p", 6, [-1.0, 0.0, 0.0], 0)]
 

@@ -180,3 +180,11 @@ def test_random_structures_on_gpu(gpu_ctx):
         if np.any(b["phi"]):
             tr.check(gpu_ctx, b)
     tr.check(gpu_ctx, tr.random_bond(np.random.default_rng(3), "haagerup", [0.0, -1.0, 0.0], [3], [5]))
+
+
+@pytest.mark.parametrize("q", [0, 1])
+def test_ground_state_kat_haagerupq_l8_config5(gpu_ctx, q):
+    # BASELINE config 5's physical chain: haagerupq periodic L=8, j=(-1,0,0) (real, Z3 block-sparse), charge sectors 0 and 1;
+    # ED: -4.780039219700 (q=0), -4.697342254060 (q=1, two-fold degenerate).  cutoff 1e-8 limits the DMRG energy to ~1e-7.
+    en, psi, site = common.check_ground_state_kat(gpu_ctx, "haagerupq", "p", 8, [-1.0, 0.0, 0.0], q, tol=5e-7, nrep=10)
+    assert max(psi.bond_dims()) <= 1296
