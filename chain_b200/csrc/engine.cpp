@@ -1089,18 +1089,45 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
     const int64_t nref = n - 1;
     Buf Y(be, (int64_t)es * n * NB), S(be, (int64_t)es * NB * NB), Tn(be, (int64_t)es * NB * NB);
     Buf W1(be, (int64_t)es * NB * m), W2(be, (int64_t)es * NB * m);
+    // S = Y^H Y and W1 = Y^H Z are skinny products (64 rows) with a long inner dimension: one CTA per output tile would walk
+    // the whole K range alone.  Split K over up to MAX_LC tasks writing partial results, then add the partials (split-K).
+    const int PMAX = MAX_LC;
+    Buf Sp(be, (int64_t)es * NB * NB * PMAX), W1p(be, (int64_t)es * NB * m * PMAX);
     for (int64_t j0 = ((nref - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
       const int nbk = (int)std::min<int64_t>(NB, nref - j0);
       const int64_t r0 = j0 + 1, len = n - r0;
       launch_form_y(be, cx, h.A.p, n, h.tau.p, h.scl.p, j0, nbk, Y.p);
+      const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, len / 256));
+      const int64_t chunk = (len + P - 1) / P;
       GemmPlan ps, pw1, pw2, pz;
-      { GemmBuilder g(cx); g.begin(0, nbk, nbk, nbk, GEMM_TRANS_A | GEMM_CONJ_A); g.seg(0, len, 0, len, len); g.end(); g.finish(be, ps, true, false); }
-      { GemmBuilder g(cx); g.begin(0, nbk, nbk, m, GEMM_TRANS_A | GEMM_CONJ_A); g.seg(0, len, r0, n, len); g.end(); g.finish(be, pw1, true, false); }
+      {
+        GemmBuilder g(cx), g1(cx);
+        for (int pp = 0; pp < P; ++pp) {
+          const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+          if (kn <= 0) break;
+          g.begin((int64_t)pp * nbk * nbk, nbk, nbk, nbk, GEMM_TRANS_A | GEMM_CONJ_A);
+          g.seg(k0, len, k0, len, kn);
+          g.end();
+          g1.begin((int64_t)pp * nbk * m, nbk, nbk, m, GEMM_TRANS_A | GEMM_CONJ_A);
+          g1.seg(k0, len, r0 + k0, n, kn);
+          g1.end();
+        }
+        g.finish(be, ps, true, false);
+        g1.finish(be, pw1, true, false);
+      }
       { GemmBuilder g(cx); g.begin(0, nbk, nbk, m, 0); g.seg(0, nbk, 0, nbk, nbk); g.end(); g.finish(be, pw2, false, false); }
       { GemmBuilder g(cx); g.begin(r0, n, len, m, GEMM_ACCUM); g.seg(0, len, 0, nbk, nbk); g.end(); g.finish(be, pz, false, false); }
-      run_gemm(c, cx, ps, Y.p, Y.p, S.p);
+      const int np = ps.tasks.n;
+      const void* xs[MAX_LC];
+      double ones[2 * MAX_LC];
+      for (int pp = 0; pp < np; ++pp) { ones[2 * pp] = 1.0; ones[2 * pp + 1] = 0.0; }
+      run_gemm(c, cx, ps, Y.p, Y.p, Sp.p);
+      for (int pp = 0; pp < np; ++pp) xs[pp] = (const char*)Sp.p + es * (size_t)pp * nbk * nbk;
+      lincomb(be, cx, np, xs, ones, 0.0, 0.0, S.p, (int64_t)nbk * nbk);
       launch_wy_t(be, cx, S.p, (const char*)h.tau.p + es * (size_t)j0, nbk, Tn.p);
-      run_gemm(c, cx, pw1, Y.p, V.p, W1.p);
+      run_gemm(c, cx, pw1, Y.p, V.p, W1p.p);
+      for (int pp = 0; pp < np; ++pp) xs[pp] = (const char*)W1p.p + es * (size_t)pp * nbk * m;
+      lincomb(be, cx, np, xs, ones, 0.0, 0.0, W1.p, (int64_t)nbk * m);
       run_gemm(c, cx, pw2, Tn.p, W1.p, W2.p);
       run_gemm(c, cx, pz, Y.p, W2.p, V.p);
     }
