@@ -1028,10 +1028,12 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   dev_h2d(b, d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size());
   dev_h2d(b, d_segs, segs.data(), sizeof(GemmSeg) * segs.size());
   long long nn = n;
+  static const int fsplit_env = [] { const char* v = getenv("CB200_TRI_FSPLIT"); return v ? atoi(v) : 1; }();
+  int fsplit = std::max(1, std::min(fsplit_env, TRI_WARPS));
   for (int pi = 0; pi < npanel; ++pi) {
     long long j0 = (long long)pi * NB;
     int nbk = (int)std::min<int64_t>(NB, nref - j0);
-    void* args[] = {&A, &nn, &j0, &nbk, &d, &e, &tau, &scl, &p, &gbuf, &partial, &Vp, &W, &Vn, &Wn, &Vt, &Wt};
+    void* args[] = {&A, &nn, &j0, &nbk, &d, &e, &tau, &scl, &p, &gbuf, &partial, &Vp, &W, &Vn, &Wn, &Vt, &Wt, &fsplit};
     CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(TRI_THREADS), args, 0, b->stream));
     CB_LAUNCH_CHECK(b, "tridiag_panel_kernel");
     const int64_t t0 = j0 + nbk;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(TRI_THREADS, 2)
 tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
                      void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
                      double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_,
-                     void* __restrict__ Vt_, void* __restrict__ Wt_) {
+                     void* __restrict__ Vt_, void* __restrict__ Wt_, int fsplit_long) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   cg::grid_group grid = cg::this_grid();
   T* A = reinterpret_cast<T*>(A_);
@@ -225,8 +225,10 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
       const long long ncol = m + 2 * i;
       int f = 1;
       // (only for columns long enough to be bandwidth-bound: the two extra CTA barriers cost more than they save on short ones)
-      if (m * (long long)sizeof(T) >= 16384)
+      if (m * (long long)sizeof(T) >= 16384) {
         while (f < TRI_WARPS && ncol * (2 * f) <= GW) f *= 2;
+        if (f < fsplit_long) f = fsplit_long;     // long columns: few wide streams per CTA instead of one narrow stream per warp
+      }
       if (f == 1) {   // the common (latency-bound) case: one warp per column, no CTA barriers
         for (long long cc = gw; cc < ncol; cc += GW) {
           const T* col = cc < m ? A + (j + 1) + (j + 1 + cc) * n : (cc < m + i ? W + (j + 1) + (cc - m) * n : Vp + (j + 1) + (cc - m - i) * n);
