@@ -56,6 +56,7 @@ SYMBOLS = [
     ("cb200_mps_entropies", C.c_int, [vp, C.POINTER(MpsC), i32, C.POINTER(i32), C.POINTER(dbl)]),
     ("cb200_mps_translate", C.c_int, [vp, C.POINTER(MpsC), i32, C.POINTER(i32), dbl, C.POINTER(vp)]),
     ("cb200_mps_overlap", C.c_int, [vp, C.POINTER(MpsC), C.POINTER(MpsC), i32, C.POINTER(i32), C.POINTER(dbl)]),
+    ("cb200_mps_mpo_element", C.c_int, [vp, C.POINTER(MpsC), C.POINTER(MpoC), C.POINTER(MpsC), C.POINTER(dbl)]),
     ("cb200_result_nsites", i32, [vp]),
     ("cb200_result_dtype", i32, [vp]),
     ("cb200_result_link_dim", i64, [vp, i32]),

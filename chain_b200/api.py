@@ -264,6 +264,16 @@ def overlap(a, b, site_charges=None, ctx=None):
     return complex(z[0], z[1])
 
 
+def mpo_element(bra, O, ket, ctx=None):
+    """<bra| O |ket> for an MPO and two (different) dense MPS (nq = 1)."""
+    ctx = ctx or default_context()
+    keep = []
+    bc, oc, kc = bra._to_c(keep), O._to_c(keep), ket._to_c(keep)
+    z = (C.c_double * 2)()
+    ctx.check(ctx.lib.cb200_mps_mpo_element(ctx.h, C.byref(bc), C.byref(oc), C.byref(kc), z))
+    return complex(z[0], z[1])
+
+
 def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
     """(energy, psi) = dmrg(H, psis, psi0, sweeps, {"Weight": weight}) -- same meaning as itensor::dmrg at
     src/dmrg.h:544: `psis` are the previously found states to be penalised with `weight`."""

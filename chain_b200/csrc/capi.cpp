@@ -202,6 +202,30 @@ int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, in
   });
 }
 
+int cb200_mps_mpo_element(cb200_ctx* ctx, const cb200_mps* bra, const cb200_mpo* O, const cb200_mps* ket, double* re_im) {
+  if (!ctx || !bra || !O || !ket || !re_im) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    if (O->nq != 1 || bra->nq != 1 || ket->nq != 1) fail(CB200_ERR_INVALID, "mpo_element: dense (nq = 1) operands only");
+    MpoIn mi;
+    mi.n = O->n; mi.nq = 1; mi.d = O->d; mi.site_charge = nullptr;
+    mi.link.resize(O->n + 1);
+    for (int j = 0; j <= O->n; ++j) mi.link[j] = IndexMap::from_labels(1, O->link[j].dim, nullptr);
+    mi.site.resize(O->n);
+    for (int j = 0; j < O->n; ++j) {
+      const cb200_tensor& t = O->site[j];
+      if (t.rank != 4 || t.dims[0] != O->link[j].dim || t.dims[1] != O->d || t.dims[2] != O->d || t.dims[3] != O->link[j + 1].dim)
+        fail(CB200_ERR_INVALID, "MPO site tensor " + std::to_string(j) + " has inconsistent dimensions");
+      if (j == 0) mi.cplx = t.dtype == 1;
+      else if ((t.dtype == 1) != mi.cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside the MPO");
+      mi.site[j] = t.data;
+    }
+    bool cbr = false, ck = false;
+    HostMPS hb = to_host_mps(bra, 1, O->d, &cbr), hk = to_host_mps(ket, 1, O->d, &ck);
+    const cplx_t z = mps_mpo_element(&ctx->c, O->d, hb, cbr, mi, hk, ck);
+    re_im[0] = z.real(); re_im[1] = z.imag();
+  });
+}
+
 int32_t cb200_result_nsites(const cb200_result* r) { return r ? r->r->psi.n : 0; }
 int32_t cb200_result_dtype(const cb200_result* r) { return r && r->r->cplx ? 1 : 0; }
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link) {

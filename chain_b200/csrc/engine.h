@@ -314,6 +314,10 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
 std::unique_ptr<DmrgResult> mps_translate(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx, double cutoff);
 // innerC(a, b) = <a|b>
 cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& a, bool a_cplx, const HostMPS& b, bool b_cplx);
+// <bra| O |ket> for an MPO O and two DIFFERENT dense (nq = 1) MPS: a left-to-right environment sweep with the bra and the ket taken
+// from different states (the sweep's own environment update has bra = ket).  Used for the rho-defect matrix elements of
+// Measure("rho") (src/dmrg.h:871-1047), which the reference evaluates on QN-free states too.
+cplx_t mps_mpo_element(Ctx* c, int d, const HostMPS& bra, bool bra_cplx, const MpoIn& O, const HostMPS& ket, bool ket_cplx);
 // CalcEE (src/utility.cpp:5-27) on the device truncation path
 std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_charge, const HostMPS& psi, bool cplx);
 

@@ -689,4 +689,103 @@ cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const Host
   return rd(h.data(), cplx, 0);
 }
 
+// ------------------------------------------------------------------------------------------------ <bra| MPO |ket>
+cplx_t mps_mpo_element(Ctx* c, int d, const HostMPS& bra, bool bra_cplx, const MpoIn& O, const HostMPS& ket, bool ket_cplx) {
+  const int n = O.n;
+  if (bra.n != n || ket.n != n || n < 1) fail(-2, "mpo_element: length mismatch");
+  if (O.nq != 1) fail(-2, "mpo_element: dense (nq = 1) states only -- the reference removes the QNs before measuring rho (src/dmrg.h:781-784)");
+  const bool cplx = bra_cplx || ket_cplx || O.cplx;
+  Backend* be = c->be;
+  const size_t es = esz(cplx);
+  SiteInfo S = SiteInfo::make(1, d, nullptr);
+  // environment E[x' (bra), a, x (ket)], element x' + Db*(a + k*x); starts as the 1x1x1 identity
+  int64_t Db = 1, Dk = 1, k = 1;
+  Buf E(be, (int64_t)es);
+  {
+    std::vector<char> one(es, 0);
+    wr(one.data(), cplx, 0, cplx_t(1, 0));
+    dev_h2d(be, E.p, one.data(), one.size());
+  }
+  for (int j = 0; j < n; ++j) {
+    DevSite3 Ak, Ab;
+    import_site3_t(c, cplx, ket_cplx, S, ket.link[j], ket.link[j + 1], ket.site[j].data(), Ak);
+    import_site3_t(c, cplx, bra_cplx, S, bra.link[j], bra.link[j + 1], bra.site[j].data(), Ab);
+    HostW W = import_w(1, d, S, O.link[j], O.link[j + 1], O.cplx, O.site[j]);
+    const int64_t kl = W.KL.total(), kr = W.KR.total();
+    const int64_t Dkr = Ak.lay.Y.total(), Dbr = Ab.lay.Y.total();
+    if (Ak.lay.X.total() != Dk || Ab.lay.X.total() != Db || kl != k) fail(-2, "mpo_element: inconsistent bond dimensions at site " + std::to_string(j));
+    // stage 1: X[(x',a), (s,m)] = sum_x E[(x',a), x] Aket[x, (s,m)]
+    const int64_t M1 = Db * kl, N1 = (int64_t)d * Dkr;
+    Buf X(be, (int64_t)es * std::max<int64_t>(M1 * N1, 1));
+    {
+      GB gb(cplx);
+      gb.begin(0, M1, M1, N1, 0);
+      gb.seg(0, M1, 0, Dk, Dk);
+      gb.end();
+      gb.run(c, false, false, E.p, Ak.buf.p, X.p);
+    }
+    // stage 2 (sparse W): Y[(x',t), (a',m)] = sum_{a,s} W[a,t,s,a'] X[(x',a), (s,m)]
+    const int64_t MY = Db * d;
+    Buf Y(be, (int64_t)es * std::max<int64_t>(MY * kr * Dkr, 1), true);
+    {
+      std::vector<MixPanel> panels(1);
+      std::vector<MixIn> ins;
+      std::vector<MixOut> outs;
+      std::vector<MixEntry> ents;
+      std::vector<int> slot((size_t)kl * d, -1);
+      MixPanel& p = panels[0];
+      p = MixPanel{};
+      p.rows = (int32_t)Db; p.nr = (int32_t)Dkr;
+      for (int t = 0; t < d; ++t)
+        for (int64_t ap = 0; ap < kr; ++ap) {
+          MixOut o{};
+          o.off = Db * t + MY * ap; o.rstride = MY * kr; o.e_begin = (int32_t)ents.size();
+          for (int s2 = 0; s2 < d; ++s2)
+            for (int64_t a = 0; a < kl; ++a) {
+              const cplx_t v = W.at(a, t, s2, ap);
+              if (v == cplx_t(0, 0)) continue;
+              int& sl = slot[(size_t)(a + kl * s2)];
+              if (sl < 0) {
+                sl = (int)ins.size();
+                MixIn mi{};
+                mi.off = Db * a + M1 * s2; mi.rstride = M1 * d;      // X column (s, m) = s + d*m
+                ins.push_back(mi);
+              }
+              MixEntry e{};
+              e.slot = sl; e.cre = v.real(); e.cim = v.imag();
+              ents.push_back(e);
+            }
+          o.e_end = (int32_t)ents.size();
+          outs.push_back(o);
+        }
+      p.out_begin = 0; p.out_end = (int32_t)outs.size();
+      p.in_begin = 0; p.in_count = (int32_t)ins.size();
+      if (Db > 0 && Dkr > 0 && !ins.empty()) {
+        const int rpb = mix_rows_per_block(cplx, p.in_count);
+        p.blk_begin = 0; p.row_chunks = (int32_t)((Db + rpb - 1) / rpb);
+        const int blocks = p.row_chunks * (int)Dkr;
+        DevList<MixPanel> dp; DevList<MixIn> di; DevList<MixOut> dox; DevList<MixEntry> de;
+        dp.upload(be, panels); di.upload(be, ins); dox.upload(be, outs); de.upload(be, ents);
+        launch_mix(be, cplx, X.p, Y.p, dp.ptr(), 1, di.ptr(), dox.ptr(), de.ptr(), blocks, p.in_count);
+      }
+    }
+    // stage 3: E'[m', (a',m)] = sum_{(x',t)} conj(Abra[(x',t), m']) Y[(x',t), (a',m)]
+    Buf En(be, (int64_t)es * std::max<int64_t>(Dbr * kr * Dkr, 1), true);
+    {
+      GB gb(cplx);
+      gb.begin(0, Dbr, Dbr, kr * Dkr, GEMM_TRANS_A | GEMM_CONJ_A);
+      gb.seg(0, MY, 0, MY, MY);
+      gb.end();
+      gb.run(c, true, false, Ab.buf.p, Y.p, En.p);
+    }
+    E = std::move(En);
+    Db = Dbr; Dk = Dkr; k = kr;
+  }
+  if (Db != 1 || Dk != 1 || k != 1) fail(-2, "mpo_element: outer bonds must have dimension 1");
+  std::vector<char> h(es, 0);
+  dev_d2h(be, h.data(), E.p, h.size());
+  check_dev(c);
+  return rd(h.data(), cplx, 0);
+}
+
 }  // namespace cb200

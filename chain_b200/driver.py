@@ -11,8 +11,7 @@ Nothing here does tensor arithmetic: Hamiltonians come from chain_b200.models (h
 Differences from the reference, all deliberate: output goes under --out (the reference compiles the parent of the cwd in,
 src/path_template.h:8); --seed makes the random product start reproducible (the reference never seeds); there is no
 pgs/ checkpoint (ITensor's private binary format); mode 5 runs the simulation and then the energy /
-translation measurements and the {energy, momentum} table (AnalyzeWithoutRho); the rho-defect column of mode 1/5 is the one
-part of SURVEY 8f row f2 that is not built.
+translation / rho measurements and the {energy, momentum, rho} table of Analyze (AnalyzeWithoutRho for charged sectors).
 """
 import argparse
 import os
@@ -197,13 +196,42 @@ class Simulation:
         return self.energies, self.states
 
 
+def analyze_full(energies, T, R, n, bc):
+    """Analyze, src/dmrg.h:1118-1174: m = E/L + T + R (periodic) | E/L + R (Dirichlet); eigen(m); rotate E, T, R into its eigenbasis;
+    momentum_i = round(Re(log(T_ii)/(2 pi i) L) 1e6)/1e6 with -L/2 -> L/2, rho_i = round(Re R_ii 1e6)/1e6; rows sorted by energy."""
+    E = np.diag(np.asarray(energies, dtype=complex))
+    m = E / n + (np.asarray(T) + np.asarray(R) if bc == "p" else np.asarray(R))
+    w, U = np.linalg.eig(m)
+    Ui = np.linalg.inv(U)
+    Er, Tr, Rr = Ui @ E @ U, Ui @ T @ U, Ui @ R @ U
+    rows = []
+    for i in range(len(energies)):
+        mom = np.round((np.log(Tr[i, i]) / (2j * np.pi) * n).real * 1e6) / 1e6
+        if mom == -(n // 2):
+            mom = n // 2
+        rho = np.round(Rr[i, i].real * 1e6) / 1e6 + 0.0           # "+ 0.0": -0 -> 0 as in the reference
+        rows.append((float(Er[i, i].real), float(mom), float(rho)))
+    return sorted(rows)
+
+
+def rho_matrix(sim, states):
+    """Measure("rho"), src/dmrg.h:871-1047 + :1068-1072: R_ij = <psi_i| rho |psi_j>.  The reference applies RhoOp approximately
+    (applyMPO "Fit", cutoff 1e-5) and then takes the overlap; here the matrix element itself is contracted on the device
+    (cb200_mps_mpo_element) with the ring operator written as a sum of d^2-bond MPOs (models.rho_defect_mpos)."""
+    if sim.site_type == "haagerupq":
+        states = [models.to_haagerup_basis(p) for p in states]
+    mpos = [cb.MPO(m, None, None, nq=1) for m in models.rho_defect_mpos(sim.site_type, sim.n, periodic=(sim.bc in ("p", "sp")))]
+    return np.array([[sum(cb.mpo_element(a, O, b, ctx=sim.ctx) for O in mpos) for b in states] for a in states])
+
+
 def analyze(sim, log=print):
     """What mode 5 runs after the simulation (src/dmrg.h:637-648): Measure("energy") rewrites .en with 1-based state numbers
-    (:752-755) and dumps the energy matrix to .m; for periodic / Dirichlet chains Measure("translation") (L-1 swaps per state on
-    the device, kCutoff = 1e-5) + T_ij = innerC(psi_i, T psi_j) + AnalyzeWithoutRho give the {energy, momentum} table in .an.
-    The rho-defect column of the charge-0 Analyze (RhoOp / applyMPO, src/chain.cpp:65-214) is not built: charge-0 runs get the
-    AnalyzeWithoutRho table too, and that is said on stdout."""
+    (:752-755) and dumps the energy matrix to .m; periodic chains get Measure("translation") (L-1 swaps per state on the device,
+    kCutoff = 1e-5; T_ij = innerC(psi_i, T psi_j)); charge-0 periodic / Dirichlet chains get Measure("rho") and the
+    {energy, momentum, rho} table of Analyze; charged sectors the {energy, momentum} table of AnalyzeWithoutRho; every other
+    boundary condition Energies()."""
     n, ens, states = sim.n, sim.energies, sim.states
+    bc = "p" if sim.bc == "sp" else sim.bc
     if os.path.exists(sim.en_path):
         os.remove(sim.en_path)
     for i, e in enumerate(ens):
@@ -211,19 +239,28 @@ def analyze(sim, log=print):
     if os.path.exists(sim.m_path):
         os.remove(sim.m_path)
     dump_mathematica(sim.m_path, "energy", np.diag(np.asarray(ens, dtype=complex)))
-    if sim.bc not in ("p", "d", "sp"):
+    if bc not in ("p", "d"):
         rows = [(e,) for e in ens]                               # Energies(), src/dmrg.h:1221-1244
         dump_matrix(sim.an_path, rows)
         return rows
     sq = sim.sites.charges
-    acted = [cb.translate(p, sq, 1e-5, ctx=sim.ctx) for p in states]
-    T = np.array([[cb.overlap(a, t, sq, ctx=sim.ctx) for t in acted] for a in states])
+    nst = len(states)
+    if bc == "p":
+        acted = [cb.translate(p, sq, 1e-5, ctx=sim.ctx) for p in states]
+        T = np.array([[cb.overlap(a, t, sq, ctx=sim.ctx) for t in acted] for a in states])
+    else:
+        T = np.eye(nst, dtype=complex)
     dump_mathematica(sim.m_path, "translation", T)
-    rows = analyze_without_rho(ens, T, n)
-    dump_matrix(sim.an_path, rows)
     if sim.charge == 0:
-        log("> note: charge 0: the reference's Analyze() adds a rho-defect column (not built, SURVEY 8f row f2); {energy, momentum} written")
-    log("\nSpectrum:  {energy, momentum}")
+        R = rho_matrix(sim, states)
+        dump_mathematica(sim.m_path, "rho", R)
+        rows = analyze_full(ens, T, R, n, bc)
+        head = "{energy, momentum, rho}"
+    else:
+        rows = analyze_without_rho(ens, T, n)
+        head = "{energy, momentum}"
+    dump_matrix(sim.an_path, rows)
+    log("\nSpectrum:  %s" % head)
     for r in rows:
         log("{%s}" % ",".join("%.10f" % v for v in r))
     return rows

@@ -89,6 +89,91 @@ def haagerup_fdata():
     return HaagerupIzumi(3, lambda s: tab[s])
 
 
+# --------------------------------------------------------------------------------------------- rho defect (measurement)
+def rho_defect_cell(site_type):
+    """G[i1, j1, i2, j2] = F(rho, i1, rho, j2; j1, i2) sqrt(QD(i1)/QD(i2)) -- FData::RhoDefectCell, src/f_data.cpp:94-111
+    (i = ket / unprimed value, j = bra / primed value of the two neighbouring sites; 0-based here).  golden uses GoldenFData,
+    haagerup and haagerupq (after the Z3 Fourier map) HaagerupFData (src/chain.cpp:118-131)."""
+    f = golden_fdata() if site_type == "golden" else haagerup_fdata()
+    rk = f.rank
+    qd = [1.0 if f.inv(i) else f.qdim for i in range(1, rk + 1)]
+    G = np.zeros((rk, rk, rk, rk))
+    for i1 in range(1, rk + 1):
+        for j1 in range(1, rk + 1):
+            for i2 in range(1, rk + 1):
+                for j2 in range(1, rk + 1):
+                    G[i1 - 1, j1 - 1, i2 - 1, j2 - 1] = f.F(f.rho, i1, f.rho, j2, j1, i2) * math.sqrt(qd[i1 - 1] / qd[i2 - 1])
+    return G
+
+
+def rho_defect_mpos(site_type, n, periodic=True):
+    """The rho-defect operator of RhoOp / OpenRhoOp (src/chain.cpp:65-185) as a SUM of MPOs with bond dimension d^2.
+
+    Every MPO site tensor of the reference is B[j-1] * A[j] tied to the physical legs by copy tensors, i.e. the operator is a
+    product of cells: <s'|rho|s> = prod_j G[s_j, s'_j, s_{j+1}, s'_{j+1}] (site n+1 = site 1 on a ring, absent on an open
+    chain).  With the pair p_j = (s_j, s'_j) as the MPO bond this is W_j[p_{j-1}; s', s; p_j] = G[p_{j-1}, p_j] delta(p_j, (s, s'));
+    the ring closure G[p_n, p_1] needs p_1 at the last site, so the ring operator is returned as one MPO per value of p_1
+    (at most d^2 of them; their matrix elements add).  Returns a list of site-tensor lists [k_l, d(out), d(in), k_r]."""
+    G = rho_defect_cell(site_type)
+    d = G.shape[0]
+    k = d * d
+    pair = lambda i, j: i + d * j               # (ket value, bra value)
+
+    def bulk():
+        W = np.zeros((k, d, d, k))
+        for ip in range(d):
+            for jp in range(d):
+                for i in range(d):
+                    for j in range(d):
+                        g = G[ip, jp, i, j]
+                        if g != 0.0:
+                            W[pair(ip, jp), j, i, pair(i, j)] = g
+        return W
+    Wb = bulk()
+    mpos = []
+    firsts = [(i1, j1) for i1 in range(d) for j1 in range(d)] if periodic else [None]
+    for p1 in firsts:
+        W1 = np.zeros((1, d, d, k))
+        for i in range(d):
+            for j in range(d):
+                if p1 is None or (i, j) == p1:
+                    W1[0, j, i, pair(i, j)] = 1.0
+        Wn = np.zeros((k, d, d, 1))
+        for ip in range(d):
+            for jp in range(d):
+                for i in range(d):
+                    for j in range(d):
+                        g = G[ip, jp, i, j] * (G[i, j, p1[0], p1[1]] if p1 is not None else 1.0)
+                        if g != 0.0:
+                            Wn[pair(ip, jp), j, i, 0] = g
+        if not np.any(Wn):
+            continue
+        mpos.append([W1] + [Wb] * (n - 2) + [Wn])
+    return mpos
+
+
+def z3_fourier_matrix():
+    """Z3FourierMatrix, src/chain.cpp:311-335: U[s_old, s_new] taking the haagerupq site basis to the haagerup one."""
+    U = np.zeros((6, 6), dtype=complex)
+    nrm = 1 / math.sqrt(3)
+    om, omb = complex(-0.5, math.sqrt(3) / 2), complex(-0.5, -math.sqrt(3) / 2)
+    for i in range(3):
+        U[i, 0] = U[0, i] = nrm
+        U[i + 3, 3] = U[3, i + 3] = nrm
+    U[1, 1] = U[2, 2] = U[4, 4] = U[5, 5] = nrm * om
+    U[1, 2] = U[2, 1] = U[4, 5] = U[5, 4] = nrm * omb
+    return U
+
+
+def to_haagerup_basis(psi):
+    """removeQNs + Z3FourierTransform (src/dmrg.h:781-784, src/chain.cpp:337-345): a relabelling of the input of the rho
+    measurement (site-local 6x6 unitary on each site tensor, link charges dropped), done on the host like the reference's
+    other format conversions."""
+    from .api import MPS
+    U = z3_fourier_matrix()
+    return MPS([np.einsum("lsr,st->ltr", np.asarray(a, dtype=complex), U) for a in psi.sites], None, nq=1, center=psi.center)
+
+
 # --------------------------------------------------------------------------------------------- site sets
 def _unit(d, pairs):
     """Operator from (in_state, out_state, value) triples, 1-based states; stored as O[out, in]."""

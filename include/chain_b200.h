@@ -119,6 +119,9 @@ int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const i
 int cb200_mps_translate(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const int32_t* site_charge, double cutoff, cb200_result** out);
 /* innerC(a, b) = <a|b> (src/dmrg.h:1063); re_im[2] */
 int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, int32_t d, const int32_t* site_charge, double* re_im);
+/* <bra| O |ket> for an MPO and two different dense (nq = 1) MPS: the matrix elements of the rho-defect operator that
+ * Measure("rho") needs (/root/reference/src/dmrg.h:871-1047, :1068-1072; the reference removes the QNs first, :781-784) */
+int cb200_mps_mpo_element(cb200_ctx* ctx, const cb200_mps* bra, const cb200_mpo* O, const cb200_mps* ket, double* re_im);
 int32_t cb200_result_nsites(const cb200_result* r);
 int32_t cb200_result_dtype(const cb200_result* r);                                  /* 0 f64, 1 c128 */
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link);                 /* link in [0, n] */

@@ -399,6 +399,43 @@ def swap_translate(psi, cutoff=1e-5):
     return psi
 
 
+def rho_element(bra, G, ket, periodic=True):
+    """<bra| rho |ket> with <s'|rho|s> = prod_j G[s_j, s'_j, s_{j+1}, s'_{j+1}] (RhoOp / OpenRhoOp, src/chain.cpp:65-185, written as a
+    product of RhoDefectCells): transfer contraction carrying the first pair (ring closure) and the current pair."""
+    d = G.shape[0]
+    A, B = [np.asarray(x, dtype=complex) for x in ket.A], [np.asarray(x, dtype=complex) for x in bra.A]
+    n = len(A)
+    # X[i1, j1, i, j, m', m]: first pair, current pair, bra link, ket link
+    X = np.zeros((d, d, d, d) + (B[0].shape[2], A[0].shape[2]), dtype=complex)
+    for i in range(d):
+        for j in range(d):
+            X[i, j, i, j] = np.outer(B[0][0, j, :].conj(), A[0][0, i, :])
+    for s in range(1, n):
+        # X'[i1,j1,i,j,m',m] = sum_{ip,jp,x',x} X[i1,j1,ip,jp,x',x] G[ip,jp,i,j] conj(B[x',j,m']) A[x,i,m]
+        X = np.einsum("abpqxy,pqij,xjm,yin->abijmn", X, G, B[s].conj(), A[s], optimize=True)
+    if periodic:
+        return np.einsum("abijmn,ijab->", X, G)          # ring closure G[p_n, p_1]; the outer links have dimension 1
+    return X.sum()                                        # open chain: no closure factor
+
+
+def full_analysis(energies, T, R, n, bc="p"):
+    """Analyze, src/dmrg.h:1118-1174: m = E/L + T + R (periodic) | E/L + R (Dirichlet) | E/L; eigen(m); rotate; momentum and rho rounded
+    to 1e-6; rows {energy, momentum, rho} sorted by energy."""
+    E = np.diag(np.asarray(energies, dtype=complex))
+    m = E / n + (T + R if bc == "p" else (R if bc == "d" else 0))
+    w, U = np.linalg.eig(m)
+    Ui = np.linalg.inv(U)
+    Er, Tr, Rr = Ui @ E @ U, Ui @ T @ U, Ui @ R @ U
+    out = []
+    for i in range(len(energies)):
+        mom = np.round((np.log(Tr[i, i]) / (2j * np.pi) * n).real * 1e6) / 1e6
+        if mom == -(n // 2):
+            mom = n // 2
+        rho = np.round(Rr[i, i].real * 1e6) / 1e6 + 0.0
+        out.append((Er[i, i].real, float(mom), float(rho)))
+    return sorted(out)
+
+
 def momentum_analysis(energies, T, n):
     """AnalyzeWithoutRho, src/dmrg.h:1177-1218: m = E/L + T, eigen(m), rotate E and T, momentum_i = round(Re(log(T_ii)/(2 pi i) L) 1e5)/1e5
     (with -L/2 -> L/2), rows sorted by energy."""

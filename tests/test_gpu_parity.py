@@ -188,3 +188,11 @@ def test_ground_state_kat_haagerupq_l8_config5(gpu_ctx, q):
     # ED: -4.780039219700 (q=0), -4.697342254060 (q=1, two-fold degenerate).  cutoff 1e-8 limits the DMRG energy to ~1e-7.
     en, psi, site = common.check_ground_state_kat(gpu_ctx, "haagerupq", "p", 8, [-1.0, 0.0, 0.0], q, tol=5e-7, nrep=10)
     assert max(psi.bond_dims()) <= 1296
+
+
+def test_rho_defect_and_full_analysis_on_gpu(gpu_ctx, tmp_path):
+    # Measure("rho") + Analyze through the CUDA path: matrix elements against the oracle, eigenvalues in the documented sets
+    import test_rho_defect as tr
+    tr.test_rho_matrix_elements_match_oracle_golden(gpu_ctx)
+    tr.test_rho_through_the_z3_fourier_map(gpu_ctx)
+    tr.test_full_analysis_golden(gpu_ctx, tmp_path)
