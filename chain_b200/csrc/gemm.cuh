@@ -96,7 +96,11 @@ struct GemmCfg {
   static constexpr int A_ELEMS = (BK * (BM + PAD_MN) > BM * LDK) ? BK * (BM + PAD_MN) : BM * LDK;
   static constexpr int B_ELEMS = (BK * (BN + PAD_MN) > BN * LDK) ? BK * (BN + PAD_MN) : BN * LDK;
   static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * ES;
-  static constexpr int STAGES = CPLX ? CB200_STAGES_CPLX : CB200_STAGES_REAL;
+#ifndef CB200_STAGES_CPLX_NARROW
+#define CB200_STAGES_CPLX_NARROW 3
+#endif
+  // (the 64x128 complex tile fits 3 stages of k-tile 16 in 227 KB; the 64x96 / 64x64 tiles of the 3M kernel would fit 4: measured no gain)
+  static constexpr int STAGES = CPLX ? (BN_ <= 96 ? CB200_STAGES_CPLX_NARROW : CB200_STAGES_CPLX) : CB200_STAGES_REAL;
   static constexpr int AHEAD = STAGES - 2;            // k-tiles in flight; one stage of slack decouples the warps
   static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES;
   static constexpr int CONSUMERS = 256;             // 8 DMMA warps
