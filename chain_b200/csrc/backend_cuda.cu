@@ -39,6 +39,11 @@ struct Backend {
   std::unordered_map<void*, size_t> live_size;
   std::multimap<size_t, void*> parked;
   size_t parked_bytes = 0, parked_cap = (size_t)48 << 30;
+  // Pinned staging ring for small host->device uploads (task lists, scalars): the data is copied into the ring and sent with an
+  // asynchronous copy, so the dozens of descriptor uploads per bond no longer cost a stream synchronisation each.  The stream is
+  // synchronised only when the ring wraps.
+  char* h_ring = nullptr;
+  size_t ring_bytes = (size_t)8 << 20, ring_off = 0;
   double* d_bounds = nullptr;     // eigensolver scratch (Gershgorin bounds, pivmin, ||T||)
   // multi-GPU: symmetric area [flags (256 B) | landing 0 | landing 1] + the peers' mappings (CUDA IPC)
   char* sym = nullptr;
@@ -101,7 +106,8 @@ Backend* backend_create(int device, char* err, size_t errlen) {
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&b->d_partial, sizeof(double) * 2 * MAX_LC * DOT_BLOCKS) != cudaSuccess ||
       cudaMalloc(&b->d_dot_out, sizeof(double) * 2 * MAX_LC) != cudaSuccess ||
-      cudaMallocHost(&b->h_dot_out, sizeof(double) * 2 * MAX_LC) != cudaSuccess) {
+      cudaMallocHost(&b->h_dot_out, sizeof(double) * 2 * MAX_LC) != cudaSuccess ||
+      cudaMallocHost(&b->h_ring, b->ring_bytes) != cudaSuccess) {
     snprintf(err, errlen, "chain_b200: backend init failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete b;
     return nullptr;
@@ -158,6 +164,7 @@ void backend_destroy(Backend* b) {
   cudaFree(b->d_partial);
   cudaFree(b->d_dot_out);
   cudaFreeHost(b->h_dot_out);
+  if (b->h_ring) cudaFreeHost(b->h_ring);
   cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -209,6 +216,18 @@ void dev_free(Backend* b, void* p) {
 void dev_memset0(Backend* b, void* p, size_t bytes) { if (bytes) CB_CHECK(b, cudaMemsetAsync(p, 0, bytes, b->stream)); }
 void dev_h2d(Backend* b, void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
+  if (b->h_ring && bytes <= ((size_t)256 << 10)) {
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (b->ring_off + need > b->ring_bytes) {          // wrap: everything staged so far must have left the ring
+      CB_CHECK(b, cudaStreamSynchronize(b->stream));
+      b->ring_off = 0;
+    }
+    char* stage = b->h_ring + b->ring_off;
+    memcpy(stage, src, bytes);
+    b->ring_off += need;
+    CB_CHECK(b, cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, b->stream));
+    return;
+  }
   CB_CHECK(b, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream));
   CB_CHECK(b, cudaStreamSynchronize(b->stream));   // source may be pageable / short-lived
 }
