@@ -8,7 +8,8 @@ bond dimension D = 1600 as Z3 sectors (534,533,533), complex128, block-sparse.  
 in the allowed charge blocks.
 
   value  : algorithmic FP64 TFLOP/s (F_alg of SURVEY 8d: block-sparse, sparse-W flops only) with phi resident in HBM
-  e2e    : the same through the C-ABI call cb200_bond_apply with pinned HOST buffers (H2D phi + D2H result per step)
+  e2e    : the same through the C-ABI call cb200_bond_apply_blocks with pinned HOST buffers in ITensor's QDense block storage
+           (H2D phi + D2H result per step); e2e.dense_layout = cb200_bond_apply on dense arrays with zeros
   roofline: the DMMA GEMM kernel (both D^3 stages) against the FP64 peak measured live (cuBLAS DGEMM 8192^3)
   cpu_baseline / --impl reference: the oracle's port of ITensor's block-pair permute+zgemm loop on the host cores
 
@@ -276,8 +277,31 @@ def main():
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_dense_v = falg * args.steps / float(e2e_t.item()) / 1e12
+    e2e_dense_ms = e2e_s / args.steps * 1e3
+    nbytes_dense = int(phi.size * phi.itemsize)
+    del xh, yh, xn, yn
+
+    # the headline e2e: the same call on ITensor's own QN storage (QDense block list, cb200_bond_apply_blocks) -- only the
+    # charge-allowed blocks cross PCIe; for a dense model (nq = 1) the two layouts coincide
+    nb = bond.phi_blocks_elems
+    xbh = torch.empty(nb * (2 if w["dims"]["cplx"] else 1), dtype=torch.float64, pin_memory=True)
+    ybh = torch.empty_like(xbh, pin_memory=True)
+    xb, yb = xbh.numpy().view(dt), ybh.numpy().view(dt)
+    xb[...] = bond.pack(phi)
+    for _ in range(2):
+        bond.apply_blocks(xb, out=yb)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bond.apply_blocks(xb, out=yb)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_v = falg * args.steps / float(e2e_t.item()) / 1e12
-    nbytes = int(phi.size * phi.itemsize)
+    nbytes = int(nb * phi.itemsize)
 
     # ---- one complete bond update resident on the device (davidson -> svdBond -> makeL): the unit a DMRG sweep is made of
     bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)           # warm-up (grows the memory pool)
@@ -318,7 +342,10 @@ def main():
                            "l2": "inputs larger than L2 (phi + environments + intermediates >> 126 MB)",
                            "parallelism": "single GPU" if world == 1 else "matvec row-sharded x%d, exchange=%s" % (world, exchange)},
                 "clocks": clocks,
-                "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3},
+                "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3,
+                        "call": "cb200_bond_apply_blocks: pinned host vectors in ITensor's QDense block storage, H2D + product + D2H every step",
+                        "dense_layout": {"value": e2e_dense_v, "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": nbytes_dense, "d2h_bytes_per_step": nbytes_dense,
+                                         "call": "cb200_bond_apply: dense [l,s1,s2,r] arrays with zeros in the forbidden blocks"}},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "wall_s_timed_region": wall}
         emit(line)
     bond.close()

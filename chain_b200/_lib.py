@@ -73,6 +73,9 @@ SYMBOLS = [
     ("cb200_bond_phi_elems", i64, [vp]),
     ("cb200_bond_matvec_flops", dbl, [vp]),
     ("cb200_bond_apply", C.c_int, [vp, vp, vp]),
+    ("cb200_bond_phi_blocks_elems", i64, [vp]),
+    ("cb200_bond_phi_blocks", C.c_int, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
+    ("cb200_bond_apply_blocks", C.c_int, [vp, vp, vp]),
     ("cb200_bond_apply_timed", C.c_int, [vp, vp, i32, i32, C.POINTER(dbl)]),
     ("cb200_bond_stage_times", C.c_int, [vp, vp, i32, C.POINTER(dbl), C.POINTER(dbl)]),
     ("cb200_bond_update_timed", C.c_int, [vp, vp, i32, i32, dbl, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)]),

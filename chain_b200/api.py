@@ -373,6 +373,35 @@ class Bond:
         self.ctx.check(self.ctx.lib.cb200_bond_apply(self.h, ptr(x), ptr(y)))
         return y
 
+    # ---- ITensor's QDense storage at the boundary: only the charge-allowed blocks cross PCIe (include/chain_b200.h)
+    @property
+    def phi_blocks_elems(self):
+        return int(self.ctx.lib.cb200_bond_phi_blocks_elems(self.h))
+
+    def phi_blocks(self):
+        """[(offset, (len_l, len_s1, len_s2, len_r))] of the block-packed layout, in storage order."""
+        n = C.c_int32()
+        self.ctx.check(self.ctx.lib.cb200_bond_phi_blocks(self.h, C.byref(n), None, None))
+        off = (C.c_int64 * max(n.value, 1))()
+        dims = (C.c_int64 * max(4 * n.value, 1))()
+        self.ctx.check(self.ctx.lib.cb200_bond_phi_blocks(self.h, C.byref(n), off, dims))
+        return [(off[i], tuple(dims[4 * i:4 * i + 4])) for i in range(n.value)]
+
+    def pack(self, phi):
+        return pack_phi_blocks(self._phi(phi), self.q[0], self.sq, self.q[1], self.nq)
+
+    def unpack(self, xb):
+        return unpack_phi_blocks(xb, self.q[0], self.sq, self.q[1], self.nq)
+
+    def apply_blocks(self, xb, out=None):
+        """LocalMPO::product with block-packed host vectors (1-D arrays of phi_blocks_elems elements)."""
+        x = np.ascontiguousarray(xb, dtype=self.dt)
+        if x.size != self.phi_blocks_elems:
+            raise ValueError("block-packed phi has %d elements, expected %d" % (x.size, self.phi_blocks_elems))
+        y = out if out is not None else np.zeros(x.size, self.dt)
+        self.ctx.check(self.ctx.lib.cb200_bond_apply_blocks(self.h, ptr(x), ptr(y)))
+        return y
+
     def apply_timed(self, phi, reps=5, warmup=3):
         x = self._phi(phi)
         ms = C.c_double()
@@ -433,6 +462,44 @@ class Bond:
 
 
 # ---- kernel-level helpers (unit tests / calibration) -------------------------------------------------------------
+def _charge_runs(q):
+    """Sectors of an index = maximal runs of equal charge label: [(start, stop, charge)]."""
+    q = np.asarray(q)
+    if q.size == 0:
+        return []
+    cut = np.flatnonzero(np.diff(q)) + 1
+    starts = np.concatenate([[0], cut])
+    stops = np.concatenate([cut, [q.size]])
+    return [(int(a), int(b), int(q[a])) for a, b in zip(starts, stops)]
+
+
+def _phi_block_slices(ql, sq, qr, nq):
+    rl, rs, rr = _charge_runs(ql), _charge_runs(sq), _charge_runs(qr)
+    for (r0, r1, cr) in rr:
+        for (b0, b1, c2) in rs:
+            for (a0, a1, c1) in rs:
+                for (l0, l1, cl) in rl:
+                    if (cl + c1 + c2 - cr) % nq == 0:
+                        yield (slice(l0, l1), slice(a0, a1), slice(b0, b1), slice(r0, r1))
+
+
+def pack_phi_blocks(phi, ql, sq, qr, nq):
+    """Dense [l, s1, s2, r] -> the block-packed ("QDense order") 1-D layout of include/chain_b200.h (host-side helper)."""
+    parts = [np.asarray(phi[sl]).ravel(order="F") for sl in _phi_block_slices(ql, sq, qr, nq)]
+    return np.concatenate(parts) if parts else np.zeros(0, phi.dtype)
+
+
+def unpack_phi_blocks(xb, ql, sq, qr, nq):
+    out = np.zeros((len(ql), len(sq), len(sq), len(qr)), dtype=np.asarray(xb).dtype, order="F")
+    o = 0
+    for sl in _phi_block_slices(ql, sq, qr, nq):
+        shp = tuple(s.stop - s.start for s in sl)
+        n = int(np.prod(shp))
+        out[sl] = np.asarray(xb[o:o + n]).reshape(shp, order="F")
+        o += n
+    return out
+
+
 def k_gemm(A, B, C0, M, N, Ks, a_offs, b_offs, lda, ldb, c_off, ldc, trans_a=False, trans_b=False, conj_a=False,
            accumulate=False, reps=0, ctx=None):
     ctx = ctx or default_context()

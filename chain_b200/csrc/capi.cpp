@@ -324,6 +324,51 @@ int cb200_bond_apply(cb200_bond* B, const void* phi, void* out) {
   });
 }
 
+int64_t cb200_bond_phi_blocks_elems(const cb200_bond* B) { return B ? B->b.philay.total : 0; }
+
+int cb200_bond_phi_blocks(const cb200_bond* B, int32_t* nblocks, int64_t* offsets, int64_t* dims4) {
+  if (!B || !nblocks) return CB200_ERR_INVALID;
+  // the block list of the packed layout in storage order: offsets[i] (elements) and dims4[4*i..] = (len_l, len_s1, len_s2, len_r)
+  int32_t n = 0;
+  int64_t off = 0;
+  auto runs = [](const IndexMap& m) {
+    std::vector<std::pair<int64_t, int>> v;   // (length, charge)
+    for (size_t i = 0; i < m.charge_ext.size();) {
+      size_t j = i;
+      while (j < m.charge_ext.size() && m.charge_ext[j] == m.charge_ext[i]) ++j;
+      v.push_back({(int64_t)(j - i), m.charge_ext[i]});
+      i = j;
+    }
+    return v;
+  };
+  const auto rl = runs(B->l), rs = runs(B->S.map), rr = runs(B->r);
+  for (auto& ur : rr)
+    for (auto& u2 : rs)
+      for (auto& u1 : rs)
+        for (auto& ul : rl) {
+          if ((ul.second + u1.second + u2.second - ur.second) % B->nq != 0) continue;
+          if (offsets) offsets[n] = off;
+          if (dims4) { dims4[4 * n] = ul.first; dims4[4 * n + 1] = u1.first; dims4[4 * n + 2] = u2.first; dims4[4 * n + 3] = ur.first; }
+          off += ul.first * u1.first * u2.first * ur.first;
+          ++n;
+        }
+  *nblocks = n;
+  return CB200_OK;
+}
+
+int cb200_bond_apply_blocks(cb200_bond* B, const void* phi_blocks, void* out_blocks) {
+  if (!B || !phi_blocks || !out_blocks) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    Buf x(c->be, (int64_t)es * n), y(c->be, (int64_t)es * n);
+    import_phi_blocks(c, B->cplx, B->S, B->l, B->r, B->b.philay, phi_blocks, x.p);
+    B->b.apply(x.p, y.p);
+    export_phi_blocks(c, B->cplx, B->S, B->l, B->r, B->b.philay, y.p, out_blocks);
+  });
+}
+
 int cb200_bond_apply_timed(cb200_bond* B, const void* phi, int32_t reps, int32_t warmup, double* ms_mean) {
   if (!B || !phi || !ms_mean || reps < 1) return CB200_ERR_INVALID;
   return guard(B->ctx, [&] {

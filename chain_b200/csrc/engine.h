@@ -278,6 +278,10 @@ void import_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const v
 void export_env(Ctx* c, bool cplx, const IndexMap& x, const IndexMap& k, const DevEnv& in, void* ext);
 void import_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev);
 void export_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext);
+// block-packed ("QDense order") host layout of a phi-shaped tensor: see engine_io.cpp; phi_block_tasks returns the packed element count
+int64_t phi_block_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, bool to_internal, std::vector<CopyTask>* tasks);
+void import_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev);
+void export_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext);
 
 // ---- the sweep driver (itensor::dmrg) --------------------------------------------------------------------------
 struct SweepParams { int maxdim, mindim, niter; double cutoff, noise; };

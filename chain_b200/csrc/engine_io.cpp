@@ -222,6 +222,79 @@ void export_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const I
   for_phi(S, l, r, pl, [&](int64_t e, int64_t i) { wr(ext, cplx, e, rd(h.data(), cplx, i)); });
 }
 
+// ---- block-packed boundary ("QDense order") -----------------------------------------------------------------------------
+// ITensor keeps a QN tensor as a list of dense blocks (QDense), never as a dense array with zeros.  The block-packed host layout
+// accepted here is that storage: every index is cut into sectors = maximal runs of equal charge label; the blocks are the sector
+// tuples (i_l, i_s1, i_s2, i_r) of zero flux, q(l)+q(s1)+q(s2) = q(r), enumerated with i_l fastest and i_r slowest; each block is
+// dense column-major [len_l, len_s1, len_s2, len_r]; blocks follow each other without gaps.  Only 1/nq of the dense array crosses
+// PCIe, and the (un)packing is one strided-copy launch on the device (internal order is a stable sort by charge, so a sector is a
+// contiguous internal range).
+namespace {
+struct Run { int64_t start, len; int q; };
+std::vector<Run> runs_of(const IndexMap& m) {
+  std::vector<Run> v;
+  const int64_t n = (int64_t)m.charge_ext.size();
+  for (int64_t i = 0; i < n;) {
+    int64_t j = i;
+    while (j < n && m.charge_ext[j] == m.charge_ext[i]) ++j;
+    v.push_back({i, j - i, m.charge_ext[i]});
+    i = j;
+  }
+  return v;
+}
+}  // namespace
+int64_t phi_block_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, bool to_internal,
+                        std::vector<CopyTask>* tasks) {
+  const int nq = S.nq, d = S.d;
+  const std::vector<Run> rl = runs_of(l), rs = runs_of(S.map), rr = runs_of(r);
+  int64_t boff = 0;
+  for (const Run& ur : rr)
+    for (const Run& u2 : rs)
+      for (const Run& u1 : rs)
+        for (const Run& ul : rl) {
+          if (qsub(qadd(qadd(ul.q, u1.q, nq), u2.q, nq), ur.q, nq) != 0) continue;
+          const int64_t bsz = ul.len * u1.len * u2.len * ur.len;
+          if (tasks) {
+            const int ql = ul.q, qr = ur.q, qd = qsub(qr, ql, nq);
+            const int64_t dlq = l.g.dim[ql], ns = S.ns(qd);
+            const int64_t l_loc = l.ext2int[ul.start] - l.g.off(ql), r_loc = r.ext2int[ur.start] - r.g.off(qr);
+            for (int64_t b2 = 0; b2 < u2.len; ++b2)
+              for (int64_t b1 = 0; b1 < u1.len; ++b1) {
+                const int s1i = (int)S.map.ext2int[u1.start + b1], s2i = (int)S.map.ext2int[u2.start + b2];
+                const int64_t sr = S.srow_index[(size_t)s1i * d + s2i];
+                const int64_t eoff = boff + ul.len * (b1 + u1.len * b2);
+                const int64_t ioff = pl.o(ql, qr) + l_loc + dlq * (sr + ns * r_loc);
+                CopyTask t{};
+                t.n0 = (int32_t)ul.len; t.n1 = (int32_t)ur.len; t.n2 = 1;
+                const int64_t es1 = ul.len * u1.len * u2.len, is1 = dlq * ns;
+                if (to_internal) { t.src_off = eoff; t.dst_off = ioff; t.ss0 = 1; t.ss1 = es1; t.ds0 = 1; t.ds1 = is1; }
+                else { t.src_off = ioff; t.dst_off = eoff; t.ss0 = 1; t.ss1 = is1; t.ds0 = 1; t.ds1 = es1; }
+                tasks->push_back(t);
+              }
+          }
+          boff += bsz;
+        }
+  return boff;
+}
+void import_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev) {
+  std::vector<CopyTask> tasks;
+  const int64_t tot = phi_block_tasks(S, l, r, pl, true, &tasks);
+  if (tot != pl.total) fail(-2, "block-packed phi: element count does not match the charge structure");
+  if (tot == 0) return;
+  Buf stage(c->be, (int64_t)esz(cplx) * tot);
+  dev_h2d(c->be, stage.p, ext, esz(cplx) * (size_t)tot);
+  run_copy_tasks(c, cplx, tasks, stage.p, dev);
+}
+void export_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext) {
+  std::vector<CopyTask> tasks;
+  const int64_t tot = phi_block_tasks(S, l, r, pl, false, &tasks);
+  if (tot != pl.total) fail(-2, "block-packed phi: element count does not match the charge structure");
+  if (tot == 0) return;
+  Buf stage(c->be, (int64_t)esz(cplx) * tot);
+  run_copy_tasks(c, cplx, tasks, dev, stage.p);
+  dev_d2h(c->be, ext, stage.p, esz(cplx) * (size_t)tot);
+}
+
 // ------------------------------------------------------------------------------------------------ overlap environments
 namespace {
 

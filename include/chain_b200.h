@@ -152,6 +152,16 @@ int64_t cb200_bond_phi_elems(const cb200_bond* b);   /* Dl*d*d*Dr */
 double cb200_bond_matvec_flops(const cb200_bond* b); /* F_alg of SURVEY 8(d): block-sparse, sparse-W */
 /* LocalMPO(_MPS)::product: host phi in, host H_eff*phi out (copies included) */
 int cb200_bond_apply(cb200_bond* b, const void* phi, void* out);
+/* LocalMPO(_MPS)::product on ITensor's own QN storage: phi and the result cross the boundary BLOCK-PACKED ("QDense order"),
+ * the way itensor::QDense<T> holds a QN tensor (a list of dense blocks over one contiguous buffer), instead of as a dense array
+ * with exact zeros -- 1/nq of the bytes over PCIe and no scatter pass in the adapter.  Layout: every index is cut into sectors =
+ * maximal runs of equal charge label (an ITensor QN index is such a list of (QN, dim) sectors); the stored blocks are the sector
+ * tuples (i_l, i_s1, i_s2, i_r) with q(l)+q(s1)+q(s2) = q(r), in increasing block number i_l + n_l*(i_s1 + n_s*(i_s2 + n_s*i_r));
+ * each block is dense column-major [len_l, len_s1, len_s2, len_r]; no gaps.  cb200_bond_phi_blocks_elems = total element count;
+ * cb200_bond_phi_blocks lists the blocks (call with offsets = dims4 = NULL for the count).  For nq = 1 this is the dense array. */
+int64_t cb200_bond_phi_blocks_elems(const cb200_bond* b);
+int cb200_bond_phi_blocks(const cb200_bond* b, int32_t* nblocks, int64_t* offsets, int64_t* dims4 /* 4 per block */);
+int cb200_bond_apply_blocks(cb200_bond* b, const void* phi_blocks, void* out_blocks);
 /* same product, device-resident, repeated `reps` times; returns mean milliseconds (CUDA events) */
 int cb200_bond_apply_timed(cb200_bond* b, const void* phi, int32_t reps, int32_t warmup, double* ms_mean);
 /* per-stage device time of the product (ms, mean of reps) and algorithmic flops: [0] L-stage GEMM, [1] W (x) W mix, [2] R-stage GEMM */

@@ -128,6 +128,39 @@ def check_bond_ops(ctx, case, rtol=1e-12):
     B.close()
 
 
+def check_bond_blocks(ctx, case, shuffle=False):
+    """cb200_bond_apply_blocks (ITensor QDense storage at the boundary) == block-packing of the dense product; also checks the
+    block list against an independent enumeration.  shuffle=True interleaves the link charge labels (many short sectors)."""
+    st, bc, n, cp, q, bond = case
+    site, W, qk, c = capture_bond(st, bc, n, cp, q, bond)
+    c = dict(c)
+    if shuffle:
+        rng = np.random.default_rng(5)
+        pl, pr = rng.permutation(len(c["ql"])), rng.permutation(len(c["qr"]))
+        c["ql"], c["qr"] = np.asarray(c["ql"])[pl], np.asarray(c["qr"])[pr]
+        c["L"] = c["L"][pl][:, :, pl]
+        c["R"] = c["R"][pr][:, :, pr]
+        c["phi"] = c["phi"][pl][:, :, :, pr]
+    B = make_bond(ctx, site, qk, c)
+    phi = c["phi"]
+    yo = od.heff_apply(c["L"], c["W1"], c["W2"], c["R"], phi)
+    # the packed layout holds every allowed element exactly once
+    mask = (np.asarray(c["ql"])[:, None, None, None] + np.asarray(site.charges)[None, :, None, None]
+            + np.asarray(site.charges)[None, None, :, None] - np.asarray(c["qr"])[None, None, None, :]) % site.nq == 0
+    assert B.phi_blocks_elems == int(mask.sum())
+    blocks = B.phi_blocks()
+    assert sum(int(np.prod(d)) for _, d in blocks) == B.phi_blocks_elems
+    assert [o for o, _ in blocks] == list(np.cumsum([0] + [int(np.prod(d)) for _, d in blocks[:-1]]))
+    xb = B.pack(phi)
+    assert xb.size == B.phi_blocks_elems
+    assert np.array_equal(B.unpack(xb), np.asarray(phi, dtype=xb.dtype) * mask)
+    yb = B.apply_blocks(xb)
+    assert np.abs(B.unpack(yb) - yo).max() <= 1e-12 * np.abs(yo).max()
+    # bit-identical to the dense-boundary call (same device path, different (un)packing)
+    assert np.array_equal(yb, B.pack(B.apply(phi)))
+    B.close()
+
+
 DMRG_CASES = [
     # site, bc, n, couplings, charge, nstates, product-state start?
     ("golden", "p", 6, [-1.0], 0, 3, True),

@@ -13,6 +13,12 @@ def test_bond_ops_match_oracle(emu_ctx, case):
     common.check_bond_ops(emu_ctx, case)
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("case", common.BOND_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
+def test_bond_apply_block_packed_boundary(emu_ctx, case, shuffle):
+    common.check_bond_blocks(emu_ctx, case, shuffle)
+
+
 @pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
 def test_dmrg_trajectory_matches_oracle(emu_ctx, case):
     common.check_dmrg_trajectory(emu_ctx, case, nsweep=8)
