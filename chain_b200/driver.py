@@ -9,11 +9,15 @@ Nothing here does tensor arithmetic: Hamiltonians come from chain_b200.models (h
     python -m chain_b200.driver -s golden -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 1 -m 0 [--out DIR] [--seed N]
 
 Differences from the reference, all deliberate: output goes under --out (the reference compiles the parent of the cwd in,
-src/path_template.h:8); --seed makes the random product start reproducible (the reference never seeds); there is no
-pgs/ checkpoint (ITensor's private binary format); mode 5 runs the simulation and then the energy /
-translation / rho measurements and the {energy, momentum, rho} table of Analyze (AnalyzeWithoutRho for charged sectors).
+src/path_template.h:8); --seed makes the random product start reproducible (the reference never seeds); the pgs/ checkpoint
+has DMRGProgress's semantics (src/dmrg.h:15-257: written after every dmrg() call, a finished job is recognised, an interrupted
+one resumes at the sweep it stopped before) but its own container -- one NumPy .npz per job instead of ITensor's private binary
+streams, SURVEY 8f row f4 -- and also stores the stopping-rule counters the reference leaves uninitialised on resume; mode 5
+runs the simulation and then the energy / translation / rho measurements and the {energy, momentum, rho} table of Analyze
+(AnalyzeWithoutRho for charged sectors).
 """
 import argparse
+import io
 import os
 import sys
 import time
@@ -93,11 +97,97 @@ def state_name(k):
     return {0: "1st state", 1: "2nd state", 2: "3rd state"}.get(k, "%dth state" % (k + 1))
 
 
+class DMRGProgress:
+    """DMRGProgress<SiteSet>, src/dmrg.h:15-257, with the same member names: per state the latest (times swept, bond dimension,
+    energy, MPS); the last entry is the state being simulated, everything before it is done.  The Hamiltonian is not stored (the
+    reference keeps a copy per state, :24; it is a pure function of the job parameters, which are in the file name) -- `stage`
+    records which Hamiltonian a `-b sp` job is on instead (hot_start of src/dmrg.h:521-524), and (min_en, cnt) the stopping rule.
+    File: <stem>.pgs = one .npz, written to a temporary and renamed so that a kill during the write cannot corrupt it (the
+    reference answers that case with .bk copies and RecoverStates, :164-199); site tensors are stored without their forbidden
+    charge blocks."""
+
+    def __init__(self):
+        self.num_sweeps_vec_, self.max_dims_, self.ens_, self.psis_ = [], [], [], []
+        self.stage, self.min_en, self.cnt = None, 1000000.0, 0
+        self.sp_seed = None          # `-b sp` only: the SSD result that seeds the PBC re-warm-up (init_state_ of src/dmrg.h:616)
+
+    def Update(self, times_swept, max_dim, en, psi):
+        self.num_sweeps_vec_[-1], self.max_dims_[-1], self.ens_[-1], self.psis_[-1] = int(times_swept), int(max_dim), float(en), psi
+
+    def NextState(self):
+        self.num_sweeps_vec_.append(0)
+        self.max_dims_.append(0)
+        self.ens_.append(0.0)
+        self.psis_.append(None)
+
+    def All(self):
+        return self.num_sweeps_vec_[-1], self.max_dims_[-1], self.ens_[-1], self.psis_[-1]
+
+    def DoneStates(self):
+        return list(self.psis_[:-1])
+
+    def Energies(self):
+        return list(self.ens_[:-1])
+
+    def NumDoneStates(self):
+        return len(self.psis_) - 1
+
+    @staticmethod
+    def _mask(psi, j, site_charges):
+        ql, qr = np.asarray(psi.link_charges[j]), np.asarray(psi.link_charges[j + 1])
+        return (ql[:, None, None] + np.asarray(site_charges)[None, :, None] - qr[None, None, :]) % psi.nq == 0
+
+    def Write(self, path, site_charges, backup=False):
+        z = {"num_sweeps_vec": np.asarray(self.num_sweeps_vec_, np.int64), "max_dims": np.asarray(self.max_dims_, np.int64),
+             "ens": np.asarray(self.ens_, np.float64), "stage": np.asarray(-2 if self.stage is None else self.stage, np.int64),
+             "min_en": np.asarray(self.min_en), "cnt": np.asarray(self.cnt, np.int64), "site_charges": np.asarray(site_charges, np.int32),
+             "present": np.asarray([p is not None for p in self.psis_], np.int8)}
+        for i, psi in list(enumerate(self.psis_)) + [("eed", self.sp_seed)]:
+            if psi is None:
+                continue
+            z["s%s_meta" % i] = np.asarray([psi.n, psi.nq, psi.center or 0, int(psi.is_complex())], np.int64)
+            for j in range(psi.n + 1):
+                z["s%s_q%d" % (i, j)] = np.asarray(psi.link_charges[j], np.int32)
+            for j in range(psi.n):
+                z["s%s_a%d" % (i, j)] = np.asarray(psi.sites[j])[self._mask(psi, j, site_charges)]
+        buf = io.BytesIO()
+        np.savez(buf, **z)
+        dst = path + (".pgs.bk" if backup else ".pgs")
+        with open(dst + ".tmp", "wb") as f:
+            f.write(buf.getvalue())
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(dst + ".tmp", dst)
+
+    def Read(self, path, backup=False):
+        with np.load(path + (".pgs.bk" if backup else ".pgs")) as z:
+            self.num_sweeps_vec_ = [int(v) for v in z["num_sweeps_vec"]]
+            self.max_dims_ = [int(v) for v in z["max_dims"]]
+            self.ens_ = [float(v) for v in z["ens"]]
+            st = int(z["stage"])
+            self.stage, self.min_en, self.cnt = (None if st == -2 else st), float(z["min_en"]), int(z["cnt"])
+            sq = z["site_charges"]
+            def load(i):
+                n, nq, center, cplx = (int(v) for v in z["s%s_meta" % i])
+                q = [z["s%s_q%d" % (i, j)] for j in range(n + 1)]
+                sites = []
+                for j in range(n):
+                    m = (q[j][:, None, None] + sq[None, :, None] - q[j + 1][None, None, :]) % nq == 0
+                    a = np.zeros(m.shape, complex if cplx else float)
+                    a[m] = z["s%s_a%d" % (i, j)]
+                    sites.append(a)
+                return cb.MPS(sites, q, nq=nq, center=center)
+            self.psis_ = [load(i) if present else None for i, present in enumerate(z["present"])]
+            self.sp_seed = load("eed") if "seed_meta" in z.files else None
+        if not (len(self.num_sweeps_vec_) == len(self.max_dims_) == len(self.ens_) == len(self.psis_) >= 1):
+            raise IndexError("corrupt progress file %s" % path)      # the std::out_of_range Simulate catches, src/dmrg.h:454
+
+
 class Simulation:
     """SimulateRaw (src/dmrg.h:474-655) with the same member names where they exist."""
 
     def __init__(self, site, bc, n, maxdim, cutoff, precision, coupling_str, u, charge, nstates, out=".", seed=None, ctx=None,
-                 log=print):
+                 log=print, checkpoint=True):
         if bc not in ("p", "o", "s", "d", "sp"):
             raise ValueError("Invalid boundary condition")
         self.site_type, self.bc, self.n = site, bc, n
@@ -117,12 +207,14 @@ class Simulation:
         self.log = log
         stem = file_stem(site, bc, n, self.max_bond_dim, self.svd_cutoff, self.precision, coupling_str, self.u, charge)
         self.stem = stem
-        for sub in ("ee", "en", "m", "an"):
+        self.checkpoint = bool(checkpoint)
+        for sub in ("ee", "en", "m", "an") + (("pgs",) if checkpoint else ()):
             os.makedirs(os.path.join(out, sub), exist_ok=True)
         self.ee_path = os.path.join(out, "ee", stem + ".ee")
         self.en_path = os.path.join(out, "en", stem + ".en")
         self.m_path = os.path.join(out, "m", stem + ".m")
         self.an_path = os.path.join(out, "an", stem + ".an")
+        self.progress_path = os.path.join(out, "pgs", stem)       # progress_path_, src/dmrg.h:361
         self.energies, self.states, self.sweep_log = [], [], []
 
     def hamiltonian(self, bc):
@@ -142,57 +234,91 @@ class Simulation:
         return en, psi
 
     def run(self):
+        """SimulateRaw, src/dmrg.h:474-655, including its progress file: every dmrg() call is followed by Update + Write, a job whose
+        file already holds the requested number of states returns at once, an interrupted job continues with the sweep it was
+        stopped before (same energies as the uninterrupted run: the stopping-rule counters are part of the file)."""
         n, c = self.n, self.svd_cutoff
-        H = self.hamiltonian(self.bc)
+        prog = self.dmrg_progress_ = DMRGProgress()
+        sq = self.sites.charges
+        ck = self.checkpoint
+        save = (lambda backup=False: prog.Write(self.progress_path, sq, backup)) if ck else (lambda backup=False: None)
+        hot_start = 1 if self.bc == "sp" else -1
+        if ck and os.path.exists(self.progress_path + ".pgs"):
+            try:
+                prog.Read(self.progress_path)                # job was run before, read progress (:489-491)
+            except Exception as err:                         # Simulate's answer to a corrupt file: the backup copy (:454-462)
+                self.log("%s\nReplace progress files with backup progress files." % err)
+                prog.Read(self.progress_path, backup=True)
+                save()
+            if prog.stage is not None:
+                hot_start = prog.stage
+            if prog.NumDoneStates() >= self.num_states:
+                self.log("\n> Job already complete\n> Requested number of states: %d \n> Completed number of states: %d\n" % (
+                    self.num_states, prog.NumDoneStates()))
+                self.energies, self.states = prog.Energies(), prog.DoneStates()
+                return self.energies, self.states
+        else:                                                # new job (:513-517)
+            prog.NextState()
+            prog.stage = hot_start
+            save()
+        H = self.hamiltonian("p" if (self.bc == "sp" and hot_start != 1) else self.bc)
         self._complex = H.is_complex()
         init_state = self.default_init_state()
-        hot_start = 1 if self.bc == "sp" else -1
-        done = []                    # dmrg_progress_.DoneStates()
+        if hot_start == 0 and prog.sp_seed is not None:      # resumed between the SSD stage and the PBC re-warm-up
+            init_state = prog.sp_seed
         while True:
-            name = state_name(len(done))
+            name = state_name(prog.NumDoneStates())
             self.log("\n> Simulation: %s" % name)
-            min_en, cnt, num_sweeps = 1000000.0, self.num_reps_til_stable, 0          # ResetDMRG
-            bond_dim = 200
-            if hot_start != 0:       # warm-up ladder, src/dmrg.h:538-547
-                sw = cb.Sweeps(self.init_num_sweeps_per_rep, [10, 20, 40, 80, 200],
-                               [max(1e-5, c), max(1e-6, c), max(1e-7, c), max(1e-8, c), max(1e-9, c)], niter=2, noise=self.noise)
-            else:                    # SSD -> PBC re-warm-up, :548-567
-                sw = cb.Sweeps(self.init_num_sweeps_per_rep, bond_dim, c, niter=2, noise=self.noise)
-            en, psi = self._dmrg(H, done, init_state, sw)
-            num_sweeps += self.init_num_sweeps_per_rep
-            while True:              # :576-609
-                if len(done) == 0:   # IsSimulatingFirstState
-                    dump_ee(self.ee_path, n, cb.calc_ee(psi, self.sites.charges, ctx=self.ctx))
+            if prog.num_sweeps_vec_[-1] == 0:
+                prog.min_en, prog.cnt, num_sweeps = 1000000.0, self.num_reps_til_stable, 0          # ResetDMRG
+                bond_dim = 200
+                if hot_start != 0:       # warm-up ladder, src/dmrg.h:538-547
+                    sw = cb.Sweeps(self.init_num_sweeps_per_rep, [10, 20, 40, 80, 200],
+                                   [max(1e-5, c), max(1e-6, c), max(1e-7, c), max(1e-8, c), max(1e-9, c)], niter=2, noise=self.noise)
+                else:                    # SSD -> PBC re-warm-up, :548-567
+                    sw = cb.Sweeps(self.init_num_sweeps_per_rep, bond_dim, c, niter=2, noise=self.noise)
+                en, psi = self._dmrg(H, prog.DoneStates(), init_state, sw)
+                num_sweeps += self.init_num_sweeps_per_rep
+                prog.Update(num_sweeps, bond_dim, en, psi)
+                save()
+            # else: warm-up previously completed, no more warm-up (:568-572)
+            while prog.cnt > 0:      # :576-609 (a job killed right after its last rep was saved resumes past the loop)
+                num_sweeps, bond_dim, en, psi = prog.All()
+                if prog.NumDoneStates() == 0:   # IsSimulatingFirstState
+                    dump_ee(self.ee_path, n, cb.calc_ee(psi, sq, ctx=self.ctx))
                 if bond_dim <= self.max_bond_dim - 200:
                     bond_dim += 200
-                en, psi = self._dmrg(H, done, psi, cb.Sweeps(self.num_sweeps_per_rep, bond_dim, c, niter=2, noise=self.noise))
-                if abs(min_en - en) * n < self.precision:
-                    cnt -= 1
+                en, psi = self._dmrg(H, prog.DoneStates(), psi, cb.Sweeps(self.num_sweeps_per_rep, bond_dim, c, niter=2, noise=self.noise))
+                if abs(prog.min_en - en) * n < self.precision:
+                    prog.cnt -= 1
                 else:
-                    cnt, min_en = self.num_reps_til_stable, en
+                    prog.cnt, prog.min_en = self.num_reps_til_stable, en
                 num_sweeps += self.num_sweeps_per_rep
+                prog.Update(num_sweeps, bond_dim, en, psi)
+                save()
                 self.log("  > Sweep #%d  %s  E=%.12f  bond_dim=%d (reached %d)" % (num_sweeps, name, en, bond_dim, max(psi.bond_dims())))
-                if cnt == 0:
-                    break
-            if hot_start == 1:       # :613-621
+            num_sweeps, bond_dim, en, psi = prog.All()
+            if hot_start == 1:       # :613-621: the SSD result seeds the PBC run and the progress object is replaced
                 H = self.hamiltonian("p")
                 init_state = psi
-                done = []
+                prog = self.dmrg_progress_ = DMRGProgress()
+                prog.sp_seed = psi
+                save = (lambda backup=False: prog.Write(self.progress_path, sq, backup)) if ck else (lambda backup=False: None)
                 hot_start = 0
-                ndone_after = 0      # the progress object was replaced before NextState()
-            else:
-                if hot_start == 0:
-                    init_state = self.default_init_state()
-                    hot_start = -1
-                done.append(psi)
-                self.states.append(psi)
-                self.energies.append(en)
-                ndone_after = len(done)
+            elif hot_start == 0:
+                init_state = self.default_init_state()
+                prog.sp_seed = None
+                hot_start = -1
+            prog.NextState()         # even if there is no next state, this marks completion of the current one (:623-629)
+            prog.stage = hot_start
+            save()
+            save(backup=True)
             # DumpEnergy(NumDoneStates()+1, en) is called AFTER NextState(): the first state is written with index 2 (:625-633)
-            dump_energy(self.en_path, ndone_after + 1, en)
+            dump_energy(self.en_path, prog.NumDoneStates() + 1, en)
             self.log("\n> Energy of %s: %g\n" % (name, en))
-            if ndone_after >= self.num_states:
+            if prog.NumDoneStates() >= self.num_states:
                 break
+        self.energies, self.states = prog.Energies(), prog.DoneStates()
         return self.energies, self.states
 
 
@@ -282,6 +408,7 @@ def main(argv=None):
     ap.add_argument("-h", "--help", action="help")
     ap.add_argument("--out", default=".")
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--no-checkpoint", action="store_true", help="do not write / read the pgs/ progress file")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--lib", default=None, help="path of the C-ABI library (default: chain_b200/libchain_b200.so)")
     a = ap.parse_args(argv)
@@ -290,7 +417,7 @@ def main(argv=None):
                  "(SURVEY 8f row f2) or ITensor's checkpoint files; the hot path is modes 0 and 5" % a.mode)
     ctx = cb.Context(device=a.device, lib_path=a.lib)
     sim = Simulation(a.site, a.bc, a.length, a.maxdim, a.cutoff, a.precision, a.couplings, a.penalty, a.charge, a.nstates,
-                     out=a.out, seed=a.seed, ctx=ctx)
+                     out=a.out, seed=a.seed, ctx=ctx, checkpoint=not a.no_checkpoint)
     print("\n> %s %s:  L=%d  bond_dim=%d  svd_cutoff=%g  precision=%g  penalty=%g  couplings=%s  charge=%d" % (
         a.site, a.bc, a.length, a.maxdim, sim.svd_cutoff, sim.precision, sim.u, a.couplings, a.charge))
     t0 = time.perf_counter()

@@ -63,3 +63,84 @@ def test_calc_ee_matches_oracle(emu_ctx, case):
 def test_cli_rejects_unbuilt_modes():
     with pytest.raises(SystemExit):
         driver.main("-s golden -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 1 -m 1".split())
+
+
+class _Stop(Exception):
+    pass
+
+
+def _run_interrupted(ctx, out, bc, nstates, seed, stop_after):
+    """Run the job, killing it right after the `stop_after`-th dmrg() call has been checkpointed; returns #calls made."""
+    sim = driver.Simulation("golden", bc, 6, 100, 1e-8, 1e-7, "-1", 2.0, 0, nstates, out=out, seed=seed, ctx=ctx, log=lambda *a: None)
+    calls = [0]
+    write = driver.DMRGProgress.Write
+
+    def counting_write(self, path, sq, backup=False):
+        write(self, path, sq, backup)
+        if stop_after != "transition" and self.num_sweeps_vec_[-1] > 0 and not backup:
+            calls[0] += 1
+            if calls[0] == stop_after:
+                raise _Stop()
+    driver.DMRGProgress.Write = counting_write
+    if stop_after == "transition":                          # -b sp: killed between the SSD stage and the PBC re-warm-up
+        inner = sim._dmrg
+
+        def guarded(H, done, psi, sweeps):
+            if sim.dmrg_progress_.stage == 0 and sim.dmrg_progress_.num_sweeps_vec_[-1] == 0:
+                calls[0] = stop_after
+                raise _Stop()
+            return inner(H, done, psi, sweeps)
+        sim._dmrg = guarded
+    try:
+        sim.run()
+        return sim, None
+    except _Stop:
+        return sim, calls[0]
+    finally:
+        driver.DMRGProgress.Write = write
+
+
+@pytest.mark.parametrize("bc,nstates,stops", [("p", 2, (1, 3, 7)), ("sp", 1, (2, 4, "transition", 6))], ids=["periodic-2-states", "ssd-hot-start"])
+def test_checkpoint_resume_reproduces_the_uninterrupted_run(emu_ctx, tmp_path, bc, nstates, stops):
+    # DMRGProgress semantics (src/dmrg.h:15-257, :489-517): progress written after every dmrg() call, resume at the next sweep
+    ref = driver.Simulation("golden", bc, 6, 100, 1e-8, 1e-7, "-1", 2.0, 0, nstates, out=str(tmp_path / "ref"), seed=4, ctx=emu_ctx, log=lambda *a: None)
+    ens_ref, _ = ref.run()
+    ncalls_ref = len(ref.sweep_log)
+    for stop in stops:
+        out = str(tmp_path / ("cut%s" % stop))
+        sim1, n1 = _run_interrupted(emu_ctx, out, bc, nstates, 4, stop)
+        assert n1 == stop                                   # it really was interrupted
+        sim2 = driver.Simulation("golden", bc, 6, 100, 1e-8, 1e-7, "-1", 2.0, 0, nstates, out=out, seed=4, ctx=emu_ctx, log=lambda *a: None)
+        ens2, states2 = sim2.run()
+        assert len(sim1.sweep_log) + len(sim2.sweep_log) == ncalls_ref      # no sweep repeated, none skipped
+        assert ens2 == ens_ref                              # bit-identical: the MPS and the stopping-rule counters round-trip exactly
+        assert open(sim2.en_path).read() == open(ref.en_path).read()
+        # a third start finds the job complete and does no DMRG at all (src/dmrg.h:492-511)
+        sim3 = driver.Simulation("golden", bc, 6, 100, 1e-8, 1e-7, "-1", 2.0, 0, nstates, out=out, seed=4, ctx=emu_ctx, log=lambda *a: None)
+        ens3, states3 = sim3.run()
+        assert sim3.sweep_log == [] and ens3 == ens_ref and len(states3) == nstates
+        assert all(np.array_equal(a, b) for p, q in zip(states2, states3) for a, b in zip(p.sites, q.sites))
+
+
+def test_checkpoint_roundtrip_block_sparse_complex(tmp_path):
+    # site tensors are stored without their forbidden charge blocks; links, centre and dtype survive
+    rng = np.random.default_rng(0)
+    sq = np.array([0, 1, 2, 0, 1, 2], np.int32)
+    q = [np.array([0], np.int32), np.array([0, 1, 1, 2], np.int32), np.array([2, 0, 0, 1, 1], np.int32), np.array([0], np.int32)]
+    sites = []
+    for j in range(3):
+        m = (q[j][:, None, None] + sq[None, :, None] - q[j + 1][None, None, :]) % 3 == 0
+        sites.append((rng.standard_normal(m.shape) + 1j * rng.standard_normal(m.shape)) * m)
+    prog = driver.DMRGProgress()
+    prog.NextState()
+    prog.Update(7, 400, -1.25, cb.MPS(sites, q, nq=3, center=2))
+    prog.NextState()
+    prog.stage, prog.min_en, prog.cnt = -1, -1.25, 2
+    prog.Write(str(tmp_path / "job"), sq)
+    back = driver.DMRGProgress()
+    back.Read(str(tmp_path / "job"))
+    assert back.num_sweeps_vec_ == [7, 0] and back.max_dims_ == [400, 0] and back.ens_ == [-1.25, 0.0]
+    assert back.NumDoneStates() == 1 and back.psis_[1] is None and (back.stage, back.min_en, back.cnt) == (-1, -1.25, 2)
+    p = back.psis_[0]
+    assert p.nq == 3 and p.center == 2 and p.is_complex()
+    assert all(np.array_equal(a, b) for a, b in zip(p.sites, sites)) and all(np.array_equal(a, b) for a, b in zip(p.link_charges, q))

@@ -12,7 +12,7 @@ cases = {
 }
 name = sys.argv[1]
 ctx = cb.Context(0)
-sim = driver.Simulation(*cases[name], out="/tmp/drv_" + name, seed=1, ctx=ctx, log=lambda *a: None)
+sim = driver.Simulation(*cases[name], out="/tmp/drv_" + name, seed=1, ctx=ctx, log=lambda *a: None, checkpoint=False)
 t0 = time.perf_counter()
 ens, states = sim.run()
 wall = time.perf_counter() - t0
