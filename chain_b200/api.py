@@ -230,7 +230,7 @@ def _unpack_result(ctx, res, d):
         charges.append(q)
     sites = []
     for j in range(n):
-        a = np.zeros((dims[j], d, dims[j + 1]), dtype=dt, order="F")
+        a = np.empty((dims[j], d, dims[j + 1]), dtype=dt, order="F")      # the library writes every element (zeros included)
         ctx.check(lib.cb200_result_site(res, j, ptr(a)))
         sites.append(a)
     return sites, charges

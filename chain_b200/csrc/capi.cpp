@@ -126,8 +126,8 @@ static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
       fail(CB200_ERR_INVALID, "MPS site tensor " + std::to_string(j) + " has inconsistent dimensions");
     if (j == 0) *cplx = t.dtype == 1;
     else if ((t.dtype == 1) != *cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside one MPS");
-    const size_t bytes = (size_t)(t.dtype == 1 ? 16 : 8) * t.dims[0] * t.dims[1] * t.dims[2];
-    h.site[j].assign((const char*)t.data, (const char*)t.data + bytes);
+    if (!t.data) fail(CB200_ERR_INVALID, "MPS site tensor " + std::to_string(j) + " has no data");
+    h.site[j] = t.data;
   }
   return h;
 }
@@ -239,10 +239,18 @@ int cb200_result_link_charges(const cb200_result* r, int32_t link, int32_t* out)
   return CB200_OK;
 }
 int cb200_result_site(const cb200_result* r, int32_t site, void* out) {
-  if (!r || !out || site < 0 || site >= r->r->psi.n) return CB200_ERR_INVALID;
-  const auto& s = r->r->psi.site[site];
-  std::memcpy(out, s.data(), s.size());
-  return CB200_OK;
+  if (!r || !out || site < 0 || site >= r->r->psi.n || !r->r->ctx) return CB200_ERR_INVALID;
+  Ctx* c = r->r->ctx;
+  try {
+    result_site_export(*r->r, site, out);
+    return CB200_OK;
+  } catch (const EngineError& e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = std::string("internal error: ") + e.what();
+    return CB200_ERR_INVALID;
+  }
 }
 int32_t cb200_result_nstats(const cb200_result* r) { return r ? (int32_t)r->r->stats.size() : 0; }
 int cb200_result_stats(const cb200_result* r, cb200_bond_stat* out) {

@@ -287,20 +287,26 @@ void export_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, 
 struct SweepParams { int maxdim, mindim, niter; double cutoff, noise; };
 struct BondStat { int sweep, bond, dir, m; double energy, truncerr; };
 
-struct HostMPS {       // an MPS in external dense form (what crosses the C ABI)
+struct HostMPS {       // an MPS in external dense form (what crosses the C ABI); the site tensors are VIEWS of the caller's buffers
   int n = 0;
   std::vector<IndexMap> link;                 // n+1
-  std::vector<std::vector<char>> site;        // dense [Dl,d,Dr] bytes
+  std::vector<const void*> site;              // dense [Dl,d,Dr], column-major (empty for a result: see DmrgResult::dev)
   int center = 0;
 };
 
+// The optimised MPS stays on the device until the caller asks for a site tensor (cb200_result_site), which is then packed to the
+// dense external form by one strided-copy launch and copied straight into the caller's buffer: no host pass over the data.
 struct DmrgResult {
   double energy = 0;
-  HostMPS psi;
+  HostMPS psi;                                // links, centre (psi.site unused)
+  std::vector<DevSite3> dev;                  // site tensors, internal layout, owned until the result is freed
+  SiteInfo S;
+  Ctx* ctx = nullptr;
   std::vector<BondStat> stats;
   Timers tm;
   bool cplx = false;
 };
+void result_site_export(const DmrgResult& r, int site, void* out);
 
 struct MpoIn {
   int n = 0, nq = 1, d = 0;

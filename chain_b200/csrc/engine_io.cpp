@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "engine.h"
 
@@ -49,6 +50,9 @@ HostW import_w(int nq, int d, const SiteInfo& S, const IndexMap& kl, const Index
   return W;
 }
 
+// site tensors with at least this many dense elements are (un)packed on the device (below it the host loop is cheaper than a launch)
+// (CB200_PACK_MIN overrides the threshold; read per call so that a test can exercise both paths on the same tensors)
+static int64_t site3_pack_min() { const char* e = std::getenv("CB200_PACK_MIN"); return e ? std::atoll(e) : (int64_t)4096; }
 // generic 3-index transfer: ext[xe + Dx*(se + d*ye)] <-> block (qx,qs) element xi_loc + Dx_q*(s_loc + ds*y_loc)
 template <class F>
 static void for_site3(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const Site3Layout& lay, F f) {
@@ -72,9 +76,61 @@ static void for_site3(const SiteInfo& S, const IndexMap& l, const IndexMap& r, c
     }
 }
 
+static void run_copy_tasks(Ctx* c, bool cplx, std::vector<CopyTask>& tasks, const void* src, void* dst);
+// Device-side (un)packing of a dense [x, s, y] site tensor: one strided-copy task per (sector of x, site value, sector of y),
+// sectors = maximal runs of equal charge label (internal order is a stable sort by charge, so a run is a contiguous internal
+// range).  Returns false when the labels are so interleaved that the task list would be longer than the host loop is slow.
+static bool site3_copy_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const Site3Layout& lay, bool to_internal,
+                             std::vector<CopyTask>& tasks) {
+  const int nq = S.nq, d = S.d;
+  const int64_t Dx = l.g.total();
+  struct Run { int64_t start, len; int q; };
+  auto runs = [](const IndexMap& m) {
+    std::vector<Run> v;
+    const int64_t n = (int64_t)m.charge_ext.size();
+    for (int64_t i = 0; i < n;) {
+      int64_t j = i;
+      while (j < n && m.charge_ext[j] == m.charge_ext[i]) ++j;
+      v.push_back({i, j - i, m.charge_ext[i]});
+      i = j;
+    }
+    return v;
+  };
+  const std::vector<Run> rl = runs(l), rr = runs(r);
+  if ((int64_t)rl.size() * (int64_t)rr.size() * d > 16384) return false;
+  for (const Run& uy : rr)
+    for (int se = 0; se < d; ++se) {
+      const int si = (int)S.map.ext2int[se], qs = S.q_int[si];
+      const int64_t s_loc = S.loc_int[si], dsq = S.map.g.dim[qs];
+      for (const Run& ux : rl) {
+        if (qadd(ux.q, qs, nq) != uy.q) continue;
+        const int64_t dx = l.g.dim[ux.q];
+        const int64_t x_loc = l.ext2int[ux.start] - l.g.off(ux.q), y_loc = r.ext2int[uy.start] - r.g.off(uy.q);
+        const int64_t eoff = ux.start + Dx * (se + (int64_t)d * uy.start), es1 = Dx * d;
+        const int64_t ioff = lay.o(ux.q, qs) + x_loc + dx * (s_loc + dsq * y_loc), is1 = dx * dsq;
+        CopyTask t{};
+        t.n0 = (int32_t)ux.len; t.n1 = (int32_t)uy.len; t.n2 = 1;
+        if (to_internal) { t.src_off = eoff; t.dst_off = ioff; t.ss0 = 1; t.ss1 = es1; t.ds0 = 1; t.ds1 = is1; }
+        else { t.src_off = ioff; t.dst_off = eoff; t.ss0 = 1; t.ss1 = is1; t.ds0 = 1; t.ds1 = es1; }
+        tasks.push_back(t);
+      }
+    }
+  return true;
+}
+
 static void import_site3_t(Ctx* c, bool cplx, bool src_cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext,
                            DevSite3& out) {
   out.lay.build(l.g, r.g, &S);
+  const int64_t tot = l.g.total() * S.d * r.g.total();
+  std::vector<CopyTask> tasks;
+  if (cplx == src_cplx && tot >= site3_pack_min() && site3_copy_tasks(S, l, r, out.lay, true, tasks)) {
+    // the dense array crosses PCIe as it is and the block gather is one launch (no host pass over the data)
+    out.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(out.lay.total, 1));
+    Buf stage(c->be, (int64_t)esz(cplx) * tot);
+    dev_h2d(c->be, stage.p, ext, esz(cplx) * (size_t)tot);
+    run_copy_tasks(c, cplx, tasks, stage.p, out.buf.p);
+    return;
+  }
   std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(out.lay.total, 1), 0);
   for_site3(S, l, r, out.lay, [&](int64_t e, int64_t i) { wr(h.data(), cplx, i, rd(ext, src_cplx, e)); });
   out.buf = Buf(c->be, (int64_t)h.size());
@@ -84,6 +140,16 @@ void import_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const
   import_site3_t(c, cplx, cplx, S, l, r, ext, out);
 }
 void export_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const DevSite3& in, void* ext) {
+  {
+    const int64_t tot = l.g.total() * S.d * r.g.total();
+    std::vector<CopyTask> tasks;
+    if (tot >= site3_pack_min() && site3_copy_tasks(S, l, r, in.lay, false, tasks)) {
+      Buf stage(c->be, (int64_t)esz(cplx) * tot, true);
+      run_copy_tasks(c, cplx, tasks, in.buf.p, stage.p);
+      dev_d2h(c->be, ext, stage.p, esz(cplx) * (size_t)tot);
+      return;
+    }
+  }
   std::vector<char> h(esz(cplx) * (size_t)std::max<int64_t>(in.lay.total, 1));
   dev_d2h(c->be, h.data(), in.buf.p, esz(cplx) * (size_t)in.lay.total);
   const int64_t tot = l.g.total() * S.d * r.g.total();
@@ -456,7 +522,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   // current state
   std::vector<IndexMap> link = psi0.link;
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, psi0_cplx, S, link[j], link[j + 1], psi0.site[j].data(), A[j]);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, psi0_cplx, S, link[j], link[j + 1], psi0.site[j], A[j]);
   if (link[0].g.total() != 1 || link[n].g.total() != 1) fail(-2, "outer MPS links must have dimension 1");
   // previous states
   const int np = (int)prev.size();
@@ -464,7 +530,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   for (int p = 0; p < np; ++p) {
     if (prev[p].n != n) fail(-2, "previous state length mismatch");
     P[p].resize(n);
-    for (int j = 0; j < n; ++j) import_site3_t(c, cplx, prev_cplx[p], S, prev[p].link[j], prev[p].link[j + 1], prev[p].site[j].data(), P[p][j]);
+    for (int j = 0; j < n; ++j) import_site3_t(c, cplx, prev_cplx[p], S, prev[p].link[j], prev[p].link[j + 1], prev[p].site[j], P[p][j]);
   }
 
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {   // sites i, i+1 (0-based)
@@ -605,17 +671,21 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   res->psi.n = n;
   res->psi.center = 1;
   res->psi.link.resize(n + 1);
-  res->psi.site.resize(n);
   for (int j = 0; j <= n; ++j) res->psi.link[j] = IndexMap::from_grading(j == 0 ? A[0].lay.X : A[j - 1].lay.Y);
-  for (int j = 0; j < n; ++j) {
-    const int64_t tot = A[j].lay.X.total() * S.d * A[j].lay.Y.total();
-    res->psi.site[j].assign(esz(cplx) * (size_t)tot, 0);
-    // site index is exported in the caller's order (S.map), links in internal (charge-sorted) order
-    export_site3(c, cplx, S, res->psi.link[j], res->psi.link[j + 1], A[j], res->psi.site[j].data());
-  }
+  // the site tensors stay on the device; result_site_export packs one on request (site index in the caller's order, S.map;
+  // links in internal, charge-sorted order)
+  res->dev = std::move(A);
+  res->S = S;
+  for (auto& t : res->dev) t.lay.S = &res->S;
+  res->ctx = c;
   res->tm = c->tm;
   check_dev(c);
   return res;
+}
+
+void result_site_export(const DmrgResult& r, int site, void* out) {
+  export_site3(r.ctx, r.cplx, r.S, r.psi.link[site], r.psi.link[site + 1], r.dev[site], out);
+  check_dev(r.ctx);
 }
 
 // ------------------------------------------------------------------------------------------------ CalcEE
@@ -627,7 +697,7 @@ std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_cha
   if (n < 2) fail(-2, "entropies need at least 2 sites");
   SiteInfo S = SiteInfo::make(nq, d, site_charge);
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j].data(), A[j]);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j], A[j]);
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
     pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
     phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
@@ -665,13 +735,11 @@ void export_mps(Ctx* c, bool cplx, const SiteInfo& S, std::vector<DevSite3>& A, 
   res.cplx = cplx;
   res.psi.n = n;
   res.psi.link.resize(n + 1);
-  res.psi.site.resize(n);
   for (int j = 0; j <= n; ++j) res.psi.link[j] = IndexMap::from_grading(j == 0 ? A[0].lay.X : A[j - 1].lay.Y);
-  for (int j = 0; j < n; ++j) {
-    const int64_t tot = A[j].lay.X.total() * S.d * A[j].lay.Y.total();
-    res.psi.site[j].assign(esz(cplx) * (size_t)tot, 0);
-    export_site3(c, cplx, S, res.psi.link[j], res.psi.link[j + 1], A[j], res.psi.site[j].data());
-  }
+  res.dev = std::move(A);
+  res.S = S;
+  for (auto& t : res.dev) t.lay.S = &res.S;
+  res.ctx = c;
 }
 }  // namespace
 
@@ -680,7 +748,7 @@ std::unique_ptr<DmrgResult> mps_translate(Ctx* c, int nq, int d, const int32_t* 
   if (n < 2) fail(-2, "translation needs at least 2 sites");
   SiteInfo S = SiteInfo::make(nq, d, site_charge);
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j].data(), A[j]);
+  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j], A[j]);
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
     pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
     phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
@@ -738,16 +806,16 @@ cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const Host
   DevMat F;
   {
     DevSite3 A0, B0;
-    import_site3_t(c, cplx, a_cplx, S, a.link[0], a.link[1], a.site[0].data(), A0);
-    import_site3_t(c, cplx, b_cplx, S, b.link[0], b.link[1], b.site[0].data(), B0);
+    import_site3_t(c, cplx, a_cplx, S, a.link[0], a.link[1], a.site[0], A0);
+    import_site3_t(c, cplx, b_cplx, S, b.link[0], b.link[1], b.site[0], B0);
     if (A0.lay.X.total() != 1 || B0.lay.X.total() != 1) fail(-2, "overlap: outer links must have dimension 1");
     if (!(A0.lay.X == B0.lay.X)) return cplx_t(0, 0);          // different total charge
     site3H_times_site3(c, cplx, &S, A0, B0, F);                 // F[m, n] = sum_{l,s} conj(A[l,s,m]) B[l,s,n]
   }
   for (int j = 1; j < n; ++j) {
     DevSite3 Aj, Bj, X;
-    import_site3_t(c, cplx, a_cplx, S, a.link[j], a.link[j + 1], a.site[j].data(), Aj);
-    import_site3_t(c, cplx, b_cplx, S, b.link[j], b.link[j + 1], b.site[j].data(), Bj);
+    import_site3_t(c, cplx, a_cplx, S, a.link[j], a.link[j + 1], a.site[j], Aj);
+    import_site3_t(c, cplx, b_cplx, S, b.link[j], b.link[j + 1], b.site[j], Bj);
     // X[m, s, n'] = sum_n F[m, n] B[n, s, n'] ; F'[m', n'] = sum_{m,s} conj(A[m,s,m']) X[m,s,n']
     mat_times_site3(c, cplx, &S, F, Bj, X);
     DevMat Fn;
@@ -781,8 +849,8 @@ cplx_t mps_mpo_element(Ctx* c, int d, const HostMPS& bra, bool bra_cplx, const M
   }
   for (int j = 0; j < n; ++j) {
     DevSite3 Ak, Ab;
-    import_site3_t(c, cplx, ket_cplx, S, ket.link[j], ket.link[j + 1], ket.site[j].data(), Ak);
-    import_site3_t(c, cplx, bra_cplx, S, bra.link[j], bra.link[j + 1], bra.site[j].data(), Ab);
+    import_site3_t(c, cplx, ket_cplx, S, ket.link[j], ket.link[j + 1], ket.site[j], Ak);
+    import_site3_t(c, cplx, bra_cplx, S, bra.link[j], bra.link[j + 1], bra.site[j], Ab);
     HostW W = import_w(1, d, S, O.link[j], O.link[j + 1], O.cplx, O.site[j]);
     const int64_t kl = W.KL.total(), kr = W.KR.total();
     const int64_t Dkr = Ak.lay.Y.total(), Dbr = Ab.lay.Y.total();

@@ -126,7 +126,10 @@ int32_t cb200_result_nsites(const cb200_result* r);
 int32_t cb200_result_dtype(const cb200_result* r);                                  /* 0 f64, 1 c128 */
 int64_t cb200_result_link_dim(const cb200_result* r, int32_t link);                 /* link in [0, n] */
 int cb200_result_link_charges(const cb200_result* r, int32_t link, int32_t* out);  /* dim labels */
-int cb200_result_site(const cb200_result* r, int32_t site, void* out);             /* dense [Dl,d,Dr], caller-sized */
+/* dense [Dl,d,Dr], caller-sized.  The optimised MPS stays on the device until it is asked for: this call packs one site tensor to
+ * the dense external form on the device and copies it straight into `out` (every element is written, zeros included), so a result
+ * holds device memory and must be freed before its context is destroyed */
+int cb200_result_site(const cb200_result* r, int32_t site, void* out);
 int32_t cb200_result_nstats(const cb200_result* r);
 int cb200_result_stats(const cb200_result* r, cb200_bond_stat* out);
 /* seconds spent in: [0] env update, [1] H_eff matvec, [2] Davidson level-1, [3] truncation, [4] other; [5] matvec count, [6] matvec flop */

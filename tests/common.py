@@ -161,6 +161,38 @@ def check_bond_blocks(ctx, case, shuffle=False):
     B.close()
 
 
+def check_mps_boundary_paths(ctx, case, monkeypatch):
+    """The MPS crosses the boundary as dense arrays; large site tensors are (un)packed by a strided-copy launch on the device,
+    small ones by a host loop (CB200_PACK_MIN).  Both paths, sorted and interleaved link labels: bit-identical results."""
+    st, bc, n, cp, q, nst, product = case
+    site, W, qk = build_model(st, bc, n, cp)
+    psi0 = warm_start(site, W, n, q, seed=9, maxdim=12)
+    H = cb.MPO(W, qk, site.charges, nq=site.nq)
+    sw = cb.Sweeps(2, [16, 24], 1e-10)
+    out = {}
+    for tag, pack_min in (("device", "1"), ("host", str(10 ** 15))):
+        monkeypatch.setenv("CB200_PACK_MIN", pack_min)
+        en, psi = cb.dmrg(H, [], to_cb(psi0), sw, ctx=ctx)
+        ee = cb.calc_ee(psi, site.charges, ctx=ctx)
+        out[tag] = (en, psi, ee)
+    assert out["device"][0] == out["host"][0]
+    assert all(np.array_equal(a, b) for a, b in zip(out["device"][1].sites, out["host"][1].sites))
+    assert all(np.array_equal(a, b) for a, b in zip(out["device"][1].link_charges, out["host"][1].link_charges))
+    assert np.array_equal(out["device"][2], out["host"][2])
+    # interleaved labels on the inner links (many short sectors): permute the link index of a copy of the start state
+    rng = np.random.default_rng(2)
+    m = to_cb(psi0)
+    for j in range(1, n):
+        p = rng.permutation(len(m.link_charges[j]))
+        m.link_charges[j] = np.ascontiguousarray(m.link_charges[j][p])
+        m.sites[j - 1] = np.asfortranarray(m.sites[j - 1][:, :, p])
+        m.sites[j] = np.asfortranarray(m.sites[j][p])
+    monkeypatch.setenv("CB200_PACK_MIN", "1")
+    en_p, _ = cb.dmrg(H, [], m, sw, ctx=ctx)
+    assert abs(en_p - out["host"][0]) <= 1e-12 * abs(en_p)
+    monkeypatch.delenv("CB200_PACK_MIN")
+
+
 DMRG_CASES = [
     # site, bc, n, couplings, charge, nstates, product-state start?
     ("golden", "p", 6, [-1.0], 0, 3, True),

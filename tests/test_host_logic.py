@@ -75,3 +75,8 @@ def test_hermitian_eigensolver_driver(emu_ctx, cplx, n, m, decay):
     assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
     assert np.abs(A @ V - V @ (V.conj().T @ A @ V)).max() <= 2e-14 * np.sqrt(n)
     assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[:m]).max() <= 1e-14 * np.sqrt(n)
+
+
+@pytest.mark.parametrize("case", [common.DMRG_CASES[0], common.DMRG_CASES[3], common.DMRG_CASES[4]], ids=["golden", "haagerupq-real", "haagerupq-complex"])
+def test_mps_boundary_device_packing_equals_host_loop(emu_ctx, case, monkeypatch):
+    common.check_mps_boundary_paths(emu_ctx, case, monkeypatch)
