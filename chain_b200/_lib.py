@@ -88,6 +88,7 @@ SYMBOLS = [
     ("cb200_k_jacobi_eig", C.c_int, [vp, i32, i32, vp, vp, dbl, C.POINTER(i64)]),
     ("cb200_k_svd", C.c_int, [vp, i32, i64, i64, vp, vp, C.POINTER(dbl), C.POINTER(i32)]),
     ("cb200_k_heig", C.c_int, [vp, i32, i64, vp, i64, C.POINTER(dbl), vp, C.POINTER(i32)]),
+    ("cb200_k_heig_batched", C.c_int, [vp, i32, i32, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.POINTER(dbl)), C.POINTER(vp)]),
     ("cb200_k_dots", C.c_int, [vp, i32, i32, i64, vp, vp, C.POINTER(dbl)]),
     ("cb200_k_lincomb", C.c_int, [vp, i32, i32, i64, vp, C.POINTER(dbl), dbl, dbl, vp]),
     ("cb200_k_gemm_peak", C.c_int, [vp, i32, i32, i32, C.POINTER(dbl)]),

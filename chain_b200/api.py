@@ -556,6 +556,24 @@ def k_heig(A, m, ctx=None):
     return w, v[:, :m], it.value
 
 
+def k_heig_batched(As, ms, ctx=None):
+    """k_heig for several Hermitian matrices in one batched call (the charge blocks of one bond): [(w, V)]."""
+    ctx = ctx or default_context()
+    cplx = any(np.iscomplexobj(A) for A in As)
+    dt = np.complex128 if cplx else np.float64
+    k = len(As)
+    a = [_lib.fcol(A, dt) for A in As]
+    ns = (C.c_int64 * k)(*[x.shape[0] for x in a])
+    mm = (C.c_int64 * k)(*[int(m) for m in ms])
+    w = [np.zeros(x.shape[0]) for x in a]
+    v = [np.zeros((x.shape[0], max(int(m), 1)), dtype=dt, order="F") for x, m in zip(a, ms)]
+    ap = (C.c_void_p * k)(*[x.ctypes.data for x in a])
+    wp = (C.POINTER(C.c_double) * k)(*[x.ctypes.data_as(C.POINTER(C.c_double)) for x in w])
+    vp_ = (C.c_void_p * k)(*[x.ctypes.data for x in v])
+    ctx.check(ctx.lib.cb200_k_heig_batched(ctx.h, 1 if cplx else 0, k, ns, ap, mm, wp, vp_))
+    return [(wi, vi[:, :int(m)]) for wi, vi, m in zip(w, v, ms)]
+
+
 def k_dots(xs, y, ctx=None):
     ctx = ctx or default_context()
     cplx = np.iscomplexobj(xs) or np.iscomplexobj(y)

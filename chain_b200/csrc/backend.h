@@ -102,6 +102,21 @@ void launch_set_identity(Backend*, bool cplx, void* X, int64_t ld, int64_t n);
 //     acting on rows j+1.. (LAPACK zhetd2 'L' convention; the unscaled column stays in A).  tau/scl have A's element type.
 //     p_work: n elements of A's type.  Returns false when the backend has no such kernel (the engine then uses block Jacobi).
 bool launch_tridiag(Backend*, bool cplx, void* A, int64_t n, double* d, double* e, void* tau, void* scl, void* p_work);
+//     Batched form for the charge blocks of one bond (independent matrices of different sizes): every panel step is ONE
+//     cooperative launch in which each matrix owns a slice of the grid and its own barrier, so the per-step latency of the blocks
+//     (two barriers + dependent L2 round trips, the bound below n ~ 4000) overlaps instead of adding up.  Same results, bit for bit,
+//     as nprob calls of launch_tridiag as long as the per-matrix CTA counts agree -- they need not: every cross-CTA sum is
+//     fixed-order for a GIVEN CTA count, and replicated ranks use the same count.
+struct TriProblem {
+  void* A;
+  int64_t n;
+  double* d;
+  double* e;
+  void* tau;
+  void* scl;
+  void* p_work;
+};
+bool launch_tridiag_batched(Backend*, bool cplx, const TriProblem* probs, int nprob);
 // (2) all n eigenvalues of T by Sturm bisection, ascending
 void launch_bisect(Backend*, const double* d, const double* e, int64_t n, double* w);
 // (3) inverse iteration for m given eigenvalues (one thread per eigenvalue); Zt[i*m + j] = component i of eigenvector j, unit

@@ -1063,6 +1063,158 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   return true;
 }
 
+bool launch_tridiag_batched(Backend* b, bool cplx, const TriProblem* probs, int nprob) {
+  static const bool enabled = [] { const char* v = getenv("CB200_TRI_BATCH"); return !(v && atoi(v) == 0); }();
+  static const bool unblocked = [] { const char* v = getenv("CB200_TRIDIAG"); return v && std::string(v) == "unblocked"; }();
+  // matrices that take part in the batched launches; the rest (tiny ones) go through the single-matrix path
+  std::vector<int> big;
+  for (int k = 0; k < nprob; ++k)
+    if (probs[k].n >= 3) big.push_back(k);
+  constexpr int MAX_BATCH = 8;
+  if (!enabled || unblocked || big.size() < 2 || big.size() > MAX_BATCH) {
+    for (int k = 0; k < nprob; ++k)
+      if (!launch_tridiag(b, cplx, probs[k].A, probs[k].n, probs[k].d, probs[k].e, probs[k].tau, probs[k].scl, probs[k].p_work)) return false;
+    return true;
+  }
+  for (int k = 0; k < nprob; ++k)
+    if (probs[k].n > 0 && probs[k].n < 3)
+      launch_tridiag(b, cplx, probs[k].A, probs[k].n, probs[k].d, probs[k].e, probs[k].tau, probs[k].scl, probs[k].p_work);
+  const int NB = 64;
+  const size_t es = cplx ? 16 : 8;
+  const int np = (int)big.size();
+  static int capacity[2] = {0, 0};
+  const void* fn = cplx ? (const void*)tridiag_panel_batched_kernel<true> : (const void*)tridiag_panel_batched_kernel<false>;
+  if (!capacity[cplx]) {
+    int per_sm = 0, sms = 0;
+    CB_CHECK(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TRI_THREADS, 0));
+    CB_CHECK(b, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+    capacity[cplx] = std::max(1, per_sm) * std::max(1, sms);
+  }
+  if (capacity[cplx] < np) {   // cannot give every matrix a CTA: one after the other
+    for (int k : big)
+      if (!launch_tridiag(b, cplx, probs[k].A, probs[k].n, probs[k].d, probs[k].e, probs[k].tau, probs[k].scl, probs[k].p_work)) return false;
+    return true;
+  }
+  static const int fsplit_env = [] { const char* v = getenv("CB200_TRI_FSPLIT"); return v ? atoi(v) : 1; }();
+  const int fsplit = std::max(1, std::min(fsplit_env, TRI_WARPS));
+  // CTAs per matrix: an equal share of the co-resident capacity, but no more than one warp per column needs
+  struct Work {
+    int64_t n = 0, nref = 0;
+    int npanel = 0, blocks = 0;
+    char* pan = nullptr; char* gbuf = nullptr; double* partial = nullptr;
+    GemmTask* d_tasks = nullptr; GemmSeg* d_segs = nullptr;
+    std::vector<int> tiles;
+  };
+  std::vector<Work> w(np);
+  int npanel_max = 0;
+  const int share = capacity[cplx] / np;
+  const int bm = gemm_tile_m(cplx), bn = gemm_tile_n(cplx, GEMM_TILE_WIDE);
+  bool ok = true;
+  for (int q = 0; q < np; ++q) {
+    const TriProblem& P = probs[big[q]];
+    Work& x = w[q];
+    x.n = P.n; x.nref = P.n - 1;
+    x.npanel = (int)((x.nref + NB - 1) / NB);
+    npanel_max = std::max(npanel_max, x.npanel);
+    x.blocks = (int)std::min<int64_t>(share, std::max<int64_t>(1, (P.n + TRI_WARPS - 1) / TRI_WARPS));
+    x.pan = (char*)dev_alloc(b, 6 * es * (size_t)P.n * NB);          // Vp | W | Vn | Wn (n x NB, ld n) | Vt | Wt (NB x n, ld NB)
+    x.gbuf = (char*)dev_alloc(b, es * 128);
+    x.partial = (double*)dev_alloc(b, sizeof(double) * (size_t)x.blocks);
+    x.d_tasks = (GemmTask*)dev_alloc(b, sizeof(GemmTask) * (size_t)x.npanel);
+    x.d_segs = (GemmSeg*)dev_alloc(b, sizeof(GemmSeg) * 2 * (size_t)x.npanel);
+    if (!x.pan || !x.gbuf || !x.partial || !x.d_tasks || !x.d_segs) { ok = false; break; }
+    // rank-2nb updates after each panel: A[t0:, t0:] += conj( conj(Vn) W^T + conj(Wn) Vp^T ) = -(V W^H + W V^H)   (as in launch_tridiag)
+    std::vector<GemmTask> tasks(x.npanel);
+    std::vector<GemmSeg> segs(2 * (size_t)x.npanel);
+    x.tiles.assign(x.npanel, 0);
+    const int64_t n = P.n;
+    for (int pi = 0; pi < x.npanel; ++pi) {
+      const int64_t j0 = (int64_t)pi * NB;
+      const int nbk = (int)std::min<int64_t>(NB, x.nref - j0);
+      const int64_t t0 = j0 + nbk, mt = n - t0;
+      GemmTask t{};
+      t.c_off = t0 + t0 * n; t.c_off2 = t.c_off; t.ldc = n;
+      t.M = (int32_t)mt; t.N = (int32_t)mt; t.n_split = (int32_t)mt;
+      t.seg_begin = 2 * pi; t.seg_count = 2;
+      t.tile_begin = 0; t.tiles_m = (int32_t)((mt + bm - 1) / bm);
+      t.flags = GEMM_ACCUM | (cplx ? (GEMM_CONJ_A | GEMM_CONJ_OUT) : 0u);
+      x.tiles[pi] = t.tiles_m * (int)((mt + bn - 1) / bn);
+      tasks[pi] = t;
+      GemmSeg s1{}, s2{};
+      s1.a_off = t0; s1.lda = n; s1.b_off = t0; s1.ldb = n; s1.K = nbk;
+      s2.a_off = t0 + (int64_t)n * NB; s2.lda = n; s2.b_off = t0 - (int64_t)n * NB; s2.ldb = n; s2.K = nbk;
+      segs[2 * pi] = s1; segs[2 * pi + 1] = s2;
+    }
+    dev_h2d(b, x.d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size());
+    dev_h2d(b, x.d_segs, segs.data(), sizeof(GemmSeg) * segs.size());
+  }
+  // descriptors of every (panel step, matrix) + one arrival counter each, uploaded once
+  std::vector<TriDesc> descs;
+  std::vector<int> first(npanel_max + 1, 0);
+  TriDesc* d_descs = nullptr;
+  unsigned int* d_ctr = nullptr;
+  if (ok) {
+    d_ctr = (unsigned int*)dev_alloc(b, sizeof(unsigned int) * (size_t)npanel_max * np);
+    if (d_ctr) dev_memset0(b, d_ctr, sizeof(unsigned int) * (size_t)npanel_max * np);
+    for (int pi = 0; pi < npanel_max; ++pi) {
+      first[pi] = (int)descs.size();
+      int blk = 0;
+      for (int q = 0; q < np; ++q) {
+        const Work& x = w[q];
+        if (pi >= x.npanel) continue;
+        const TriProblem& P = probs[big[q]];
+        const size_t pn = es * (size_t)x.n * NB;
+        TriDesc D{};
+        D.A = P.A; D.n = x.n; D.j0 = (long long)pi * NB;
+        D.nbk = (int)std::min<int64_t>(NB, x.nref - D.j0);
+        D.d = P.d; D.e = P.e; D.tau = P.tau; D.scl = P.scl; D.p = P.p_work; D.g = x.gbuf; D.partial = x.partial;
+        D.Vp = x.pan; D.W = x.pan + pn; D.Vn = x.pan + 2 * pn; D.Wn = x.pan + 3 * pn; D.Vt = x.pan + 4 * pn; D.Wt = x.pan + 5 * pn;
+        D.ctr = d_ctr ? d_ctr + descs.size() : nullptr;
+        D.blk_begin = blk; D.blk_count = x.blocks; D.fsplit = fsplit;
+        blk += x.blocks;
+        descs.push_back(D);
+      }
+    }
+    first[npanel_max] = (int)descs.size();
+    d_descs = (TriDesc*)dev_alloc(b, sizeof(TriDesc) * descs.size());
+    if (!d_ctr || !d_descs) ok = false;
+    else dev_h2d(b, d_descs, descs.data(), sizeof(TriDesc) * descs.size());
+  }
+  if (ok) {
+    for (int pi = 0; pi < npanel_max; ++pi) {
+      const int nd = first[pi + 1] - first[pi];
+      const TriDesc* dp = d_descs + first[pi];
+      const TriDesc& last = descs[first[pi + 1] - 1];
+      int grid = last.blk_begin + last.blk_count;
+      int ndv = nd;
+      void* args[] = {(void*)&dp, &ndv};
+      CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TRI_THREADS), args, 0, b->stream));
+      CB_LAUNCH_CHECK(b, "tridiag_panel_batched_kernel");
+      for (int q = 0; q < np; ++q) {
+        const Work& x = w[q];
+        if (pi >= x.npanel) continue;
+        const int64_t j0 = (int64_t)pi * NB;
+        const int nbk = (int)std::min<int64_t>(NB, x.nref - j0);
+        const int64_t t0 = j0 + nbk;
+        if (t0 < x.n - 1 && x.tiles[pi] > 0) {
+          const size_t pn = es * (size_t)x.n * NB;
+          launch_gemm(b, cplx, false, true, GEMM_TILE_WIDE, x.pan + 2 * pn, x.pan + pn, probs[big[q]].A, x.d_tasks + pi, 1, x.d_segs, x.tiles[pi]);
+        }
+      }
+    }
+  }
+  for (Work& x : w) {
+    if (x.pan) dev_free(b, x.pan);
+    if (x.gbuf) dev_free(b, x.gbuf);
+    if (x.partial) dev_free(b, x.partial);
+    if (x.d_tasks) dev_free(b, x.d_tasks);
+    if (x.d_segs) dev_free(b, x.d_segs);
+  }
+  if (d_ctr) dev_free(b, d_ctr);
+  if (d_descs) dev_free(b, d_descs);
+  return true;
+}
+
 static double* tri_bounds(Backend* b, const double* d, const double* e, int64_t n) {
   if (!b->d_bounds) CB_CHECK(b, cudaMalloc(&b->d_bounds, 8 * sizeof(double)));
   tri_bounds_kernel<<<1, 256, 0, b->stream>>>(d, e, (long long)n, b->d_bounds);

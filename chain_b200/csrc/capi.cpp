@@ -601,6 +601,35 @@ int cb200_k_heig(cb200_ctx* ctx, int32_t dtype, int64_t n, const void* A, int64_
   });
 }
 
+int cb200_k_heig_batched(cb200_ctx* ctx, int32_t dtype, int32_t nprob, const int64_t* n, const void* const* A, const int64_t* m,
+                         double* const* w, void* const* V) {
+  if (!ctx || !n || !A || !m || !w || !V || nprob < 1) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    std::vector<Buf> dA(nprob);
+    std::vector<int64_t> ns(nprob);
+    std::vector<Heig> hs(nprob);
+    std::vector<Heig*> hp(nprob);
+    for (int k = 0; k < nprob; ++k) {
+      if (n[k] < 1 || m[k] < 0 || m[k] > n[k]) fail(CB200_ERR_INVALID, "k_heig_batched: bad sizes");
+      dA[k] = Buf(c->be, (int64_t)es * n[k] * n[k]);
+      dev_h2d(c->be, dA[k].p, A[k], es * (size_t)n[k] * n[k]);
+      ns[k] = n[k];
+      hp[k] = &hs[k];
+    }
+    if (!heig_values_batched(c, cx, dA, ns, hp)) fail(CB200_ERR_INVALID, "k_heig_batched: this backend has no tridiagonalisation kernel");
+    for (int k = 0; k < nprob; ++k) {
+      for (int64_t i = 0; i < n[k]; ++i) w[k][i] = hs[k].w[i];
+      if (m[k] > 0) {
+        Buf dV = heig_vectors(c, hs[k], m[k]);
+        dev_d2h(c->be, V[k], dV.p, es * (size_t)n[k] * m[k]);
+      }
+    }
+  });
+}
+
 int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out) {
   if (!ctx) return CB200_ERR_INVALID;
   return guard(ctx, [&] {

@@ -1024,6 +1024,40 @@ bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   return true;
 }
 
+bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vector<int64_t>& ns, const std::vector<Heig*>& hs) {
+  Backend* be = c->be;
+  const size_t es = esz(cplx);
+  const int np = (int)hs.size();
+  std::vector<Buf> pw(np);
+  std::vector<TriProblem> probs(np);
+  for (int k = 0; k < np; ++k) {
+    Heig& h = *hs[k];
+    const int64_t n = ns[k];
+    h.n = n; h.cplx = cplx;
+    h.A = std::move(As[k]);
+    h.d = Buf(be, 8 * std::max<int64_t>(n, 1));
+    h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
+    h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
+    h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
+    pw[k] = Buf(be, (int64_t)es * std::max<int64_t>(n, 1));
+    probs[k] = TriProblem{h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, pw[k].p};
+  }
+  if (!launch_tridiag_batched(be, cplx, probs.data(), np)) return false;
+  for (int k = 0; k < np; ++k) {
+    Heig& h = *hs[k];
+    h.wdev = Buf(be, 8 * std::max<int64_t>(h.n, 1));
+    launch_bisect(be, (const double*)h.d.p, (const double*)h.e.p, h.n, (double*)h.wdev.p);
+  }
+  for (int k = 0; k < np; ++k) {
+    Heig& h = *hs[k];
+    h.w.resize(h.n);
+    dev_d2h(be, h.w.data(), h.wdev.p, 8 * (size_t)h.n);
+    std::reverse(h.w.begin(), h.w.end());
+  }
+  check_dev(c);
+  return true;
+}
+
 Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
   Backend* be = c->be;
   const int64_t n = h.n;
@@ -1189,7 +1223,11 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     if (dir == 0) { b.n = nl; b.rows = nr; b.colbase = lbase; b.rowbase = rbase; }
     else { b.n = nr; b.rows = nl; b.colbase = rbase; b.rowbase = lbase; }
   }
-  // ---- gather + Jacobi per middle-charge block
+  // ---- gather (+ rho, or Jacobi) per middle-charge block
+  std::vector<Buf> rhos;
+  std::vector<int64_t> rho_n;
+  std::vector<Heig*> rho_h;
+  std::vector<int> rho_q;
   for (int qm = 0; qm < nq; ++qm) {
     Blk& b = blk[qm];
     if (b.n == 0) continue;
@@ -1224,7 +1262,7 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       continue;
     }
     if (tri) {
-      // rho = X^H X (what ITensor's denmatDecomp forms), then its eigenvalues through the tridiagonal form
+      // rho = X^H X (what ITensor's denmatDecomp forms); its eigenvalues are taken below, for all blocks of the bond at once
       Buf rho(be, (int64_t)es * b.n * b.n);
       GemmBuilder gb(cplx);
       gb.begin(0, b.n, b.n, b.n, GEMM_TRANS_A | GEMM_CONJ_A);
@@ -1233,19 +1271,14 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       GemmPlan gp;
       gb.finish(be, gp, true, false);
       run_gemm(c, cplx, gp, X.p, X.p, rho.p);
-      if (heig_values(c, cplx, std::move(rho), b.n, b.h)) {
-        b.wd = b.h.w;
-        if (b.rows < b.n) {   // rank(X^H X) <= rows: the n - rows smallest eigenvalues are rounding noise (device copy is ascending)
-          for (int64_t k = b.rows; k < b.n; ++k) b.wd[k] = 0.0;
-          dev_memset0(be, b.h.wdev.p, 8 * (size_t)(b.n - b.rows));
-        }
-        b.X = std::move(X);
-      } else {
-        if (qm != 0) fail(-3, "split_bond: eigensolver became unavailable mid-way");
-        tri = false;
-      }
+      b.X = std::move(X);
+      rhos.push_back(std::move(rho));
+      rho_n.push_back(b.n);
+      rho_h.push_back(&b.h);
+      rho_q.push_back(qm);
+      continue;
     }
-    if (!tri) {
+    {
       b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n);
       const int64_t npad = (int64_t)b.jo.w.size();
       b.order.resize(npad);
@@ -1253,6 +1286,32 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
       b.wd.resize(b.n);
       for (int64_t k = 0; k < b.n; ++k) b.wd[k] = b.jo.w[b.order[k]];
+    }
+  }
+  if (tri && !rhos.empty()) {
+    // eigenvalues through the tridiagonal form: the blocks of this bond advance side by side (batched panel launches)
+    if (heig_values_batched(c, cplx, rhos, rho_n, rho_h)) {
+      for (int qm : rho_q) {
+        Blk& b = blk[qm];
+        b.wd = b.h.w;
+        if (b.rows < b.n) {   // rank(X^H X) <= rows: the n - rows smallest eigenvalues are rounding noise (device copy is ascending)
+          for (int64_t k = b.rows; k < b.n; ++k) b.wd[k] = 0.0;
+          dev_memset0(be, b.h.wdev.p, 8 * (size_t)(b.n - b.rows));
+        }
+      }
+    } else {   // a backend without the tridiagonalisation kernel: one-sided block Jacobi on the gathered matrices
+      tri = false;
+      for (int qm : rho_q) {
+        Blk& b = blk[qm];
+        b.jo = jacobi_svd(c, cplx, b.X.p, b.rows, b.n);
+        b.X.reset();
+        const int64_t npad = (int64_t)b.jo.w.size();
+        b.order.resize(npad);
+        std::iota(b.order.begin(), b.order.end(), 0);
+        std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
+        b.wd.resize(b.n);
+        for (int64_t k = 0; k < b.n; ++k) b.wd[k] = b.jo.w[b.order[k]];
+      }
     }
   }
   if (spread) {   // eigenvalues of every block to every rank

@@ -267,6 +267,9 @@ struct Heig {
   int ns_iters = 0;
 };
 bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h);   // false: backend has no tridiagonalisation kernel
+// the same for several independent matrices at once (the charge blocks of one bond): batched tridiagonalisation, then bisection
+// per matrix; As[k] is consumed into hs[k]->A
+bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vector<int64_t>& ns, const std::vector<Heig*>& hs);
 Buf heig_vectors(Ctx* c, Heig& h, int64_t m);                       // n x m column-major, orthonormal, spans the top-m eigenspace
 
 

@@ -158,6 +158,32 @@ __global__ void __launch_bounds__(TRI_THREADS, 2) tridiag_kernel(void* __restric
   if (blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
 }
 
+// Grid-wide barrier policies of the panel kernel: the whole cooperative grid (one matrix per launch), or a slice of it (batched
+// launch: the charge blocks of one bond side by side, each on its own CTAs with its own arrival counter; all CTAs of the launch
+// are co-resident because the launch is cooperative, the counter only grows -- barrier k completes at k * nblocks arrivals).
+struct TriGridSync {
+  cg::grid_group grid;
+  __device__ __forceinline__ void sync() { grid.sync(); }
+};
+struct TriSliceSync {
+  unsigned int* ctr;
+  unsigned int nblocks, target;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += nblocks;
+      __threadfence();                                   // publish this CTA's writes before arriving
+      atomicAdd(ctr, 1u);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      } while (seen < target);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
 // Blocked variant (LAPACK zlatrd 'L' restated for one persistent kernel per panel of <= 64 reflectors): the trailing matrix is
 // NOT updated inside a panel -- the matrix-vector product is corrected with the panel's V and W columns instead -- so a step
 // makes ONE pass over the trailing block (the unblocked kernel makes three) and the rank-2nb update after the panel is a GEMM
@@ -166,14 +192,13 @@ __global__ void __launch_bounds__(TRI_THREADS, 2) tridiag_kernel(void* __restric
 //          columns, g1 = W^H v, g2 = V^H v for the panel columns
 //   S4+S1' one thread per row: w = tau (p - V g1 - W g2) + alpha v (column i of W), then the deferred update of the NEXT column
 //          of A with all panel reflectors so far, and the partial norms the next step's Householder vector needs
-template <bool CPLX>
-__global__ void __launch_bounds__(TRI_THREADS, 2)
-tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
-                     void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
-                     double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_,
-                     void* __restrict__ Vt_, void* __restrict__ Wt_, int fsplit_long) {
+template <bool CPLX, class SYNC>
+__device__ __forceinline__ void
+tridiag_panel_body(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
+                   void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
+                   double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_,
+                   void* __restrict__ Vt_, void* __restrict__ Wt_, int fsplit_long, const int bid, const int nblk, SYNC& gsync) {
   using T = typename std::conditional<CPLX, double2, double>::type;
-  cg::grid_group grid = cg::this_grid();
   T* A = reinterpret_cast<T*>(A_);
   T* tau = reinterpret_cast<T*>(tau_);
   T* scl = reinterpret_cast<T*>(scl_);
@@ -190,17 +215,17 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
   __shared__ T sg1[64], sg2[64], swp[64], svp[64];
   __shared__ T sa2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long gw = (long long)blockIdx.x * TRI_WARPS + warp, GW = (long long)gridDim.x * TRI_WARPS;
-  const long long gtid = (long long)blockIdx.x * TRI_THREADS + threadIdx.x, GT = (long long)gridDim.x * TRI_THREADS;
-  const int G = gridDim.x;
+  const long long gw = (long long)bid * TRI_WARPS + warp, GW = (long long)nblk * TRI_WARPS;
+  const long long gtid = (long long)bid * TRI_THREADS + threadIdx.x, GT = (long long)nblk * TRI_THREADS;
+  const int G = nblk;
   const T zero = t_zero(T()), one = t_one(T());
   {   // prologue: the first column of the panel is up to date (rank-2nb GEMM of the previous panel); its partial norms are not
     double part = 0.0;
     for (long long r = j0 + 2 + gtid; r < n; r += GT) part += t_norm2(A[r + j0 * n]);
     const double sblk = tri_block_sum(part, redd);
-    if (threadIdx.x == 0) partial[blockIdx.x] = sblk;
+    if (threadIdx.x == 0) partial[bid] = sblk;
   }
-  grid.sync();
+  gsync.sync();
   for (int i = 0; i < nbk; ++i) {
     const long long j = j0 + i, m = n - j - 1;
     const T* x = A + (j + 1) + j * n;
@@ -218,7 +243,7 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
       tj = t_make((beta - ar) / beta, -ai / beta, alpha);
       sc = t_inv(t_sub(alpha, t_make(beta, 0.0, alpha)));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { d[j] = t_re(A[j + j * n]); e[j] = beta; tau[j] = tj; scl[j] = sc; }
+    if (bid == 0 && threadIdx.x == 0) { d[j] = t_re(A[j + j * n]); e[j] = beta; tau[j] = tj; scl[j] = sc; }
     // ---- S3: f warps of one CTA share a column when there are fewer columns than warps (more bytes in flight per column,
     // shorter dependent chain per warp); their partial sums are combined in a fixed order through shared memory
     if (!off) {
@@ -291,7 +316,7 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
       }
       }
     }
-    grid.sync();
+    gsync.sync();
     // ---- S4 + S1'
     T sp = zero;
     if (!off)
@@ -355,10 +380,44 @@ tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, 
       }
     }
     const double sblk = tri_block_sum(part, redd);
-    if (threadIdx.x == 0) partial[blockIdx.x] = sblk;
-    grid.sync();
+    if (threadIdx.x == 0) partial[bid] = sblk;
+    gsync.sync();
   }
-  if (j0 + nbk == n - 1 && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
+  if (j0 + nbk == n - 1 && bid == 0 && threadIdx.x == 0) d[n - 1] = t_re(A[(n - 1) + (n - 1) * n]);
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(TRI_THREADS, 2)
+tridiag_panel_kernel(void* __restrict__ A_, long long n, long long j0, int nbk, double* __restrict__ d, double* __restrict__ e,
+                     void* __restrict__ tau_, void* __restrict__ scl_, void* __restrict__ p_, void* __restrict__ g_,
+                     double* __restrict__ partial, void* __restrict__ Vp_, void* __restrict__ W_, void* __restrict__ Vn_, void* __restrict__ Wn_,
+                     void* __restrict__ Vt_, void* __restrict__ Wt_, int fsplit_long) {
+  TriGridSync gsync{cg::this_grid()};
+  tridiag_panel_body<CPLX>(A_, n, j0, nbk, d, e, tau_, scl_, p_, g_, partial, Vp_, W_, Vn_, Wn_, Vt_, Wt_, fsplit_long, (int)blockIdx.x,
+                           (int)gridDim.x, gsync);
+}
+
+// Batched form: descs[k] is one matrix (one charge block of the bond) advancing through the SAME panel step on CTAs
+// [blk_begin, blk_begin + blk_count) of a cooperative launch.  Below n ~ 4000 a Householder step is bound by its two grid barriers
+// and its dependent L2 round trips, not by bandwidth: running the blocks side by side overlaps exactly that latency.
+struct TriDesc {
+  void* A;
+  long long n, j0;
+  double *d, *e;
+  void *tau, *scl, *p, *g;
+  double* partial;
+  void *Vp, *W, *Vn, *Wn, *Vt, *Wt;
+  unsigned int* ctr;
+  int nbk, blk_begin, blk_count, fsplit;
+};
+template <bool CPLX>
+__global__ void __launch_bounds__(TRI_THREADS, 2) tridiag_panel_batched_kernel(const TriDesc* __restrict__ descs, int ndesc) {
+  int k = 0;
+  while (k + 1 < ndesc && (int)blockIdx.x >= descs[k + 1].blk_begin) ++k;
+  const TriDesc D = descs[k];
+  TriSliceSync gsync{D.ctr, (unsigned int)D.blk_count, 0u};
+  tridiag_panel_body<CPLX>(D.A, D.n, D.j0, D.nbk, D.d, D.e, D.tau, D.scl, D.p, D.g, D.partial, D.Vp, D.W, D.Vn, D.Wn, D.Vt, D.Wt, D.fsplit,
+                           (int)blockIdx.x - D.blk_begin, D.blk_count, gsync);
 }
 
 // bounds[0..3] = Gershgorin lower / upper bound (widened), pivmin, ||T||_1

@@ -199,6 +199,10 @@ int cb200_k_svd(cb200_ctx* ctx, int32_t dtype, int64_t rows, int64_t cols, void*
  * V [n x m] an orthonormal basis of the invariant subspace of the m largest.  Replaces LAPACK dsyev/zheev inside
  * ITensor's diagHermitian(rho). */
 int cb200_k_heig(cb200_ctx* ctx, int32_t dtype, int64_t n, const void* A, int64_t m, double* w, void* V, int32_t* ns_iters);
+/* the same for nprob independent matrices at once -- the charge blocks of one bond: their tridiagonalisations advance side by side
+ * in one cooperative launch per panel step, each matrix on its own slice of the grid (the path cb200_bond_truncate takes for nq > 1) */
+int cb200_k_heig_batched(cb200_ctx* ctx, int32_t dtype, int32_t nprob, const int64_t* n, const void* const* A, const int64_t* m,
+                         double* const* w, void* const* V);
 /* out[j] = <x_j | y>, dst = beta*dst + sum c_j x_j */
 int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out_re_im);
 int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const double* c_re_im, double beta_re,

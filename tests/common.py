@@ -193,6 +193,33 @@ def check_mps_boundary_paths(ctx, case, monkeypatch):
     monkeypatch.delenv("CB200_PACK_MIN")
 
 
+def check_heig_batched(ctx, cplx, sizes):
+    """Batched Hermitian eigensolver (charge blocks of one bond side by side) against numpy.eigh, matrix by matrix."""
+    rng = np.random.default_rng(sum(n * 7 + m for n, m in sizes) + cplx)
+    As = []
+    for n, m in sizes:
+        X = (rng.standard_normal((n + 3, n)) + (1j * rng.standard_normal((n + 3, n)) if cplx else 0)) * (10.0 ** (-0.05 * np.arange(n)))
+        A = X.conj().T @ X
+        As.append(A / np.trace(A).real)
+    out = cb.k_heig_batched(As, [m for _, m in sizes], ctx=ctx)
+    for A, (n, m), (w, V) in zip(As, sizes, out):
+        ev = np.linalg.eigvalsh(A)[::-1]
+        assert np.abs(w - ev).max() <= 1e-14 * np.sqrt(n)
+        if m:
+            assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
+            assert np.abs(A @ V - V @ (V.conj().T @ A @ V)).max() <= 2e-14 * np.sqrt(n)
+            assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[:m]).max() <= 1e-14 * np.sqrt(n)
+
+
+HEIG_BATCHES = [
+    [(70, 30), (64, 64), (129, 5)],                   # three blocks of different sizes (different panel counts)
+    [(200, 80), (1, 1), (2, 1), (333, 100)],          # tiny matrices ride along on the single-matrix path
+    [(40, 10)] * 8,                                   # the largest batch
+    [(33, 3)] * 9,                                    # more matrices than one batch takes: sequential
+    [(515, 0), (130, 130)],                           # eigenvalues only for one of them
+]
+
+
 DMRG_CASES = [
     # site, bc, n, couplings, charge, nstates, product-state start?
     ("golden", "p", 6, [-1.0], 0, 3, True),

@@ -288,6 +288,12 @@ bool launch_tridiag(Backend* b, bool cplx, void* A, int64_t n, double* d, double
   return true;
 }
 
+bool launch_tridiag_batched(Backend* b, bool cplx, const TriProblem* probs, int nprob) {
+  for (int k = 0; k < nprob; ++k)
+    if (!launch_tridiag(b, cplx, probs[k].A, probs[k].n, probs[k].d, probs[k].e, probs[k].tau, probs[k].scl, probs[k].p_work)) return false;
+  return true;
+}
+
 void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, double* w) {
   b->launches++;
   double gl = d[0], gu = d[0], emax2 = 0, tn = 0;

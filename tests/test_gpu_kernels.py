@@ -137,6 +137,14 @@ def test_hermitian_eigensolver(gpu_ctx, cplx, n, m, decay):
     assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[::-1][:m]).max() <= 1e-14 * np.sqrt(n)
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("sizes", common.HEIG_BATCHES + [[(1000, 200), (997, 300), (1003, 100)]], ids=lambda s: "x".join(str(n) for n, _ in s))
+def test_hermitian_eigensolver_batched(gpu_ctx, cplx, sizes):
+    """The charge blocks of one bond side by side: one cooperative launch per panel step, each matrix on its own slice of the grid
+    with its own arrival-counter barrier (tridiag_panel_batched_kernel)."""
+    common.check_heig_batched(gpu_ctx, cplx, sizes)
+
+
 @pytest.mark.parametrize("mode", ["1", "2", "3"])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
 def test_gemm_narrow_and_3m_tiles(gpu_ctx, monkeypatch, mode, ta, tb):
