@@ -1232,7 +1232,9 @@ void launch_bisect(Backend* b, const double* d, const double* e, int64_t n, doub
 void launch_invit(Backend* b, const double* d, const double* e, int64_t n, const double* lam, int64_t m, double* Zt, double* work) {
   if (n <= 0 || m <= 0) return;
   double* bounds = tri_bounds(b, d, e, n);
-  invit_kernel<<<(unsigned)((m + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, lam, (long long)m, bounds, Zt, work);
+  static const bool ref = [] { const char* v = getenv("CB200_INVIT"); return v && std::string(v) == "ref"; }();
+  if (ref) invit_ref_kernel<<<(unsigned)((m + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, lam, (long long)m, bounds, Zt, work);
+  else invit_kernel<<<(unsigned)((m + 127) / 128), 128, 0, b->stream>>>(d, e, (long long)n, lam, (long long)m, bounds, Zt, work);
   CB_LAUNCH_CHECK(b, "invit_kernel");
 }
 

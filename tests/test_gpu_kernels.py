@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import chain_b200 as cb
+import common
 
 pytestmark = pytest.mark.gpu
 
