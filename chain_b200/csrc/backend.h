@@ -134,6 +134,9 @@ void launch_backtransform(Backend*, bool cplx, const void* A, int64_t n, const v
 void launch_zt_to_v(Backend*, bool cplx, const double* Zt, int64_t n, int64_t m, void* V);
 void launch_form_y(Backend*, bool cplx, const void* A, int64_t n, const void* tau, const void* scl, int64_t j0, int nbk, void* Y);
 void launch_wy_t(Backend*, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg);
+//     all blocks of one matrix in one launch: S / Tneg hold npanel slots of 64*64 elements (block k: nb x nb, ld nb, nb = 64 except
+//     nb_last for the last block), tau is the whole tau array (block k starts at tau[64 k])
+void launch_wy_t_batched(Backend*, bool cplx, const void* S, const void* tau, int npanel, int nb_last, void* Tneg);
 
 // ITensor's truncate() evaluated on the device: pooled[n] (device, any order) is rank-sorted descending into sorted[n], then ONE
 // thread applies the rule of SURVEY App. A.5 verbatim (negative tail zeroed, maxdim, relative cutoff on the discarded weight,

@@ -1282,6 +1282,21 @@ void launch_form_y(Backend* b, bool cplx, const void* A, int64_t n, const void* 
   CB_LAUNCH_CHECK(b, "form_y_kernel");
 }
 
+void launch_wy_t_batched(Backend* b, bool cplx, const void* S, const void* tau, int npanel, int nb_last, void* Tneg) {
+  if (npanel <= 0) return;
+  if (nb_last <= 0 || nb_last > 64) { set_err(b, "launch_wy_t_batched: block size out of range", cudaErrorInvalidValue); return; }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wy_t_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 16);
+    cudaFuncSetAttribute(wy_t_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 8);
+    attr_done = true;
+  }
+  const size_t smem = (size_t)64 * 64 * (cplx ? 16 : 8);
+  if (cplx) wy_t_batched_kernel<true><<<npanel, 64, smem, b->stream>>>(S, tau, npanel, nb_last, Tneg);
+  else wy_t_batched_kernel<false><<<npanel, 64, smem, b->stream>>>(S, tau, npanel, nb_last, Tneg);
+  CB_LAUNCH_CHECK(b, "wy_t_batched_kernel");
+}
+
 void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int nbk, void* Tneg) {
   if (nbk <= 0 || nbk > 64) { set_err(b, "launch_wy_t: block size out of range", cudaErrorInvalidValue); return; }
   static bool attr_done = false;

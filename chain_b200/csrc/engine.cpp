@@ -882,6 +882,10 @@ static int jacobi_inner_sweeps() {
   }
   return v;
 }
+static bool wy_upfront() {   // T factors and Y T of all reflector blocks before the sequential application (CB200_WY_UPFRONT=0: per block)
+  static const bool v = [] { const char* e = getenv("CB200_WY_UPFRONT"); return !(e && atoi(e) == 0); }();
+  return v;
+}
 static int64_t wy_min_n() {   // below this the per-column kernel wins (CB200_WY_MIN_N overrides)
   static int64_t v = -1;
   if (v < 0) {
@@ -1114,9 +1118,78 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
   Buf V(be, (int64_t)es * n * m);
   if (n < wy_min_n()) {
     launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
+  } else if (wy_upfront()) {
+    // Q Z = B_0 (B_1 (... (B_last Z))) with B_k = H_j0 ... H_{j0+nb-1} = I - Y_k T_k Y_k^H (compact WY) on the DMMA kernel.
+    // Everything that does not depend on Z is done for ALL blocks first, in four launches: the explicit reflector blocks Y_k,
+    // S_k = Y_k^H Y_k (one grouped GEMM), the T factors (one launch, a CTA per block) and YT_k = Y_k (-T_k) (one grouped GEMM).
+    // The sequential part is then Z -= YT_k (Y_k^H Z): two GEMMs and the split-K sum per block.
+    const bool cx = h.cplx;
+    launch_zt_to_v(be, cx, (const double*)zc, n, m, V.p);
+    const int NB = 64;
+    const int64_t nref = n - 1;
+    const int npan = (int)((nref + NB - 1) / NB);
+    std::vector<int64_t> yoff(npan + 1, 0);
+    for (int k = 0; k < npan; ++k) yoff[k + 1] = yoff[k] + (n - ((int64_t)k * NB + 1)) * NB;     // Y_k: len_k x 64 slot, ld = len_k
+    Buf Yall(be, (int64_t)es * yoff[npan]), YTall(be, (int64_t)es * yoff[npan]);
+    Buf Sall(be, (int64_t)es * NB * NB * npan), Tall(be, (int64_t)es * NB * NB * npan);
+    const int nb_last = (int)(nref - (int64_t)(npan - 1) * NB);
+    {
+      GemmBuilder gs(cx), gt(cx);
+      for (int k = 0; k < npan; ++k) {
+        const int64_t j0 = (int64_t)k * NB, len = n - (j0 + 1);
+        const int nbk = k == npan - 1 ? nb_last : NB;
+        launch_form_y(be, cx, h.A.p, n, h.tau.p, h.scl.p, j0, nbk, (char*)Yall.p + es * (size_t)yoff[k]);
+        gs.begin((int64_t)k * NB * NB, nbk, nbk, nbk, GEMM_TRANS_A | GEMM_CONJ_A);
+        gs.seg(yoff[k], len, yoff[k], len, len);
+        gs.end();
+        gt.begin(yoff[k], len, len, nbk, 0);
+        gt.seg(yoff[k], len, (int64_t)k * NB * NB, nbk, nbk);
+        gt.end();
+      }
+      GemmPlan ps, pt;
+      gs.finish(be, ps, true, false);
+      gt.finish(be, pt, false, false);
+      run_gemm(c, cx, ps, Yall.p, Yall.p, Sall.p);
+      launch_wy_t_batched(be, cx, Sall.p, h.tau.p, npan, nb_last, Tall.p);
+      run_gemm(c, cx, pt, Yall.p, Tall.p, YTall.p);
+    }
+    Buf W1(be, (int64_t)es * NB * m);
+    const int PMAX = MAX_LC;
+    Buf W1p(be, (int64_t)es * NB * m * PMAX);
+    for (int k = npan - 1; k >= 0; --k) {
+      const int64_t j0 = (int64_t)k * NB, r0 = j0 + 1, len = n - r0;
+      const int nbk = k == npan - 1 ? nb_last : NB;
+      // W1 = Y_k^H Z: 64 rows with a long inner dimension -- split K over up to MAX_LC tasks writing partials, then add them
+      const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, len / 256));
+      const int64_t chunk = (len + P - 1) / P;
+      GemmPlan pw1, pz;
+      {
+        GemmBuilder g1(cx);
+        for (int pp = 0; pp < P; ++pp) {
+          const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+          if (kn <= 0) break;
+          g1.begin((int64_t)pp * nbk * m, nbk, nbk, m, GEMM_TRANS_A | GEMM_CONJ_A);
+          g1.seg(yoff[k] + k0, len, r0 + k0, n, kn);
+          g1.end();
+        }
+        g1.finish(be, pw1, true, false);
+      }
+      { GemmBuilder g(cx); g.begin(r0, n, len, m, GEMM_ACCUM); g.seg(yoff[k], len, 0, nbk, nbk); g.end(); g.finish(be, pz, false, false); }
+      const int np = pw1.tasks.n;
+      const void* xs[MAX_LC];
+      double ones[2 * MAX_LC];
+      for (int pp = 0; pp < np; ++pp) { ones[2 * pp] = 1.0; ones[2 * pp + 1] = 0.0; }
+      run_gemm(c, cx, pw1, Yall.p, V.p, W1p.p);
+      const void* w1 = W1p.p;
+      if (np > 1) {
+        for (int pp = 0; pp < np; ++pp) xs[pp] = (const char*)W1p.p + es * (size_t)pp * nbk * m;
+        lincomb(be, cx, np, xs, ones, 0.0, 0.0, W1.p, (int64_t)nbk * m);
+        w1 = W1.p;
+      }
+      run_gemm(c, cx, pz, YTall.p, w1, V.p);
+    }
   } else {
-    // Q Z = B_0 (B_1 (... (B_last Z))) with B_k = H_j0 ... H_{j0+nb-1} = I - Y T Y^H (compact WY): four GEMMs per block of 64
-    // reflectors on the DMMA kernel instead of 64 memory-bound rank-1 updates
+    // (CB200_WY_UPFRONT=0) the same product with S_k, T_k formed block by block inside the sequential loop: four GEMMs per block
     const bool cx = h.cplx;
     launch_zt_to_v(be, cx, (const double*)zc, n, m, V.p);
     const int NB = 64;

@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(256) form_y_kernel(const void* __restrict__ A_
 }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(64) wy_t_kernel(const void* __restrict__ S_, const void* __restrict__ tau_, int nb, void* __restrict__ Tn_) {
+__device__ __forceinline__ void wy_t_body(const void* __restrict__ S_, const void* __restrict__ tau_, int nb, void* __restrict__ Tn_) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   const T* S = reinterpret_cast<const T*>(S_);
   const T* tau = reinterpret_cast<const T*>(tau_);
@@ -782,6 +782,20 @@ __global__ void __launch_bounds__(64) wy_t_kernel(const void* __restrict__ S_, c
     __syncthreads();
   }
   for (int k = r; k < nb * nb; k += 64) Tn[k] = t_scale(Ts[k], -1.0);
+}
+template <bool CPLX>
+__global__ void __launch_bounds__(64) wy_t_kernel(const void* __restrict__ S_, const void* __restrict__ tau_, int nb, void* __restrict__ Tn_) {
+  wy_t_body<CPLX>(S_, tau_, nb, Tn_);
+}
+// all reflector blocks of one matrix at once (they are independent): CTA k builds the T factor of block k from S_k = Y_k^H Y_k stored at
+// S + k*64*64 (nb x nb, ld nb) and tau[k*64 ..]; every block has 64 reflectors except the last one (nb_last)
+template <bool CPLX>
+__global__ void __launch_bounds__(64) wy_t_batched_kernel(const void* __restrict__ S_, const void* __restrict__ tau_, int npanel, int nb_last,
+                                                          void* __restrict__ Tn_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const int k = blockIdx.x;
+  wy_t_body<CPLX>(reinterpret_cast<const T*>(S_) + (size_t)k * 4096, reinterpret_cast<const T*>(tau_) + (size_t)k * 64,
+                  k == npanel - 1 ? nb_last : 64, reinterpret_cast<T*>(Tn_) + (size_t)k * 4096);
 }
 
 // ---- cutoff / maxdim selection on the device (ITensor truncate()) ------------------------------------------

@@ -464,6 +464,13 @@ void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int n
   if (cplx) wy_t_t<cd>((const cd*)S, (const cd*)tau_j0, nbk, (cd*)Tneg); else wy_t_t<double>((const double*)S, (const double*)tau_j0, nbk, (double*)Tneg);
 }
 
+void launch_wy_t_batched(Backend* b, bool cplx, const void* S, const void* tau, int npanel, int nb_last, void* Tneg) {
+  const size_t es = cplx ? sizeof(cd) : sizeof(double);
+  for (int k = 0; k < npanel; ++k)
+    launch_wy_t(b, cplx, (const char*)S + es * 4096 * (size_t)k, (const char*)tau + es * 64 * (size_t)k, k == npanel - 1 ? nb_last : 64,
+                (char*)Tneg + es * 4096 * (size_t)k);
+}
+
 void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* P,
                             double* out3) {
   b->launches++;
