@@ -11,6 +11,7 @@ in the allowed charge blocks.
   e2e    : the same through the C-ABI call cb200_bond_apply_blocks with pinned HOST buffers in ITensor's QDense block storage
            (H2D phi + D2H result per step); e2e.dense_layout = cb200_bond_apply on dense arrays with zeros
   roofline: the DMMA GEMM kernel (both D^3 stages) against the FP64 peak measured live (cuBLAS DGEMM 8192^3)
+  bond_update / sweep: one complete two-site bond update resident on the device, and ONE whole DMRG sweep through cb200_dmrg (host MPS in/out)
   cpu_baseline / --impl reference: the oracle's port of ITensor's block-pair permute+zgemm loop on the host cores
 
 N > 1 (torchrun): ONE matvec row-sharded over the N GPUs (strong scaling): every rank holds phi, applies
@@ -168,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the whole-sweep measurement (the `sweep` key)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how the ranks exchange output rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -319,6 +321,28 @@ def main():
                    "note": "one two-site bond update (3 matvecs, Gram-Schmidt, truncation to maxdim=D, environment update) with everything "
                            "resident in HBM; the sweep figure is 2(L-1) such updates, an upper bound since the edge bonds are smaller"}
 
+    # ---- the other half of the BASELINE metric: DMRG sweep wall time.  ONE whole sweep (2(L-1) bond updates) through cb200_dmrg --
+    # host MPS in, host MPS out -- on a seeded random right-canonical MPS with the capped bond profile of an L = 12 chain of the same
+    # model at the same D (tools/sweep_bench.py); sweep 0 warms the memory pool, sweep 1 is reported.  N = 1 only (the scaling of whole
+    # sweeps is in profiles/, the context here is sharded with min_dim = 0 for the matvec measurement)
+    sweep = None
+    if world == 1 and not args.no_sweep and args.workload in ("cfg2", "cfg3", "tiny"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sweep_bench as sb
+        from chain_b200 import models
+        st, bc, _, cp, D, _ = WORKLOADS[args.workload]
+        Ls = {"cfg2": 12, "cfg3": 24, "tiny": 8}[args.workload]
+        ss = models.make_siteset(st, Ls)
+        mpo = ss.hamiltonian(bc, Ls, 2.0, cp)
+        Hs = cb.MPO(mpo.sites, mpo.link_charges, ss.charges, nq=ss.nq)
+        psi_s, dims_s = sb.random_right_canonical(ss, Ls, D, Hs.is_complex(), seed=0)
+        sw = sb.run_sweeps(ctx, Hs, psi_s, D, 2)[-1]
+        del psi_s
+        sweep = {"wall_s": sw["wall_s"], "workload": "%s %s L=%d D=%d, synthetic right-canonical MPS, true MPO; one sweep = one cb200_dmrg call with host MPS in/out" % (st, bc, Ls, D),
+                 "bond_updates": sw["bond_updates"], "bond_profile": [int(x.sum()) for x in dims_s], "matvec_s": sw["matvec_s"], "truncation_s": sw["trunc_s"],
+                 "env_update_s": sw["env_s"], "davidson_level1_s": sw["level1_s"], "other_s": sw["other_s"], "matvecs": sw["matvecs"],
+                 "matvec_tflops": sw["matvec_tflops"], "gpu_launches": sw["launches"], "energy": sw["energy"]}
+
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_%s_summary.json" % args.workload)) as f:
@@ -346,7 +370,7 @@ def main():
                         "call": "cb200_bond_apply_blocks: pinned host vectors in ITensor's QDense block storage, H2D + product + D2H every step",
                         "dense_layout": {"value": e2e_dense_v, "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": nbytes_dense, "d2h_bytes_per_step": nbytes_dense,
                                          "call": "cb200_bond_apply: dense [l,s1,s2,r] arrays with zeros in the forbidden blocks"}},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "wall_s_timed_region": wall}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "sweep": sweep, "wall_s_timed_region": wall}
         emit(line)
     bond.close()
     if world > 1:

@@ -90,6 +90,22 @@ def random_right_canonical(ss, n, D, cplx, seed):
     return cb.MPS(sites, labels, nq=nq, center=1), dims
 
 
+def run_sweeps(ctx, H, psi, D, nsweep):
+    """nsweep calls of cb200_dmrg with ONE sweep each (what the reference's rep loop does, src/dmrg.h:589-596), maxdim = D binding."""
+    out = []
+    for sw in range(nsweep):                             # sweep 0 also pays the first-touch growth of the memory pool
+        info = cb.DmrgInfo()
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        en, psi = cb.dmrg(H, [], psi, cb.Sweeps(1, D, 1e-16, niter=2), ctx=ctx, info=info)
+        wall = time.perf_counter() - t0
+        t = info.timers
+        out.append(dict(sweep=sw, wall_s=wall, energy=en, bond_updates=len(info.stats), max_m=max(s["m"] for s in info.stats),
+                        env_s=t["env"], matvec_s=t["matvec"], level1_s=t["level1"], trunc_s=t["trunc"], other_s=t["other"],
+                        matvecs=int(t["nmatvec"]), matvec_tflops=t["matvec_flops"] / max(t["matvec"], 1e-12) / 1e12, launches=ctx.launches - l0))
+    return out
+
+
 def main():
     st, bc, n, D, cp = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), [float(x) for x in sys.argv[5].split(",")]
     nsweep = int(sys.argv[6]) if len(sys.argv) > 6 else 2
@@ -109,17 +125,7 @@ def main():
         big = max(int(a.sum()) for a in dims)
         ctx.shard(rank, world, mode="p2p", landing_bytes=big * big * ss.d * ss.d * (16 if H.is_complex() else 8) // max(ss.nq, 1) + (1 << 20),
                   min_dim=int(os.environ.get("CB200_SHARD_MIN_DIM", "1600")))
-    out = []
-    for sw in range(nsweep):                             # sweep 0 also pays the first-touch growth of the memory pool
-        info = cb.DmrgInfo()
-        l0 = ctx.launches
-        t0 = time.perf_counter()
-        en, psi = cb.dmrg(H, [], psi, cb.Sweeps(1, D, 1e-16, niter=2), ctx=ctx, info=info)
-        wall = time.perf_counter() - t0
-        t = info.timers
-        out.append(dict(sweep=sw, wall_s=wall, energy=en, bond_updates=len(info.stats), max_m=max(s["m"] for s in info.stats),
-                        env_s=t["env"], matvec_s=t["matvec"], level1_s=t["level1"], trunc_s=t["trunc"], other_s=t["other"],
-                        matvecs=int(t["nmatvec"]), matvec_tflops=t["matvec_flops"] / max(t["matvec"], 1e-12) / 1e12, launches=ctx.launches - l0))
+    out = run_sweeps(ctx, H, psi, D, nsweep)
     if rank != 0:
         return
     print(json.dumps(dict(n_gpus=world, workload="%s %s L=%d D=%d j=%s (synthetic right-canonical MPS, true MPO k=%d)" % (st, bc, n, D, sys.argv[5], max(len(q) for q in mpo.link_charges)),
