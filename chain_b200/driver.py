@@ -8,6 +8,9 @@ Nothing here does tensor arithmetic: Hamiltonians come from chain_b200.models (h
 
     python -m chain_b200.driver -s golden -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 1 -m 0 [--out DIR] [--seed N]
 
+Modes as in src/dmrg.cpp:44-60: 0 Simulate, 5 Simulate + analysis, 1 / 2 / 3 Analyze / AnalyzeWithoutRho / Energies and 4 NormalizeEnergies
+on the progress file of an earlier run, 6 Repair (RecoverStates), 7 Test (exact levels of the Hamiltonian MPO, host-side as in the reference).
+
 Differences from the reference, all deliberate: output goes under --out (the reference compiles the parent of the cwd in,
 src/path_template.h:8); --seed makes the random product start reproducible (the reference never seeds); the pgs/ checkpoint
 has DMRGProgress's semantics (src/dmrg.h:15-257: written after every dmrg() call, a finished job is recognised, an interrupted
@@ -233,6 +236,13 @@ class Simulation:
                                    timers=info.timers))
         return en, psi
 
+    def load_progress(self):
+        """What every analysis mode starts with (Measure, src/dmrg.h:733-741): the finished states of the progress file."""
+        prog = self.dmrg_progress_ = DMRGProgress()
+        prog.Read(self.progress_path)
+        self.energies, self.states = prog.Energies(), prog.DoneStates()
+        return prog.NumDoneStates()
+
     def run(self):
         """SimulateRaw, src/dmrg.h:474-655, including its progress file: every dmrg() call is followed by Update + Write, a job whose
         file already holds the requested number of states returns at once, an interrupted job continues with the sweep it was
@@ -350,23 +360,30 @@ def rho_matrix(sim, states):
     return np.array([[sum(cb.mpo_element(a, O, b, ctx=sim.ctx) for O in mpos) for b in states] for a in states])
 
 
-def analyze(sim, log=print):
-    """What mode 5 runs after the simulation (src/dmrg.h:637-648): Measure("energy") rewrites .en with 1-based state numbers
+def analyze(sim, log=print, which=None):
+    """`which` = None: what mode 5 runs after the simulation (src/dmrg.h:637-648): Measure("energy") rewrites .en with 1-based state numbers
     (:752-755) and dumps the energy matrix to .m; periodic chains get Measure("translation") (L-1 swaps per state on the device,
     kCutoff = 1e-5; T_ij = innerC(psi_i, T psi_j)); charge-0 periodic / Dirichlet chains get Measure("rho") and the
     {energy, momentum, rho} table of Analyze; charged sectors the {energy, momentum} table of AnalyzeWithoutRho; every other
-    boundary condition Energies()."""
-    n, ens, states = sim.n, sim.energies, sim.states
+    boundary condition Energies().  `which` = "full" | "without_rho" | "energies": modes 1 / 2 / 3 of the CLI (Analyze,
+    AnalyzeWithoutRho, Energies: src/dmrg.h:1118-1244) on the states of the progress file.  Only the first -n states are analysed
+    (num_states = min(NumDoneStates, num_states_), :741), the .en file lists every finished state (:752-755)."""
+    n = sim.n
     bc = "p" if sim.bc == "sp" else sim.bc
     if os.path.exists(sim.en_path):
         os.remove(sim.en_path)
-    for i, e in enumerate(ens):
+    for i, e in enumerate(sim.energies):
         dump_energy(sim.en_path, i + 1, e)
+    k = min(len(sim.states), sim.num_states)
+    ens, states = list(sim.energies[:k]), list(sim.states[:k])
     if os.path.exists(sim.m_path):
         os.remove(sim.m_path)
     dump_mathematica(sim.m_path, "energy", np.diag(np.asarray(ens, dtype=complex)))
-    if bc not in ("p", "d"):
+    if which is None:
+        which = "energies" if bc not in ("p", "d") else ("full" if sim.charge == 0 else "without_rho")
+    if which == "energies":
         rows = [(e,) for e in ens]                               # Energies(), src/dmrg.h:1221-1244
+        log("{{%s},{%s}}," % (sim.coupling_str, ",".join("%.10f" % e for e in ens)))
         dump_matrix(sim.an_path, rows)
         return rows
     sq = sim.sites.charges
@@ -377,7 +394,7 @@ def analyze(sim, log=print):
     else:
         T = np.eye(nst, dtype=complex)
     dump_mathematica(sim.m_path, "translation", T)
-    if sim.charge == 0:
+    if which == "full":
         R = rho_matrix(sim, states)
         dump_mathematica(sim.m_path, "rho", R)
         rows = analyze_full(ens, T, R, n, bc)
@@ -390,6 +407,80 @@ def analyze(sim, log=print):
     for r in rows:
         log("{%s}" % ",".join("%.10f" % v for v in r))
     return rows
+
+
+def normalize_energies(sim, log=print):
+    """NormalizeEnergies (mode 4), src/dmrg.h:1247-1276: (E_i - E_0) / (E_1 - E_0) of the sorted energies of the progress file."""
+    ens = sorted(sim.energies[:min(len(sim.energies), sim.num_states)])
+    if len(ens) <= 2:
+        log("Fewer than 3 states available")
+        return None
+    gap = ens[1] - ens[0]
+    out = [0.0, 1.0] + [(e - ens[0]) / gap for e in ens[2:]]
+    log("{{%s},%g,{%s}}," % (sim.coupling_str, gap, ",".join("%.10f" % v for v in out)))
+    return gap, out
+
+
+def repair(sim, log=print):
+    """Repair (mode 6) = DMRGProgress::RecoverStates, src/dmrg.h:164-199: re-read the progress file (the backup if the file itself does
+    not load), touch every finished state (innerC(psi, psi) on the device) and write a clean file holding exactly the states that
+    survived.  With the atomic .npz container a torn write cannot happen any more; what is left to repair is a missing / unreadable
+    primary file."""
+    prog = DMRGProgress()
+    try:
+        prog.Read(sim.progress_path)
+    except Exception as err:
+        log("%s\nReplace progress files with backup progress files." % err)
+        prog.Read(sim.progress_path, backup=True)
+    sq = sim.sites.charges
+    good = DMRGProgress()
+    good.NextState()
+    log("Recover states from corrupt vector.")
+    ndone = prog.NumDoneStates()
+    for i in range(ndone):
+        nrm = cb.overlap(prog.psis_[i], prog.psis_[i], sq, ctx=sim.ctx)
+        if not np.isfinite(abs(nrm)) or abs(nrm) == 0:
+            break
+        log("State %d/%d is OK." % (i + 1, ndone))
+        good.Update(prog.num_sweeps_vec_[i], prog.max_dims_[i], prog.ens_[i], prog.psis_[i])
+        good.NextState()
+    if good.NumDoneStates() == ndone and prog.psis_[-1] is not None:      # the state in progress survives as well
+        good.Update(*prog.All())
+        good.min_en, good.cnt = prog.min_en, prog.cnt
+    good.stage = prog.stage if prog.stage is not None else (1 if sim.bc == "sp" else -1)
+    good.sp_seed = prog.sp_seed
+    good.Write(sim.progress_path, sq)
+    good.Write(sim.progress_path, sq, backup=True)
+    return good
+
+
+def exact_levels(mpo_sites, k):
+    """Test (mode 7), src/dmrg.h:1283-1300: the reference contracts the whole MPO into one tensor and reads the lowest levels off
+    svd(exp(-H)) -- its only built-in cross-check of a Hamiltonian.  Same numbers here from the same object (the product-side MPO of
+    chain_b200.models, QNs ignored): dense eigvalsh up to dimension 4096, Lanczos on the MPO-vector product above.  Host-side, like
+    the reference's; this is a check of the MPO, not part of the hot path."""
+    n, d = len(mpo_sites), mpo_sites[0].shape[1]
+    dim = d ** n
+
+    def matvec(x):
+        x = np.asarray(x).reshape((1,) + (d,) * n)                  # [a, s_1 .. s_n], s_1 slowest
+        for j, W in enumerate(mpo_sites):                           # W[a, s_out, s_in, a']
+            x = np.tensordot(W, x, axes=([0, 2], [0, j + 1]))       # -> [s_out, a', rest...]
+            x = np.moveaxis(x, 0, j + 1)                            # a' first again, s_out back in place j+1
+        return x.reshape(dim)
+    cplx = any(np.iscomplexobj(W) and np.abs(np.imag(W)).max() > 0 for W in mpo_sites)
+    dt = complex if cplx else float
+    if dim <= 4096:
+        Hm = np.stack([matvec(np.eye(dim, dtype=dt)[:, i]) for i in range(dim)], axis=1)
+        return np.linalg.eigvalsh((Hm + Hm.conj().T) / 2)[:k].tolist()
+    # Lanczos (ARPACK) on the MPO-vector product; k + 4 levels are converged and the lowest k returned.  A Krylov method sees one vector
+    # per degenerate level unless rounding splits it, so a multiplet can come back with fewer copies than it has -- the level VALUES are
+    # exact (that is what the cross-check compares)
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    op = LinearOperator((dim, dim), matvec=lambda v: matvec(np.asarray(v, dtype=dt).reshape(dim)), dtype=dt)
+    kk = min(k + 4, dim - 2)
+    w = eigsh(op, k=kk, which="SA", tol=1e-12, ncv=max(4 * kk, 48), return_eigenvectors=False, v0=np.random.default_rng(0).standard_normal(dim).astype(dt))
+    return sorted(np.real(w).tolist())[:k]
 
 
 def main(argv=None):
@@ -412,14 +503,31 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--lib", default=None, help="path of the C-ABI library (default: chain_b200/libchain_b200.so)")
     a = ap.parse_args(argv)
-    if a.mode not in (0, 5):
-        sys.exit("mode %d is not available in the stand-in driver: 1/2/3/4/6/7 need the measurement operators of src/chain.cpp "
-                 "(SURVEY 8f row f2) or ITensor's checkpoint files; the hot path is modes 0 and 5" % a.mode)
+    if a.mode == 7:                                            # Test(): needs neither a device nor a progress file
+        ss = models.make_siteset(a.site, a.length)
+        mpo = ss.hamiltonian(a.bc, a.length, float(np.float32(a.penalty)), parse_couplings(a.couplings))
+        print("{%s}" % ",".join("%.10f" % e for e in exact_levels(mpo.sites, a.nstates)))
+        return 0
     ctx = cb.Context(device=a.device, lib_path=a.lib)
     sim = Simulation(a.site, a.bc, a.length, a.maxdim, a.cutoff, a.precision, a.couplings, a.penalty, a.charge, a.nstates,
                      out=a.out, seed=a.seed, ctx=ctx, checkpoint=not a.no_checkpoint)
     print("\n> %s %s:  L=%d  bond_dim=%d  svd_cutoff=%g  precision=%g  penalty=%g  couplings=%s  charge=%d" % (
         a.site, a.bc, a.length, a.maxdim, sim.svd_cutoff, sim.precision, sim.u, a.couplings, a.charge))
+    if a.mode in (1, 2, 3, 4, 6):                              # measurements and analysis on the progress file (src/dmrg.cpp:44-60)
+        if not os.path.exists(sim.progress_path + ".pgs") and not (a.mode == 6 and os.path.exists(sim.progress_path + ".pgs.bk")):
+            print("\n> No progress file available")
+            return 0
+        if a.mode == 6:
+            good = repair(sim)
+            print("> %d finished state(s) kept in %s.pgs" % (good.NumDoneStates(), sim.progress_path))
+            return 0
+        sim.load_progress()
+        if a.mode == 4:
+            normalize_energies(sim)
+        else:
+            analyze(sim, which={1: "full", 2: "without_rho", 3: "energies"}[a.mode])
+            print("> wrote %s and %s" % (sim.m_path, sim.an_path))
+        return 0
     t0 = time.perf_counter()
     ens, _ = sim.run()
     wall = time.perf_counter() - t0

@@ -1,6 +1,7 @@
 """Stand-in driver (chain_b200/driver.py): CLI flags, schedule, file names and .en/.ee formats of the reference
 (src/dmrg.cpp:10-23, src/dmrg.h:360, :527-653, src/utility.cpp:30-53), and CalcEE on the device path.
 Host-logic run on the emulation backend; tests/test_gpu_parity.py repeats the config-1 run on the GPU."""
+import os
 import re
 
 import numpy as np
@@ -60,9 +61,12 @@ def test_calc_ee_matches_oracle(emu_ctx, case):
     assert np.abs(np.array(ee_o) - np.array(cb.calc_ee(m, site.charges, ctx=emu_ctx))).max() <= 1e-10
 
 
-def test_cli_rejects_unbuilt_modes():
-    with pytest.raises(SystemExit):
-        driver.main("-s golden -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 1 -m 1".split())
+def test_cli_mode7_needs_no_device_and_bad_site_is_rejected(capsys):
+    assert driver.main("-s golden -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 3 -m 7".split()) == 0
+    got = [float(x) for x in capsys.readouterr().out.strip().strip("{}").split(",")]
+    assert np.allclose(got, common.ed_level("golden", "p", 6, [-1.0], None)[:3], atol=1e-9)
+    with pytest.raises(SystemExit):      # src/dmrg.cpp:110: "Invalid site type."
+        driver.main("-s fibonacci -b p -l 6 -d 100 -c 1e-8 -p 1e-9 -j -1 -u 2 -q 0 -n 1 -m 0".split())
 
 
 class _Stop(Exception):
@@ -144,3 +148,57 @@ def test_checkpoint_roundtrip_block_sparse_complex(tmp_path):
     p = back.psis_[0]
     assert p.nq == 3 and p.center == 2 and p.is_complex()
     assert all(np.array_equal(a, b) for a, b in zip(p.sites, sites)) and all(np.array_equal(a, b) for a, b in zip(p.link_charges, q))
+
+
+@pytest.mark.parametrize("st,bc,n,cp", [("golden", "p", 6, [-1.0]), ("golden", "o", 6, [-1.0]), ("golden", "p", 8, [-1.0])])
+def test_mode7_exact_levels_of_the_product_side_mpo(st, bc, n, cp):
+    # Test(), src/dmrg.h:1283-1300: the reference's own cross-check -- here also a KAT of chain_b200.models against the ED vectors
+    from chain_b200 import models
+    mpo = models.make_siteset(st, n).hamiltonian(bc, n, 2.0, cp)
+    want = common.ed_level(st, bc, n, cp, None)
+    got = driver.exact_levels(mpo.sites, len(want))
+    assert np.allclose(got, want, atol=1e-9)
+
+
+def test_analysis_modes_on_the_progress_file(emu_ctx, tmp_path, capsys):
+    # modes 1 / 2 / 3 / 4 / 6 of src/dmrg.cpp:44-60 start from the progress file of an earlier run
+    from conftest import EMU_LIB
+    base = ["-s", "golden", "-b", "p", "-l", "6", "-d", "100", "-c", "1e-8", "-p", "1e-9", "-j", "-1", "-u", "2", "-q", "0",
+            "--out", str(tmp_path), "--seed", "3", "--lib", EMU_LIB]
+    assert driver.main(base + ["-n", "3", "-m", "1"]) == 0
+    assert "No progress file available" in capsys.readouterr().out
+    assert driver.main(base + ["-n", "3", "-m", "0"]) == 0
+    want = common.ed_level("golden", "p", 6, [-1.0], None)[:3]
+    stem = driver.file_stem("golden", "p", 6, 100, float(np.float32(1e-8)), float(np.float32(1e-9)), "-1", 2.0, 0)
+    an = str(tmp_path / "an" / (stem + ".an"))
+
+    def table():
+        return [[float(x) for x in ln.strip("{},\n").split(",")] for ln in open(an).read().splitlines()[1:-1]]
+    capsys.readouterr()
+    assert driver.main(base + ["-n", "3", "-m", "1"]) == 0                 # Analyze: {energy, momentum, rho}
+    out = capsys.readouterr().out
+    assert "Spectrum:  {energy, momentum, rho}" in out
+    rows = table()
+    assert np.allclose([r[0] for r in rows], want, atol=2e-9)
+    assert [r[1] for r in rows] == [0.0, 3.0, 0.0]                         # momenta of the three lowest golden L=6 levels
+    phi = (1 + 5 ** 0.5) / 2
+    assert all(min(abs(r[2] - phi), abs(r[2] - (1 - phi))) < 2e-6 for r in rows)      # rho eigenvalues (src/dmrg.h:1100-1105)
+    assert driver.main(base + ["-n", "2", "-m", "2"]) == 0                 # AnalyzeWithoutRho on the first two states only
+    rows2 = table()
+    assert len(rows2) == 2 and all(len(r) == 2 for r in rows2) and np.allclose([r[0] for r in rows2], want[:2], atol=2e-9)
+    en_lines = open(str(tmp_path / "en" / (stem + ".en"))).read().splitlines()
+    assert len(en_lines) == 3 and en_lines[0].startswith("{1,")            # Measure("energy") lists every finished state, 1-based
+    capsys.readouterr()
+    assert driver.main(base + ["-n", "3", "-m", "3"]) == 0                 # Energies
+    out = capsys.readouterr().out
+    assert "{{-1},{%s}}," % ",".join("%.10f" % e for e in [r[0] for r in table()]) in out
+    assert driver.main(base + ["-n", "3", "-m", "4"]) == 0                 # NormalizeEnergies
+    out = capsys.readouterr().out
+    gap = want[1] - want[0]
+    assert ("{{-1},%g,{0.0000000000,1.0000000000,%.10f}}," % (gap, (want[2] - want[0]) / gap))[:24] in out
+    # Repair: the primary file is lost, the backup of the last finished state brings everything back
+    os.remove(str(tmp_path / "pgs" / (stem + ".pgs")))
+    assert driver.main(base + ["-n", "3", "-m", "6"]) == 0
+    assert "3 finished state(s)" in capsys.readouterr().out
+    assert driver.main(base + ["-n", "3", "-m", "3"]) == 0
+    assert np.allclose([r[0] for r in table()], want, atol=2e-9)
