@@ -61,6 +61,21 @@ def test_random_z3_structures(emu_ctx, seed):
     if b["phi"].size == 0 or not np.any(b["phi"]):
         pytest.skip("no allowed block for this draw")
     check(emu_ctx, b)
+    check_blocks(emu_ctx, b)
+
+
+def check_blocks(ctx, b):
+    """The block-packed (QDense order) boundary on the same random structure: shuffled labels = many short sectors, empty charges."""
+    site = b["site"]
+    B = cb.Bond(b["L"], b["W1"], b["W2"], b["R"], ql=b["ql"], qr=b["qr"], qkl=b["kl"], qkm=b["km"], qkr=b["kr"],
+                site_charges=site.charges, nq=site.nq, ctx=ctx)
+    assert B.phi_blocks_elems == int(b["pm"].sum())
+    xb = B.pack(b["phi"])
+    assert np.array_equal(B.unpack(xb), np.asarray(b["phi"], dtype=xb.dtype))
+    blocks = B.phi_blocks()
+    assert sum(int(np.prod(d)) for _, d in blocks) == xb.size
+    assert np.array_equal(B.apply_blocks(xb), B.pack(B.apply(b["phi"])))
+    B.close()
 
 
 @pytest.mark.parametrize("st,cp,dl,dr", [("golden", [-1.0], [7], [3]), ("haagerup", [0.0, -1.0, 0.0], [3], [5]), ("golden", [-1.0], [1], [9])])
