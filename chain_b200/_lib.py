@@ -32,7 +32,7 @@ class BondStat(C.Structure):
 
 class MpsC(C.Structure):
     _fields_ = [("n", C.c_int32), ("nq", C.c_int32), ("site", C.POINTER(Tensor)), ("link", C.POINTER(Index)),
-                ("ortho_center", C.c_int32), ("pad_", C.c_int32)]
+                ("ortho_center", C.c_int32), ("layout", C.c_int32)]
 
 
 class MpoC(C.Structure):
@@ -62,6 +62,9 @@ SYMBOLS = [
     ("cb200_result_link_dim", i64, [vp, i32]),
     ("cb200_result_link_charges", C.c_int, [vp, i32, C.POINTER(i32)]),
     ("cb200_result_site", C.c_int, [vp, i32, vp]),
+    ("cb200_site_blocks_elems", i64, [i32, i32, C.POINTER(i32), C.POINTER(Index), C.POINTER(Index)]),
+    ("cb200_result_site_blocks_elems", i64, [vp, i32]),
+    ("cb200_result_site_blocks", C.c_int, [vp, i32, vp]),
     ("cb200_result_nstats", i32, [vp]),
     ("cb200_result_stats", C.c_int, [vp, C.POINTER(BondStat)]),
     ("cb200_result_timers", C.c_int, [vp, C.POINTER(dbl)]),

@@ -168,6 +168,88 @@ class MPS:
         return m
 
 
+def _site_block_slices(ql, sq, qr, nq):
+    rl, rs, rr = _charge_runs(ql), _charge_runs(sq), _charge_runs(qr)
+    for (r0, r1, cr) in rr:
+        for (a0, a1, cs) in rs:
+            for (l0, l1, cl) in rl:
+                if (cl + cs - cr) % nq == 0:
+                    yield (slice(l0, l1), slice(a0, a1), slice(r0, r1))
+
+
+def pack_site_blocks(A, ql, sq, qr, nq):
+    """Dense [l, s, r] -> the block-packed ("QDense order") layout of cb200_mps.layout = 1 (host-side helper)."""
+    parts = [np.asarray(A[sl]).ravel(order="F") for sl in _site_block_slices(ql, sq, qr, nq)]
+    return np.concatenate(parts) if parts else np.zeros(0, np.asarray(A).dtype)
+
+
+def unpack_site_blocks(xb, ql, sq, qr, nq):
+    out = np.zeros((len(ql), len(sq), len(qr)), dtype=np.asarray(xb).dtype, order="F")
+    o = 0
+    for sl in _site_block_slices(ql, sq, qr, nq):
+        shp = tuple(x.stop - x.start for x in sl)
+        k = int(np.prod(shp))
+        out[sl] = np.asarray(xb[o:o + k]).reshape(shp, order="F")
+        o += k
+    return out
+
+
+class PackedMPS:
+    """An MPS whose site tensors cross the boundary block-packed (cb200_mps.layout = 1): what an adapter hands over when it passes
+    ITensor's QDense storage as it is.  blocks[j] is the 1-D packed array of site j."""
+
+    def __init__(self, blocks, link_charges, site_charges, nq=1, center=0):
+        self.blocks = [np.ascontiguousarray(b) for b in blocks]
+        self.link_charges = [np.ascontiguousarray(q, dtype=np.int32) for q in link_charges]
+        self.site_charges = np.ascontiguousarray(site_charges, dtype=np.int32)
+        assert len(self.link_charges) == len(self.blocks) + 1
+        self.nq, self.center = nq, center
+
+    @staticmethod
+    def from_dense(psi, site_charges):
+        sq = np.ascontiguousarray(site_charges, dtype=np.int32)
+        return PackedMPS([pack_site_blocks(a, psi.link_charges[j], sq, psi.link_charges[j + 1], psi.nq) for j, a in enumerate(psi.sites)],
+                         psi.link_charges, sq, nq=psi.nq, center=psi.center)
+
+    def to_dense(self):
+        return MPS([unpack_site_blocks(b, self.link_charges[j], self.site_charges, self.link_charges[j + 1], self.nq)
+                    for j, b in enumerate(self.blocks)], self.link_charges, nq=self.nq, center=self.center)
+
+    @property
+    def n(self):
+        return len(self.blocks)
+
+    @property
+    def d(self):
+        return len(self.site_charges)
+
+    def bond_dims(self):
+        return [len(q) for q in self.link_charges[1:-1]]
+
+    def is_complex(self):
+        return any(np.iscomplexobj(b) for b in self.blocks)
+
+    def _to_c(self, keep):
+        dt = np.complex128 if self.is_complex() else np.float64
+        n = self.n
+        ts = (Tensor * n)()
+        ls = (Index * (n + 1))()
+        for j, b in enumerate(self.blocks):
+            f = np.ascontiguousarray(b, dtype=dt)
+            keep.append(f)
+            ts[j].dtype = 1 if dt is np.complex128 else 0
+            ts[j].rank = 3
+            ts[j].dims[0], ts[j].dims[1], ts[j].dims[2] = len(self.link_charges[j]), self.d, len(self.link_charges[j + 1])
+            ts[j].data = f.ctypes.data
+        for j, q in enumerate(self.link_charges):
+            ls[j].dim = len(q)
+            ls[j].charge = i32ptr(q)
+        keep += [ts, ls]
+        m = MpsC()
+        m.n, m.nq, m.site, m.link, m.ortho_center, m.layout = n, self.nq, ts, ls, int(self.center or 0), 1
+        return m
+
+
 class MPO:
     def __init__(self, sites, link_charges=None, site_charges=None, nq=1):
         self.sites = [np.asarray(w) for w in sites]
@@ -218,6 +300,25 @@ class DmrgInfo:
         self.timers = {}
 
 
+def _unpack_result_blocks(ctx, res):
+    """The result's site tensors in the block-packed layout (cb200_result_site_blocks): (blocks, link charges)."""
+    lib = ctx.lib
+    n = lib.cb200_result_nsites(res)
+    dt = np.complex128 if lib.cb200_result_dtype(res) == 1 else np.float64
+    charges = []
+    for j in range(n + 1):
+        q = np.zeros(int(lib.cb200_result_link_dim(res, j)), np.int32)
+        ctx.check(lib.cb200_result_link_charges(res, j, i32ptr(q)))
+        charges.append(q)
+    blocks = []
+    for j in range(n):
+        b = np.empty(max(int(lib.cb200_result_site_blocks_elems(res, j)), 0), dtype=dt)
+        if b.size:
+            ctx.check(lib.cb200_result_site_blocks(res, j, ptr(b)))
+        blocks.append(b)
+    return blocks, charges
+
+
 def _unpack_result(ctx, res, d):
     lib = ctx.lib
     n = lib.cb200_result_nsites(res)
@@ -257,7 +358,9 @@ def overlap(a, b, site_charges=None, ctx=None):
     ctx = ctx or default_context()
     keep = []
     ac, bc = a._to_c(keep), b._to_c(keep)
-    d = a.sites[0].shape[1]
+    d = a.d if isinstance(a, PackedMPS) else a.sites[0].shape[1]
+    if site_charges is None and isinstance(a, PackedMPS):
+        site_charges = a.site_charges
     sq = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
     z = (C.c_double * 2)()
     ctx.check(ctx.lib.cb200_mps_overlap(ctx.h, C.byref(ac), C.byref(bc), d, i32ptr(sq), z))
@@ -291,7 +394,12 @@ def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
     ctx.check(lib.cb200_dmrg(ctx.h, C.byref(Hc), prev, len(psis), C.byref(p0), sw, sweeps.nsweep, float(weight),
                              C.byref(energy), C.byref(res)))
     try:
-        sites, charges = _unpack_result(ctx, res, H.d)
+        if isinstance(psi0, PackedMPS):      # the answer comes back in the layout the start state arrived in
+            blocks, charges = _unpack_result_blocks(ctx, res)
+            out = PackedMPS(blocks, charges, H.site_charges, nq=H.nq, center=1)
+        else:
+            sites, charges = _unpack_result(ctx, res, H.d)
+            out = MPS(sites, charges, nq=H.nq, center=1)
         if info is not None:
             ns = lib.cb200_result_nstats(res)
             arr = (BondStat * max(ns, 1))()
@@ -303,7 +411,7 @@ def dmrg(H, psis, psi0, sweeps, weight=1.0, ctx=None, info=None):
             info.timers = dict(env=t[0], matvec=t[1], level1=t[2], trunc=t[3], other=t[4], nmatvec=t[5], matvec_flops=t[6])
     finally:
         lib.cb200_result_free(res)
-    return energy.value, MPS(sites, charges, nq=H.nq, center=1)
+    return energy.value, out
 
 
 def calc_ee(psi, site_charges=None, ctx=None):
@@ -311,7 +419,9 @@ def calc_ee(psi, site_charges=None, ctx=None):
     ctx = ctx or default_context()
     keep = []
     pc = psi._to_c(keep)
-    d = psi.sites[0].shape[1]
+    d = psi.d if isinstance(psi, PackedMPS) else psi.sites[0].shape[1]
+    if site_charges is None and isinstance(psi, PackedMPS):
+        site_charges = psi.site_charges
     sq = np.ascontiguousarray(site_charges if site_charges is not None else np.zeros(d), dtype=np.int32)
     out = np.zeros(psi.n - 1)
     ctx.check(ctx.lib.cb200_mps_entropies(ctx.h, C.byref(pc), d, i32ptr(sq), out.ctypes.data_as(C.POINTER(C.c_double))))

@@ -119,6 +119,8 @@ static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
   h.link.resize(m->n + 1);
   for (int j = 0; j <= m->n; ++j) h.link[j] = IndexMap::from_labels(nq, m->link[j].dim, m->link[j].charge);
   h.site.resize(m->n);
+  if (m->layout != 0 && m->layout != 1) fail(CB200_ERR_INVALID, "MPS layout must be 0 (dense) or 1 (block-packed)");
+  h.packed = m->layout == 1;
   *cplx = false;
   for (int j = 0; j < m->n; ++j) {
     const cb200_tensor& t = m->site[j];
@@ -243,6 +245,34 @@ int cb200_result_site(const cb200_result* r, int32_t site, void* out) {
   Ctx* c = r->r->ctx;
   try {
     result_site_export(*r->r, site, out);
+    return CB200_OK;
+  } catch (const EngineError& e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = std::string("internal error: ") + e.what();
+    return CB200_ERR_INVALID;
+  }
+}
+int64_t cb200_site_blocks_elems(int32_t nq, int32_t d, const int32_t* site_charge, const cb200_index* l, const cb200_index* r) {
+  if (nq < 1 || d < 1 || !l || !r) return -1;
+  try {
+    SiteInfo S = SiteInfo::make(nq, d, site_charge);
+    IndexMap ml = IndexMap::from_labels(nq, l->dim, l->charge), mr = IndexMap::from_labels(nq, r->dim, r->charge);
+    return site3_block_tasks(S, ml, mr, nullptr, true, nullptr);
+  } catch (...) {
+    return -1;
+  }
+}
+int64_t cb200_result_site_blocks_elems(const cb200_result* r, int32_t site) {
+  if (!r || site < 0 || site >= r->r->psi.n) return -1;
+  return result_site_blocks_elems(*r->r, site);
+}
+int cb200_result_site_blocks(const cb200_result* r, int32_t site, void* out) {
+  if (!r || !out || site < 0 || site >= r->r->psi.n || !r->r->ctx) return CB200_ERR_INVALID;
+  Ctx* c = r->r->ctx;
+  try {
+    result_site_export_blocks(*r->r, site, out);
     return CB200_OK;
   } catch (const EngineError& e) {
     c->err = e.msg;

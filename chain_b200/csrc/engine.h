@@ -294,6 +294,7 @@ struct HostMPS {       // an MPS in external dense form (what crosses the C ABI)
   int n = 0;
   std::vector<IndexMap> link;                 // n+1
   std::vector<const void*> site;              // dense [Dl,d,Dr], column-major (empty for a result: see DmrgResult::dev)
+  bool packed = false;                        // site tensors are block-packed (QDense order, cb200_mps.layout = 1) instead of dense
   int center = 0;
 };
 
@@ -310,6 +311,11 @@ struct DmrgResult {
   bool cplx = false;
 };
 void result_site_export(const DmrgResult& r, int site, void* out);
+int64_t result_site_blocks_elems(const DmrgResult& r, int site);
+void result_site_export_blocks(const DmrgResult& r, int site, void* out);
+// element count / copy tasks of the block-packed layout of a site tensor [l, s, r] (engine_io.cpp)
+int64_t site3_block_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const Site3Layout* lay, bool to_internal,
+                          std::vector<CopyTask>* tasks);
 
 struct MpoIn {
   int n = 0, nq = 1, d = 0;

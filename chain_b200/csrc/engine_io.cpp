@@ -139,6 +139,87 @@ static void import_site3_t(Ctx* c, bool cplx, bool src_cplx, const SiteInfo& S, 
 void import_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext, DevSite3& out) {
   import_site3_t(c, cplx, cplx, S, l, r, ext, out);
 }
+
+// ---- block-packed ("QDense order") MPS site tensors: cb200_mps.layout = 1 --------------------------------------------------------
+// Sectors = maximal runs of equal charge label on l, s and r; the stored blocks are the zero-flux sector triples q(l)+q(s) = q(r) in
+// increasing block number i_l + n_l*(i_s + n_s*i_r); each block dense column-major [len_l, len_s, len_r]; no gaps.  One strided-copy
+// task per (block, site value inside the block's site sector).  tasks == nullptr: only the element count is returned.
+int64_t site3_block_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const Site3Layout* lay, bool to_internal,
+                          std::vector<CopyTask>* tasks) {
+  const int nq = S.nq;
+  struct Run { int64_t start, len; int q; };
+  auto runs = [](const IndexMap& m) {
+    std::vector<Run> v;
+    const int64_t n = (int64_t)m.charge_ext.size();
+    for (int64_t i = 0; i < n;) {
+      int64_t j = i;
+      while (j < n && m.charge_ext[j] == m.charge_ext[i]) ++j;
+      v.push_back({i, j - i, m.charge_ext[i]});
+      i = j;
+    }
+    return v;
+  };
+  const std::vector<Run> rl = runs(l), rs = runs(S.map), rr = runs(r);
+  int64_t boff = 0;
+  for (const Run& uy : rr)
+    for (const Run& us : rs)
+      for (const Run& ux : rl) {
+        if (qadd(ux.q, us.q, nq) != uy.q) continue;
+        if (tasks) {
+          const int64_t dx = l.g.dim[ux.q];
+          const int64_t x_loc = l.ext2int[ux.start] - l.g.off(ux.q), y_loc = r.ext2int[uy.start] - r.g.off(uy.q);
+          for (int64_t b1 = 0; b1 < us.len; ++b1) {
+            const int si = (int)S.map.ext2int[us.start + b1], qs = S.q_int[si];
+            const int64_t s_loc = S.loc_int[si], dsq = S.map.g.dim[qs];
+            const int64_t eoff = boff + ux.len * b1, es1 = ux.len * us.len;
+            const int64_t ioff = lay->o(ux.q, qs) + x_loc + dx * (s_loc + dsq * y_loc), is1 = dx * dsq;
+            CopyTask t{};
+            t.n0 = (int32_t)ux.len; t.n1 = (int32_t)uy.len; t.n2 = 1;
+            if (to_internal) { t.src_off = eoff; t.dst_off = ioff; t.ss0 = 1; t.ss1 = es1; t.ds0 = 1; t.ds1 = is1; }
+            else { t.src_off = ioff; t.dst_off = eoff; t.ss0 = 1; t.ss1 = is1; t.ds0 = 1; t.ds1 = es1; }
+            tasks->push_back(t);
+          }
+        }
+        boff += ux.len * us.len * uy.len;
+      }
+  return boff;
+}
+static void import_site3_blocks(Ctx* c, bool cplx, bool src_cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const void* ext,
+                                DevSite3& out) {
+  out.lay.build(l.g, r.g, &S);
+  std::vector<CopyTask> tasks;
+  const int64_t tot = site3_block_tasks(S, l, r, &out.lay, true, &tasks);
+  if (tot != out.lay.total) fail(-2, "block-packed site tensor: element count does not match the charge structure");
+  out.buf = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(tot, 1));
+  if (tot == 0) return;
+  Buf stage(c->be, (int64_t)esz(cplx) * tot);
+  if (cplx == src_cplx) {
+    dev_h2d(c->be, stage.p, ext, esz(cplx) * (size_t)tot);
+  } else {   // real data into a complex run (a real start state under a complex Hamiltonian): widen on the host
+    std::vector<char> h(esz(cplx) * (size_t)tot);
+    for (int64_t i = 0; i < tot; ++i) wr(h.data(), cplx, i, rd(ext, src_cplx, i));
+    dev_h2d(c->be, stage.p, h.data(), h.size());
+  }
+  run_copy_tasks(c, cplx, tasks, stage.p, out.buf.p);
+}
+// site j of an MPS that crossed the boundary in either layout
+static void import_mps_site(Ctx* c, bool cplx, bool src_cplx, const SiteInfo& S, const HostMPS& m, int j, DevSite3& out) {
+  if (m.packed) import_site3_blocks(c, cplx, src_cplx, S, m.link[j], m.link[j + 1], m.site[j], out);
+  else import_site3_t(c, cplx, src_cplx, S, m.link[j], m.link[j + 1], m.site[j], out);
+}
+int64_t result_site_blocks_elems(const DmrgResult& r, int site) { return r.dev[site].lay.total; }
+void result_site_export_blocks(const DmrgResult& r, int site, void* out) {
+  Ctx* c = r.ctx;
+  const DevSite3& in = r.dev[site];
+  std::vector<CopyTask> tasks;
+  const int64_t tot = site3_block_tasks(r.S, r.psi.link[site], r.psi.link[site + 1], &in.lay, false, &tasks);
+  if (tot != in.lay.total) fail(-2, "block-packed site tensor: element count does not match the charge structure");
+  if (tot == 0) return;
+  Buf stage(c->be, (int64_t)esz(r.cplx) * tot);
+  run_copy_tasks(c, r.cplx, tasks, in.buf.p, stage.p);
+  dev_d2h(c->be, out, stage.p, esz(r.cplx) * (size_t)tot);
+  check_dev(c);
+}
 void export_site3(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const DevSite3& in, void* ext) {
   {
     const int64_t tot = l.g.total() * S.d * r.g.total();
@@ -522,7 +603,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   // current state
   std::vector<IndexMap> link = psi0.link;
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, psi0_cplx, S, link[j], link[j + 1], psi0.site[j], A[j]);
+  for (int j = 0; j < n; ++j) import_mps_site(c, cplx, psi0_cplx, S, psi0, j, A[j]);
   if (link[0].g.total() != 1 || link[n].g.total() != 1) fail(-2, "outer MPS links must have dimension 1");
   // previous states
   const int np = (int)prev.size();
@@ -530,7 +611,7 @@ std::unique_ptr<DmrgResult> run_dmrg(Ctx* c, const MpoIn& H, const std::vector<H
   for (int p = 0; p < np; ++p) {
     if (prev[p].n != n) fail(-2, "previous state length mismatch");
     P[p].resize(n);
-    for (int j = 0; j < n; ++j) import_site3_t(c, cplx, prev_cplx[p], S, prev[p].link[j], prev[p].link[j + 1], prev[p].site[j], P[p][j]);
+    for (int j = 0; j < n; ++j) import_mps_site(c, cplx, prev_cplx[p], S, prev[p], j, P[p][j]);
   }
 
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {   // sites i, i+1 (0-based)
@@ -697,7 +778,7 @@ std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_cha
   if (n < 2) fail(-2, "entropies need at least 2 sites");
   SiteInfo S = SiteInfo::make(nq, d, site_charge);
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j], A[j]);
+  for (int j = 0; j < n; ++j) import_mps_site(c, cplx, cplx, S, psi, j, A[j]);
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
     pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
     phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
@@ -748,7 +829,7 @@ std::unique_ptr<DmrgResult> mps_translate(Ctx* c, int nq, int d, const int32_t* 
   if (n < 2) fail(-2, "translation needs at least 2 sites");
   SiteInfo S = SiteInfo::make(nq, d, site_charge);
   std::vector<DevSite3> A(n);
-  for (int j = 0; j < n; ++j) import_site3_t(c, cplx, cplx, S, psi.link[j], psi.link[j + 1], psi.site[j], A[j]);
+  for (int j = 0; j < n; ++j) import_mps_site(c, cplx, cplx, S, psi, j, A[j]);
   auto phi_of = [&](int i, PhiLayout& pl, Buf& phi) {
     pl.build(A[i].lay.X, A[i + 1].lay.Y, &S);
     phi = Buf(c->be, (int64_t)esz(cplx) * std::max<int64_t>(pl.total, 1), true);
@@ -806,16 +887,16 @@ cplx_t mps_overlap(Ctx* c, int nq, int d, const int32_t* site_charge, const Host
   DevMat F;
   {
     DevSite3 A0, B0;
-    import_site3_t(c, cplx, a_cplx, S, a.link[0], a.link[1], a.site[0], A0);
-    import_site3_t(c, cplx, b_cplx, S, b.link[0], b.link[1], b.site[0], B0);
+    import_mps_site(c, cplx, a_cplx, S, a, 0, A0);
+    import_mps_site(c, cplx, b_cplx, S, b, 0, B0);
     if (A0.lay.X.total() != 1 || B0.lay.X.total() != 1) fail(-2, "overlap: outer links must have dimension 1");
     if (!(A0.lay.X == B0.lay.X)) return cplx_t(0, 0);          // different total charge
     site3H_times_site3(c, cplx, &S, A0, B0, F);                 // F[m, n] = sum_{l,s} conj(A[l,s,m]) B[l,s,n]
   }
   for (int j = 1; j < n; ++j) {
     DevSite3 Aj, Bj, X;
-    import_site3_t(c, cplx, a_cplx, S, a.link[j], a.link[j + 1], a.site[j], Aj);
-    import_site3_t(c, cplx, b_cplx, S, b.link[j], b.link[j + 1], b.site[j], Bj);
+    import_mps_site(c, cplx, a_cplx, S, a, j, Aj);
+    import_mps_site(c, cplx, b_cplx, S, b, j, Bj);
     // X[m, s, n'] = sum_n F[m, n] B[n, s, n'] ; F'[m', n'] = sum_{m,s} conj(A[m,s,m']) X[m,s,n']
     mat_times_site3(c, cplx, &S, F, Bj, X);
     DevMat Fn;
@@ -849,8 +930,8 @@ cplx_t mps_mpo_element(Ctx* c, int d, const HostMPS& bra, bool bra_cplx, const M
   }
   for (int j = 0; j < n; ++j) {
     DevSite3 Ak, Ab;
-    import_site3_t(c, cplx, ket_cplx, S, ket.link[j], ket.link[j + 1], ket.site[j], Ak);
-    import_site3_t(c, cplx, bra_cplx, S, bra.link[j], bra.link[j + 1], bra.site[j], Ab);
+    import_mps_site(c, cplx, ket_cplx, S, ket, j, Ak);
+    import_mps_site(c, cplx, bra_cplx, S, bra, j, Ab);
     HostW W = import_w(1, d, S, O.link[j], O.link[j + 1], O.cplx, O.site[j]);
     const int64_t kl = W.KL.total(), kr = W.KR.total();
     const int64_t Dkr = Ak.lay.Y.total(), Dbr = Ab.lay.Y.total();

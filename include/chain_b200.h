@@ -94,7 +94,10 @@ typedef struct cb200_mps {
   const cb200_tensor* site;          /* n tensors [Dl, d, Dr] */
   const cb200_index* link;           /* n+1 */
   int32_t ortho_center;              /* 1-based; 0 = unknown (the library orthogonalises to site 1) */
-  int32_t pad_;
+  int32_t layout;                    /* 0: site[j].data is the dense [Dl,d,Dr] array; 1: it is BLOCK-PACKED, the way itensor::QDense<T> holds a
+                                      * QN tensor: every index cut into sectors (maximal runs of equal charge label), the zero-flux sector
+                                      * triples q(l)+q(s) = q(r) in increasing block number i_l + n_l*(i_s + n_s*i_r), each block dense
+                                      * column-major [len_l, len_s, len_r], no gaps (cb200_site_blocks_elems elements).  dims stay (Dl, d, Dr). */
 } cb200_mps;
 
 typedef struct cb200_mpo {
@@ -130,6 +133,11 @@ int cb200_result_link_charges(const cb200_result* r, int32_t link, int32_t* out)
  * the dense external form on the device and copies it straight into `out` (every element is written, zeros included), so a result
  * holds device memory and must be freed before its context is destroyed */
 int cb200_result_site(const cb200_result* r, int32_t site, void* out);
+/* block-packed counterparts (cb200_mps.layout = 1): element count of a site tensor for given link labels, and the result's tensors in
+ * that layout (links of a result are charge-sorted: one sector per charge) */
+int64_t cb200_site_blocks_elems(int32_t nq, int32_t d, const int32_t* site_charge, const cb200_index* l, const cb200_index* r);
+int64_t cb200_result_site_blocks_elems(const cb200_result* r, int32_t site);
+int cb200_result_site_blocks(const cb200_result* r, int32_t site, void* out);
 int32_t cb200_result_nstats(const cb200_result* r);
 int cb200_result_stats(const cb200_result* r, cb200_bond_stat* out);
 /* seconds spent in: [0] env update, [1] H_eff matvec, [2] Davidson level-1, [3] truncation, [4] other; [5] matvec count, [6] matvec flop */

@@ -309,3 +309,45 @@ def check_ground_state_kat(ctx, st, bc, n, cp, q, tol, nrep=12, seed=1):
     e_ed = ed_level(st, bc, n, cp, q if site.nq > 1 else None)[0]
     assert abs(en - e_ed) <= tol * abs(e_ed), (en, e_ed)
     return en, psi, site
+
+
+def check_packed_mps_boundary(ctx, case, shuffle=False):
+    """cb200_mps.layout = 1 (ITensor QDense storage for the MPS of the coarse call): same run, bit for bit, as with dense arrays;
+    previous states and the start state may arrive in different layouts; CalcEE and innerC take either."""
+    st, bc, n, cp, q, nst, product = case
+    site, W, qk = build_model(st, bc, n, cp)
+    sq = site.charges
+    psi0 = to_cb(warm_start(site, W, n, q, seed=13, maxdim=10))
+    if shuffle:
+        rng = np.random.default_rng(3)
+        for j in range(1, n):
+            p = rng.permutation(len(psi0.link_charges[j]))
+            psi0.link_charges[j] = np.ascontiguousarray(psi0.link_charges[j][p])
+            psi0.sites[j - 1] = np.asfortranarray(psi0.sites[j - 1][:, :, p])
+            psi0.sites[j] = np.asfortranarray(psi0.sites[j][p])
+        psi0.center = 0
+    H = cb.MPO(W, qk, sq, nq=site.nq)
+    sw = cb.Sweeps(2, [12, 20], 1e-10)
+    pk0 = cb.PackedMPS.from_dense(psi0, sq)
+    assert all(np.array_equal(a, b) for a, b in zip(pk0.to_dense().sites, psi0.sites))          # the packing itself loses nothing
+    nelem = sum(int(((np.asarray(psi0.link_charges[j])[:, None, None] + np.asarray(sq)[None, :, None]
+                      - np.asarray(psi0.link_charges[j + 1])[None, None, :]) % site.nq == 0).sum()) for j in range(n))
+    assert sum(b.size for b in pk0.blocks) == nelem
+    e_d, out_d = cb.dmrg(H, [], psi0, sw, ctx=ctx)
+    e_p, out_p = cb.dmrg(H, [], pk0, sw, ctx=ctx)
+    assert isinstance(out_p, cb.PackedMPS) and e_p == e_d
+    assert all(np.array_equal(a, b) for a, b in zip(out_p.to_dense().sites, out_d.sites))
+    assert all(np.array_equal(a, b) for a, b in zip(out_p.link_charges, out_d.link_charges))
+    assert np.array_equal(cb.calc_ee(out_p, ctx=ctx), cb.calc_ee(out_d, sq, ctx=ctx))
+    assert cb.overlap(out_p, out_p, ctx=ctx) == cb.overlap(out_d, out_d, sq, ctx=ctx)
+    # an excited state with the penalty term: previous state packed, start state dense -- and the other way round
+    e1, x1 = cb.dmrg(H, [out_p], psi0, sw, weight=1000.0, ctx=ctx)
+    e2, x2 = cb.dmrg(H, [out_d], pk0, sw, weight=1000.0, ctx=ctx)
+    assert e1 == e2 and all(np.array_equal(a, b) for a, b in zip(x2.to_dense().sites, x1.sites))
+    # a REAL start state under a complex Hamiltonian: the packed data is widened at the boundary like the dense data
+    if np.iscomplexobj(W[1]) and np.abs(np.imag(W[1])).max() > 0:
+        pr = to_cb(od.product_mps(site, n, q, np.random.default_rng(4), dtype=float))
+        assert not pr.is_complex()
+        e3, x3 = cb.dmrg(H, [], pr, sw, ctx=ctx)
+        e4, x4 = cb.dmrg(H, [], cb.PackedMPS.from_dense(pr, sq), sw, ctx=ctx)
+        assert e3 == e4 and all(np.array_equal(a, b) for a, b in zip(x4.to_dense().sites, x3.sites))

@@ -28,6 +28,12 @@ def test_bond_apply_block_packed_boundary(gpu_ctx, case, shuffle):
     common.check_bond_blocks(gpu_ctx, case, shuffle)
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_block_packed_mps_boundary(gpu_ctx, shuffle):
+    # cb200_mps.layout = 1 through the CUDA path: complex128 Z3 block-sparse MPS in ITensor's QDense storage, in and out
+    common.check_packed_mps_boundary(gpu_ctx, common.DMRG_CASES[4], shuffle)
+
+
 @pytest.mark.parametrize("case", common.DMRG_CASES, ids=lambda c: "%s-%s-%d-q%d" % (c[0], c[1], c[2], c[4]))
 def test_dmrg_trajectory_matches_oracle(gpu_ctx, case):
     common.check_dmrg_trajectory(gpu_ctx, case, nsweep=10)

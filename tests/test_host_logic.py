@@ -86,3 +86,9 @@ def test_mps_boundary_device_packing_equals_host_loop(emu_ctx, case, monkeypatch
 @pytest.mark.parametrize("sizes", common.HEIG_BATCHES, ids=lambda s: "x".join(str(n) for n, _ in s))
 def test_hermitian_eigensolver_batched_driver(emu_ctx, cplx, sizes):
     common.check_heig_batched(emu_ctx, cplx, sizes)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("case", [common.DMRG_CASES[0], common.DMRG_CASES[3], common.DMRG_CASES[4]], ids=["golden", "haagerupq-real", "haagerupq-complex"])
+def test_block_packed_mps_boundary(emu_ctx, case, shuffle):
+    common.check_packed_mps_boundary(emu_ctx, case, shuffle)
