@@ -7,6 +7,7 @@ N(0,1) matrix, per charge block) and the Hamiltonian is the model's true compres
 
   python tools/sweep_bench.py haagerupq p 12 1600 0,-1,0      # BASELINE configs[1] at a chain long enough to reach D
   python tools/sweep_bench.py golden p 24 800 -1               # BASELINE configs[2]
+  CB200_SWEEP_PACKED=1 python tools/sweep_bench.py ...         # host MPS in ITensor's QDense block storage instead of dense arrays
 """
 import json
 import os
@@ -125,6 +126,8 @@ def main():
         big = max(int(a.sum()) for a in dims)
         ctx.shard(rank, world, mode="p2p", landing_bytes=big * big * ss.d * ss.d * (16 if H.is_complex() else 8) // max(ss.nq, 1) + (1 << 20),
                   min_dim=int(os.environ.get("CB200_SHARD_MIN_DIM", "1600")))
+    if os.environ.get("CB200_SWEEP_PACKED", "0") == "1":  # the MPS crosses the boundary in the QDense block layout (cb200_mps.layout = 1)
+        psi = cb.PackedMPS.from_dense(psi, ss.charges)
     out = run_sweeps(ctx, H, psi, D, nsweep)
     if rank != 0:
         return
