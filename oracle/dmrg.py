@@ -14,7 +14,6 @@ E[x', a, x] (bra link, MPO link, ket link). Z_N symmetric runs are done with den
 carrying a charge label per link value: dense arithmetic keeps forbidden blocks exactly zero,
 and only the truncation (per-charge-block eigendecomposition, pooled selection) looks at labels.
 """
-import math
 import numpy as np
 
 
