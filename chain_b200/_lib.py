@@ -110,7 +110,7 @@ _cache = {}
 
 def load(path=None):
     """Load the C-ABI library and declare every prototype. Raises if the file or any symbol is missing."""
-    path = os.path.abspath(path or os.environ.get("CHAIN_B200_LIB") or DEFAULT_LIB)   # CHAIN_B200_LIB: A/B builds of the kernels
+    path = os.path.abspath(path or DEFAULT_LIB)   # no environment override: the product library is the only default
     if path in _cache:
         return _cache[path]
     if not os.path.exists(path):
