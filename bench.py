@@ -136,7 +136,7 @@ def run_reference(args, rank):
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c128" if w["cplx"] else "f64", "data": "synthetic",
             "config": {"workload": desc, "note": "each step = a bounded sample of the matvec's block-pair GEMMs on the host cores"},
-            "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": cbz.host_threads(), "kind": "port", "sample": sample + " per step"},
+            "cpu_baseline": {"value": v, "unit": "TFLOP/s", "cores": cbz.host_threads(), "host_cores": cbz.host_cores(), "kind": "port", "sample": sample + " per step"},
             "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
@@ -286,17 +286,20 @@ def main():
 
     # the headline e2e: the same call on ITensor's own QN storage (QDense block list, cb200_bond_apply_blocks) -- only the
     # charge-allowed blocks cross PCIe; for a dense model (nq = 1) the two layouts coincide
+    # N > 1: rank g carries only ITS slice of the block-packed vector over PCIe (cb200_bond_apply_blocks_sharded): the slices are
+    # all-gathered between the GPUs over NVLink, and the result crosses PCIe once (1/N per rank) instead of N times
     nb = bond.phi_blocks_elems
-    xbh = torch.empty(nb * (2 if w["dims"]["cplx"] else 1), dtype=torch.float64, pin_memory=True)
+    b0, cnt = bond.phi_blocks_slice()
+    xbh = torch.empty(max(cnt, 1) * (2 if w["dims"]["cplx"] else 1), dtype=torch.float64, pin_memory=True)
     ybh = torch.empty_like(xbh, pin_memory=True)
-    xb, yb = xbh.numpy().view(dt), ybh.numpy().view(dt)
-    xb[...] = bond.pack(phi)
+    xb, yb = xbh.numpy().view(dt)[:cnt], ybh.numpy().view(dt)[:cnt]
+    xb[...] = bond.pack(phi)[b0:b0 + cnt]
     for _ in range(2):
-        bond.apply_blocks(xb, out=yb)
+        bond.apply_blocks_sharded(xb, out=yb)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        bond.apply_blocks(xb, out=yb)
+        bond.apply_blocks_sharded(xb, out=yb)
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -341,16 +344,49 @@ def main():
         sweep = {"wall_s": sw["wall_s"], "workload": "%s %s L=%d D=%d, synthetic right-canonical MPS, true MPO; one sweep = one cb200_dmrg call with host MPS in/out" % (st, bc, Ls, D),
                  "bond_updates": sw["bond_updates"], "bond_profile": [int(x.sum()) for x in dims_s], "matvec_s": sw["matvec_s"], "truncation_s": sw["trunc_s"],
                  "env_update_s": sw["env_s"], "davidson_level1_s": sw["level1_s"], "other_s": sw["other_s"], "matvecs": sw["matvecs"],
-                 "matvec_tflops": sw["matvec_tflops"], "gpu_launches": sw["launches"], "energy": sw["energy"]}
+                 "matvec_tflops": sw["matvec_tflops"], "gpu_launches": sw["launches"], "energy": sw["energy"],
+                 "matvec_flops": sw["matvec_tflops"] * 1e12 * sw["matvec_s"],
+                 # environment update = one D^3 stage pair per site instead of per site pair: matvec flops of one product / d
+                 "env_flops_est": sw["matvec_tflops"] * 1e12 * sw["matvec_s"] / max(sw["matvecs"], 1) * sw["bond_updates"] / ss.d,
+                 "rho_block_sizes": sb.rho_block_sizes(ss, dims_s)}
 
-    traffic = None
+    # DRAM traffic of the dominant kernel: a constant read from the committed ncu --set full summary of this workload (it cannot be
+    # measured outside a profiler); the summary says which launches it covers
+    traffic, traffic_src = None, None
+    for rnd in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", "%s_ncu_gemm_%s_summary.json" % (rnd, args.workload))) as f:
+                js = json.load(f)
+            traffic = js.get("dram_bytes_per_matvec_gemm_launches")
+            traffic_src = "profiles/%s_ncu_gemm_%s_summary.json: %s" % (rnd, args.workload, js.get("dram_bytes_covers", "dram__bytes_read.sum + dram__bytes_write.sum of the L-stage launch ONLY (the R-stage counters were not captured)"))
+            if traffic:
+                break
+        except Exception:
+            pass
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = traffic_src
+    by = bond.stage_bytes()
+    roofline["algorithmic_bytes"] = {"gemm_L": by[0], "mix": by[1], "gemm_R": by[2]}
+
+    # ---- HBM-bound kernels of the path against the measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs; north_star asks for both rooflines)
+    hbm_peak, hbm_src = 6551.4, "fallback (MEASURED_PEAKS.json absent)"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_%s_summary.json" % args.workload)) as f:
-            traffic = json.load(f).get("dram_bytes_per_matvec_gemm_launches")
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
-    roofline["traffic"] = traffic
-    roofline["traffic_source"] = "dram__bytes_read.sum + dram__bytes_write.sum of the L-stage + R-stage launches, ncu --set full (profiles/)" if traffic else None
+    es = phi.itemsize
+    nvec = 3
+    l1 = cb.k_level1_timed(bond.phi_blocks_elems, nv=nvec, cplx=bool(w["dims"]["cplx"]), reps=10, ctx=ctx)
+
+    def hbm(kernel, nbytes, ms, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        return {"kernel": kernel, "bytes": nbytes, "ms": ms, "GB/s": gbs, "frac": gbs / hbm_peak if gbs else None, "what": what}
+    roofline_hbm = {"peak_GB/s": hbm_peak, "peak_source": hbm_src, "kernels": [
+        hbm("mix_smem_kernel", by[1], st_ms[1], "Omega = W_b (x) W_{b+1} applied between the two GEMM stages: |T1| read + |T2| written"),
+        hbm("dot_partial+dot_final (multi_dot)", (nvec + 1) * bond.phi_blocks_elems * es, l1[0], "Davidson Gram-Schmidt / penalty overlaps: %d dots in one pass over y" % nvec),
+        hbm("lincomb_kernel", (nvec + 2) * bond.phi_blocks_elems * es, l1[1], "Davidson Ritz vector / residual / projector update: dst += sum of %d vectors" % nvec),
+        hbm("device copy", 2 * bond.phi_blocks_elems * es, l1[2], "Krylov vector copy (cudaMemcpyAsync D2D)")]}
 
     if rank == 0:
         cpu = None
@@ -358,7 +394,15 @@ def main():
             from oracle import cpu_baseline as cbz     # the one place bench.py touches the oracle: the reported CPU baseline
             d = w["dims"]
             r = cbz.matvec_sample(d["Dl"], d["Dr"], d["kl"], d["kr"], d["ds"], d["cplx"], budget_s=12.0)
-            cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": cbz.host_threads(), "kind": "port", "sample": r["sample"]}
+            cpu = {"value": r["tflops"], "unit": "TFLOP/s", "cores": cbz.host_threads(), "host_cores": cbz.host_cores(), "kind": "port", "sample": r["sample"]}
+            if sweep is not None:
+                # the CPU sweep time beside the GPU sweep: same bond profile, same flops, LAPACK *syev per rho block
+                est = cbz.sweep_estimate(sweep["matvec_flops"], sweep["env_flops_est"], sweep["rho_block_sizes"], d["cplx"], r["tflops"])
+                cpu["sweep_s"] = est["seconds"]
+                cpu["sweep_parts"] = {"contraction_s": est["contraction_s"], "eigensolver_s": est["eigensolver_s"]}
+                cpu["sweep_how"] = est["how"]
+                sweep["cpu_sweep_s"] = est["seconds"]
+                sweep.pop("rho_block_sizes", None)
         line = {"metric": "heff_matvec_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "c128" if w["dims"]["cplx"] else "f64", "data": "synthetic",
@@ -367,10 +411,11 @@ def main():
                            "parallelism": "single GPU" if world == 1 else "matvec row-sharded x%d, exchange=%s" % (world, exchange)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_s / args.steps * 1e3,
-                        "call": "cb200_bond_apply_blocks: pinned host vectors in ITensor's QDense block storage, H2D + product + D2H every step",
+                        "call": ("cb200_bond_apply_blocks: pinned host vectors in ITensor's QDense block storage, H2D + product + D2H every step" if world == 1 else
+                                 "cb200_bond_apply_blocks_sharded: each rank uploads/downloads its 1/%d slice of the block-packed vector (pinned), slices all-gathered over NVLink; bytes are the whole job's" % world),
                         "dense_layout": {"value": e2e_dense_v, "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": nbytes_dense, "d2h_bytes_per_step": nbytes_dense,
                                          "call": "cb200_bond_apply: dense [l,s1,s2,r] arrays with zeros in the forbidden blocks"}},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "bond_update": bond_update, "sweep": sweep, "wall_s_timed_region": wall}
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "bond_update": bond_update, "sweep": sweep, "wall_s_timed_region": wall}
         emit(line)
     bond.close()
     if world > 1:

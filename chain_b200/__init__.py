@@ -6,5 +6,5 @@ fine-grained entry points. Importing the package does not load the library; the 
 loudly if the library or a usable device is missing.
 """
 from .api import (Context, Sweeps, MPS, PackedMPS, pack_site_blocks, unpack_site_blocks, MPO, DmrgInfo, dmrg, calc_ee, translate, overlap, mpo_element, Bond, default_context,  # noqa: F401
-                  k_gemm, k_jacobi_eig, k_svd, k_heig, k_heig_batched, k_dots, pack_phi_blocks, unpack_phi_blocks, k_lincomb, k_gemm_peak, k_fp64_peak)
+                  k_gemm, k_jacobi_eig, k_svd, k_heig, k_heig_batched, k_dots, pack_phi_blocks, unpack_phi_blocks, k_lincomb, k_gemm_peak, k_fp64_peak, k_level1_timed)
 from ._lib import ChainB200Error, DEFAULT_LIB  # noqa: F401

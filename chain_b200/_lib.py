@@ -79,6 +79,9 @@ SYMBOLS = [
     ("cb200_bond_phi_blocks_elems", i64, [vp]),
     ("cb200_bond_phi_blocks", C.c_int, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     ("cb200_bond_apply_blocks", C.c_int, [vp, vp, vp]),
+    ("cb200_bond_stage_bytes", C.c_int, [vp, C.POINTER(dbl)]),
+    ("cb200_bond_phi_blocks_slice", C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    ("cb200_bond_apply_blocks_sharded", C.c_int, [vp, vp, vp]),
     ("cb200_bond_apply_timed", C.c_int, [vp, vp, i32, i32, C.POINTER(dbl)]),
     ("cb200_bond_stage_times", C.c_int, [vp, vp, i32, C.POINTER(dbl), C.POINTER(dbl)]),
     ("cb200_bond_update_timed", C.c_int, [vp, vp, i32, i32, dbl, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32), C.POINTER(dbl)]),
@@ -94,6 +97,7 @@ SYMBOLS = [
     ("cb200_k_heig_batched", C.c_int, [vp, i32, i32, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.POINTER(dbl)), C.POINTER(vp)]),
     ("cb200_k_dots", C.c_int, [vp, i32, i32, i64, vp, vp, C.POINTER(dbl)]),
     ("cb200_k_lincomb", C.c_int, [vp, i32, i32, i64, vp, C.POINTER(dbl), dbl, dbl, vp]),
+    ("cb200_k_level1_timed", C.c_int, [vp, i32, i32, i64, i32, C.POINTER(dbl)]),
     ("cb200_k_gemm_peak", C.c_int, [vp, i32, i32, i32, C.POINTER(dbl)]),
     ("cb200_k_fp64_peak", C.c_int, [vp, i32, i32, C.POINTER(dbl)]),
 ]

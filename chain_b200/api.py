@@ -512,6 +512,28 @@ class Bond:
         self.ctx.check(self.ctx.lib.cb200_bond_apply_blocks(self.h, ptr(x), ptr(y)))
         return y
 
+    def stage_bytes(self):
+        """Algorithmic HBM bytes of [L-stage GEMM, W(x)W mix, R-stage GEMM] of one product."""
+        by = (C.c_double * 3)()
+        self.ctx.check(self.ctx.lib.cb200_bond_stage_bytes(self.h, by))
+        return list(by)
+
+    def phi_blocks_slice(self):
+        """(begin, count): the contiguous slice of the block-packed vector this rank carries in apply_blocks_sharded."""
+        b, n = C.c_int64(), C.c_int64()
+        self.ctx.check(self.ctx.lib.cb200_bond_phi_blocks_slice(self.h, C.byref(b), C.byref(n)))
+        return b.value, n.value
+
+    def apply_blocks_sharded(self, x_slice, out=None):
+        """The product on a sharded context with only this rank's slice of the block-packed vectors crossing the host boundary."""
+        b, n = self.phi_blocks_slice()
+        x = np.ascontiguousarray(x_slice, dtype=self.dt)
+        if x.size != n:
+            raise ValueError("slice has %d elements, expected %d" % (x.size, n))
+        y = out if out is not None else np.zeros(max(n, 1), self.dt)[:n]
+        self.ctx.check(self.ctx.lib.cb200_bond_apply_blocks_sharded(self.h, ptr(x), ptr(y)))
+        return y
+
     def apply_timed(self, phi, reps=5, warmup=3):
         x = self._phi(phi)
         ms = C.c_double()
@@ -714,6 +736,14 @@ def k_gemm_peak(n=8192, reps=5, cplx=False, ctx=None):
     tf = C.c_double()
     ctx.check(ctx.lib.cb200_k_gemm_peak(ctx.h, 1 if cplx else 0, n, reps, C.byref(tf)))
     return tf.value
+
+
+def k_level1_timed(n, nv=3, cplx=False, reps=5, ctx=None):
+    """Mean device milliseconds of (multi_dot with nv vectors, lincomb with nv vectors, device copy) on n-element vectors."""
+    ctx = ctx or default_context()
+    ms = (C.c_double * 3)()
+    ctx.check(ctx.lib.cb200_k_level1_timed(ctx.h, 1 if cplx else 0, nv, n, reps, ms))
+    return list(ms)
 
 
 def k_fp64_peak(which=0, iters=20000, ctx=None):

@@ -61,6 +61,8 @@ void launch_gemm_peer(Backend*, bool cplx, int mode, const void* A, const void* 
 // barrier (bytes must fit one landing half; the engine chunks), or ncclBroadcast
 void shard_bcast_p2p(Backend*, void* buf, int64_t bytes, int root, int which);
 void nccl_bcast(Backend*, void* buf, int64_t bytes, int root);
+// all-gather in place: rank g holds the slice [g*chunk, min((g+1)*chunk, total)) of buf (chunk a multiple of 16 bytes) and ends up with all of it
+void shard_allgather_p2p(Backend*, void* buf, int64_t total_bytes, int64_t chunk_bytes, int which);
 // NCCL, loaded at run time (libnccl.so.2): unique id for rank 0, communicator, in-place sum all-reduce on the context stream
 int nccl_unique_id(Backend*, void* out128);
 int nccl_init(Backend*, const void* uid128, int rank, int world);

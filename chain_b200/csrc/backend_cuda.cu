@@ -391,6 +391,29 @@ void shard_bcast_p2p(Backend* b, void* buf, int64_t bytes, int root, int which) 
   if (b->rank != root) CB_CHECK(b, cudaMemcpyAsync(buf, shard_landing(b, which), (size_t)bytes, cudaMemcpyDeviceToDevice, b->stream));
 }
 
+// All-gather of a buffer whose slice [rank*chunk, min((rank+1)*chunk, total)) is valid on each rank: every rank pushes its slice into
+// every landing half `which` (own included) over NVLink, one flag barrier, then the peers' slices are copied out of the own landing half.
+void shard_allgather_p2p(Backend* b, void* buf, int64_t total_bytes, int64_t chunk_bytes, int which) {
+  if (b->world <= 1 || total_bytes <= 0) return;
+  if (total_bytes > b->landing_each || (chunk_bytes & 15)) { set_err(b, "shard_allgather_p2p: message larger than the landing area / chunk not 16-byte granular", cudaErrorInvalidValue); return; }
+  const int64_t off = std::min<int64_t>((int64_t)b->rank * chunk_bytes, total_bytes);
+  const int64_t mine = std::min<int64_t>(chunk_bytes, total_bytes - off);
+  if (mine > 0) {
+    PeerBases pb;
+    shard_peer_bases(b, which, &pb);
+    for (int r = 0; r < pb.n; ++r) pb.base[r] += off;
+    const long long n16 = (mine + 15) / 16;
+    const int blocks = (int)std::min<long long>((n16 + 255) / 256, 148 * 8);
+    peer_push_kernel<<<blocks, 256, 0, b->stream>>>(pb, (const uint4*)((const char*)buf + off), n16);
+    CB_LAUNCH_CHECK(b, "peer_push_kernel");
+  }
+  shard_barrier(b);
+  const char* land = (const char*)shard_landing(b, which);
+  if (off > 0) CB_CHECK(b, cudaMemcpyAsync(buf, land, (size_t)off, cudaMemcpyDeviceToDevice, b->stream));
+  if (off + mine < total_bytes)
+    CB_CHECK(b, cudaMemcpyAsync((char*)buf + off + mine, land + off + mine, (size_t)(total_bytes - off - mine), cudaMemcpyDeviceToDevice, b->stream));
+}
+
 void nccl_bcast(Backend* b, void* buf, int64_t bytes, int root) {
   if (!b->comm || !b->p_ncclBroadcast) { set_err(b, "nccl_bcast: no communicator", cudaErrorInvalidValue); return; }
   ncclResult_t r = b->p_ncclBroadcast(buf, buf, (size_t)bytes, ncclChar, root, b->comm, b->stream);

@@ -407,6 +407,58 @@ int cb200_bond_apply_blocks(cb200_bond* B, const void* phi_blocks, void* out_blo
   });
 }
 
+// slice of the block-packed vector that rank `rank` of `world` carries across PCIe in cb200_bond_apply_blocks_sharded
+static void phi_slice(const cb200_bond* B, int rank, int world, int64_t* begin, int64_t* count) {
+  const int64_t n = B->b.philay.total;
+  int64_t chunk = (n + world - 1) / world;
+  chunk = (chunk + 1) / 2 * 2;                              // 16-byte granular for f64 as well
+  *begin = std::min<int64_t>((int64_t)rank * chunk, n);
+  *count = std::min<int64_t>(chunk, n - *begin);
+}
+int cb200_bond_phi_blocks_slice(const cb200_bond* B, int64_t* begin, int64_t* count) {
+  if (!B || !begin || !count) return CB200_ERR_INVALID;
+  const ShardState& sh = B->ctx->c.shard;
+  phi_slice(B, sh.rank, sh.world, begin, count);
+  return CB200_OK;
+}
+
+int cb200_bond_apply_blocks_sharded(cb200_bond* B, const void* phi_slice_in, void* out_slice) {
+  if (!B || !phi_slice_in || !out_slice) return CB200_ERR_INVALID;
+  return guard(B->ctx, [&] {
+    Ctx* c = &B->ctx->c;
+    const ShardState& sh = c->shard;
+    if (sh.world > 1 && sh.mode == 0) fail(CB200_ERR_INVALID, "cb200_bond_apply_blocks_sharded needs an exchange mode (nccl or p2p)");
+    const size_t es = B->cplx ? 16 : 8;
+    const int64_t n = std::max<int64_t>(B->b.philay.total, 1);
+    int64_t b0, cnt;
+    phi_slice(B, sh.rank, sh.world, &b0, &cnt);
+    int64_t chunk = (B->b.philay.total + sh.world - 1) / sh.world;
+    chunk = (chunk + 1) / 2 * 2;
+    Buf x(c->be, (int64_t)es * n), y(c->be, (int64_t)es * n), stage(c->be, (int64_t)es * n);
+    std::vector<CopyTask> tin, tout;
+    if (phi_block_tasks(B->S, B->l, B->r, B->b.philay, true, &tin) != B->b.philay.total) fail(-2, "block-packed phi: element count does not match the charge structure");
+    phi_block_tasks(B->S, B->l, B->r, B->b.philay, false, &tout);
+    // rank g uploads ONLY its slice; the slices are all-gathered on the device side (NVLink peer stores or ncclBroadcast per root)
+    if (cnt > 0) dev_h2d(c->be, (char*)stage.p + es * (size_t)b0, phi_slice_in, es * (size_t)cnt);
+    if (sh.world > 1) {
+      if (sh.mode == 2) {
+        shard_allgather_p2p(c->be, stage.p, (int64_t)es * B->b.philay.total, (int64_t)es * chunk, c->shard.flip);
+        c->shard.flip ^= 1;
+      } else {
+        for (int g = 0; g < sh.world; ++g) {
+          const int64_t gb = std::min<int64_t>((int64_t)g * chunk, B->b.philay.total), gc = std::min<int64_t>(chunk, B->b.philay.total - gb);
+          if (gc > 0) nccl_bcast(c->be, (char*)stage.p + es * (size_t)gb, (int64_t)es * gc, g);
+        }
+      }
+    }
+    run_copy_tasks(c, B->cplx, tin, stage.p, x.p);
+    B->b.apply(x.p, y.p);
+    // every rank holds the whole product (the exchange is fused into the R-stage); each downloads its slice: the result crosses PCIe once
+    run_copy_tasks(c, B->cplx, tout, y.p, stage.p);
+    if (cnt > 0) dev_d2h(c->be, out_slice, (char*)stage.p + es * (size_t)b0, es * (size_t)cnt); else dev_sync(c->be);
+  });
+}
+
 int cb200_bond_apply_timed(cb200_bond* B, const void* phi, int32_t reps, int32_t warmup, double* ms_mean) {
   if (!B || !phi || !ms_mean || reps < 1) return CB200_ERR_INVALID;
   return guard(B->ctx, [&] {
@@ -437,6 +489,17 @@ int cb200_bond_stage_times(cb200_bond* B, const void* phi, int32_t reps, double*
     B->b.stage_times(x.p, y.p, reps, ms3);
     if (flops3) { flops3[0] = B->b.g1.flops; flops3[1] = B->b.mix.flops; flops3[2] = B->b.g2.flops; }
   });
+}
+
+int cb200_bond_stage_bytes(const cb200_bond* B, double* bytes3) {
+  if (!B || !bytes3) return CB200_ERR_INVALID;
+  // algorithmic HBM traffic of the three stages of one product: every operand read once, every result written once
+  const double es = B->cplx ? 16.0 : 8.0;
+  const double phi = (double)B->b.philay.total, t1 = (double)B->b.t1_elems, t2 = (double)B->b.t2_elems;
+  bytes3[0] = es * ((double)B->L.lay.total + phi + t1);
+  bytes3[1] = es * (t1 + t2);
+  bytes3[2] = es * (t2 + (double)B->R.lay.total + phi);
+  return CB200_OK;
 }
 
 int cb200_bond_update_timed(cb200_bond* B, const void* phi, int32_t dir, int32_t maxdim, double cutoff, int32_t niter,
@@ -689,6 +752,35 @@ int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const 
     for (int j = 0; j < nv; ++j) xs[j] = (const char*)dx.p + es * (size_t)n * j;
     lincomb(c->be, cx, nv, xs.data(), coef, beta_re, beta_im, dd.p, n);
     dev_d2h(c->be, dst, dd.p, es * n);
+  });
+}
+
+int cb200_k_level1_timed(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, int32_t reps, double* ms3) {
+  if (!ctx || !ms3 || nv < 1 || nv > MAX_LC || n < 1 || reps < 1) return CB200_ERR_INVALID;
+  return guard(ctx, [&] {
+    Ctx* c = &ctx->c;
+    const bool cx = dtype == 1;
+    const size_t es = cx ? 16 : 8;
+    Buf dx(c->be, (int64_t)es * n * nv, true), dy(c->be, (int64_t)es * n, true);
+    std::vector<const void*> xs(nv);
+    for (int j = 0; j < nv; ++j) xs[j] = (const char*)dx.p + es * (size_t)n * j;
+    std::vector<double> out(2 * (size_t)nv), coef(2 * (size_t)nv, 0.0);
+    for (int j = 0; j < nv; ++j) coef[2 * j] = 1e-3;
+    multi_dot(c->be, cx, nv, xs.data(), dy.p, n, out.data());                     // warm-up of all three
+    lincomb(c->be, cx, nv, xs.data(), coef.data(), 1.0, 0.0, dy.p, n);
+    dev_d2d(c->be, dy.p, dx.p, es * n);
+    dev_event_record(c->be, 0);
+    for (int r = 0; r < reps; ++r) multi_dot(c->be, cx, nv, xs.data(), dy.p, n, out.data());
+    dev_event_record(c->be, 1);
+    ms3[0] = dev_event_elapsed_ms(c->be, 0, 1) / reps;
+    dev_event_record(c->be, 0);
+    for (int r = 0; r < reps; ++r) lincomb(c->be, cx, nv, xs.data(), coef.data(), 1.0, 0.0, dy.p, n);
+    dev_event_record(c->be, 1);
+    ms3[1] = dev_event_elapsed_ms(c->be, 0, 1) / reps;
+    dev_event_record(c->be, 0);
+    for (int r = 0; r < reps; ++r) dev_d2d(c->be, dy.p, dx.p, es * n);
+    dev_event_record(c->be, 1);
+    ms3[2] = dev_event_elapsed_ms(c->be, 0, 1) / reps;
   });
 }
 

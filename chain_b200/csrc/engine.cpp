@@ -729,6 +729,9 @@ DavidsonResult davidson(Bond& b, void* phi, int niter) {
   const int maxiter = niter;
   const int actual_maxiter = (int)std::min<int64_t>(maxiter, n - 1);
   if (actual_maxiter + 1 > MAX_LC) fail(-2, "davidson: niter too large for this build (max " + std::to_string(MAX_LC - 1) + ")");
+  // exchange-free shard mode returns PARTIAL products (the caller sums the ranks' vectors): an eigensolver on them would be silently wrong
+  if (b.sharded && c->shard.mode == 0)
+    fail(-2, "davidson / dmrg on a context sharded with mode 'none' (no exchange): Bond::apply returns partial rows there; use mode nccl or p2p");
 
   double t0 = now_s();
   double nrm2 = norm2_dev(c, cx, phi, n);

@@ -283,6 +283,8 @@ void import_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const I
 void export_phi(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext);
 // block-packed ("QDense order") host layout of a phi-shaped tensor: see engine_io.cpp; phi_block_tasks returns the packed element count
 int64_t phi_block_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, bool to_internal, std::vector<CopyTask>* tasks);
+// one strided-copy launch over a task list (block offsets are assigned here)
+void run_copy_tasks(Ctx* c, bool cplx, std::vector<CopyTask>& tasks, const void* src, void* dst);
 void import_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* ext, void* dev);
 void export_phi_blocks(Ctx* c, bool cplx, const SiteInfo& S, const IndexMap& l, const IndexMap& r, const PhiLayout& pl, const void* dev, void* ext);
 

@@ -76,7 +76,7 @@ static void for_site3(const SiteInfo& S, const IndexMap& l, const IndexMap& r, c
     }
 }
 
-static void run_copy_tasks(Ctx* c, bool cplx, std::vector<CopyTask>& tasks, const void* src, void* dst);
+
 // Device-side (un)packing of a dense [x, s, y] site tensor: one strided-copy task per (sector of x, site value, sector of y),
 // sectors = maximal runs of equal charge label (internal order is a stable sort by charge, so a run is a contiguous internal
 // range).  Returns false when the labels are so interleaved that the task list would be longer than the host loop is slow.
@@ -318,7 +318,7 @@ static void phi_copy_tasks(const SiteInfo& S, const IndexMap& l, const IndexMap&
       }
     }
 }
-static void run_copy_tasks(Ctx* c, bool cplx, std::vector<CopyTask>& tasks, const void* src, void* dst) {
+void run_copy_tasks(Ctx* c, bool cplx, std::vector<CopyTask>& tasks, const void* src, void* dst) {
   if (tasks.empty()) return;
   const int epb = copy_elems_per_block();
   int blocks = 0;

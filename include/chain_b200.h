@@ -173,10 +173,18 @@ int cb200_bond_apply(cb200_bond* b, const void* phi, void* out);
 int64_t cb200_bond_phi_blocks_elems(const cb200_bond* b);
 int cb200_bond_phi_blocks(const cb200_bond* b, int32_t* nblocks, int64_t* offsets, int64_t* dims4 /* 4 per block */);
 int cb200_bond_apply_blocks(cb200_bond* b, const void* phi_blocks, void* out_blocks);
+/* The same product on a sharded context (cb200_shard_setup, world > 1) without redundant PCIe traffic: rank g passes only ITS contiguous
+ * slice [begin, begin+count) of the block-packed vector (cb200_bond_phi_blocks_slice), the slices are all-gathered between the GPUs
+ * (NVLink peer stores / ncclBroadcast), the row-sharded product runs, and rank g receives the same slice of the result -- the union of
+ * the ranks' out_slice buffers is the whole vector.  With world = 1 it is cb200_bond_apply_blocks. */
+int cb200_bond_phi_blocks_slice(const cb200_bond* b, int64_t* begin, int64_t* count);
+int cb200_bond_apply_blocks_sharded(cb200_bond* b, const void* phi_slice, void* out_slice);
 /* same product, device-resident, repeated `reps` times; returns mean milliseconds (CUDA events) */
 int cb200_bond_apply_timed(cb200_bond* b, const void* phi, int32_t reps, int32_t warmup, double* ms_mean);
 /* per-stage device time of the product (ms, mean of reps) and algorithmic flops: [0] L-stage GEMM, [1] W (x) W mix, [2] R-stage GEMM */
 int cb200_bond_stage_times(cb200_bond* b, const void* phi, int32_t reps, double* ms3, double* flops3);
+/* algorithmic HBM bytes of the same three stages (operands read once + result written once): the HBM-roofline numerator of the mix */
+int cb200_bond_stage_bytes(const cb200_bond* b, double* bytes3);
 /* one complete bond update resident on the device (davidson -> svdBond -> makeL/makeR), phase wall times in seconds:
  * [0] H_eff matvecs, [1] Davidson level-1, [2] truncation, [3] environment update */
 int cb200_bond_update_timed(cb200_bond* b, const void* phi, int32_t dir, int32_t maxdim, double cutoff, int32_t niter,
@@ -184,8 +192,10 @@ int cb200_bond_update_timed(cb200_bond* b, const void* phi, int32_t dir, int32_t
 /* itensor::davidson (MaxIter = niter): phi in/out (host), eigenvalue out */
 int cb200_bond_davidson(cb200_bond* b, void* phi, int32_t niter, double* eigenvalue, int32_t* nmatvec);
 /* MPS::svdBond: phi (host) -> A [Dl,d,m], B [m,d,Dr]; call with A=B=NULL first to get m and charges_mid
- * (caller-sized to min(Dl*d, d*Dr)), then again with buffers.  dir 0 Fromleft, 1 Fromright; use_svd != 0 selects
- * ITensor's "cutoff < 1e-12" branch (identical on this path: the SVD is always used). */
+ * (caller-sized to min(Dl*d, d*Dr)), then again with buffers.  dir 0 Fromleft, 1 Fromright.  Branch selection is ITensor's
+ * (MPS::svdBond): cutoff >= 1e-12 takes the denmatDecomp path (rho = phi phi^H, Hermitian eigensolver, truncate on the eigenvalues);
+ * cutoff < 1e-12 (noise is always 0 here) takes the true-SVD path, which resolves singular values down to eps*sigma_max instead of
+ * sqrt(eps)*sigma_max (one-sided Jacobi on the QR-reduced block; truncate applied to sigma^2). */
 int cb200_bond_truncate(cb200_bond* b, const void* phi, int32_t dir, int32_t maxdim, int32_t mindim, double cutoff,
                         int32_t* m, int32_t* charges_mid, double* truncerr, double* spectrum, void* A, void* B);
 /* LocalMPO::makeL / makeR: new environment from the bond's L (dir 0, uses A [Dl,d,m] and W1) or R (dir 1, B [m,d,Dr], W2);
@@ -215,6 +225,9 @@ int cb200_k_heig_batched(cb200_ctx* ctx, int32_t dtype, int32_t nprob, const int
 int cb200_k_dots(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const void* y, double* out_re_im);
 int cb200_k_lincomb(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, const void* x, const double* c_re_im, double beta_re,
                     double beta_im, void* dst);
+/* device-resident timing of the Davidson level-1 kernels on n-element vectors (HBM roofline entries of bench.py): mean milliseconds of
+ * [0] multi_dot with nv vectors ((nv+1) n elements read), [1] lincomb dst = dst + sum_j c_j x_j ((nv+1) n read, n written), [2] device copy */
+int cb200_k_level1_timed(cb200_ctx* ctx, int32_t dtype, int32_t nv, int64_t n, int32_t reps, double* ms3);
 /* FP64 calibration: achieved TFLOP/s of the DMMA GEMM kernel on a square problem (device-resident, CUDA events) */
 int cb200_k_gemm_peak(cb200_ctx* ctx, int32_t dtype, int32_t n, int32_t reps, double* tflops);
 /* FP64 pipe issue-rate loops without memory traffic: which 0 = DMMA.8x8x4 (mma.sync.m8n8k4.f64), 1 = DFMA */

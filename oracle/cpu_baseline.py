@@ -12,11 +12,54 @@ import time
 import numpy as np
 
 
-def host_threads():
+def host_cores():
     try:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """Set the BLAS pool to every host core this process may run on and return the thread count ACTUALLY in use.
+    torchrun exports OMP_NUM_THREADS=1 to its workers, which silently pinned OpenBLAS to one thread in round 1 while the line still
+    said `cores: 32`; the pool size is therefore set explicitly (threadpoolctl -> openblas_set_num_threads) and read back."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    threadpool_limits(limits=host_cores(), user_api="blas")
+    n = [i["num_threads"] for i in threadpool_info() if i.get("user_api") == "blas"]
+    return max(n) if n else 1
+
+
+def host_threads():
+    return use_all_host_threads()
+
+
+def eigh_seconds(n, cplx, seed=0):
+    """Wall time of LAPACK *syev / *heev (the driver ITensor's diagHermitian calls) on an n x n density-matrix-like input."""
+    import scipy.linalg as sla
+    use_all_host_threads()
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+    A = X @ X.conj().T
+    A /= np.trace(A).real
+    t0 = time.perf_counter()
+    sla.eigh(A, driver="ev", check_finite=False)
+    return time.perf_counter() - t0
+
+
+def sweep_estimate(matvec_flops_total, env_flops_total, block_sizes, cplx, gemm_tflops, n_meas_cap=None):
+    """CPU seconds of one sweep of the SAME workload the GPU sweep ran: the sweep's contraction flops at the CPU GEMM rate measured by
+    matvec_sample, plus one *syev / *heev per density-matrix block, timed at min(largest block, cap) and scaled with n^3.
+    block_sizes: the orders of all rho blocks of all bond updates of the sweep.  Returns dict(seconds, parts, how)."""
+    nmax = max(block_sizes) if block_sizes else 0
+    cap = n_meas_cap or (1200 if cplx else 1600)
+    nm = max(2, min(nmax, cap))
+    t_m = eigh_seconds(nm, cplx)
+    t_eig = sum(t_m * (n / nm) ** 3 for n in block_sizes)
+    t_gemm = (matvec_flops_total + env_flops_total) / (gemm_tflops * 1e12)
+    return dict(seconds=t_gemm + t_eig, contraction_s=t_gemm, eigensolver_s=t_eig,
+                how="EXTRAPOLATED: (matvec + environment flops of the sweep) / the CPU block-pair GEMM rate measured above + one LAPACK %s per "
+                    "rho block, timed at n=%d (%.2f s) and scaled with n^3 over the %d blocks of the sweep (largest n=%d)"
+                    % ("zheev" if cplx else "dsyev", nm, t_m, len(block_sizes), nmax))
 
 
 def block_pair_list(Dl, Dr, kl, kr, ds):
@@ -38,6 +81,7 @@ def block_pair_list(Dl, Dr, kl, kr, ds):
 def matvec_sample(Dl, Dr, kl, kr, ds, cplx, budget_s=15.0, seed=0):
     """Run block-pair GEMMs (with ITensor's explicit permute copy of one operand) until the time budget is used.
     Returns dict(tflops, seconds, flops, sample)."""
+    use_all_host_threads()
     rng = np.random.default_rng(seed)
     shapes = block_pair_list(Dl, Dr, kl, kr, ds)
     order = np.arange(len(shapes))

@@ -158,6 +158,9 @@ def check_bond_blocks(ctx, case, shuffle=False):
     assert np.abs(B.unpack(yb) - yo).max() <= 1e-12 * np.abs(yo).max()
     # bit-identical to the dense-boundary call (same device path, different (un)packing)
     assert np.array_equal(yb, B.pack(B.apply(phi)))
+    # unsharded context: the slice form carries the whole vector and is the same call
+    assert B.phi_blocks_slice() == (0, xb.size)
+    assert np.array_equal(B.apply_blocks_sharded(xb), yb)
     B.close()
 
 

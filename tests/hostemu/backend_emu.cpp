@@ -518,5 +518,6 @@ int nccl_init(Backend*, const void*, int, int) { return -1; }
 void nccl_allreduce_sum(Backend*, void*, int64_t) {}
 void shard_bcast_p2p(Backend*, void*, int64_t, int, int) {}
 void nccl_bcast(Backend*, void*, int64_t, int) {}
+void shard_allgather_p2p(Backend*, void*, int64_t, int64_t, int) {}
 
 }  // namespace cb200

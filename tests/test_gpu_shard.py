@@ -38,6 +38,13 @@ def _worker(rank, world, port, mode, q):
             for rep in range(3):                                              # both landing halves + reuse
                 got = B.apply(c["phi"] * (rep + 1))
                 out["%s rep%d" % (st, rep)] = (float(np.abs(got - (rep + 1) * want).max()), float(np.abs(want).max()))
+            # end-to-end form: each rank carries only its slice of the block-packed vector over PCIe (all-gather on the device side)
+            xb = B.pack(c["phi"])
+            b0, cnt = B.phi_blocks_slice()
+            wantb = B.pack(want)
+            for rep in range(2):
+                ys = B.apply_blocks_sharded(xb[b0:b0 + cnt] * (rep + 1))
+                out["%s slice rep%d" % (st, rep)] = (float(np.abs(ys - (rep + 1) * wantb[b0:b0 + cnt]).max()) if cnt else 0.0, float(np.abs(want).max()))
             ev, x, nmv = B.davidson(c["phi"], 2)
             evr, xr, _ = common.make_bond(ref, site, qk, c).davidson(c["phi"], 2)
             out["%s davidson" % st] = (abs(ev - evr), abs(evr))

@@ -99,3 +99,21 @@ def test_two_processes_gloo_allreduce():
         assert p.exitcode == 0
     for rank, err, scale in res:
         assert err <= 1e-12 * max(1.0, scale)
+
+
+def test_eigensolver_refuses_exchange_free_sharding(emu_ctx):
+    """ADVICE r1: with mode 'none' Bond::apply returns partial rows (the caller sums the ranks); davidson / dmrg on such a context
+    would compute Rayleigh quotients from partial vectors, so they must fail loudly instead."""
+    st, bc, n, cp, q, bond = common.BOND_CASES[0]
+    site, W, qk, c = common.capture_bond(st, bc, n, cp, q, bond)
+    ctx = cb.Context(lib_path=EMU_LIB)
+    ctx.shard(0, 2, mode="none", min_dim=0)
+    B = common.make_bond(ctx, site, qk, c)
+    with pytest.raises(cb.ChainB200Error):
+        B.davidson(c["phi"], 2)
+    B.close()
+    site, W, qk = common.build_model("golden", "p", 6, [-1.0])
+    H = cb.MPO(W, qk, site.charges, nq=1)
+    psi0 = common.to_cb(common.warm_start(site, W, 6, 0, seed=3))
+    with pytest.raises(cb.ChainB200Error):
+        cb.dmrg(H, [], psi0, cb.Sweeps(1, 20, 1e-8), ctx=ctx)

@@ -62,6 +62,20 @@ def link_profile(ss, n, D, qtot=0):
     return dims
 
 
+def rho_block_sizes(ss, dims):
+    """Orders of the density-matrix blocks of every bond update of one sweep (right half-sweep: rho over (l_{b-1}, s_b); left: over
+    (s_{b+1}, l_{b+1})), one block per charge of the middle link -- what the CPU baseline's eigensolver model needs."""
+    nq = ss.nq
+    sq = np.asarray(ss.charges)
+    n = len(dims) - 1
+    out = []
+    for b in range(1, n):                                  # bond (b, b+1), sites 1-based
+        left = [sum(int(dims[b - 1][ql]) for ql in range(nq) for s in sq if (ql + int(s)) % nq == q) for q in range(nq)]
+        right = [sum(int(dims[b + 1][qr]) for qr in range(nq) for s in sq if (qr - int(s)) % nq == q) for q in range(nq)]
+        out += [x for x in left if x > 0] + [x for x in right if x > 0]
+    return out
+
+
 def random_right_canonical(ss, n, D, cplx, seed):
     nq, d = ss.nq, ss.d
     sq = np.asarray(ss.charges)
