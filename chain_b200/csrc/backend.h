@@ -140,6 +140,41 @@ void launch_wy_t(Backend*, bool cplx, const void* S, const void* tau_j0, int nbk
 //     nb_last for the last block), tau is the whole tau array (block k starts at tau[64 k])
 void launch_wy_t_batched(Backend*, bool cplx, const void* S, const void* tau, int npanel, int nb_last, void* Tneg);
 
+// ---- two-stage reduction for large matrices: dense -> band (semi-bandwidth SB_B) with QR panels whose two-sided block updates run on
+// the DMMA GEMM kernel, then band -> tridiagonal by bulge chasing in ONE persistent kernel; both sets of reflectors are kept for the
+// back-transformation of the kept eigenvectors.  (The one-stage reduction above reads the whole trailing matrix once per reflector:
+// n^3/3 elements of HBM traffic, memory-bound by construction.)
+constexpr int SB_B = 64;            // semi-bandwidth of the intermediate band matrix = width of the QR panels
+constexpr int SB_LD = 2 * SB_B;     // leading dimension of the band storage: AB[(i - j) + j*SB_LD], 0 <= i - j < 2*SB_B (room for the bulge)
+constexpr int SB_VLD = 2 * SB_B;    // leading dimension of a block of bulge-chasing reflectors (window of SB_B + SB_B - 1 rows)
+// (1) Householder QR of the panel P = A[r0 : n, j0 : j0 + SB_B], r0 = j0 + SB_B, len = n - r0 >= 2 (A column-major, ld = n), in place: the
+//     panel is overwritten with R (rows <= columns) and zeros; Y (len x SB_B, ld = len) receives the kp = min(SB_B, len - 1) reflectors as
+//     explicit columns (unit diagonal, zeros above it, columns >= kp zero); Tn = -T and Tnh = -T/2 (SB_B x SB_B, ld SB_B, upper
+//     triangular, zero-padded) with H_0 ... H_{kp-1} = I - Y T Y^H.  A is then updated two-sidedly by the caller (GEMMs).
+void launch_panel_qr(Backend*, bool cplx, void* A, int64_t n, int64_t j0, void* Y, void* Tn, void* Tnh);
+// (2) AB = lower band of A (distances 0..SB_B), zero beyond
+void launch_band_extract(Backend*, bool cplx, const void* A, int64_t n, void* AB);
+// (3) band -> real symmetric tridiagonal (d[n], e[n-1]) by bulge chasing, for nprob independent matrices in one launch.  Sweep s
+//     (column s) consists of tasks k = 0, 1, ... acting on rows c0 = s + 1 + k*SB_B .. c0 + 2*SB_B - 1; task (s, k) waits for task
+//     (s-1, k+2) (progress counters prog[s], zero-initialised by the caller, n ints).  Reflector (s, k) (LAPACK larfg convention, explicit
+//     leading 1) is stored for the back-transformation in block blk = g*K0 - g(g-1)/2 + k  (g = s / SB_B, K0 = ceil((n-1)/SB_B)) of V2
+//     (SB_VLD x SB_B elements per block, zero-initialised by the caller), column s % SB_B, rows s % SB_B ...; tau2[blk*SB_B + s % SB_B].
+struct ChaseProblem {
+  void* AB;
+  int64_t n;
+  double* d;
+  double* e;
+  void* V2;
+  void* tau2;
+  int* prog;
+};
+int64_t chase_blocks(int64_t n);                       // number of reflector blocks of an n x n problem
+void launch_bulge_chase(Backend*, bool cplx, const ChaseProblem* probs, int nprob);
+// (4) Z <- Q2 Z for the n x m matrix Z (column-major, ld = n) with Q2 the product of the bulge-chasing reflectors (applied blockwise:
+//     sweep groups descending, k ascending inside a group, sweeps descending inside a block -- the order that respects every
+//     non-commuting pair)
+void launch_q2_apply(Backend*, bool cplx, const void* V2, const void* tau2, int64_t n, void* Z, int64_t m);
+
 // ITensor's truncate() evaluated on the device: pooled[n] (device, any order) is rank-sorted descending into sorted[n], then ONE
 // thread applies the rule of SURVEY App. A.5 verbatim (negative tail zeroed, maxdim, relative cutoff on the discarded weight,
 // degeneracy guard on docut).  out3 (device): [0] = m, [1] = truncerr, [2] = docut.

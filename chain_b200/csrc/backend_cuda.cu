@@ -19,6 +19,7 @@
 #include "backend.h"
 #include "gemm.cuh"
 #include "heig.cuh"
+#include "heig2.cuh"
 
 namespace cb200 {
 
@@ -1332,6 +1333,94 @@ void launch_wy_t(Backend* b, bool cplx, const void* S, const void* tau_j0, int n
   if (cplx) wy_t_kernel<true><<<1, 64, smem, b->stream>>>(S, tau_j0, nbk, Tneg);
   else wy_t_kernel<false><<<1, 64, smem, b->stream>>>(S, tau_j0, nbk, Tneg);
   CB_LAUNCH_CHECK(b, "wy_t_kernel");
+}
+
+// ---- two-stage reduction (heig2.cuh) ------------------------------------------------------------------------------------------
+static int sm_count(Backend* b) {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+  return std::max(1, sms);
+}
+static void opt_in_smem(const void* fn, size_t bytes) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+
+void launch_panel_qr(Backend* b, bool cplx, void* A, int64_t n, int64_t j0, void* Y, void* Tn, void* Tnh) {
+  const int64_t len = n - (j0 + SB_B);
+  if (len < 2) { set_err(b, "launch_panel_qr: panel with fewer than two rows", cudaErrorInvalidValue); return; }
+  const size_t es = cplx ? 16 : 8;
+  const int rmax = cplx ? PQ_MAXROWS_CPLX : PQ_MAXROWS_REAL;
+  const void* fn = cplx ? (const void*)panel_qr_kernel<true> : (const void*)panel_qr_kernel<false>;
+  opt_in_smem(fn, cplx ? pq_smem_bytes<true>(rmax) : pq_smem_bytes<false>(rmax));     // per device; cheap
+  const int cap = sm_count(b);                                                           // 1 CTA per SM (launch bounds), co-resident
+  int nblk = (int)std::min<int64_t>(cap, std::max<int64_t>(1, (len + 63) / 64));
+  int R = (int)((len + nblk - 1) / nblk);
+  if (R > rmax) { nblk = (int)((len + rmax - 1) / rmax); R = (int)((len + nblk - 1) / nblk); }
+  if (nblk > cap) { set_err(b, "launch_panel_qr: matrix too large for the co-resident panel kernel", cudaErrorInvalidValue); return; }
+  const size_t smem = cplx ? pq_smem_bytes<true>(R) : pq_smem_bytes<false>(R);
+  char* scratch = (char*)dev_alloc(b, es * (2 * (size_t)nblk * SB_B + 2 * SB_B));
+  if (!scratch) return;
+  void* part = scratch;
+  void* rowc = scratch + es * 2 * (size_t)nblk * SB_B;
+  long long nn = n, jj = j0;
+  void* args[] = {&A, &nn, &jj, &R, &Y, &Tn, &Tnh, &part, &rowc};
+  CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(nblk), dim3(PQ_THREADS), args, smem, b->stream));
+  CB_LAUNCH_CHECK(b, "panel_qr_kernel");
+  dev_free(b, scratch);
+}
+
+void launch_band_extract(Backend* b, bool cplx, const void* A, int64_t n, void* AB) {
+  const int blocks = (int)std::min<int64_t>((n * SB_LD + 255) / 256, 148 * 16);
+  if (cplx) band_extract_kernel<true><<<blocks, 256, 0, b->stream>>>(A, n, AB);
+  else band_extract_kernel<false><<<blocks, 256, 0, b->stream>>>(A, n, AB);
+  CB_LAUNCH_CHECK(b, "band_extract_kernel");
+}
+
+int64_t chase_blocks(int64_t n) {
+  const int64_t K0 = (n - 1 + SB_B - 1) / SB_B;
+  return std::max<int64_t>(K0 * (K0 + 1) / 2, 1);
+}
+
+void launch_bulge_chase(Backend* b, bool cplx, const ChaseProblem* probs, int nprob) {
+  if (nprob <= 0) return;
+  std::vector<ChaseDesc> descs(nprob);
+  int64_t max_sweeps = 0;
+  for (int p = 0; p < nprob; ++p) {
+    descs[p] = ChaseDesc{probs[p].AB, (long long)probs[p].n, probs[p].d, probs[p].e, probs[p].V2, probs[p].tau2, probs[p].prog};
+    max_sweeps = std::max<int64_t>(max_sweeps, probs[p].n - 1);
+  }
+  if (max_sweeps <= 0) return;
+  const void* fn = cplx ? (const void*)bulge_chase_kernel<true> : (const void*)bulge_chase_kernel<false>;
+  const size_t smem = cplx ? bc_smem_bytes<true>() : bc_smem_bytes<false>();
+  opt_in_smem(fn, smem);
+  int per_sm = 0;
+  CB_CHECK(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BC_THREADS, smem));
+  const int64_t cap = (int64_t)std::max(1, per_sm) * sm_count(b);
+  // at most ~n/(3 SB_B) sweeps of one matrix are in flight at a time (each waits for its predecessor to be three tasks ahead)
+  int64_t useful = 0;
+  for (int p = 0; p < nprob; ++p) useful += probs[p].n / (3 * SB_B) + 2;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cap, std::min<int64_t>(useful, max_sweeps * nprob)));
+  char* scratch = (char*)dev_alloc(b, sizeof(ChaseDesc) * (size_t)nprob + 64);
+  if (!scratch) return;
+  dev_memset0(b, scratch, 64);
+  dev_h2d(b, scratch + 64, descs.data(), sizeof(ChaseDesc) * (size_t)nprob);
+  const ChaseDesc* dp = (const ChaseDesc*)(scratch + 64);
+  unsigned long long* ticket = (unsigned long long*)scratch;
+  long long ms = max_sweeps;
+  int np = nprob;
+  void* args[] = {(void*)&dp, &np, &ms, &ticket};
+  CB_CHECK(b, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(BC_THREADS), args, smem, b->stream));
+  CB_LAUNCH_CHECK(b, "bulge_chase_kernel");
+  dev_free(b, scratch);
+}
+
+void launch_q2_apply(Backend* b, bool cplx, const void* V2, const void* tau2, int64_t n, void* Z, int64_t m) {
+  if (n < 2 || m <= 0) return;
+  const void* fn = cplx ? (const void*)q2_apply_kernel<true> : (const void*)q2_apply_kernel<false>;
+  const size_t smem = cplx ? q2_smem_bytes<true>() : q2_smem_bytes<false>();
+  opt_in_smem(fn, smem);
+  const int grid = (int)((m + Q2_NC - 1) / Q2_NC);
+  if (cplx) q2_apply_kernel<true><<<grid, Q2_THREADS, smem, b->stream>>>(V2, tau2, n, Z, m);
+  else q2_apply_kernel<false><<<grid, Q2_THREADS, smem, b->stream>>>(V2, tau2, n, Z, m);
+  CB_LAUNCH_CHECK(b, "q2_apply_kernel");
 }
 
 void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* sorted,

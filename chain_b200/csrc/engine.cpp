@@ -1011,6 +1011,123 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
 }
 
 // ------------------------------------------------------------------------------------------------ Hermitian eigensolver
+static int64_t two_stage_min_n() {   // matrices at least this large take the two-stage reduction (CB200_TWOSTAGE_MIN_N; 0 = never)
+  const char* e = getenv("CB200_TWOSTAGE_MIN_N");      // read per call (cheap): tests switch the path inside one process
+  return e ? atoll(e) : (int64_t)1536;
+}
+static bool use_two_stage(int64_t n) { return two_stage_min_n() > 0 && n >= std::max<int64_t>(two_stage_min_n(), 4 * SB_B); }
+
+// Stage 1 of the two-stage reduction: A (Hermitian, both triangles, consumed) -> band matrix of semi-bandwidth SB_B.
+// Per panel: Householder QR of the block below the band (launch_panel_qr), then the two-sided update of the trailing matrix
+//   A22 <- Q^H A22 Q = A22 - W Y^H - Y W^H,   W = X - 1/2 Y (T^H Y^H X),  X = A22 Y T
+// as five launches of the DMMA GEMM kernel (the n^3 work: A22 Y and the rank-2b update).  Everything is kept negated (Tn = -T,
+// Wn = -W) so that the update is a pure accumulation.
+static void sb_stage1(Ctx* c, Heig& h) {
+  Backend* be = c->be;
+  const bool cx = h.cplx;
+  const size_t es = esz(cx);
+  const int64_t n = h.n;
+  const int B = SB_B;
+  h.npan = 0;
+  h.yoff.assign(1, 0);
+  for (int64_t j0 = 0; n - (j0 + B) >= 2; j0 += B) { h.yoff.push_back(h.yoff.back() + (n - (j0 + B)) * B); ++h.npan; }
+  const int npan = h.npan;
+  const int PMAX = 8;
+  const int64_t len0 = n - B;
+  // arena: [Y panels | X (len0 x B) | W0 partials (PMAX x len0 x B) | S2 partials (PMAX x B x B) | Mm (B x B)]
+  const int64_t oX = h.yoff[npan], oW0 = oX + len0 * B, oS2 = oW0 + (int64_t)PMAX * len0 * B, oM = oS2 + (int64_t)PMAX * B * B, tot = oM + B * B;
+  h.Yall = Buf(be, (int64_t)es * tot);
+  h.Tall = Buf(be, (int64_t)es * 2 * std::max(npan, 1) * B * B);
+  const int64_t oTh = (int64_t)npan * B * B;
+  const int narrow = cx ? GEMM_TILE_NARROW_3M : GEMM_TILE_NARROW;
+  const uint32_t cj = cx ? (uint32_t)GEMM_CONJ_A : 0u;
+  for (int p = 0; p < npan; ++p) {
+    const int64_t j0 = (int64_t)p * B, r0 = j0 + B, len = n - r0;
+    const int64_t oY = h.yoff[p], oT = (int64_t)p * B * B;
+    launch_panel_qr(be, cx, h.A.p, n, j0, (char*)h.Yall.p + es * (size_t)oY, (char*)h.Tall.p + es * (size_t)oT, (char*)h.Tall.p + es * (size_t)(oTh + oT));
+    const int64_t a22 = r0 + r0 * n;
+    // split K so that the skinny products fill the machine: tiles(len/128) x P ~ 2 waves
+    const int tm = gemm_tile_m(cx);
+    const int64_t tiles = (len + tm - 1) / tm;
+    const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, std::min<int64_t>((296 + tiles - 1) / tiles, len / 256)));
+    const int64_t chunk = ((len + P - 1) / P + 15) / 16 * 16;
+    GemmPlan p_w0, p_x, p_s2, p_m, p_wn, p_up;
+    {   // W0_pp = A22[:, k-range] * Y[k-range, :]
+      GemmBuilder g(cx, narrow);
+      for (int pp = 0; pp < P; ++pp) {
+        const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+        if (kn <= 0) break;
+        g.begin(oW0 + (int64_t)pp * len * B, len, len, B, 0);
+        g.seg(a22 + k0 * n, n, oY + k0, len, kn);
+        g.end();
+      }
+      g.finish(be, p_w0, false, false);
+    }
+    const int np = p_w0.tasks.n;
+    {   // X' = sum_pp W0_pp * Tn
+      GemmBuilder g(cx, GEMM_TILE_NARROW);
+      g.begin(oX, len, len, B, 0);
+      for (int pp = 0; pp < np; ++pp) g.seg(oW0 + (int64_t)pp * len * B, len, oT, B, B);
+      g.end();
+      g.finish(be, p_x, false, false);
+    }
+    {   // S2'_pp = Y[k-range]^H X'[k-range]
+      GemmBuilder g(cx, GEMM_TILE_NARROW);
+      for (int pp = 0; pp < np; ++pp) {
+        const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+        g.begin(oS2 + (int64_t)pp * B * B, B, B, B, GEMM_TRANS_A | cj);
+        g.seg(oY + k0, len, oX + k0, len, kn);
+        g.end();
+      }
+      g.finish(be, p_s2, true, false);
+    }
+    {   // Mm = sum_pp Tnh^H S2'_pp  ( = 1/2 T^H Y^H X )
+      GemmBuilder g(cx, GEMM_TILE_NARROW);
+      g.begin(oM, B, B, B, GEMM_TRANS_A | cj);
+      for (int pp = 0; pp < np; ++pp) g.seg(oTh + oT, B, oS2 + (int64_t)pp * B * B, B, B);
+      g.end();
+      g.finish(be, p_m, true, false);
+    }
+    {   // Wn = X' + Y Mm
+      GemmBuilder g(cx, GEMM_TILE_NARROW);
+      g.begin(oX, len, len, B, GEMM_ACCUM);
+      g.seg(oY, len, oM, B, B);
+      g.end();
+      g.finish(be, p_wn, false, false);
+    }
+    {   // A22 += Wn Y^H + Y Wn^H   (complex: conj(conj(Wn) Y^T + conj(Y) Wn^T))
+      GemmBuilder g(cx, heavy_mode(cx));
+      g.begin(a22, n, len, len, GEMM_ACCUM | (cx ? (uint32_t)(GEMM_CONJ_A | GEMM_CONJ_OUT) : 0u));
+      g.seg(oX, len, oY, len, B);
+      g.seg(oY, len, oX, len, B);
+      g.end();
+      g.finish(be, p_up, false, true);
+    }
+    run_gemm(c, cx, p_w0, h.A.p, h.Yall.p, h.Yall.p);
+    run_gemm(c, cx, p_x, h.Yall.p, h.Tall.p, h.Yall.p);
+    run_gemm(c, cx, p_s2, h.Yall.p, h.Yall.p, h.Yall.p);
+    run_gemm(c, cx, p_m, h.Tall.p, h.Yall.p, h.Yall.p);
+    run_gemm(c, cx, p_wn, h.Yall.p, h.Yall.p, h.Yall.p);
+    run_gemm(c, cx, p_up, h.Yall.p, h.Yall.p, h.A.p);
+  }
+  h.AB = Buf(be, (int64_t)es * SB_LD * n);
+  launch_band_extract(be, cx, h.A.p, n, h.AB.p);
+  h.A = Buf();                                              // the dense matrix is not needed any more
+  const int64_t nblk = chase_blocks(n);
+  h.V2 = Buf(be, (int64_t)es * nblk * SB_VLD * B, true);
+  h.tau2 = Buf(be, (int64_t)es * nblk * B, true);
+  h.prog = Buf(be, 4 * std::max<int64_t>(n, 1), true);
+  h.two_stage = true;
+}
+
+// stage 2 for one or several matrices (the charge blocks of one bond chase their bulges side by side in one launch)
+static void sb_stage2(Ctx* c, bool cplx, const std::vector<Heig*>& hs) {
+  std::vector<ChaseProblem> probs;
+  for (Heig* h : hs)
+    if (h->two_stage) probs.push_back(ChaseProblem{h->AB.p, h->n, (double*)h->d.p, (double*)h->e.p, h->V2.p, h->tau2.p, (int*)h->prog.p});
+  if (!probs.empty()) launch_bulge_chase(c->be, cplx, probs.data(), (int)probs.size());
+}
+
 bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   Backend* be = c->be;
   const size_t es = esz(cplx);
@@ -1020,8 +1137,13 @@ bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
   h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
   h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
-  Buf p(be, (int64_t)es * std::max<int64_t>(n, 1));
-  if (!launch_tridiag(be, cplx, h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, p.p)) return false;
+  if (use_two_stage(n)) {
+    sb_stage1(c, h);
+    sb_stage2(c, cplx, {&h});
+  } else {
+    Buf p(be, (int64_t)es * std::max<int64_t>(n, 1));
+    if (!launch_tridiag(be, cplx, h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, p.p)) return false;
+  }
   h.wdev = Buf(be, 8 * std::max<int64_t>(n, 1));
   launch_bisect(be, (const double*)h.d.p, (const double*)h.e.p, n, (double*)h.wdev.p);
   h.w.resize(n);
@@ -1036,7 +1158,7 @@ bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vec
   const size_t es = esz(cplx);
   const int np = (int)hs.size();
   std::vector<Buf> pw(np);
-  std::vector<TriProblem> probs(np);
+  std::vector<TriProblem> probs;
   for (int k = 0; k < np; ++k) {
     Heig& h = *hs[k];
     const int64_t n = ns[k];
@@ -1046,10 +1168,12 @@ bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vec
     h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
     h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
     h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
+    if (use_two_stage(n)) { sb_stage1(c, h); continue; }
     pw[k] = Buf(be, (int64_t)es * std::max<int64_t>(n, 1));
-    probs[k] = TriProblem{h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, pw[k].p};
+    probs.push_back(TriProblem{h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, pw[k].p});
   }
-  if (!launch_tridiag_batched(be, cplx, probs.data(), np)) return false;
+  sb_stage2(c, cplx, hs);
+  if (!probs.empty() && !launch_tridiag_batched(be, cplx, probs.data(), (int)probs.size())) return false;
   for (int k = 0; k < np; ++k) {
     Heig& h = *hs[k];
     h.wdev = Buf(be, 8 * std::max<int64_t>(h.n, 1));
@@ -1119,7 +1243,58 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
   }
   h.ns_iters = it;
   Buf V(be, (int64_t)es * n * m);
-  if (n < wy_min_n()) {
+  if (h.two_stage) {
+    // eigenvectors of A = Q1 Q2 z:  Q2 = bulge-chasing reflectors (blockwise, launch_q2_apply), Q1 = the QR panels of stage 1 in compact WY
+    const bool cx = h.cplx;
+    const int B = SB_B;
+    launch_zt_to_v(be, cx, (const double*)zc, n, m, V.p);
+    launch_q2_apply(be, cx, h.V2.p, h.tau2.p, n, V.p, m);
+    const int npan = h.npan;
+    if (npan > 0) {
+      // YTn_p = Y_p (-T_p) for all panels in one grouped launch
+      Buf YT(be, (int64_t)es * h.yoff[npan]);
+      {
+        GemmBuilder g(cx, GEMM_TILE_NARROW);
+        for (int p = 0; p < npan; ++p) {
+          const int64_t len = n - ((int64_t)p * B + B);
+          g.begin(h.yoff[p], len, len, B, 0);
+          g.seg(h.yoff[p], len, (int64_t)p * B * B, B, B);
+          g.end();
+        }
+        GemmPlan pl;
+        g.finish(be, pl, false, false);
+        run_gemm(c, cx, pl, h.Yall.p, h.Tall.p, YT.p);
+      }
+      const int PMAX = 8;
+      Buf W1p(be, (int64_t)es * B * m * PMAX);
+      for (int p = npan - 1; p >= 0; --p) {
+        const int64_t r0 = (int64_t)p * B + B, len = n - r0;
+        const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, len / 256));
+        const int64_t chunk = ((len + P - 1) / P + 15) / 16 * 16;
+        GemmPlan pw1, pz;
+        {
+          GemmBuilder g1(cx);
+          for (int pp = 0; pp < P; ++pp) {
+            const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+            if (kn <= 0) break;
+            g1.begin((int64_t)pp * B * m, B, B, m, GEMM_TRANS_A | (cx ? (uint32_t)GEMM_CONJ_A : 0u));
+            g1.seg(h.yoff[p] + k0, len, r0 + k0, n, kn);
+            g1.end();
+          }
+          g1.finish(be, pw1, true, false);
+        }
+        {
+          GemmBuilder g(cx);
+          g.begin(r0, n, len, m, GEMM_ACCUM);
+          for (int pp = 0; pp < pw1.tasks.n; ++pp) g.seg(h.yoff[p], len, (int64_t)pp * B * m, B, B);
+          g.end();
+          g.finish(be, pz, false, false);
+        }
+        run_gemm(c, cx, pw1, h.Yall.p, V.p, W1p.p);
+        run_gemm(c, cx, pz, YT.p, W1p.p, V.p);
+      }
+    }
+  } else if (n < wy_min_n()) {
     launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
   } else if (wy_upfront()) {
     // Q Z = B_0 (B_1 (... (B_last Z))) with B_k = H_j0 ... H_{j0+nb-1} = I - Y_k T_k Y_k^H (compact WY) on the DMMA kernel.

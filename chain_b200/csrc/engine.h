@@ -262,6 +262,12 @@ struct Heig {
   int64_t n = 0;
   bool cplx = false;
   Buf A, d, e, tau, scl;
+  // two-stage reduction (n >= two_stage_min_n): A -> band (QR panels Y_p, compact-WY factors) -> tridiagonal (bulge-chasing reflectors V2)
+  bool two_stage = false;
+  int npan = 0;
+  std::vector<int64_t> yoff;  // element offset of Y_p (len_p x SB_B, ld len_p) inside Yall
+  Buf Yall, Tall;             // Tall: [npan x SB_B^2 of -T][npan x SB_B^2 of -T/2]
+  Buf AB, V2, tau2, prog;
   Buf wdev;                   // all eigenvalues on the device, ASCENDING (bisection order)
   std::vector<double> w;      // all eigenvalues, descending (host copy: shifts of the inverse iteration, spectrum output)
   int ns_iters = 0;

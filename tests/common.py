@@ -354,3 +354,30 @@ def check_packed_mps_boundary(ctx, case, shuffle=False):
         e3, x3 = cb.dmrg(H, [], pr, sw, ctx=ctx)
         e4, x4 = cb.dmrg(H, [], cb.PackedMPS.from_dense(pr, sq), sw, ctx=ctx)
         assert e3 == e4 and all(np.array_equal(a, b) for a, b in zip(x4.to_dense().sites, x3.sites))
+
+
+TWO_STAGE_SIZES = [(300, 120), (257, 257), (449, 60), (641, 200)]
+
+
+def check_heig_two_stage(ctx, cplx, n, m, monkeypatch):
+    """The two-stage reduction (dense -> band by QR panels + GEMM block updates, band -> tridiagonal by bulge chasing, back-transformation
+    through the chasing reflectors and the compact-WY panels) forced on at a small size, against numpy.eigh."""
+    monkeypatch.setenv("CB200_TWOSTAGE_MIN_N", "256")
+    rng = np.random.default_rng(n * 3 + m + cplx)
+    X = (rng.standard_normal((n + 5, n)) + (1j * rng.standard_normal((n + 5, n)) if cplx else 0)) * (10.0 ** (-0.04 * np.arange(n)))
+    X[:, 7] = X[:, 3]                                                      # an exactly rank-deficient direction
+    A = X.conj().T @ X
+    A /= np.trace(A).real
+    w, V, it = cb.k_heig(A, m, ctx=ctx)
+    ev = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(w - ev).max() <= 1e-14 * np.sqrt(n)
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
+    assert np.abs(A @ V - V @ (V.conj().T @ A @ V)).max() <= 2e-14 * np.sqrt(n)
+    assert np.abs(np.sort(np.linalg.eigvalsh(V.conj().T @ A @ V))[::-1] - ev[:m]).max() <= 1e-14 * np.sqrt(n)
+    # batched form: two-stage and one-stage matrices in the same call (the bulges of all two-stage blocks are chased in one launch)
+    out = cb.k_heig_batched([A, A[:200, :200].copy(), A + 0.01 * np.eye(n)], [m, 50, m], ctx=ctx)
+    assert np.abs(out[0][0] - ev).max() <= 1e-14 * np.sqrt(n)
+    assert np.abs(out[2][0] - (ev + 0.01)).max() <= 1e-13 * np.sqrt(n)
+    for (wi, Vi), Ai in zip(out, [A, A[:200, :200], A + 0.01 * np.eye(n)]):
+        assert np.abs(Vi.conj().T @ Vi - np.eye(Vi.shape[1])).max() <= 1e-13
+        assert np.abs(Ai @ Vi - Vi @ (Vi.conj().T @ Ai @ Vi)).max() <= 2e-14 * np.sqrt(n)

@@ -471,6 +471,195 @@ void launch_wy_t_batched(Backend* b, bool cplx, const void* S, const void* tau, 
                 (char*)Tneg + es * 4096 * (size_t)k);
 }
 
+// ---- two-stage reduction (serial restatement of the device algorithm in heig2.cuh: same formulas, same storage conventions)
+template <class T>
+static void larfg_t(int64_t len, T* x, T* tau_out, double* beta_out) {      // x[0] = alpha; on exit x = v with v[0] = 1
+  const T alpha = x[0];
+  double sigma = 0;
+  for (int64_t i = 1; i < len; ++i) sigma += re_(x[i]) * re_(x[i]) + im_(x[i]) * im_(x[i]);
+  const double ar = re_(alpha), ai = im_(alpha);
+  if (sigma == 0.0 && ai == 0.0) { *tau_out = T(0); *beta_out = ar; x[0] = T(1); for (int64_t i = 1; i < len; ++i) x[i] = T(0); return; }
+  const double beta = -std::copysign(std::sqrt(ar * ar + ai * ai + sigma), ar);
+  *tau_out = mk<T>((beta - ar) / beta, -ai / beta);
+  const T sc = T(1) / (alpha - T(beta));
+  for (int64_t i = 1; i < len; ++i) x[i] *= sc;
+  x[0] = T(1);
+  *beta_out = beta;
+}
+
+template <class T>
+static void panel_qr_t(T* A, int64_t n, int64_t j0, T* Y, T* Tn, T* Tnh) {
+  const int B = SB_B;
+  const int64_t r0 = j0 + B, len = n - r0;
+  const int kp = (int)std::min<int64_t>(B, len - 1);
+  std::vector<T> P((size_t)len * B), Tm((size_t)B * B, T(0)), tau(B, T(0));
+  for (int c = 0; c < B; ++c) for (int64_t r = 0; r < len; ++r) P[r + (size_t)c * len] = A[(r0 + r) + (j0 + c) * n];
+  for (int c = 0; c < kp; ++c) {
+    T* x = &P[c + (size_t)c * len];
+    double beta;
+    larfg_t<T>(len - c, x, &tau[c], &beta);
+    // apply H_c^H = I - conj(tau) v v^H to the columns to the right
+    for (int j = c + 1; j < B; ++j) {
+      T* pj = &P[c + (size_t)j * len];
+      T sdot(0);
+      for (int64_t r = 0; r < len - c; ++r) sdot += cj(x[r]) * pj[r];
+      sdot *= cj(tau[c]);
+      for (int64_t r = 0; r < len - c; ++r) pj[r] -= sdot * x[r];
+    }
+    // T(0:c, c) = -tau_c T(0:c,0:c) (Y(:,0:c)^H v_c),  T(c,c) = tau_c     (LAPACK larft, forward / columnwise)
+    std::vector<T> z(c, T(0));
+    for (int k = 0; k < c; ++k) {
+      const T* yk = &P[(size_t)k * len];     // column k holds v_k below its diagonal (explicit 1 at row k)
+      T acc(0);
+      for (int64_t r = c; r < len; ++r) acc += cj(yk[r]) * P[r + (size_t)c * len];
+      z[k] = acc;
+    }
+    for (int r = 0; r < c; ++r) {
+      T acc(0);
+      for (int k = r; k < c; ++k) acc += Tm[r + (size_t)k * B] * z[k];
+      Tm[r + (size_t)c * B] = -tau[c] * acc;
+    }
+    Tm[c + (size_t)c * B] = tau[c];
+    // keep beta aside: the diagonal slot currently holds the explicit 1 of v_c
+    A[(r0 + c) + (j0 + c) * n] = T(beta);
+  }
+  // outputs: Y explicit, R into A (rows <= columns; diagonal of reflector columns already written), zeros below
+  for (int c = 0; c < B; ++c)
+    for (int64_t r = 0; r < len; ++r) {
+      T y(0);
+      if (c < kp && r >= c) y = P[r + (size_t)c * len];
+      Y[r + (size_t)c * len] = y;
+      T a;
+      if (r < c) a = P[r + (size_t)c * len];
+      else if (r == c) a = (c < kp) ? A[(r0 + r) + (j0 + c) * n] : P[r + (size_t)c * len];
+      else a = (c < kp) ? T(0) : P[r + (size_t)c * len];
+      A[(r0 + r) + (j0 + c) * n] = a;
+    }
+  for (size_t k = 0; k < Tm.size(); ++k) { Tn[k] = -Tm[k]; Tnh[k] = T(-0.5) * Tm[k]; }
+}
+void launch_panel_qr(Backend* b, bool cplx, void* A, int64_t n, int64_t j0, void* Y, void* Tn, void* Tnh) {
+  b->launches++;
+  if (cplx) panel_qr_t<cd>((cd*)A, n, j0, (cd*)Y, (cd*)Tn, (cd*)Tnh); else panel_qr_t<double>((double*)A, n, j0, (double*)Y, (double*)Tn, (double*)Tnh);
+}
+
+template <class T>
+static void band_extract_t(const T* A, int64_t n, T* AB) {
+  for (int64_t j = 0; j < n; ++j)
+    for (int dd = 0; dd < SB_LD; ++dd) {
+      const int64_t i = j + dd;
+      AB[dd + j * SB_LD] = (dd <= SB_B && i < n) ? A[i + j * n] : T(0);
+    }
+}
+void launch_band_extract(Backend* b, bool cplx, const void* A, int64_t n, void* AB) {
+  b->launches++;
+  if (cplx) band_extract_t<cd>((const cd*)A, n, (cd*)AB); else band_extract_t<double>((const double*)A, n, (double*)AB);
+}
+
+int64_t chase_blocks(int64_t n) {
+  const int64_t K0 = (n - 1 + SB_B - 1) / SB_B;
+  return std::max<int64_t>(K0 * (K0 + 1) / 2, 1);
+}
+
+template <class T>
+static void bulge_chase_t(T* AB, int64_t n, double* d, double* e, T* V2, T* tau2) {
+  const int B = SB_B;
+  const int64_t K0 = (n - 1 + B - 1) / B;
+  auto el = [&](int64_t i, int64_t j) -> T& { return AB[(i - j) + j * SB_LD]; };     // i >= j, i - j < SB_LD
+  std::vector<T> D((size_t)B * B), Bk((size_t)B * B), v(B), vn(B), w(B), z(B), y(B);
+  for (int64_t s = 0; s + 1 < n; ++s) {
+    const int64_t g = s / B, sp = s % B;
+    T tau(0);
+    for (int64_t k = 0;; ++k) {
+      const int64_t c0 = s + 1 + k * B;
+      if (c0 > n - 1) break;
+      const int nd = (int)std::min<int64_t>(B, n - c0);
+      const int nb2 = (int)std::max<int64_t>(0, std::min<int64_t>(B, n - c0 - B));
+      if (k == 0) {
+        d[s] = re_(el(s, s));
+        for (int i = 0; i < nd; ++i) v[i] = el(c0 + i, s);
+        double beta;
+        larfg_t<T>(nd, v.data(), &tau, &beta);
+        e[s] = beta;
+        el(c0, s) = T(beta);
+        for (int i = 1; i < nd; ++i) el(c0 + i, s) = T(0);
+      }
+      // store the reflector for the back-transformation
+      {
+        const int64_t blk = g * K0 - g * (g - 1) / 2 + k;
+        T* dst = V2 + blk * (int64_t)SB_VLD * B + sp * (int64_t)SB_VLD + sp;
+        for (int i = 0; i < nd; ++i) dst[i] = v[i];
+        tau2[blk * B + sp] = tau;
+      }
+      // D <- H^H D H  (Hermitian nd x nd, lower triangle stored)
+      for (int j = 0; j < nd; ++j) for (int i = 0; i < nd; ++i) D[i + (size_t)j * B] = (i >= j) ? el(c0 + i, c0 + j) : cj(el(c0 + j, c0 + i));
+      for (int i = 0; i < nd; ++i) { T acc(0); for (int j = 0; j < nd; ++j) acc += D[i + (size_t)j * B] * v[j]; w[i] = tau * acc; }
+      T vp(0);
+      for (int i = 0; i < nd; ++i) vp += cj(v[i]) * w[i];
+      const T a2 = T(-0.5) * cj(tau) * vp;
+      for (int i = 0; i < nd; ++i) w[i] += a2 * v[i];
+      for (int j = 0; j < nd; ++j) for (int i = j; i < nd; ++i) el(c0 + i, c0 + j) = D[i + (size_t)j * B] - v[i] * cj(w[j]) - w[i] * cj(v[j]);
+      if (nb2 <= 0) {
+        if (c0 + nd == n && nd == 1) { /* 1 x 1 trailing block: unchanged by a unitary 1 x 1 similarity */ }
+        break;
+      }
+      // B <- B H (right), then the next reflector from its first column, then B <- H'^H B (left)
+      for (int j = 0; j < nd; ++j) for (int i = 0; i < nb2; ++i) Bk[i + (size_t)j * B] = el(c0 + B + i, c0 + j);
+      for (int i = 0; i < nb2; ++i) { T acc(0); for (int j = 0; j < nd; ++j) acc += Bk[i + (size_t)j * B] * v[j]; z[i] = tau * acc; }
+      for (int j = 0; j < nd; ++j) for (int i = 0; i < nb2; ++i) Bk[i + (size_t)j * B] -= z[i] * cj(v[j]);
+      for (int i = 0; i < nb2; ++i) vn[i] = Bk[i];
+      T taun;
+      double betan;
+      larfg_t<T>(nb2, vn.data(), &taun, &betan);
+      for (int j = 1; j < nd; ++j) { T acc(0); for (int i = 0; i < nb2; ++i) acc += cj(vn[i]) * Bk[i + (size_t)j * B]; y[j] = cj(taun) * acc; }
+      for (int j = 1; j < nd; ++j) for (int i = 0; i < nb2; ++i) Bk[i + (size_t)j * B] -= vn[i] * y[j];
+      Bk[0] = T(betan);
+      for (int i = 1; i < nb2; ++i) Bk[i] = T(0);
+      for (int j = 0; j < nd; ++j) for (int i = 0; i < nb2; ++i) el(c0 + B + i, c0 + j) = Bk[i + (size_t)j * B];
+      for (int i = 0; i < nb2; ++i) v[i] = vn[i];
+      for (int i = nb2; i < B; ++i) v[i] = T(0);
+      tau = taun;
+    }
+  }
+  d[n - 1] = re_(el(n - 1, n - 1));
+}
+void launch_bulge_chase(Backend* b, bool cplx, const ChaseProblem* probs, int nprob) {
+  b->launches++;
+  for (int p = 0; p < nprob; ++p) {
+    const ChaseProblem& q = probs[p];
+    if (cplx) bulge_chase_t<cd>((cd*)q.AB, q.n, q.d, q.e, (cd*)q.V2, (cd*)q.tau2); else bulge_chase_t<double>((double*)q.AB, q.n, q.d, q.e, (double*)q.V2, (double*)q.tau2);
+  }
+}
+
+template <class T>
+static void q2_apply_t(const T* V2, const T* tau2, int64_t n, T* Z, int64_t m) {
+  const int B = SB_B;
+  const int64_t K0 = (n - 1 + B - 1) / B;
+  for (int64_t g = K0 - 1; g >= 0; --g)
+    for (int64_t k = 0; k < K0 - g; ++k) {
+      const int64_t blk = g * K0 - g * (g - 1) / 2 + k;
+      const int64_t base = g * B + 1 + k * B;
+      for (int sp = B - 1; sp >= 0; --sp) {
+        const T tau = tau2[blk * B + sp];
+        if (tau == T(0)) continue;
+        const T* v = V2 + blk * (int64_t)SB_VLD * B + sp * (int64_t)SB_VLD + sp;
+        const int64_t r0 = base + sp;
+        const int len = (int)std::min<int64_t>(B, n - r0);
+        if (len <= 0) continue;
+        for (int64_t c = 0; c < m; ++c) {
+          T* zc = Z + r0 + c * n;
+          T acc(0);
+          for (int i = 0; i < len; ++i) acc += cj(v[i]) * zc[i];
+          acc *= tau;
+          for (int i = 0; i < len; ++i) zc[i] -= acc * v[i];
+        }
+      }
+    }
+}
+void launch_q2_apply(Backend* b, bool cplx, const void* V2, const void* tau2, int64_t n, void* Z, int64_t m) {
+  b->launches++;
+  if (cplx) q2_apply_t<cd>((const cd*)V2, (const cd*)tau2, n, (cd*)Z, m); else q2_apply_t<double>((const double*)V2, (const double*)tau2, n, (double*)Z, m);
+}
+
 void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* P,
                             double* out3) {
   b->launches++;

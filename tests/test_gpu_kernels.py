@@ -146,6 +146,27 @@ def test_hermitian_eigensolver_batched(gpu_ctx, cplx, sizes):
     common.check_heig_batched(gpu_ctx, cplx, sizes)
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n,m", common.TWO_STAGE_SIZES)
+def test_hermitian_eigensolver_two_stage(gpu_ctx, monkeypatch, cplx, n, m):
+    """panel_qr_kernel + GEMM block updates + bulge_chase_kernel + q2_apply_kernel + compact-WY panels, forced on at small sizes."""
+    common.check_heig_two_stage(gpu_ctx, cplx, n, m, monkeypatch)
+
+
+@pytest.mark.parametrize("cplx,n,m", [(False, 2500, 900), (True, 1700, 500)])
+def test_hermitian_eigensolver_two_stage_default_threshold(gpu_ctx, cplx, n, m):
+    """Sizes that take the two-stage path by default (n >= 1536), against numpy.eigh."""
+    rng = np.random.default_rng(n + m)
+    X = _rand(rng, (n, n), cplx) * np.exp(-np.arange(n) * (14.0 / n))[None, :]
+    A = X.conj().T @ X
+    A /= np.trace(A).real
+    w, V, it = cb.k_heig(A, m, ctx=gpu_ctx)
+    ev = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(w - ev).max() <= 1e-14 * np.sqrt(n)
+    assert np.abs(V.conj().T @ V - np.eye(m)).max() <= 1e-13
+    assert np.abs(A @ V - V @ (V.conj().T @ A @ V)).max() <= 2e-14 * np.sqrt(n)
+
+
 @pytest.mark.parametrize("mode", ["1", "2", "3"])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
 def test_gemm_narrow_and_3m_tiles(gpu_ctx, monkeypatch, mode, ta, tb):

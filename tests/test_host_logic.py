@@ -92,3 +92,10 @@ def test_hermitian_eigensolver_batched_driver(emu_ctx, cplx, sizes):
 @pytest.mark.parametrize("case", [common.DMRG_CASES[0], common.DMRG_CASES[3], common.DMRG_CASES[4]], ids=["golden", "haagerupq-real", "haagerupq-complex"])
 def test_block_packed_mps_boundary(emu_ctx, case, shuffle):
     common.check_packed_mps_boundary(emu_ctx, case, shuffle)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("n,m", common.TWO_STAGE_SIZES[:2])
+def test_hermitian_eigensolver_two_stage_driver(emu_ctx, monkeypatch, cplx, n, m):
+    """Host logic of the two-stage path (panel/GEMM/bulge-chase/back-transformation plumbing) on the emulation backend."""
+    common.check_heig_two_stage(emu_ctx, cplx, n, m, monkeypatch)
