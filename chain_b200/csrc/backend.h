@@ -156,7 +156,7 @@ void launch_panel_qr(Backend*, bool cplx, void* A, int64_t n, int64_t j0, void* 
 void launch_band_extract(Backend*, bool cplx, const void* A, int64_t n, void* AB);
 // (3) band -> real symmetric tridiagonal (d[n], e[n-1]) by bulge chasing, for nprob independent matrices in one launch.  Sweep s
 //     (column s) consists of tasks k = 0, 1, ... acting on rows c0 = s + 1 + k*SB_B .. c0 + 2*SB_B - 1; task (s, k) waits for task
-//     (s-1, k+2) (progress counters prog[s], zero-initialised by the caller, n ints).  Reflector (s, k) (LAPACK larfg convention, explicit
+//     (s-1, k+1) (progress counters prog[s], zero-initialised by the caller, n ints).  Reflector (s, k) (LAPACK larfg convention, explicit
 //     leading 1) is stored for the back-transformation in block blk = g*K0 - g(g-1)/2 + k  (g = s / SB_B, K0 = ceil((n-1)/SB_B)) of V2
 //     (SB_VLD x SB_B elements per block, zero-initialised by the caller), column s % SB_B, rows s % SB_B ...; tau2[blk*SB_B + s % SB_B].
 struct ChaseProblem {

@@ -1394,9 +1394,9 @@ void launch_bulge_chase(Backend* b, bool cplx, const ChaseProblem* probs, int np
   int per_sm = 0;
   CB_CHECK(b, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BC_THREADS, smem));
   const int64_t cap = (int64_t)std::max(1, per_sm) * sm_count(b);
-  // at most ~n/(3 SB_B) sweeps of one matrix are in flight at a time (each waits for its predecessor to be three tasks ahead)
+  // at most ~n/(2 SB_B) sweeps of one matrix are in flight at a time (each waits for its predecessor to be two tasks ahead)
   int64_t useful = 0;
-  for (int p = 0; p < nprob; ++p) useful += probs[p].n / (3 * SB_B) + 2;
+  for (int p = 0; p < nprob; ++p) useful += probs[p].n / (2 * SB_B) + 2;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cap, std::min<int64_t>(useful, max_sweeps * nprob)));
   char* scratch = (char*)dev_alloc(b, sizeof(ChaseDesc) * (size_t)nprob + 64);
   if (!scratch) return;
@@ -1414,13 +1414,27 @@ void launch_bulge_chase(Backend* b, bool cplx, const ChaseProblem* probs, int np
 
 void launch_q2_apply(Backend* b, bool cplx, const void* V2, const void* tau2, int64_t n, void* Z, int64_t m) {
   if (n < 2 || m <= 0) return;
+  const size_t es = cplx ? 16 : 8;
+  const int64_t nblk = chase_blocks(n);
+  // T factors of the groups of 8 reflectors (one warp per group), then the blockwise application
+  const int G = cplx ? q2_group<true>() : q2_group<false>();
+  void* T8 = dev_alloc(b, es * ((size_t)nblk * SB_B * G + 16));
+  if (!T8) return;
+  {
+    const long long warps = (long long)nblk * (SB_B / G);
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    if (cplx) q2_tprep_kernel<true><<<blocks, 256, 0, b->stream>>>(V2, tau2, nblk, T8);
+    else q2_tprep_kernel<false><<<blocks, 256, 0, b->stream>>>(V2, tau2, nblk, T8);
+    CB_LAUNCH_CHECK(b, "q2_tprep_kernel");
+  }
   const void* fn = cplx ? (const void*)q2_apply_kernel<true> : (const void*)q2_apply_kernel<false>;
   const size_t smem = cplx ? q2_smem_bytes<true>() : q2_smem_bytes<false>();
   opt_in_smem(fn, smem);
   const int grid = (int)((m + Q2_NC - 1) / Q2_NC);
-  if (cplx) q2_apply_kernel<true><<<grid, Q2_THREADS, smem, b->stream>>>(V2, tau2, n, Z, m);
-  else q2_apply_kernel<false><<<grid, Q2_THREADS, smem, b->stream>>>(V2, tau2, n, Z, m);
+  if (cplx) q2_apply_kernel<true><<<grid, Q2_THREADS, smem, b->stream>>>(V2, T8, n, Z, m);
+  else q2_apply_kernel<false><<<grid, Q2_THREADS, smem, b->stream>>>(V2, T8, n, Z, m);
   CB_LAUNCH_CHECK(b, "q2_apply_kernel");
+  dev_free(b, T8);
 }
 
 void launch_truncate_select(Backend* b, const double* pooled, int64_t n, int64_t maxdim, int64_t mindim, double cutoff, double* sorted,

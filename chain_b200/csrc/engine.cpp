@@ -1011,11 +1011,14 @@ JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n) 
 }
 
 // ------------------------------------------------------------------------------------------------ Hermitian eigensolver
-static int64_t two_stage_min_n() {   // matrices at least this large take the two-stage reduction (CB200_TWOSTAGE_MIN_N; 0 = never)
+// Matrices at least this large take the two-stage reduction.  Measured on B200 (profiles/r02_heig_*.txt): real n = 8000 / 18000 two-stage
+// 2.6x / 2.9x faster than the one-stage panel kernel, real n = 1600 slower (55 vs 39 ms: the bulge chase costs ~13 us per sweep whatever n);
+// complex n = 3200 slower (0.41 vs 0.30 s for the three blocks of BASELINE configs[1]).  CB200_TWOSTAGE_MIN_N overrides both (0 = never).
+static int64_t two_stage_min_n(bool cplx) {
   const char* e = getenv("CB200_TWOSTAGE_MIN_N");      // read per call (cheap): tests switch the path inside one process
-  return e ? atoll(e) : (int64_t)1536;
+  return e ? atoll(e) : (int64_t)(cplx ? 4096 : 2048);
 }
-static bool use_two_stage(int64_t n) { return two_stage_min_n() > 0 && n >= std::max<int64_t>(two_stage_min_n(), 4 * SB_B); }
+static bool use_two_stage(int64_t n, bool cplx) { return two_stage_min_n(cplx) > 0 && n >= std::max<int64_t>(two_stage_min_n(cplx), 4 * SB_B); }
 
 // Stage 1 of the two-stage reduction: A (Hermitian, both triangles, consumed) -> band matrix of semi-bandwidth SB_B.
 // Per panel: Householder QR of the block below the band (launch_panel_qr), then the two-sided update of the trailing matrix
@@ -1137,7 +1140,7 @@ bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
   h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
   h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
-  if (use_two_stage(n)) {
+  if (use_two_stage(n, cplx)) {
     sb_stage1(c, h);
     sb_stage2(c, cplx, {&h});
   } else {
@@ -1168,7 +1171,7 @@ bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vec
     h.e = Buf(be, 8 * std::max<int64_t>(n, 1), true);
     h.tau = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
     h.scl = Buf(be, (int64_t)es * std::max<int64_t>(n, 1), true);
-    if (use_two_stage(n)) { sb_stage1(c, h); continue; }
+    if (use_two_stage(n, cplx)) { sb_stage1(c, h); continue; }
     pw[k] = Buf(be, (int64_t)es * std::max<int64_t>(n, 1));
     probs.push_back(TriProblem{h.A.p, n, (double*)h.d.p, (double*)h.e.p, h.tau.p, h.scl.p, pw[k].p});
   }
@@ -1265,10 +1268,11 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
         g.finish(be, pl, false, false);
         run_gemm(c, cx, pl, h.Yall.p, h.Tall.p, YT.p);
       }
-      const int PMAX = 8;
-      Buf W1p(be, (int64_t)es * B * m * PMAX);
+      const int PMAX = MAX_LC;
+      Buf W1p(be, (int64_t)es * B * m * PMAX), W1(be, (int64_t)es * B * m);
       for (int p = npan - 1; p >= 0; --p) {
         const int64_t r0 = (int64_t)p * B + B, len = n - r0;
+        // W1 = Y_p^H V[r0:, :]: 64 rows with a long inner dimension -- split K into partial products, add them, then V[r0:, :] += YTn_p W1
         const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, len / 256));
         const int64_t chunk = ((len + P - 1) / P + 15) / 16 * 16;
         GemmPlan pw1, pz;
@@ -1283,15 +1287,18 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
           }
           g1.finish(be, pw1, true, false);
         }
-        {
-          GemmBuilder g(cx);
-          g.begin(r0, n, len, m, GEMM_ACCUM);
-          for (int pp = 0; pp < pw1.tasks.n; ++pp) g.seg(h.yoff[p], len, (int64_t)pp * B * m, B, B);
-          g.end();
-          g.finish(be, pz, false, false);
-        }
+        { GemmBuilder g(cx); g.begin(r0, n, len, m, GEMM_ACCUM); g.seg(h.yoff[p], len, 0, B, B); g.end(); g.finish(be, pz, false, false); }
         run_gemm(c, cx, pw1, h.Yall.p, V.p, W1p.p);
-        run_gemm(c, cx, pz, YT.p, W1p.p, V.p);
+        const int np = pw1.tasks.n;
+        const void* w1 = W1p.p;
+        if (np > 1) {
+          const void* xs[MAX_LC];
+          double ones[2 * MAX_LC];
+          for (int pp = 0; pp < np; ++pp) { xs[pp] = (const char*)W1p.p + es * (size_t)pp * B * m; ones[2 * pp] = 1.0; ones[2 * pp + 1] = 0.0; }
+          lincomb(be, cx, np, xs, ones, 0.0, 0.0, W1.p, (int64_t)B * m);
+          w1 = W1.p;
+        }
+        run_gemm(c, cx, pz, YT.p, w1, V.p);
       }
     }
   } else if (n < wy_min_n()) {

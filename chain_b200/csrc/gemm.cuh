@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 #include "tasks.h"
 
 namespace cb200 {
@@ -344,20 +345,69 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   const bool conj_out = (t.flags & GEMM_CONJ_OUT) != 0;
   const bool trans_c = (t.flags & GEMM_TRANS_C) != 0;
   char* Cp = Cbase + t.c_off * ES;
+  auto c_index = [&](int m, int n) -> int64_t {
+    const int64_t mc = (int64_t)(m % t.chunk) + (int64_t)(m / t.chunk) * t.chunk_stride;
+    return trans_c ? ((int64_t)(n % t.chunk) + (int64_t)(n / t.chunk) * t.chunk_stride + (int64_t)m * t.ldc)
+           : (n < t.n_split) ? (mc + (int64_t)n * t.ldc)
+                             : ((t.c_off2 - t.c_off) + mc + (int64_t)(n - t.n_split) * t.ldc);
+  };
+  if constexpr (!PEER) {
+    if (accum) {
+      // C += result.  The old values are fetched IB row groups at a time BEFORE any of their stores is issued: a load placed after a store
+      // to the same array cannot be hoisted by the compiler, and one exposed L2/HBM round trip per element (64 per thread) cost ~80 us per
+      // tile -- ten times the main loop of a rank-64 update.
+      constexpr int IB = 2;
+#pragma unroll
+      for (int i0 = 0; i0 < MT; i0 += IB) {
+        using ET = typename std::conditional<CPLX, double2, double>::type;
+        ET old[IB][NT][2];
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) {
+          const int m = m0 + wm0 + (i0 + ii) * 8 + g;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int n = n0 + wn0 + j * 8 + tq * 2 + e;
+              if constexpr (CPLX) old[ii][j][e] = make_double2(0.0, 0.0); else old[ii][j][e] = 0.0;
+              if (i0 + ii < MT && m < t.M && n < t.N) old[ii][j][e] = __ldcg(reinterpret_cast<const ET*>(Cp) + c_index(m, n));
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) {
+          const int i = i0 + ii;
+          const int m = m0 + wm0 + i * 8 + g;
+          if (i >= MT || m >= t.M) continue;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int n = n0 + wn0 + j * 8 + tq * 2 + e;
+              if (n >= t.N) continue;
+              const int64_t off = c_index(m, n);
+              if constexpr (!CPLX) {
+                reinterpret_cast<double*>(Cp)[off] = acc_re[i][j][e] + old[ii][j][e];
+              } else {
+                const double2 o = old[ii][j][e];
+                reinterpret_cast<double2*>(Cp)[off] = make_double2(acc_re[i][j][e] + o.x, (conj_out ? -acc_im[i][j][e] : acc_im[i][j][e]) + o.y);
+              }
+            }
+        }
+      }
+      return;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     const int m = m0 + wm0 + i * 8 + g;
     if (m >= t.M) continue;
-    const int64_t mc = (int64_t)(m % t.chunk) + (int64_t)(m / t.chunk) * t.chunk_stride;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int n = n0 + wn0 + j * 8 + tq * 2 + e;
         if (n >= t.N) continue;
-        const int64_t off = trans_c ? ((int64_t)(n % t.chunk) + (int64_t)(n / t.chunk) * t.chunk_stride + (int64_t)m * t.ldc)
-                            : (n < t.n_split) ? (mc + (int64_t)n * t.ldc)
-                                              : ((t.c_off2 - t.c_off) + mc + (int64_t)(n - t.n_split) * t.ldc);
+        const int64_t off = c_index(m, n);
         if constexpr (PEER) {
           // all-gather fused into the epilogue: the tile goes to every rank's landing buffer over NVLink (plain stores;
           // the cross-GPU barrier that follows the launch publishes them)
@@ -369,15 +419,9 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
           continue;
         }
         if constexpr (!CPLX) {
-          double* p = reinterpret_cast<double*>(Cp) + off;
-          double v = acc_re[i][j][e];
-          if (accum) v += *p;
-          *p = v;
+          reinterpret_cast<double*>(Cp)[off] = acc_re[i][j][e];
         } else {
-          double2* p = reinterpret_cast<double2*>(Cp) + off;
-          double2 v = make_double2(acc_re[i][j][e], conj_out ? -acc_im[i][j][e] : acc_im[i][j][e]);
-          if (accum) { double2 o = *p; v.x += o.x; v.y += o.y; }
-          *p = v;
+          reinterpret_cast<double2*>(Cp)[off] = make_double2(acc_re[i][j][e], conj_out ? -acc_im[i][j][e] : acc_im[i][j][e]);
         }
       }
     }

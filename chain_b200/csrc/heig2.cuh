@@ -215,7 +215,14 @@ struct ChaseDesc {          // device copy of ChaseProblem + derived counts
 
 // One CTA per sweep (sweeps handed out in order through an atomic ticket, so every sweep a CTA can wait for is owned by a resident CTA).
 // Task (s, k): D = A[c0:c0+B, c0:c0+B] <- H^H D H;  Bk = A[c0+B:c0+2B, c0:c0+B] <- Bk H;  next reflector H' from the first column of Bk;
-// Bk <- H'^H Bk.  It may start once sweep s-1 has finished task k+2.
+// Bk <- H'^H Bk.  It may start once sweep s-1 has finished task k+1.
+__device__ __forceinline__ void chase_wait(const int* flag, int need) {
+  int seen;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+  } while (seen < need);
+}
+
 template <bool CPLX>
 __global__ void __launch_bounds__(BC_THREADS, 1)
 bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max_sweeps, unsigned long long* __restrict__ ticket) {
@@ -224,11 +231,14 @@ bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max
   extern __shared__ __align__(16) char smem_raw[];
   T* Ds = reinterpret_cast<T*>(smem_raw);       // [B][LD]
   T* Bs = Ds + B * LD;                          // [B][LD]
-  T* pr = Bs + B * LD;                          // [4][B] partial sums
-  T* v = pr + 4 * B;                            // [B]
-  T* vn = v + B;                                // [B]
+  T* pr = Bs + B * LD;                          // [4][B] partial sums (D v, then vn^H B)
+  T* v = pr + 4 * B;                            // [B] current reflector
+  T* vn = v + B;                                // [B] next reflector
   T* w = vn + B;                                // [B]
   T* y = w + B;                                 // [B]
+  __shared__ T zr[4 * SB_B];                    // partial sums of Bk v
+  __shared__ T zz[SB_B];                        // z = tau Bk v
+  __shared__ T xs[SB_B];                        // first column of Bk H
   __shared__ unsigned long long s_ticket;
   __shared__ double s_dbl[4];
   __shared__ T s_t[4];
@@ -258,32 +268,45 @@ bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max
       const int nd = (int)(n - c0 < B ? n - c0 : B);
       const long long rem = n - c0 - B;
       const int nb2 = (int)(rem <= 0 ? 0 : (rem < B ? rem : B));
-      // ---- wait for sweep s-1 to be three tasks ahead (or finished)
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = (int)(k + 3 < nk_prev ? k + 3 : nk_prev);
-          int seen;
-          do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(P.prog + (s - 1)) : "memory");
-          } while (seen < need);
-          __threadfence();
-        }
+      // ---- (1) storage columns c0 .. c0+B-2 were last written by task (s-1, k): already awaited (k >= 1: by the previous task of this
+      // sweep; k = 0: here).  Fetch them -- and column s of the first task -- BEFORE waiting for task (s-1, k+1), which only owns the
+      // last column: the L2 round trip of the block load hides behind the wait.
+      if (s > 0 && k == 0) {
+        if (tid == 0) { chase_wait(P.prog + (s - 1), (int)(1 < nk_prev ? 1 : nk_prev)); __threadfence(); }
         __syncthreads();
       }
-      // ---- load D (Hermitian, lower triangle stored) and Bk
-      for (int jj = q; jj < B; jj += 4) {
-        T a = zero;
-        if (r >= jj && r < nd && jj < nd) a = t_ldcg(AB + (r - jj) + (c0 + jj) * SB_LD);
-        if (r >= jj) { Ds[r + jj * LD] = a; if (r > jj) Ds[jj + r * LD] = t_conj(a); }
-        T b = zero;
-        if (r < nb2 && jj < nd) b = t_ldcg(AB + (B + r - jj) + (c0 + jj) * SB_LD);
-        Bs[r + jj * LD] = b;
+      T da[16], db[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int jj = q + 4 * t;
+        da[t] = zero; db[t] = zero;
+        if (jj < B - 1) {
+          if (r >= jj && r < nd && jj < nd) da[t] = t_ldcg(AB + (r - jj) + (c0 + jj) * SB_LD);
+          if (r < nb2 && jj < nd) db[t] = t_ldcg(AB + (B + r - jj) + (c0 + jj) * SB_LD);
+        }
+      }
+      T x = zero;
+      if (k == 0 && tid < nd) x = t_ldcg(AB + (c0 + tid - s) + s * SB_LD);
+      // ---- (2) wait for task (s-1, k+1) (or the end of sweep s-1): it shares index c0+B-1 with this task; task (s-1, k+2) touches storage
+      // columns >= c0+2B-1 only, so a lag of two tasks suffices
+      if (s > 0) {
+        if (tid == 0) { chase_wait(P.prog + (s - 1), (int)(k + 2 < nk_prev ? k + 2 : nk_prev)); __threadfence(); }
+        __syncthreads();
+      }
+      if (q == 3) {           // the last column (jj = 63 = 3 + 4*15)
+        constexpr int jj = B - 1;
+        if (r >= jj && r < nd && jj < nd) da[15] = t_ldcg(AB + (r - jj) + (c0 + jj) * SB_LD);
+        if (r < nb2 && jj < nd) db[15] = t_ldcg(AB + (B + r - jj) + (c0 + jj) * SB_LD);
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int jj = q + 4 * t;
+        if (r >= jj) { Ds[r + jj * LD] = da[t]; if (r > jj) Ds[jj + r * LD] = t_conj(da[t]); }
+        Bs[r + jj * LD] = db[t];
       }
       if (k == 0) {
         // reflector of the sweep from column s: x = A[c0 : c0+nd, s]
-        T x = zero;
         if (tid < B) {
-          if (tid < nd) x = t_ldcg(AB + (c0 + tid - s) + s * SB_LD);
           double part = tid >= 1 ? t_norm2(x) : 0.0;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
@@ -313,30 +336,50 @@ bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max
         if (tid < nd) reinterpret_cast<T*>(P.V2)[blk * (long long)SB_VLD * B + (long long)sp * SB_VLD + sp + tid] = v[tid];
         if (tid == 0) reinterpret_cast<T*>(P.tau2)[blk * B + sp] = tau;
       }
-      // ---- D <- H^H D H:  p = tau D v,  w = p - 1/2 conj(tau) (v^H p) v,  D -= v w^H + w v^H
+      // ---- (3) p = D v and z = Bk v (partial sums over 16 columns per thread)
       {
-        T acc = zero;
+        T ap = zero, az = zero;
 #pragma unroll 4
-        for (int jj = q * 16; jj < q * 16 + 16; ++jj) acc = t_add(acc, t_mul(Ds[r + jj * LD], v[jj]));
-        pr[q * B + r] = acc;
+        for (int jj = q * 16; jj < q * 16 + 16; ++jj) {
+          const T vj = v[jj];
+          ap = t_add(ap, t_mul(Ds[r + jj * LD], vj));
+          az = t_add(az, t_mul(Bs[r + jj * LD], vj));
+        }
+        pr[q * B + r] = ap;
+        zr[q * B + r] = az;
       }
       __syncthreads();
       if (tid < B) {
         const T p = t_mul(tau, t_add(t_add(pr[tid], pr[B + tid]), t_add(pr[2 * B + tid], pr[3 * B + tid])));
+        const T z = t_mul(tau, t_add(t_add(zr[tid], zr[B + tid]), t_add(zr[2 * B + tid], zr[3 * B + tid])));
         w[tid] = p;
+        zz[tid] = z;
+        const T xr = t_sub(Bs[tid], z);                    // first column of Bk H  (conj(v[0]) = 1)
+        xs[tid] = xr;
         T vp = t_mul(t_conj(v[tid]), p);
+        double part = (tid >= 1 && tid < nb2) ? t_norm2(xr) : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vp = t_add(vp, t_shfl_down(vp, o));
-        if (lane == 0) s_t[1 + warp] = vp;
+        for (int o = 16; o > 0; o >>= 1) { vp = t_add(vp, t_shfl_down(vp, o)); part += __shfl_down_sync(0xffffffffu, part, o); }
+        if (lane == 0) { s_t[warp] = vp; s_dbl[warp] = part; }
       }
+      __syncthreads();
+      // ---- (4) scalars, redundantly in every thread: w = p - 1/2 conj(tau) (v^H p) v;  next reflector from the first column of Bk H
+      const T a2 = t_scale(t_mul(t_conj(tau), t_add(s_t[0], s_t[1])), -0.5);
+      double betan = 0.0;
+      T scalen = zero, taun = zero;
+      if (nb2 > 0) taun = larfg_scalars(xs[0], s_dbl[0] + s_dbl[1], &betan, &scalen);
       __syncthreads();
       if (tid < B) {
-        const T a2 = t_scale(t_mul(t_conj(tau), t_add(s_t[1], s_t[2])), -0.5);
         w[tid] = t_add(w[tid], t_mul(a2, v[tid]));
+        T vi = tid == 0 ? t_one(T()) : t_mul(xs[tid], scalen);
+        if (tid >= nb2) vi = zero;
+        vn[tid] = vi;
       }
       __syncthreads();
+      // ---- (5) D <- D - v w^H - w v^H straight to global;  partial sums of vn^H (Bk H) per column (thread (column r, rows 16q..16q+15))
       {
         const T vr = v[r], wr = w[r];
+#pragma unroll 4
         for (int jj = q; jj < B; jj += 4) {
           if (r >= jj && r < nd) {
             const T a = t_sub(Ds[r + jj * LD], t_add(t_mul(vr, t_conj(w[jj])), t_mul(wr, t_conj(v[jj]))));
@@ -346,7 +389,6 @@ bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max
         }
       }
       if (nb2 <= 0) {
-        // sweep finished: publish
         __syncthreads();
         if (tid == 0) {
           __threadfence();
@@ -355,61 +397,25 @@ bulge_chase_kernel(const ChaseDesc* __restrict__ probs, int nprob, long long max
         }
         break;
       }
-      // ---- Bk <- Bk H:  z = tau Bk v,  Bk -= z v^H
       {
         T acc = zero;
+        const T cvr = t_conj(v[r]);
 #pragma unroll 4
-        for (int jj = q * 16; jj < q * 16 + 16; ++jj) acc = t_add(acc, t_mul(Bs[r + jj * LD], v[jj]));
-        pr[q * B + r] = acc;
-      }
-      __syncthreads();
-      if (tid < B) w[tid] = t_mul(tau, t_add(t_add(pr[tid], pr[B + tid]), t_add(pr[2 * B + tid], pr[3 * B + tid])));
-      __syncthreads();
-      {
-        const T zr = w[r];
-        for (int jj = q; jj < B; jj += 4) Bs[r + jj * LD] = t_sub(Bs[r + jj * LD], t_mul(zr, t_conj(v[jj])));
-      }
-      __syncthreads();
-      // ---- next reflector from the first column of Bk
-      if (tid < B) {
-        const T x = Bs[tid];
-        double part = (tid >= 1 && tid < nb2) ? t_norm2(x) : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-        if (lane == 0) s_dbl[warp] = part;
-      }
-      __syncthreads();
-      T taun;
-      {
-        double beta;
-        T scale;
-        taun = larfg_scalars(Bs[0], s_dbl[0] + s_dbl[1], &beta, &scale);
-        if (tid < B) {
-          T vi = tid == 0 ? t_one(T()) : t_mul(Bs[tid], scale);
-          if (tid >= nb2) vi = zero;
-          vn[tid] = vi;
-        }
-        __syncthreads();
-        // first column becomes (beta, 0, ...)
-        if (tid < B) Bs[tid] = tid == 0 ? t_make(beta, 0.0, T()) : zero;
-      }
-      // ---- Bk <- H'^H Bk (columns 1..):  y_j = conj(tau') vn^H Bk[:,j],  Bk[:,j] -= vn y_j      (thread (j = r, q): rows 16q..16q+15)
-      {
-        T acc = zero;
-        if (r >= 1) {
-#pragma unroll 4
-          for (int i = q * 16; i < q * 16 + 16; ++i) acc = t_add(acc, t_mul(t_conj(vn[i]), Bs[i + r * LD]));
-        }
+        for (int i = q * 16; i < q * 16 + 16; ++i) acc = t_add(acc, t_mul(t_conj(vn[i]), t_sub(Bs[i + r * LD], t_mul(zz[i], cvr))));
         pr[q * B + r] = acc;
       }
       __syncthreads();
       if (tid < B) y[tid] = tid >= 1 ? t_mul(t_conj(taun), t_add(t_add(pr[tid], pr[B + tid]), t_add(pr[2 * B + tid], pr[3 * B + tid]))) : zero;
       __syncthreads();
+      // ---- (6) Bk <- H'^H (Bk H) straight to global: first column (beta', 0, ...), the others Bk - z v^H - vn y
       {
-        const T vr = vn[r];
+        const T zrr = zz[r], vnr = vn[r];
+#pragma unroll 4
         for (int jj = q; jj < B; jj += 4) {
           if (r < nb2 && jj < nd) {
-            const T b = jj == 0 ? Bs[r] : t_sub(Bs[r + jj * LD], t_mul(vr, y[jj]));
+            T b;
+            if (jj == 0) b = r == 0 ? t_make(betan, 0.0, T()) : zero;
+            else b = t_sub(t_sub(Bs[r + jj * LD], t_mul(zrr, t_conj(v[jj]))), t_mul(vnr, y[jj]));
             AB[(B + r - jj) + (c0 + jj) * SB_LD] = b;
           }
         }
@@ -432,35 +438,90 @@ constexpr int Q2_THREADS = 256;
 constexpr int Q2_NC = 32;                 // columns of Z per CTA: 8 warps x 4 columns, 8 lanes per column
 constexpr int Q2_VROW = SB_B + 16 + 1;    // compact reflector row: 8 zeros | 64 entries | 8 zeros (+1 pad)
 template <bool CPLX>
-constexpr size_t q2_smem_bytes() { return (size_t)(CPLX ? 16 : 8) * (2 * (size_t)SB_B * Q2_VROW + 2 * SB_B); }
+__host__ __device__ constexpr int q2_group() { return CPLX ? 4 : 8; }      // reflectors applied together as one compact-WY factor (complex: register budget)
+template <bool CPLX>
+constexpr size_t q2_smem_bytes() { return (size_t)(CPLX ? 16 : 8) * (2 * (size_t)SB_B * Q2_VROW + 2 * SB_B * q2_group<CPLX>() + 8); }
 
-template <class T>
-__device__ __forceinline__ void q2_load_block(T* Vs, T* taus, const T* __restrict__ V2, const T* __restrict__ tau2, long long blk, int tid) {
-  // compact copy of the band of the reflector block: Vs[sp][8 + i] = V2blk[sp*SB_VLD + sp + i]
+// T factors of the groups of Q2_G consecutive reflectors of every block:  H_lo H_lo+1 ... H_hi = I - V T V^H  (larft, forward/columnwise).
+// One warp per (block, group); T8[(blk*(64/G) + grp)*G*G + j*G + i] = T[i][j] (upper triangular, stored transposed for conflict-free reads).
+template <bool CPLX>
+__global__ void __launch_bounds__(256) q2_tprep_kernel(const void* __restrict__ V2_, const void* __restrict__ tau2_, long long nblk, void* __restrict__ T8_) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int B = SB_B, G = q2_group<CPLX>();
+  const T* V2 = reinterpret_cast<const T*>(V2_);
+  const T* tau2 = reinterpret_cast<const T*>(tau2_);
+  T* T8 = reinterpret_cast<T*>(T8_);
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= nblk * (B / G)) return;
+  const long long blk = wid / (B / G);
+  const int grp = (int)(wid % (B / G));
+  const T* Vb = V2 + blk * (long long)SB_VLD * B;
+  const T zero = t_zero(T());
+  __shared__ T Gs[8][G * G];
+  __shared__ T Ts[8][G * G];
+  T* Gm = Gs[threadIdx.x >> 5];
+  T* Tm = Ts[threadIdx.x >> 5];
+  // Gram entries G[j][i] = v_j^H v_i for j < i (reflector lo+i starts i-j rows below reflector lo+j)
+  for (int i = 1; i < G; ++i)
+    for (int j = 0; j < i; ++j) {
+      const int spi = grp * G + i, spj = grp * G + j, sh = i - j;
+      const T* vi = Vb + spi * SB_VLD + spi;
+      const T* vj = Vb + spj * SB_VLD + spj;
+      T acc = zero;
+      for (int r = lane; r < B - sh; r += 32) acc = t_add(acc, t_mul(t_conj(vj[sh + r]), vi[r]));
+      acc = t_warp_sum(acc);
+      if (lane == 0) Gm[j * G + i] = acc;
+    }
+  __syncwarp();
+  if (lane == 0) {
+    for (int k = 0; k < G * G; ++k) Tm[k] = zero;
+    for (int i = 0; i < G; ++i) {
+      const T tau = tau2[blk * B + grp * G + i];
+      for (int r = 0; r < i; ++r) {
+        T acc = zero;
+        for (int k = r; k < i; ++k) acc = t_add(acc, t_mul(Tm[r * G + k], Gm[k * G + i]));
+        Tm[r * G + i] = t_sub(zero, t_mul(tau, acc));
+      }
+      Tm[i * G + i] = tau;
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < G * G; k += 32) {
+    const int i = k / G, j = k % G;            // T[i][j] -> slot j*G + i
+    T8[(blk * (B / G) + grp) * (G * G) + j * G + i] = Tm[i * G + j];
+  }
+}
+
+template <int G, class T>
+__device__ __forceinline__ void q2_load_block(T* Vs, T* Tg, const T* __restrict__ V2, const T* __restrict__ T8, long long blk, int tid) {
+  // compact copy of the band of the reflector block: Vs[sp][8 + i] = V2blk[sp*SB_VLD + sp + i]; and the block's 8 T factors
   const T* src = V2 + blk * (long long)SB_VLD * SB_B;
   for (int idx = tid; idx < SB_B * SB_B; idx += Q2_THREADS) {
     const int sp = idx >> 6, i = idx & 63;
     Vs[sp * Q2_VROW + 8 + i] = src[sp * SB_VLD + sp + i];
   }
-  if (tid < SB_B) taus[tid] = tau2[blk * SB_B + tid];
+  for (int idx = tid; idx < SB_B * G; idx += Q2_THREADS) Tg[idx] = T8[blk * (SB_B * G) + idx];
 }
 
-// lane layout inside a warp: column cl = lane >> 3 (4 columns), part = lane & 7; the thread owns window rows a = part + 8 k, k = 0..15, of
-// its column in registers.  Reflector sp of a block acts on window rows sp .. sp+63: with sp = 8 kb + sm its rows in this thread are
-// k = kb .. kb+8 with v index i = part + 8 (k - kb) - sm in [-7, 71]; the zero padding of the compact rows makes the two partial ends exact.
+// Lane layout inside a warp: column cl = lane >> 3 (4 columns), part = lane & 7; the thread owns window rows a = part + 8 k, k = 0..15, of
+// its column in registers.  The 8 reflectors sp = 8 kb .. 8 kb + 7 of a group act on window rows 8 kb .. 8 kb + 70, i.e. on this thread's
+// registers k = kb .. kb+8; reflector 8 kb + i needs v index part + 8 (k - kb) - i in [-7, 71]: the zero padding of the compact rows makes
+// the two partial ends exact.  A group is applied as z <- z - V (T (V^H z)): the 8 dot products are independent instruction chains (the
+// reflector-by-reflector form is one 64-long dependent chain per block and was latency-bound at 13 us per block).
 template <bool CPLX>
 __global__ void __launch_bounds__(Q2_THREADS, 1)
-q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ tau2_, long long n, void* __restrict__ Z_, long long m) {
+q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ T8_, long long n, void* __restrict__ Z_, long long m) {
   using T = typename std::conditional<CPLX, double2, double>::type;
-  constexpr int B = SB_B;
+  constexpr int B = SB_B, G = q2_group<CPLX>();
   const T* V2 = reinterpret_cast<const T*>(V2_);
-  const T* tau2 = reinterpret_cast<const T*>(tau2_);
+  const T* T8 = reinterpret_cast<const T*>(T8_);
   T* Z = reinterpret_cast<T*>(Z_);
   extern __shared__ __align__(16) char smem_raw[];
   T* Vbuf = reinterpret_cast<T*>(smem_raw);            // [2][B][Q2_VROW]
-  T* tbuf = Vbuf + 2 * B * Q2_VROW;                    // [2][B]
+  T* tbuf = Vbuf + 2 * B * Q2_VROW;                    // [2][64/G groups][G*G] (+ slack: lanes part >= G read past their group's rows)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int part = lane & 7;
+  const int part = lane & 7, lbase = lane & ~7;
   const long long col = (long long)blockIdx.x * Q2_NC + warp * 4 + (lane >> 3);
   const bool live = col < m;
   T* zc = Z + (live ? col : 0) * n;
@@ -478,14 +539,14 @@ q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ tau2_, lo
       const long long row = base + part + 8 * k;
       z[k] = (live && row < n) ? zc[row] : zero;
     }
-    q2_load_block(Vbuf, tbuf, V2, tau2, blk0, tid);
+    q2_load_block<G>(Vbuf, tbuf, V2, T8, blk0, tid);
     __syncthreads();
     for (long long k = 0; k < nk; ++k) {
       const int cur = (int)(k & 1);
       // prefetch the next block of reflectors and the next 64 rows of Z while this block is applied
       T znext[8];
       if (k + 1 < nk) {
-        q2_load_block(Vbuf + (cur ^ 1) * B * Q2_VROW, tbuf + (cur ^ 1) * B, V2, tau2, blk0 + k + 1, tid);
+        q2_load_block<G>(Vbuf + (cur ^ 1) * B * Q2_VROW, tbuf + (cur ^ 1) * B * G, V2, T8, blk0 + k + 1, tid);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const long long row = base + 128 + part + 8 * kk;
@@ -493,25 +554,43 @@ q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ tau2_, lo
         }
       }
       const T* Vs = Vbuf + cur * B * Q2_VROW;
-      const T* ts = tbuf + cur * B;
+      const T* Tb = tbuf + cur * B * G;
 #pragma unroll
-      for (int sp = B - 1; sp >= 0; --sp) {
-        const T tau = ts[sp];
-        if (t_is_zero(tau)) continue;
-        const int kb = sp >> 3, sm = sp & 7;
-        const T* vrow = Vs + sp * Q2_VROW + 8 + part - sm;
-        T vv[9];
+      for (int gq = B / G - 1; gq >= 0; --gq) {
+        // reflectors sp = gq*G + i, i < G:  kb = sp >> 3 is the same for the whole group (G divides 8), sm = (gq*G & 7) + i
+        const int kb = (gq * G) >> 3, sm0 = (gq * G) & 7;
+        const T* vbase = Vs + (gq * G) * Q2_VROW + 8 + part - sm0;
+        // d_i = v_i^H z  (G independent chains)
+        T d[G];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) vv[t] = vrow[8 * t];
-        T acc = zero;
+        for (int i = 0; i < G; ++i) {
+          const T* vrow = vbase + i * Q2_VROW - i;
+          T acc = zero;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc = t_add(acc, t_mul(t_conj(vv[t]), z[kb + t]));
-        acc = t_add(acc, t_shfl_xor(acc, 1));
-        acc = t_add(acc, t_shfl_xor(acc, 2));
-        acc = t_add(acc, t_shfl_xor(acc, 4));
-        acc = t_mul(tau, acc);
+          for (int t = 0; t < 9; ++t) acc = t_add(acc, t_mul(t_conj(vrow[8 * t]), z[kb + t]));
+          d[i] = acc;
+        }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) z[kb + t] = t_sub(z[kb + t], t_mul(acc, vv[t]));
+        for (int i = 0; i < G; ++i) {
+          d[i] = t_add(d[i], t_shfl_xor(d[i], 1));
+          d[i] = t_add(d[i], t_shfl_xor(d[i], 2));
+          d[i] = t_add(d[i], t_shfl_xor(d[i], 4));
+        }
+        // t = T d: lane `part` (< G) forms t_part, then the G values are exchanged inside the 8-lane group
+        T tp = zero;
+        const T* Tg = Tb + gq * (G * G);
+#pragma unroll
+        for (int j = 0; j < G; ++j) tp = t_add(tp, t_mul(Tg[j * G + part], d[j]));      // T[part][j] (zero below the diagonal)
+        T tv[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) tv[i] = t_shfl(tp, lbase + i);
+        // z -= V t
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const T* vrow = vbase + i * Q2_VROW - i;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) z[kb + t] = t_sub(z[kb + t], t_mul(vrow[8 * t], tv[i]));
+        }
       }
       // rows 0..63 of the window are final for this sweep group: store them, slide the window down by 64 rows
 #pragma unroll

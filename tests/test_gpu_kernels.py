@@ -153,9 +153,9 @@ def test_hermitian_eigensolver_two_stage(gpu_ctx, monkeypatch, cplx, n, m):
     common.check_heig_two_stage(gpu_ctx, cplx, n, m, monkeypatch)
 
 
-@pytest.mark.parametrize("cplx,n,m", [(False, 2500, 900), (True, 1700, 500)])
+@pytest.mark.parametrize("cplx,n,m", [(False, 2500, 900), (True, 4100, 300)])
 def test_hermitian_eigensolver_two_stage_default_threshold(gpu_ctx, cplx, n, m):
-    """Sizes that take the two-stage path by default (n >= 1536), against numpy.eigh."""
+    """Sizes that take the two-stage path by default (real n >= 2048, complex n >= 4096), against numpy.eigh."""
     rng = np.random.default_rng(n + m)
     X = _rand(rng, (n, n), cplx) * np.exp(-np.arange(n) * (14.0 / n))[None, :]
     A = X.conj().T @ X

@@ -16,7 +16,7 @@ X *= np.exp(-np.arange(n) * (14.0 / n))[None, :]
 A = X.conj().T @ X
 A /= np.trace(A).real
 ctx = cb.Context(0)
-for mode, thr in (("two-stage", "1536"), ("one-stage", "0")):
+for mode, thr in (("two-stage", "512"), ("one-stage", "0")):
     if n > 6000 and mode == "one-stage" and os.environ.get("HEIG_SKIP_ONE"):
         continue
     os.environ["CB200_TWOSTAGE_MIN_N"] = thr
