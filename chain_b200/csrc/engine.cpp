@@ -219,7 +219,8 @@ struct GemmBuilder {
 // tile mode of the O(D^3) contractions (matvec stages, environment update): complex data uses the 3-multiplication kernel unless
 // CB200_CPLX_3M=0 (A/B switch; the 4-multiplication kernel with the wide tile is the fallback)
 int heavy_mode(bool cplx) {
-  static const int v = [] { const char* e = getenv("CB200_CPLX_3M"); return e ? atoi(e) : 96; }();   // 0 off, 64 / 96 = tile columns
+  const char* e = getenv("CB200_CPLX_3M");       // read per plan (plans are built once per bond): tests compare both kernels in one process
+  const int v = e ? atoi(e) : 96;                  // 0 off, 64 / 96 = tile columns
   return (cplx && v) ? (v == 64 ? GEMM_TILE_NARROW_3M : GEMM_TILE_MID_3M) : GEMM_TILE_WIDE;
 }
 

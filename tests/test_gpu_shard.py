@@ -106,3 +106,43 @@ def test_nccl_allreduce_two_ranks():
     if torch.cuda.device_count() < 2:
         pytest.skip("ncclAllReduce needs two GPUs (two ranks cannot share one device)")
     _run("nccl")
+
+
+def _bench_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import chain_b200 as cb
+    import bench
+    import test_gpu_bench_parity as tb
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = bench.build_workload("cfg2", seed=2000)
+        ctx = cb.Context(device=rank, lib_path=PRODUCT_LIB)
+        ctx.shard(rank, world, mode="p2p", landing_bytes=16 * w["phi"].size, min_dim=0)
+        rows = np.array([0, 266, 267, 533, 534, 1066, 1599])           # both ranks' row slices of every sector
+        rel = tb._check_rows(ctx, w, rows, 1.0)
+        q.put((rank, {"cfg2 rows": (rel, 1e11)}))                      # _check_rows asserted the bound already
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg2_bench_workload_two_ranks_rows_match_numpy():
+    """The benchmarked D = 1600 matvec row-sharded over two GPUs (fused all-gather), sampled rows against NumPy."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [mpc.Process(target=_bench_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(res) == 2
