@@ -93,13 +93,15 @@ def test_truncation_spectrum_at_bench_size_matches_eigvalsh(gpu_ctx):
         ev.append(np.linalg.eigvalsh(Xq @ Xq.conj().T))
     ev = np.sort(np.concatenate(ev))[::-1]
     m = A.shape[2]
-    assert m == D
+    assert D - 8 <= m <= D          # the degeneracy guard on docut (ITensor truncate) may drop a few states at the cut
     assert np.abs(np.sort(spec)[::-1] - ev[:m]).max() <= 1e-14 * np.sqrt(X.shape[0])
-    assert abs(terr - ev[m:].sum()) <= 1e-12
-    # the kept vectors reproduce phi up to the discarded weight: ||phi - A B||^2 = truncerr (before B is normalised)
+    # ITensor's truncate reports the weight discarded by the maxdim / cutoff rule (n = maxdim states kept); the docut degeneracy guard can
+    # then drop the few states at the cut as well (m <= maxdim), SURVEY App. A.5
+    assert abs(terr - ev[D:].sum()) <= 1e-12
+    # the kept vectors reproduce phi up to the weight actually discarded
     AB = np.tensordot(A, B, axes=([2], [0]))
     ov = abs(np.vdot(AB, phi)) ** 2 / (np.vdot(AB, AB).real * np.vdot(phi, phi).real)
-    assert abs(ov - (1.0 - terr)) <= 1e-10
+    assert abs(ov - (1.0 - ev[m:].sum())) <= 1e-10
 
 
 # golden periodic L = 24, K = -1, U = 2 (exact, 2^24-dimensional matrix-free Lanczos)
