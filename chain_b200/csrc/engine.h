@@ -253,7 +253,7 @@ struct JacobiOut {
   std::vector<double> w;
   int sweeps = 0;
 };
-JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n);
+JacobiOut jacobi_svd(Ctx* c, bool cplx, const void* X, int64_t rows, int64_t n, bool relative_only = false);
 
 // Hermitian eigensolver of the truncation (tridiagonalisation -> bisection -> inverse iteration -> back-transformation):
 // what replaces LAPACK dsyev/zheev inside ITensor's diagHermitian(rho).  Two phases, because the number of vectors wanted

@@ -381,3 +381,49 @@ def check_heig_two_stage(ctx, cplx, n, m, monkeypatch):
     for (wi, Vi), Ai in zip(out, [A, A[:200, :200], A + 0.01 * np.eye(n)]):
         assert np.abs(Vi.conj().T @ Vi - np.eye(Vi.shape[1])).max() <= 1e-13
         assert np.abs(Ai @ Vi - Vi @ (Vi.conj().T @ Ai @ Vi)).max() <= 2e-14 * np.sqrt(n)
+
+
+def check_true_svd_branch(ctx, cplx, direction="left", D=64):
+    """ITensor's svdBond switches to a true SVD when noise == 0 and cutoff < 1e-12.  A two-site wavefunction with a
+    graded singular spectrum sigma = 1 ... 1e-12 (sigma^2 down to 1e-24): the SVD branch must resolve sigma^2 far below eps * sigma_max^2,
+    the denmat branch (cutoff >= 1e-12) cannot and need not; truncate() acts on sigma^2 in both."""
+    rng = np.random.default_rng(5 + cplx)
+    d, k = 2, 3
+    n = D * d
+
+    def rnd(*shape):
+        return rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0)
+    U, _ = np.linalg.qr(rnd(n, n))
+    V, _ = np.linalg.qr(rnd(n, n))
+    sig = 10.0 ** (-12.0 * np.arange(n) / (n - 1))
+    X = (U * sig) @ V.conj().T                                           # rows (l, s1), columns (s2, r)
+    X /= np.linalg.norm(X)
+    sig = sig / np.linalg.norm(sig)
+    phi = np.asfortranarray(X.reshape(D, d, d, D, order="F"))
+    z = np.zeros(D, np.int32)
+    W = np.asfortranarray(rng.standard_normal((k, d, d, k)))
+    E = np.asfortranarray(rnd(D, k, D))                                   # complex environments make the bond problem complex128
+    bond = cb.Bond(E + 0, W, W, E + 0, ql=z, qr=z, qkl=np.zeros(k, np.int32), qkm=np.zeros(k, np.int32), qkr=np.zeros(k, np.int32),
+                   site_charges=np.zeros(d, np.int32), nq=1, ctx=ctx)
+    p = np.linalg.svd(X, compute_uv=False) ** 2                           # LAPACK on the same stored matrix (rounding moved the smallest ones)
+    assert np.abs(p / sig ** 2 - 1)[: n // 2].max() < 1e-6
+    # ---- SVD branch: cutoff 1e-22 keeps every state whose discarded tail stays below 1e-22
+    A, B, qm, spec, terr = bond.truncate(phi, direction, 10 ** 6, 1e-22)
+    tail = np.cumsum(p[::-1])[::-1]                                       # tail[i] = sum_{j >= i} p_j
+    m_want = int(np.sum(tail >= 1e-22))                                   # ITensor truncate: drop while truncerr + P(n) < cutoff
+    assert abs(len(spec) - m_want) <= 1, (len(spec), m_want)
+    got = np.sort(spec)[::-1]
+    mm = min(len(got), m_want)
+    rel = np.abs(got[:mm] / p[:mm] - 1)
+    assert rel.max() <= 1e-4 and rel[p[:mm] > 1e-14].max() <= 1e-9, rel.max()        # RELATIVE accuracy down to sigma^2 ~ 1e-22
+    AB = np.tensordot(A, B, axes=([2], [0]))
+    assert np.abs(AB / np.linalg.norm(AB) - phi).max() <= 1e-11
+    iso = A.reshape(n, -1, order="F") if direction == "left" else B.reshape(len(spec), n, order="F").T
+    assert np.abs(iso.conj().T @ iso - np.eye(len(spec))).max() <= 1e-12
+    # ---- denmat branch on the same input: same large values, nothing resolved below ~eps
+    A2, B2, _, spec2, terr2 = bond.truncate(phi, direction, 10 ** 6, 1e-12)
+    got2 = np.sort(spec2)[::-1]
+    big = p[:len(got2)] > 1e-10
+    assert np.abs(got2[big] / p[:len(got2)][big] - 1).max() <= 1e-5
+    assert len(spec2) < len(spec)
+    bond.close()

@@ -208,3 +208,10 @@ def test_rho_defect_and_full_analysis_on_gpu(gpu_ctx, tmp_path):
     tr.test_rho_matrix_elements_match_oracle_golden(gpu_ctx)
     tr.test_rho_through_the_z3_fourier_map(gpu_ctx)
     tr.test_full_analysis_golden(gpu_ctx, tmp_path)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("direction", ["left", "right"])
+def test_true_svd_branch_below_cutoff_1e12(gpu_ctx, cplx, direction):
+    """svdBond's `cutoff < 1e-12` branch (preconditioned one-sided Jacobi SVD) vs numpy on a spectrum graded over 24 decades of sigma^2."""
+    common.check_true_svd_branch(gpu_ctx, cplx, direction, D=64)

@@ -99,3 +99,9 @@ def test_block_packed_mps_boundary(emu_ctx, case, shuffle):
 def test_hermitian_eigensolver_two_stage_driver(emu_ctx, monkeypatch, cplx, n, m):
     """Host logic of the two-stage path (panel/GEMM/bulge-chase/back-transformation plumbing) on the emulation backend."""
     common.check_heig_two_stage(emu_ctx, cplx, n, m, monkeypatch)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("direction", ["left", "right"])
+def test_true_svd_branch_below_cutoff_1e12(emu_ctx, cplx, direction):
+    common.check_true_svd_branch(emu_ctx, cplx, direction, D=48)
