@@ -1444,7 +1444,7 @@ static void shard_broadcast(Ctx* c, void* buf, int64_t bytes, int root) {
 }
 
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
-                       int64_t mindim, double cutoff, bool exact_rank, bool normalize) {
+                       int64_t mindim, double cutoff, bool exact_rank, bool normalize, int use_svd) {
   Backend* be = c->be;
   const int nq = pl.L.nq, d = S->d;
   const Grading& Dl = pl.L;
@@ -1468,9 +1468,10 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   // ITensor's MPS::svdBond branch: `if (UseSVD || (noise == 0 && cutoff < 1e-12)) svd-path else denmat-path`.  Chain runs
   // with noise = 0 (src/dmrg.h:350) and cutoffs >= 1e-9 by default, i.e. on the denmat path; a user who tightens -c below 1e-12 lands on the
   // true SVD, whose singular values are resolved down to eps * sigma_max (the eigenvalues of rho = X^H X only down to eps * sigma_max^2, so
-  // sigma^2 < 1e-16 is noise there).  Here: one-sided block Jacobi on the gathered matrix, preconditioned with the eigenvectors of rho so that
-  // it starts from nearly orthogonal columns (CB200_SVD_PRECOND=0: plain Jacobi); truncate() is applied to sigma^2 exactly as on the other path.
-  const bool svd_path = !exact_rank && cutoff < 1e-12;
+  // sigma^2 < 1e-16 is noise there).  Here: one-sided block Jacobi on the gathered matrix with a purely relative stopping criterion (slow:
+  // ~17 sweeps of n/32 rounds, but exact); truncate() is applied to sigma^2 exactly as on the other path.  use_svd: -1 = ITensor's rule,
+  // 0 = always denmat (CalcEE: the p > 1e-12 rule of src/utility.cpp:18-24 needs nothing below 1e-16), 1 = always SVD.
+  const bool svd_path = !exact_rank && (use_svd < 0 ? cutoff < 1e-12 : use_svd > 0);
   bool tri = !force_jacobi && !exact_rank && !svd_path;
   // Multi-GPU: the charge blocks of the middle link are independent eigenproblems; with an exchange available (modes 1, 2) block
   // qm is solved by rank qm % world only and its eigenvalues / kept vectors are broadcast (bit-identical data on every rank, so
@@ -1545,49 +1546,10 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       continue;
     }
     {
-      static const bool precond_on = [] { const char* e = getenv("CB200_SVD_PRECOND"); return !(e && atoi(e) == 0); }();
-      if (svd_path && precond_on && b.n >= 96 && b.rows >= 1) {
-        // V0 = all eigenvectors of rho (orthonormal to working precision), Y = X V0 has nearly orthogonal columns: Jacobi needs a few
-        // sweeps instead of ~17, and the small singular values come out with high relative accuracy; V = V0 V1
-        Heig h0;
-        {
-          Buf rho(be, (int64_t)es * b.n * b.n);
-          GemmBuilder gb(cplx);
-          gb.begin(0, b.n, b.n, b.n, GEMM_TRANS_A | GEMM_CONJ_A);
-          gb.seg(0, ld, 0, ld, b.rows);
-          gb.end();
-          GemmPlan gp;
-          gb.finish(be, gp, true, false);
-          run_gemm(c, cplx, gp, X.p, X.p, rho.p);
-          if (!heig_values(c, cplx, std::move(rho), b.n, h0)) fail(-5, "split_bond: no eigensolver for the SVD preconditioner");
-        }
-        Buf V0 = heig_vectors(c, h0, b.n);
-        Buf Y(be, (int64_t)es * ld * b.n);
-        {
-          GemmBuilder gb(cplx);
-          gb.begin(0, ld, b.rows, b.n, 0);
-          gb.seg(0, ld, 0, b.n, b.n);
-          gb.end();
-          GemmPlan gp;
-          gb.finish(be, gp, false, false);
-          run_gemm(c, cplx, gp, X.p, V0.p, Y.p);
-        }
-        b.jo = jacobi_svd(c, cplx, Y.p, b.rows, b.n, true);
-        const int64_t npad = b.jo.ldv;
-        Buf Vf(be, (int64_t)es * npad * npad, true);
-        {
-          GemmBuilder gb(cplx);
-          gb.begin(0, npad, b.n, npad, 0);
-          gb.seg(0, b.n, 0, npad, b.n);
-          gb.end();
-          GemmPlan gp;
-          gb.finish(be, gp, false, false);
-          run_gemm(c, cplx, gp, V0.p, b.jo.V.p, Vf.p);
-        }
-        b.jo.V = std::move(Vf);
-      } else {
-        b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n, svd_path);
-      }
+      // (svd_path: purely relative stopping criterion -- every singular value to high relative accuracy.  Preconditioning the Jacobi
+      // iteration with the eigenvectors of rho was tried and dropped: in the regime this branch exists for, rho has a cluster of
+      // eigenvalues at rounding level whose eigenvectors inverse iteration cannot make independent.)
+      b.jo = jacobi_svd(c, cplx, X.p, b.rows, b.n, svd_path);
       const int64_t npad = (int64_t)b.jo.w.size();
       b.order.resize(npad);
       std::iota(b.order.begin(), b.order.end(), 0);

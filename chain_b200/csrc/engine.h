@@ -241,7 +241,7 @@ struct SplitResult {
 };
 // MPS::svdBond. dir 0: Fromleft (A isometry), 1: Fromright (B isometry). The weight-carrying tensor is normalised.
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
-                       int64_t mindim, double cutoff, bool exact_rank = false, bool normalize = true);
+                       int64_t mindim, double cutoff, bool exact_rank = false, bool normalize = true, int use_svd = -1);
 
 void env_update_left(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& L, const DevSite3& A, const HostW& W, DevEnv& out);
 void env_update_right(Ctx* c, bool cplx, const SiteInfo* S, const DevEnv& R, const DevSite3& B, const HostW& W, DevEnv& out);

@@ -797,7 +797,7 @@ std::vector<double> mps_entropies(Ctx* c, int nq, int d, const int32_t* site_cha
   for (int i = 0; i + 1 < n; ++i) {
     PhiLayout pl; Buf phi;
     phi_of(i, pl, phi);
-    SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 0, INT64_MAX / 4, 1, 1e-15);
+    SplitResult sr = split_bond(c, cplx, &S, pl, phi.p, 0, INT64_MAX / 4, 1, 1e-15, false, true, 0);
     double sv = 0;
     for (double p : sr.spectrum)
       if (p > 1e-12) sv += -p * std::log(p);
