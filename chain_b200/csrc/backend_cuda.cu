@@ -145,6 +145,11 @@ Backend* backend_create(int device, char* err, size_t errlen) {
     opt((const void*)gemm_grouped_kernel<true, true, false, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
     opt((const void*)gemm_grouped_kernel<true, true, true, 64, true>, GemmCfg<true, 64>::SMEM_BYTES);
   }
+  {
+    const char* e = getenv("CB200_GEMM_BULK");        // 0: per-thread cp.async tile loads for complex operands too (A/B switch)
+    const int v = e ? atoi(e) : 1;
+    cudaMemcpyToSymbol(g_gemm_bulk, &v, sizeof(int));
+  }
   cudaGetLastError();
   return b;
 }

@@ -59,6 +59,45 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
 }
 
+// ---- bulk asynchronous copies (the TMA engine, SASS UBLKCP): one instruction moves a whole contiguous tile row global -> shared and
+// reports its bytes to an mbarrier (complete_tx).  Addresses and sizes must be multiples of 16 bytes.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared.b64 st, [%0], %1;\n}\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s), "l"(gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// 1 = complex operand tiles are staged with bulk copies by ONE producer warp (set from CB200_GEMM_BULK at context creation; default on)
+__device__ int g_gemm_bulk = 1;
+
+// Stage one complex operand tile with bulk copies: a tile row (contiguous in global memory) per copy, issued by the lanes of one warp.
+//   MN_CONTIG: rows = k (kvalid of them, mnvalid elements each), smem row stride LD = BMN + PAD;  else rows = mn (mnvalid, kvalid elements), LD = LDK.
+// Rows / row tails past K must read as zero (they enter every output element) and are written with plain stores; elements past MN are left
+// stale (they only reach output rows / columns that are never stored).
+template <int BMN, int BK, int LD, bool MN_CONTIG>
+__device__ __forceinline__ void bulk_operand_tile(char* smem, const char* g, int64_t ld, int mn0, int mnvalid, int k0, int kvalid, uint64_t* bar, int lane) {
+  const double2 z2 = make_double2(0.0, 0.0);
+  if constexpr (MN_CONTIG) {
+    for (int k = lane; k < kvalid; k += 32)
+      bulk_g2s(smem + (size_t)k * LD * 16, g + ((int64_t)mn0 + (int64_t)(k0 + k) * ld) * 16, (unsigned)mnvalid * 16u, bar);
+    if (kvalid < BK) {
+      double2* s2 = reinterpret_cast<double2*>(smem);
+      for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(kvalid + idx / BMN) * LD + idx % BMN] = z2;
+    }
+  } else {
+    for (int mn = lane; mn < mnvalid; mn += 32)
+      bulk_g2s(smem + (size_t)mn * LD * 16, g + ((int64_t)k0 + (int64_t)(mn0 + mn) * ld) * 16, (unsigned)kvalid * 16u, bar);
+    if (kvalid < BK) {
+      double2* s2 = reinterpret_cast<double2*>(smem);
+      for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(idx / (BK - kvalid)) * LD + kvalid + idx % (BK - kvalid)] = z2;
+    }
+  }
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -212,9 +251,10 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   // fed by whichever of them has a landed tile.
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  const bool bulk = CPLX && g_gemm_bulk != 0;          // complex tiles: 16-byte elements, every row start is 16-byte aligned
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], Cfg::PRODUCERS); mbar_init(&empty_bar[s], Cfg::CONSUMERS / 32); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], bulk ? 1u : (unsigned)Cfg::PRODUCERS); mbar_init(&empty_bar[s], Cfg::CONSUMERS / 32); }
   }
   __syncthreads();
 
@@ -223,6 +263,30 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Cfg::PRODUCER_REGS));
     const int ptid = tid - Cfg::CONSUMERS;
     int ps = 0, pk = 0;
+    if constexpr (CPLX) {
+      if (bulk) {
+        // ---- TMA-engine producer: ONE warp issues a bulk copy per tile row and arms the stage's mbarrier with the byte count
+        if (ptid >= 32) return;
+        const int mvalid = (t.M - m0) < BM ? (t.M - m0) : BM, nvalid = (t.N - n0) < BN ? (t.N - n0) : BN;
+        for (int itl = 0; itl < total_kt; ++itl) {
+          const int stage = itl % STAGES, use = itl / STAGES;
+          if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
+          while (sg[ps].K <= 0) ++ps;
+          const GemmSeg s = sg[ps];
+          char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
+          const int kvalid = (s.K - pk) < BK ? (s.K - pk) : BK;
+          if (ptid == 0) mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(kvalid * (mvalid + nvalid)) * 16u);
+          __syncwarp();
+          bulk_operand_tile<BM, BK, TA ? Cfg::LDK : (BM + Cfg::PAD_MN), !TA>(sa, Abase + s.a_off * ES, s.lda, m0, mvalid, pk, kvalid, &full_bar[stage], ptid);
+          bulk_operand_tile<BN, BK, TB ? (BN + Cfg::PAD_MN) : Cfg::LDK, TB>(sb, Bbase + s.b_off * ES, s.ldb, n0, nvalid, pk, kvalid, &full_bar[stage], ptid);
+          if (kvalid < BK) fence_proxy_async_smem();      // the zero rows were written through the generic proxy
+          pk += BK;
+          if (pk >= s.K) { pk = 0; ++ps; }
+        }
+        return;
+      }
+    }
     for (int itl = 0; itl < total_kt; ++itl) {
       const int stage = itl % STAGES, use = itl / STAGES;
       if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
