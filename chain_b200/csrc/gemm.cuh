@@ -79,22 +79,23 @@ __device__ int g_gemm_bulk = 1;
 // Rows / row tails past K must read as zero (they enter every output element) and are written with plain stores; elements past MN are left
 // stale (they only reach output rows / columns that are never stored).
 template <int BMN, int BK, int LD, bool MN_CONTIG>
-__device__ __forceinline__ void bulk_operand_tile(char* smem, const char* g, int64_t ld, int mn0, int mnvalid, int k0, int kvalid, uint64_t* bar, int lane) {
+__device__ __forceinline__ void bulk_operand_zero_tail(char* smem, int kvalid, int lane) {
   const double2 z2 = make_double2(0.0, 0.0);
+  double2* s2 = reinterpret_cast<double2*>(smem);
+  if constexpr (MN_CONTIG) {
+    for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(kvalid + idx / BMN) * LD + idx % BMN] = z2;
+  } else {
+    for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(idx / (BK - kvalid)) * LD + kvalid + idx % (BK - kvalid)] = z2;
+  }
+}
+template <int BMN, int BK, int LD, bool MN_CONTIG>
+__device__ __forceinline__ void bulk_operand_tile(char* smem, const char* g, int64_t ld, int mn0, int mnvalid, int k0, int kvalid, uint64_t* bar, int lane) {
   if constexpr (MN_CONTIG) {
     for (int k = lane; k < kvalid; k += 32)
       bulk_g2s(smem + (size_t)k * LD * 16, g + ((int64_t)mn0 + (int64_t)(k0 + k) * ld) * 16, (unsigned)mnvalid * 16u, bar);
-    if (kvalid < BK) {
-      double2* s2 = reinterpret_cast<double2*>(smem);
-      for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(kvalid + idx / BMN) * LD + idx % BMN] = z2;
-    }
   } else {
     for (int mn = lane; mn < mnvalid; mn += 32)
       bulk_g2s(smem + (size_t)mn * LD * 16, g + ((int64_t)k0 + (int64_t)(mn0 + mn) * ld) * 16, (unsigned)kvalid * 16u, bar);
-    if (kvalid < BK) {
-      double2* s2 = reinterpret_cast<double2*>(smem);
-      for (int idx = lane; idx < (BK - kvalid) * BMN; idx += 32) s2[(idx / (BK - kvalid)) * LD + kvalid + idx % (BK - kvalid)] = z2;
-    }
   }
 }
 
@@ -251,7 +252,11 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   // fed by whichever of them has a landed tile.
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  const bool bulk = CPLX && g_gemm_bulk != 0;          // complex tiles: 16-byte elements, every row start is 16-byte aligned
+  // Bulk (TMA-engine) staging needs 16-byte aligned row starts -- always true for complex (16-byte elements), not for the odd leading
+  // dimensions of real Z_N sectors -- and pays off only when a tile row is long: with both operands contiguous along M / N (the R-stage
+  // and peer kernels, every rank-k update) a k-tile is 16 + 16 copies of >= 1 KB; a K-contiguous operand would be 64..128 copies of 256 B,
+  // measured 28 % slower than the per-thread cp.async path on the L-stage of BASELINE configs[1] (profiles/r02_bench_cfg2_n4.json).
+  const bool bulk = CPLX && !TA && TB && g_gemm_bulk != 0;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], bulk ? 1u : (unsigned)Cfg::PRODUCERS); mbar_init(&empty_bar[s], Cfg::CONSUMERS / 32); }
@@ -276,11 +281,19 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
           char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
           char* sb = sa + (size_t)Cfg::A_ELEMS * ES;
           const int kvalid = (s.K - pk) < BK ? (s.K - pk) : BK;
+          if (kvalid < BK) {
+            // last k-tile of a segment: the rows / row tails past K enter every output element and must read as zero.  Plain stores, made
+            // visible to the consumers by the release of lane 0's arrive below (after the warp-level barrier), and ordered before later
+            // async-proxy writes to the same bytes
+            bulk_operand_zero_tail<BM, BK, TA ? Cfg::LDK : (BM + Cfg::PAD_MN), !TA>(sa, kvalid, ptid);
+            bulk_operand_zero_tail<BN, BK, TB ? (BN + Cfg::PAD_MN) : Cfg::LDK, TB>(sb, kvalid, ptid);
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
           if (ptid == 0) mbar_arrive_expect_tx(&full_bar[stage], (unsigned)(kvalid * (mvalid + nvalid)) * 16u);
           __syncwarp();
           bulk_operand_tile<BM, BK, TA ? Cfg::LDK : (BM + Cfg::PAD_MN), !TA>(sa, Abase + s.a_off * ES, s.lda, m0, mvalid, pk, kvalid, &full_bar[stage], ptid);
           bulk_operand_tile<BN, BK, TB ? (BN + Cfg::PAD_MN) : Cfg::LDK, TB>(sb, Bbase + s.b_off * ES, s.ldb, n0, nvalid, pk, kvalid, &full_bar[stage], ptid);
-          if (kvalid < BK) fence_proxy_async_smem();      // the zero rows were written through the generic proxy
           pk += BK;
           if (pk >= s.K) { pk = 0; ++ps; }
         }
