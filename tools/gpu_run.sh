@@ -9,6 +9,7 @@
 #   ref[:N]             bench.py --impl reference (under torchrun when N > 1)
 #   launches[:WORKLOAD] ncu launch list (gpu__time_duration) of a short bench run
 #   ncufull:KERNEL_REGEX[:WORKLOAD]  one ncu --set full capture (first 3 matching launches after 20 skipped), raw + details pages
+#   driver:CASE         tools/driver_times.py CASE (cfg1..cfg4 physical runs; the CPU oracle's s/sweep beside the GPU's)
 #   sweep:ARGS          tools/sweep_bench.py ARGS (comma-separated -> spaces, ';' -> ',')
 #   heig:ARGS           tools/heig_bench.py ARGS
 #   py:FILE             python FILE
@@ -38,11 +39,15 @@ for step in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file ${O}_launches_${wl}.csv python bench.py --steps 2 --warmup 3 --workload $wl --no-cpu-baseline --no-sweep > ${O}_launches_${wl}.out 2>&1; echo "[$TAG] launches rc=$?"
       python tools/show_launches.py ${O}_launches_${wl}.csv | head -40 ;;
     ncufull)
-      wl=${b:-cfg2}
-      timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$a" -s 20 -c 3 -o ${O}_ncu_${wl} -f python bench.py --steps 2 --warmup 3 --workload $wl --no-cpu-baseline --no-sweep > ${O}_ncu_${wl}.out 2>&1; echo "[$TAG] ncu full rc=$?"
-      ncu -i ${O}_ncu_${wl}.ncu-rep --page raw --csv > ${O}_ncu_${wl}_raw.csv 2>/dev/null
-      ncu -i ${O}_ncu_${wl}.ncu-rep --page details > ${O}_ncu_${wl}_details.txt 2>/dev/null
-      ls -la ${O}_ncu_${wl}* ;;
+      # ncufull:KERNEL_REGEX:WORKLOAD:SKIP:COUNT:NAME  (one ncu --set full capture of COUNT launches after SKIP matching ones)
+      IFS=':' read -r kind a b c d e <<< "$step"
+      wl=${b:-cfg2}; skip=${c:-6}; cnt=${d:-1}; nm=${e:-k}
+      timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$a" -s $skip -c $cnt -o ${O}_ncu_${wl}_${nm} -f python bench.py --steps 2 --warmup 3 --workload $wl --no-cpu-baseline --no-sweep > ${O}_ncu_${wl}_${nm}.out 2>&1; echo "[$TAG] ncu full rc=$?"
+      ncu -i ${O}_ncu_${wl}_${nm}.ncu-rep --page raw --csv > ${O}_ncu_${wl}_${nm}_raw.csv 2>/dev/null
+      ncu -i ${O}_ncu_${wl}_${nm}.ncu-rep --page details > ${O}_ncu_${wl}_${nm}_details.txt 2>/dev/null
+      ls -la ${O}_ncu_${wl}_${nm}* ;;
+    driver)
+      timeout 900 python tools/driver_times.py $a > ${O}_driver_${a}.json 2> ${O}_driver_${a}.err; echo "[$TAG] driver $a rc=$?"; cut -c1-900 ${O}_driver_${a}.json ;;
     sweep)
       args=$(echo "$a" | tr ',' ' ' | tr ';' ',')
       timeout 1500 python tools/sweep_bench.py $args > ${O}_sweep.json 2> ${O}_sweep.err; echo "[$TAG] sweep rc=$?"; tail -c 1500 ${O}_sweep.json ;;
