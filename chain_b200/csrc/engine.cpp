@@ -203,10 +203,18 @@ struct GemmBuilder {
   void finish(Backend* be, GemmPlan& p, bool ta, bool tb) {
     const int tm = gemm_tile_m(cplx), tn = gemm_tile_n(cplx, mode);
     int tiles = 0;
+    const double es = cplx ? 16.0 : 8.0;
     for (auto& t : tasks) {
       t.tile_begin = tiles;
       t.tiles_m = (t.M + tm - 1) / tm;
       tiles += t.tiles_m * ((t.N + tn - 1) / tn);
+      // tile order: with M-fastest numbering the A operand is re-read from DRAM once per column tile as soon as it outgrows L2 (ncu, R-stage of
+      // BASELINE configs[1]: 58.8 GB read for 13.3 GB of operands).  When A is the large operand, number the tiles N-fastest instead: the
+      // CTAs resident at the same time share A rows, and B (tens of MB per task) stays in the 126 MB L2.
+      double ktot = 0;
+      for (int sidx = t.seg_begin; sidx < t.seg_begin + t.seg_count; ++sidx) ktot += segs[sidx].K;
+      const double bytes_a = es * t.M * ktot, bytes_b = es * t.N * ktot;
+      if (bytes_a > 48e6 && bytes_a > bytes_b && (t.N + tn - 1) / tn > 1) t.flags |= GEMM_TILE_N_FAST;
     }
     p.tasks.upload(be, tasks);
     p.segs.upload(be, segs);

@@ -238,8 +238,10 @@ __device__ __forceinline__ void gemm_grouped_body(const char* __restrict__ Abase
   }
   const GemmTask t = tasks[lo];
   const int lt = tile - t.tile_begin;
-  const int m0 = (lt % t.tiles_m) * BM;
-  const int n0 = (lt / t.tiles_m) * BN;
+  const int tiles_n = (t.N + BN - 1) / BN;
+  const bool n_fast = (t.flags & GEMM_TILE_N_FAST) != 0;
+  const int m0 = (n_fast ? lt / tiles_n : lt % t.tiles_m) * BM;
+  const int n0 = (n_fast ? lt % tiles_n : lt / t.tiles_m) * BN;
   const GemmSeg* sg = segs + t.seg_begin;
 
   int total_kt = 0;

@@ -13,6 +13,8 @@ enum : uint32_t {
   GEMM_ACCUM   = 8u,   // C += result (otherwise C = result)
   GEMM_CONJ_OUT = 16u, // complex only: store conj(result)
   GEMM_TRANS_C = 32u,  // store element (m,n) at C[n + m*ldc] (lets the planner pick the operand roles that waste fewer tile slots)
+  GEMM_TILE_N_FAST = 64u,  // number the task's tiles N-fastest: concurrently resident CTAs then share the A rows (set by the planner when
+                           // A is the large streamed operand, e.g. the 12.8 GB intermediate of the R-stage at D = 1600, and B fits in L2)
 };
 
 // One K-segment of a task: C += op(A_seg) * op(B_seg).  Offsets are in elements from the base pointers
@@ -25,7 +27,7 @@ struct GemmSeg {
 };
 
 // C (M x N, ldc) = sum over segments.  Tiles of one task are numbered tile_begin .. tile_begin+tiles-1,
-// M-fastest, so that concurrently resident CTAs share B tiles through L2.
+// M-fastest, so that concurrently resident CTAs share B tiles through L2 (N-fastest with GEMM_TILE_N_FAST).
 struct GemmTask {
   int64_t c_off, ldc;
   int64_t c_off2;       // columns n >= n_split are stored at c_off2 + (n - n_split)*ldc (block-Jacobi column shuffles)
