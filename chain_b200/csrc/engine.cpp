@@ -504,6 +504,15 @@ void Bond::plan() {
 
   // ---- GEMM1: T1(qa,ql) = L(ql+qa, qa) [ (l',a) x l ] * Phi_ql [ l x cols ]
   {
+    const char* eb = getenv("CB200_GEMM_BULK");
+    g1_tb = cplx && !(eb && atoi(eb) == 0);
+    phit_tasks.clear();
+    if (g1_tb) {
+      CopyBuilder ct;
+      for (int ql = 0; ql < nq; ++ql)   // phiT_ql[n + ncols*l] = phi_ql[l + Dl*n]
+        ct.add(philay.o(ql, 0), philay.o(ql, 0), Dl.dim[ql], 1, philay.ncols(ql), philay.ncols(ql), Dl.dim[ql], 1);
+      phit_tasks = ct.tasks;
+    }
     GemmBuilder gb(cplx, heavy_mode(cplx));
     for (int qa = 0; qa < nq; ++qa)
       for (int ql = 0; ql < nq; ++ql) {
@@ -512,10 +521,11 @@ void Bond::plan() {
         if (M == 0 || N == 0) continue;   // K == 0 still emits the task: it zero-fills the block the mix stage reads
         gb.ratio = ratio[qlp];
         gb.begin(t1off[qa * nq + ql], M, M, N, 0);
-        gb.seg(l_off(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
+        if (g1_tb) gb.seg(l_off(qlp, qa), M, philay.o(ql, 0), N, K);      // B = phiT_ql: element (k, n) at n + N*k
+        else gb.seg(l_off(qlp, qa), M, philay.o(ql, 0), Dl.dim[ql], K);
         gb.end();
       }
-    gb.finish(be, g1, false, false);
+    gb.finish(be, g1, false, g1_tb);
     flops_alg_full = gb.flops_full * (cplx ? 4.0 : 1.0);
   }
   // ---- Omega = W1 (x) W2 contracted over the middle MPO link, as a sparse map (a,s1,s2) -> (a'',t1,t2); it depends on the MPO
@@ -615,12 +625,21 @@ void Bond::plan() {
   check_dev(ctx);
 }
 
+const void* Bond::l_stage_input(const void* x) {
+  if (!g1_tb || philay.total == 0) return x;
+  void* xt = workspace(ctx, WS_PHIT, (int64_t)esz(cplx) * std::max<int64_t>(philay.total, 1));
+  CopyBuilder ct;
+  ct.tasks = phit_tasks;
+  ct.run(ctx, cplx, x, xt);
+  return xt;
+}
+
 void Bond::apply(const void* x, void* y) {
   Backend* be = ctx->be;
   const void* Lp = sharded ? Lloc.p : L;
   void* t1 = workspace(ctx, WS_T1, (int64_t)esz(cplx) * std::max<int64_t>(t1_elems, 1));
   void* t2 = workspace(ctx, WS_T2, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
-  run_gemm(ctx, cplx, g1, Lp, x, t1);
+  run_gemm(ctx, cplx, g1, Lp, l_stage_input(x), t1);
   run_mix(ctx, cplx, mix, t1, t2);
   const void* A2 = g2_swapped ? R : t2;
   const void* B2 = g2_swapped ? t2 : R;
@@ -663,7 +682,7 @@ void Bond::stage_times(const void* x, void* y, int reps, double* ms3) {
   void* t2 = workspace(ctx, WS_T2, (int64_t)esz(cplx) * std::max<int64_t>(t2_elems, 1));
   for (int i = 0; i < reps; ++i) {
     dev_event_record(be, 0);
-    run_gemm(ctx, cplx, g1, Lp, x, t1);
+    run_gemm(ctx, cplx, g1, Lp, l_stage_input(x), t1);     // (the transposition of phi is part of the stage)
     dev_event_record(be, 1);
     run_mix(ctx, cplx, mix, t1, t2);
     dev_event_record(be, 2);

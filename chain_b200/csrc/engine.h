@@ -178,7 +178,7 @@ struct Ctx {
   // a sweep does not churn multi-GB temporaries through the allocator at every bond
   std::vector<Buf> ws;
 };
-enum { WS_T1 = 0, WS_T2 = 1, WS_V = 2, WS_AV = 2 + MAX_LC, WS_Q = 2 + 2 * MAX_LC, WS_COUNT = 3 + 2 * MAX_LC };
+enum { WS_T1 = 0, WS_T2 = 1, WS_V = 2, WS_AV = 2 + MAX_LC, WS_Q = 2 + 2 * MAX_LC, WS_PHIT = 3 + 2 * MAX_LC, WS_COUNT = 4 + 2 * MAX_LC };
 void* workspace(Ctx* c, int slot, int64_t bytes);
 std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2);
 
@@ -207,6 +207,11 @@ struct Bond {
   bool g2_swapped = false;   // R-stage computed as the transposed product (see Bond::plan)
   MixPlan mix;
   int64_t t1_elems = 0, t2_elems = 0;   // intermediates live in the context workspace (WS_T1, WS_T2)
+  // complex data: the L-stage reads phi TRANSPOSED per left sector (phiT_ql[n, l], one strided-copy launch per product, < 0.5 % of the
+  // stage) so that both GEMM operands are contiguous along M / N and their tiles are staged by bulk (TMA-engine) copies
+  bool g1_tb = false;
+  std::vector<CopyTask> phit_tasks;
+  const void* l_stage_input(const void* x);
   double flops_alg = 0;      // SURVEY 8(d) F_alg
   // penalty
   std::vector<const void*> pen;   // device phi-layout vectors (not owned)
