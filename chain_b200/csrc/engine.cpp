@@ -1066,24 +1066,33 @@ static void sb_stage1(Ctx* c, Heig& h) {
   const int npan = h.npan;
   const int PMAX = 8;
   const int64_t len0 = n - B;
-  // arena: [Y panels | X (len0 x B) | W0 partials (PMAX x len0 x B) | S2 partials (PMAX x B x B) | Mm (B x B)]
-  const int64_t oX = h.yoff[npan], oW0 = oX + len0 * B, oS2 = oW0 + (int64_t)PMAX * len0 * B, oM = oS2 + (int64_t)PMAX * B * B, tot = oM + B * B;
+  // arena: [Y panels | X1 | X2 (len0 x B each) | W0 partials (PMAX x len0 x B) | S2 partials (2 PMAX x B x B) | Mm (B x B)]
+  const int64_t oX1 = h.yoff[npan], oX2 = oX1 + len0 * B, oW0 = oX2 + len0 * B, oS2 = oW0 + (int64_t)PMAX * len0 * B,
+                oM = oS2 + 2 * (int64_t)PMAX * B * B, tot = oM + B * B;
   h.Yall = Buf(be, (int64_t)es * tot);
-  h.Tall = Buf(be, (int64_t)es * 2 * std::max(npan, 1) * B * B);
-  const int64_t oTh = (int64_t)npan * B * B;
+  // Tall: [npan x B^2 of -T | npan x B^2 of -T/2 | G12T | H12T]  (the last two: coupling blocks of a panel pair, see below)
+  h.Tall = Buf(be, (int64_t)es * (2 * std::max(npan, 1) + 2) * B * B);
+  const int64_t oTh = (int64_t)npan * B * B, oG = 2 * (int64_t)npan * B * B, oH = oG + B * B;
   const int narrow = cx ? GEMM_TILE_NARROW_3M : GEMM_TILE_NARROW;
   const uint32_t cj = cx ? (uint32_t)GEMM_CONJ_A : 0u;
-  for (int p = 0; p < npan; ++p) {
-    const int64_t j0 = (int64_t)p * B, r0 = j0 + B, len = n - r0;
+  const uint32_t upd = GEMM_ACCUM | (cx ? (uint32_t)(GEMM_CONJ_A | GEMM_CONJ_OUT) : 0u);   // C += Wn Y^H + Y Wn^H as conj(conj(Wn) Y^T + conj(Y) Wn^T)
+  static const bool defer = [] { const char* e = getenv("CB200_SB_DEFER"); return !(e && atoi(e) == 0); }();
+  auto split_k = [&](int64_t len, int* P, int64_t* chunk) {
+    // split K so that the skinny products fill the machine: tiles(len / tile_m) x P ~ 2 waves
+    const int64_t tiles = (len + gemm_tile_m(cx) - 1) / gemm_tile_m(cx);
+    *P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, std::min<int64_t>((296 + tiles - 1) / tiles, len / 256)));
+    *chunk = ((len + *P - 1) / *P + 15) / 16 * 16;
+  };
+  // Wn (negated W) of panel p into arena slot oX, for the trailing matrix at element offset a22 of A.  corr = true: the trailing matrix
+  // still lacks the update of the PREVIOUS panel (deferred), whose Y / Wn rows from B on are at oYp / oXp (ld lenp):
+  //   A22' Y = A22 Y + Wn_prev (Y_prev^H Y) + Y_prev (Wn_prev^H Y)
+  auto panel_wn = [&](int p, int64_t oX, bool corr, int64_t oYp, int64_t oXp, int64_t lenp) {
+    const int64_t r0 = (int64_t)p * B + B, len = n - r0, a22 = r0 + r0 * n;
     const int64_t oY = h.yoff[p], oT = (int64_t)p * B * B;
-    launch_panel_qr(be, cx, h.A.p, n, j0, (char*)h.Yall.p + es * (size_t)oY, (char*)h.Tall.p + es * (size_t)oT, (char*)h.Tall.p + es * (size_t)(oTh + oT));
-    const int64_t a22 = r0 + r0 * n;
-    // split K so that the skinny products fill the machine: tiles(len/128) x P ~ 2 waves
-    const int tm = gemm_tile_m(cx);
-    const int64_t tiles = (len + tm - 1) / tm;
-    const int P = (int)std::max<int64_t>(1, std::min<int64_t>(PMAX, std::min<int64_t>((296 + tiles - 1) / tiles, len / 256)));
-    const int64_t chunk = ((len + P - 1) / P + 15) / 16 * 16;
-    GemmPlan p_w0, p_x, p_s2, p_m, p_wn, p_up;
+    int P;
+    int64_t chunk;
+    split_k(len, &P, &chunk);
+    GemmPlan p_w0, p_x, p_s2, p_m, p_wn, p_c1, p_c2;
     {   // W0_pp = A22[:, k-range] * Y[k-range, :]
       GemmBuilder g(cx, narrow);
       for (int pp = 0; pp < P; ++pp) {
@@ -1096,10 +1105,36 @@ static void sb_stage1(Ctx* c, Heig& h) {
       g.finish(be, p_w0, false, false);
     }
     const int np = p_w0.tasks.n;
-    {   // X' = sum_pp W0_pp * Tn
+    if (corr) {
+      {   // G12_pp = Y_prev[B:]^H Y,  H12_pp = Wn_prev[B:]^H Y   (partials over K = len)
+        GemmBuilder g(cx, GEMM_TILE_NARROW);
+        for (int pp = 0; pp < np; ++pp) {
+          const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
+          g.begin(oS2 + (int64_t)(2 * pp) * B * B, B, B, B, GEMM_TRANS_A | cj);
+          g.seg(oYp + k0, lenp, oY + k0, len, kn);
+          g.end();
+          g.begin(oS2 + (int64_t)(2 * pp + 1) * B * B, B, B, B, GEMM_TRANS_A | cj);
+          g.seg(oXp + k0, lenp, oY + k0, len, kn);
+          g.end();
+        }
+        g.finish(be, p_c1, true, false);
+      }
+      {   // G12T = (sum_pp G12_pp) Tn,  H12T = (sum_pp H12_pp) Tn   -> scratch blocks behind the T factors
+        GemmBuilder g(cx, GEMM_TILE_NARROW);
+        g.begin(oG, B, B, B, 0);
+        for (int pp = 0; pp < np; ++pp) g.seg(oS2 + (int64_t)(2 * pp) * B * B, B, oT, B, B);
+        g.end();
+        g.begin(oH, B, B, B, 0);
+        for (int pp = 0; pp < np; ++pp) g.seg(oS2 + (int64_t)(2 * pp + 1) * B * B, B, oT, B, B);
+        g.end();
+        g.finish(be, p_c2, false, false);
+      }
+    }
+    {   // X' = sum_pp W0_pp * Tn  (+ Wn_prev G12T + Y_prev H12T)
       GemmBuilder g(cx, GEMM_TILE_NARROW);
       g.begin(oX, len, len, B, 0);
       for (int pp = 0; pp < np; ++pp) g.seg(oW0 + (int64_t)pp * len * B, len, oT, B, B);
+      if (corr) { g.seg(oXp, lenp, oG, B, B); g.seg(oYp, lenp, oH, B, B); }
       g.end();
       g.finish(be, p_x, false, false);
     }
@@ -1127,20 +1162,67 @@ static void sb_stage1(Ctx* c, Heig& h) {
       g.end();
       g.finish(be, p_wn, false, false);
     }
-    {   // A22 += Wn Y^H + Y Wn^H   (complex: conj(conj(Wn) Y^T + conj(Y) Wn^T))
-      GemmBuilder g(cx, heavy_mode(cx));
-      g.begin(a22, n, len, len, GEMM_ACCUM | (cx ? (uint32_t)(GEMM_CONJ_A | GEMM_CONJ_OUT) : 0u));
-      g.seg(oX, len, oY, len, B);
-      g.seg(oY, len, oX, len, B);
-      g.end();
-      g.finish(be, p_up, false, true);
-    }
     run_gemm(c, cx, p_w0, h.A.p, h.Yall.p, h.Yall.p);
+    if (corr) {
+      run_gemm(c, cx, p_c1, h.Yall.p, h.Yall.p, h.Yall.p);
+      run_gemm(c, cx, p_c2, h.Yall.p, h.Tall.p, h.Tall.p);
+    }
     run_gemm(c, cx, p_x, h.Yall.p, h.Tall.p, h.Yall.p);
     run_gemm(c, cx, p_s2, h.Yall.p, h.Yall.p, h.Yall.p);
     run_gemm(c, cx, p_m, h.Tall.p, h.Yall.p, h.Yall.p);
     run_gemm(c, cx, p_wn, h.Yall.p, h.Yall.p, h.Yall.p);
-    run_gemm(c, cx, p_up, h.Yall.p, h.Yall.p, h.A.p);
+  };
+  auto qr = [&](int p) {
+    const int64_t oT = (int64_t)p * B * B;
+    launch_panel_qr(be, cx, h.A.p, n, (int64_t)p * B, (char*)h.Yall.p + es * (size_t)h.yoff[p], (char*)h.Tall.p + es * (size_t)oT,
+                    (char*)h.Tall.p + es * (size_t)(oTh + oT));
+  };
+  // Panels are processed in PAIRS with the trailing update deferred: after panel p only the 64 columns panel p+1 factors are updated, and
+  // the big update then carries both panels -- rank 256 instead of rank 128, i.e. 16 k-tiles of work per 128 x 128 output tile instead of 8
+  // (the rank-128 update ran at 11 TFLOP/s, a third of the kernel's rate on long contractions).
+  for (int p = 0; p < npan;) {
+    const int64_t r0 = (int64_t)p * B + B, len1 = n - r0, a22 = r0 + r0 * n, oY1 = h.yoff[p];
+    qr(p);
+    panel_wn(p, oX1, false, 0, 0, 0);
+    const bool pair = defer && p + 1 < npan;
+    if (!pair) {
+      GemmPlan p_up;
+      GemmBuilder g(cx, heavy_mode(cx));
+      g.begin(a22, n, len1, len1, upd);
+      g.seg(oX1, len1, oY1, len1, B);
+      g.seg(oY1, len1, oX1, len1, B);
+      g.end();
+      g.finish(be, p_up, false, true);
+      run_gemm(c, cx, p_up, h.Yall.p, h.Yall.p, h.A.p);
+      p += 1;
+      continue;
+    }
+    {   // the first 64 columns of the trailing matrix (all rows): A22[:, 0:B] += Wn1 Y1[0:B]^H + Y1 Wn1[0:B]^H
+      GemmPlan p_col;
+      GemmBuilder g(cx, GEMM_TILE_NARROW);
+      g.begin(a22, n, len1, B, upd);
+      g.seg(oX1, len1, oY1, len1, B);
+      g.seg(oY1, len1, oX1, len1, B);
+      g.end();
+      g.finish(be, p_col, false, true);
+      run_gemm(c, cx, p_col, h.Yall.p, h.Yall.p, h.A.p);
+    }
+    qr(p + 1);
+    const int64_t len2 = len1 - B, oY2 = h.yoff[p + 1], a22b = (r0 + B) + (r0 + B) * n;
+    panel_wn(p + 1, oX2, true, oY1 + B, oX1 + B, len1);
+    {   // A22[B:, B:] += Wn1[B:] Y1[B:]^H + Y1[B:] Wn1[B:]^H + Wn2 Y2^H + Y2 Wn2^H
+      GemmPlan p_up;
+      GemmBuilder g(cx, heavy_mode(cx));
+      g.begin(a22b, n, len2, len2, upd);
+      g.seg(oX1 + B, len1, oY1 + B, len1, B);
+      g.seg(oY1 + B, len1, oX1 + B, len1, B);
+      g.seg(oX2, len2, oY2, len2, B);
+      g.seg(oY2, len2, oX2, len2, B);
+      g.end();
+      g.finish(be, p_up, false, true);
+      run_gemm(c, cx, p_up, h.Yall.p, h.Yall.p, h.A.p);
+    }
+    p += 2;
   }
   h.AB = Buf(be, (int64_t)es * SB_LD * n);
   launch_band_extract(be, cx, h.A.p, n, h.AB.p);
