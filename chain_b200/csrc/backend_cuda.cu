@@ -1435,9 +1435,13 @@ void launch_q2_apply(Backend* b, bool cplx, const void* V2, const void* tau2, in
   const void* fn = cplx ? (const void*)q2_apply_kernel<true> : (const void*)q2_apply_kernel<false>;
   const size_t smem = cplx ? q2_smem_bytes<true>() : q2_smem_bytes<false>();
   opt_in_smem(fn, smem);
-  const int grid = (int)((m + Q2_NC - 1) / Q2_NC);
-  if (cplx) q2_apply_kernel<true><<<grid, Q2_THREADS, smem, b->stream>>>(V2, T8, n, Z, m);
-  else q2_apply_kernel<false><<<grid, Q2_THREADS, smem, b->stream>>>(V2, T8, n, Z, m);
+  // a CTA applies ALL reflector blocks to its columns, so only the columns are parallel: 4 columns per warp, as few warps per CTA as it
+  // takes to give every SM a CTA (the per-block time is shared-memory / shuffle bound and grows with the warp count)
+  const int sms = sm_count(b);
+  const int warps = (int)std::max<int64_t>(1, std::min<int64_t>(Q2_THREADS / 32, (m + 4 * (int64_t)sms - 1) / (4 * (int64_t)sms)));
+  const int grid = (int)((m + 4 * warps - 1) / (4 * warps));
+  if (cplx) q2_apply_kernel<true><<<grid, 32 * warps, smem, b->stream>>>(V2, T8, n, Z, m);
+  else q2_apply_kernel<false><<<grid, 32 * warps, smem, b->stream>>>(V2, T8, n, Z, m);
   CB_LAUNCH_CHECK(b, "q2_apply_kernel");
   dev_free(b, T8);
 }

@@ -494,14 +494,20 @@ __global__ void __launch_bounds__(256) q2_tprep_kernel(const void* __restrict__ 
 }
 
 template <int G, class T>
-__device__ __forceinline__ void q2_load_block(T* Vs, T* Tg, const T* __restrict__ V2, const T* __restrict__ T8, long long blk, int tid) {
-  // compact copy of the band of the reflector block: Vs[sp][8 + i] = V2blk[sp*SB_VLD + sp + i]; and the block's 8 T factors
+__device__ __forceinline__ void q2_load_block(T* Vs, T* Tg, const T* __restrict__ V2, const T* __restrict__ T8, long long blk, int tid, int nthr) {
+  // compact copy of the band of the reflector block: Vs[sp][8 + i] = V2blk[sp*SB_VLD + sp + i]; and the block's T factors.  Asynchronous
+  // copies (no register staging): the next block streams in while the current one is applied
   const T* src = V2 + blk * (long long)SB_VLD * SB_B;
-  for (int idx = tid; idx < SB_B * SB_B; idx += Q2_THREADS) {
+  for (int idx = tid; idx < SB_B * SB_B; idx += nthr) {
     const int sp = idx >> 6, i = idx & 63;
-    Vs[sp * Q2_VROW + 8 + i] = src[sp * SB_VLD + sp + i];
+    if constexpr (sizeof(T) == 16) cp_async16(Vs + sp * Q2_VROW + 8 + i, src + sp * SB_VLD + sp + i, 16);
+    else cp_async8(Vs + sp * Q2_VROW + 8 + i, src + sp * SB_VLD + sp + i, 8);
   }
-  for (int idx = tid; idx < SB_B * G; idx += Q2_THREADS) Tg[idx] = T8[blk * (SB_B * G) + idx];
+  for (int idx = tid; idx < SB_B * G; idx += nthr) {
+    if constexpr (sizeof(T) == 16) cp_async16(Tg + idx, T8 + blk * (SB_B * G) + idx, 16);
+    else cp_async8(Tg + idx, T8 + blk * (SB_B * G) + idx, 8);
+  }
+  cp_async_commit();
 }
 
 // Lane layout inside a warp: column cl = lane >> 3 (4 columns), part = lane & 7; the thread owns window rows a = part + 8 k, k = 0..15, of
@@ -520,13 +526,15 @@ q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ T8_, long
   extern __shared__ __align__(16) char smem_raw[];
   T* Vbuf = reinterpret_cast<T*>(smem_raw);            // [2][B][Q2_VROW]
   T* tbuf = Vbuf + 2 * B * Q2_VROW;                    // [2][64/G groups][G*G] (+ slack: lanes part >= G read past their group's rows)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   const int part = lane & 7, lbase = lane & ~7;
-  const long long col = (long long)blockIdx.x * Q2_NC + warp * 4 + (lane >> 3);
+  // blockDim.x / 32 warps of 4 columns each: the host picks the warp count so that the column chunks cover all SMs (a CTA walks ALL blocks
+  // sequentially; only the columns are parallel)
+  const long long col = (long long)blockIdx.x * (nthr >> 3) + warp * 4 + (lane >> 3);
   const bool live = col < m;
   T* zc = Z + (live ? col : 0) * n;
   const T zero = t_zero(T());
-  for (int idx = tid; idx < 2 * B * Q2_VROW; idx += Q2_THREADS) Vbuf[idx] = zero;
+  for (int idx = tid; idx < 2 * B * Q2_VROW; idx += nthr) Vbuf[idx] = zero;
   __syncthreads();
   const long long K0 = (n - 1 + B - 1) / B;
   T z[16];
@@ -539,14 +547,15 @@ q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ T8_, long
       const long long row = base + part + 8 * k;
       z[k] = (live && row < n) ? zc[row] : zero;
     }
-    q2_load_block<G>(Vbuf, tbuf, V2, T8, blk0, tid);
+    q2_load_block<G>(Vbuf, tbuf, V2, T8, blk0, tid, nthr);
+    cp_async_wait<0>();
     __syncthreads();
     for (long long k = 0; k < nk; ++k) {
       const int cur = (int)(k & 1);
       // prefetch the next block of reflectors and the next 64 rows of Z while this block is applied
       T znext[8];
       if (k + 1 < nk) {
-        q2_load_block<G>(Vbuf + (cur ^ 1) * B * Q2_VROW, tbuf + (cur ^ 1) * B * G, V2, T8, blk0 + k + 1, tid);
+        q2_load_block<G>(Vbuf + (cur ^ 1) * B * Q2_VROW, tbuf + (cur ^ 1) * B * G, V2, T8, blk0 + k + 1, tid, nthr);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const long long row = base + 128 + part + 8 * kk;
@@ -609,6 +618,7 @@ q2_apply_kernel(const void* __restrict__ V2_, const void* __restrict__ T8_, long
           if (live && row < n) zc[row] = z[kk];
         }
       }
+      cp_async_wait<0>();
       __syncthreads();
     }
   }
