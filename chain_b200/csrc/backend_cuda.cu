@@ -6,6 +6,7 @@
 //   * jacobi_eig_kernel            -> 2JB x 2JB Hermitian eigensolver in shared memory (block one-sided Jacobi SVD)
 // There is no CPU fallback here: every entry point launches a kernel or reports a CUDA error.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <cstdio>
@@ -100,6 +101,17 @@ Backend* backend_create(int device, char* err, size_t errlen) {
   if (device < 0 || device >= ndev) {
     snprintf(err, errlen, "chain_b200: device %d out of range (%d devices)", device, ndev);
     return nullptr;
+  }
+  // One device per process.  Kernel attributes (dynamic shared memory opt-ins), occupancy caches and the current-device setting are
+  // process-wide state; the multi-GPU design is one process per GPU, so a second context on a DIFFERENT device is refused
+  // instead of silently launching on the wrong one.
+  {
+    static std::atomic<int> bound_device{-1};
+    int expected = -1;
+    if (!bound_device.compare_exchange_strong(expected, device) && expected != device) {
+      snprintf(err, errlen, "chain_b200: this process already drives device %d; one device per process (launch one process per GPU)", expected);
+      return nullptr;
+    }
   }
   cudaSetDevice(device);
   Backend* b = new Backend();
@@ -518,31 +530,35 @@ __global__ void __launch_bounds__(MIX_THREADS, 1) mix_smem_kernel(const void* __
   cp_async_wait<0>();
   __syncthreads();
   T* out = reinterpret_cast<T*>(out_);
-  // One warp per output slot: the warp reads 32 entries with one coalesced load and broadcasts them lane by lane
-  // with shuffles, so the inner loop has no global-memory latency: LDS (the row's input) + 4 DFMA per entry.
+  // One warp per output slot: the warp reads 32 entries with one coalesced load, parks them in a warp-private strip of shared memory and
+  // then reads them back one by one as BROADCAST loads (every lane the same address: one wavefront each).  The inner loop is bound by the
+  // LSU / shuffle unit, not by HBM: the round-1 form broadcast (cre, cim, slot) with five 32-bit shuffles per entry.
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) double2 s_coef[MIX_THREADS];     // [warp][32]
+  __shared__ int s_slot[MIX_THREADS];
+  double2* wc = s_coef + (threadIdx.x & ~31);
+  int* ws = s_slot + (threadIdx.x & ~31);
   for (int o = p.out_begin + grp; o < p.out_end; o += G) {
     const MixOut mo = outs[o];
     double ar = 0.0, ai = 0.0;
     for (int base = mo.e_begin; base < mo.e_end; base += 32) {
       const int cnt = min(32, mo.e_end - base);
-      double cre = 0.0, cim = 0.0;
-      int slot = 0;
+      __syncwarp();
       if (lane < cnt) {
-        const double2 c = __ldg(reinterpret_cast<const double2*>(&ents[base + lane].cre));
-        cre = c.x; cim = c.y;
-        slot = __ldg(&ents[base + lane].slot);
+        wc[lane] = __ldg(reinterpret_cast<const double2*>(&ents[base + lane].cre));
+        ws[lane] = __ldg(&ents[base + lane].slot);
       }
+      __syncwarp();
+#pragma unroll 4
       for (int j = 0; j < cnt; ++j) {
-        const double cr = __shfl_sync(0xffffffffu, cre, j);
-        const int sl = __shfl_sync(0xffffffffu, slot, j);
+        const double2 c = wc[j];
+        const int sl = ws[j];
         if constexpr (!CPLX) {
-          ar = fma(cr, sm[sl * RB + lrow], ar);
+          ar = fma(c.x, sm[sl * RB + lrow], ar);
         } else {
-          const double ci = __shfl_sync(0xffffffffu, cim, j);
           const double2 v = sm[sl * RB + lrow];
-          ar = fma(cr, v.x, ar); ar = fma(-ci, v.y, ar);
-          ai = fma(cr, v.y, ai); ai = fma(ci, v.x, ai);
+          ar = fma(c.x, v.x, ar); ar = fma(-c.y, v.y, ar);
+          ai = fma(c.x, v.y, ai); ai = fma(c.y, v.x, ai);
         }
       }
     }
@@ -1241,7 +1257,8 @@ bool launch_tridiag_batched(Backend* b, bool cplx, const TriProblem* probs, int 
   }
   if (d_ctr) dev_free(b, d_ctr);
   if (d_descs) dev_free(b, d_descs);
-  return true;
+  if (!ok) set_err(b, "launch_tridiag_batched: allocation of the panel / descriptor buffers failed", cudaErrorMemoryAllocation);
+  return ok;   // false: the caller must not read d / e (they were never written)
 }
 
 static double* tri_bounds(Backend* b, const double* d, const double* e, int64_t n) {

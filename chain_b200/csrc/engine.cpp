@@ -1679,6 +1679,8 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
         }
       }
     } else {   // a backend without the tridiagonalisation kernel: one-sided block Jacobi on the gathered matrices
+      // (blocks owned by other ranks were never gathered here: under a spread truncation there is nothing to fall back to)
+      if (spread) fail(-5, "split_bond: the tridiagonal eigensolver is unavailable and the truncation is spread over the ranks");
       tri = false;
       for (int qm : rho_q) {
         Blk& b = blk[qm];

@@ -40,6 +40,8 @@ enum cb200_status {
 };
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
+/* One device per process: every context of a process must name the same device (kernel attributes and the current-device setting are
+ * process-wide); a second context on a different device fails with CB200_ERR_INVALID / CB200_ERR_NO_DEVICE.  Multi-GPU = one process per GPU. */
 int cb200_create(cb200_ctx** out, int device);
 void cb200_destroy(cb200_ctx* ctx);
 const char* cb200_last_error(const cb200_ctx* ctx);   /* ctx may be NULL: error of the last failed cb200_create */
