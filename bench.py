@@ -309,7 +309,8 @@ def main():
     nbytes = int(nb * phi.itemsize)
 
     # ---- one complete bond update resident on the device (davidson -> svdBond -> makeL): the unit a DMRG sweep is made of
-    bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)           # warm-up (grows the memory pool)
+    for _ in range(2):      # two warm-ups: the first grows the memory pool, the second still re-shapes the allocator's block cache
+        bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)    # (A/B in round 2: call 2 of a process 0.45-0.56 s, calls 1, 3, 4.. 0.29 s)
     barrier()
     bu = bond.update_timed(phi, "left", maxdim=w["dims"]["D"], cutoff=1e-12)
     barrier()
