@@ -1242,6 +1242,27 @@ static void sb_stage2(Ctx* c, bool cplx, const std::vector<Heig*>& hs) {
   if (!probs.empty()) launch_bulge_chase(c->be, cplx, probs.data(), (int)probs.size());
 }
 
+// ---- column slices over the ranks of a sharded context (dense truncation, multi-GPU) ---------------------------------------------------
+// The O(n^3) pieces of the truncation that are independent column by column -- rho = X^H X, the back-transformation of the kept
+// eigenvectors through Q2 and Q1, X V_kept -- are computed for a contiguous slice of columns per rank and the slices are exchanged with the
+// context's broadcast (NVLink peer stores or ncclBroadcast).  A column is produced by the same kernels with the same per-element
+// summation order whichever rank owns it, so every rank ends up with bit-identical data and the replicated parts stay in lockstep.
+static bool cols_sharded(const Ctx* c, int64_t ncols) { return c->shard.world > 1 && c->shard.mode != 0 && ncols >= 2 * (int64_t)c->shard.world; }
+static void col_slice(const Ctx* c, int64_t ncols, int rank, int64_t* c0, int64_t* c1) {
+  int64_t per = (ncols + c->shard.world - 1) / c->shard.world;
+  per = (per + 1) / 2 * 2;                                    // even slice starts keep every slice 16-byte aligned for real data as well
+  *c0 = std::min<int64_t>((int64_t)rank * per, ncols);
+  *c1 = std::min<int64_t>(*c0 + per, ncols);
+}
+static void shard_broadcast(Ctx* c, void* buf, int64_t bytes, int root);
+static void gather_cols(Ctx* c, void* buf, int64_t col_bytes, int64_t ncols) {
+  for (int g = 0; g < c->shard.world; ++g) {
+    int64_t c0, c1;
+    col_slice(c, ncols, g, &c0, &c1);
+    if (c1 > c0) shard_broadcast(c, (char*)buf + col_bytes * c0, col_bytes * (c1 - c0), g);
+  }
+}
+
 bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h) {
   Backend* be = c->be;
   const size_t es = esz(cplx);
@@ -1303,7 +1324,7 @@ bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vec
   return true;
 }
 
-Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
+Buf heig_vectors(Ctx* c, Heig& h, int64_t m, bool shard_cols) {
   Backend* be = c->be;
   const int64_t n = h.n;
   const size_t es = esz(h.cplx);
@@ -1362,9 +1383,15 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
     const bool cx = h.cplx;
     const int B = SB_B;
     launch_zt_to_v(be, cx, (const double*)zc, n, m, V.p);
-    launch_q2_apply(be, cx, h.V2.p, h.tau2.p, n, V.p, m);
+    // multi-GPU (dense truncation): this rank back-transforms its slice of the columns only, the slices are exchanged at the end
+    const bool sliced = shard_cols && cols_sharded(c, m);
+    int64_t c0 = 0, c1 = m;
+    if (sliced) col_slice(c, m, c->shard.rank, &c0, &c1);
+    const int64_t mc = c1 - c0;
+    char* Vs = (char*)V.p + es * (size_t)n * (size_t)c0;
+    if (mc > 0) launch_q2_apply(be, cx, h.V2.p, h.tau2.p, n, Vs, mc);
     const int npan = h.npan;
-    if (npan > 0) {
+    if (npan > 0 && mc > 0) {
       // YTn_p = Y_p (-T_p) for all panels in one grouped launch
       Buf YT(be, (int64_t)es * h.yoff[npan]);
       {
@@ -1380,7 +1407,7 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
         run_gemm(c, cx, pl, h.Yall.p, h.Tall.p, YT.p);
       }
       const int PMAX = MAX_LC;
-      Buf W1p(be, (int64_t)es * B * m * PMAX), W1(be, (int64_t)es * B * m);
+      Buf W1p(be, (int64_t)es * B * mc * PMAX), W1(be, (int64_t)es * B * mc);
       for (int p = npan - 1; p >= 0; --p) {
         const int64_t r0 = (int64_t)p * B + B, len = n - r0;
         // W1 = Y_p^H V[r0:, :]: 64 rows with a long inner dimension -- split K into partial products, add them, then V[r0:, :] += YTn_p W1
@@ -1392,26 +1419,27 @@ Buf heig_vectors(Ctx* c, Heig& h, int64_t m) {
           for (int pp = 0; pp < P; ++pp) {
             const int64_t k0 = pp * chunk, kn = std::min(chunk, len - k0);
             if (kn <= 0) break;
-            g1.begin((int64_t)pp * B * m, B, B, m, GEMM_TRANS_A | (cx ? (uint32_t)GEMM_CONJ_A : 0u));
+            g1.begin((int64_t)pp * B * mc, B, B, mc, GEMM_TRANS_A | (cx ? (uint32_t)GEMM_CONJ_A : 0u));
             g1.seg(h.yoff[p] + k0, len, r0 + k0, n, kn);
             g1.end();
           }
           g1.finish(be, pw1, true, false);
         }
-        { GemmBuilder g(cx); g.begin(r0, n, len, m, GEMM_ACCUM); g.seg(h.yoff[p], len, 0, B, B); g.end(); g.finish(be, pz, false, false); }
-        run_gemm(c, cx, pw1, h.Yall.p, V.p, W1p.p);
+        { GemmBuilder g(cx); g.begin(r0, n, len, mc, GEMM_ACCUM); g.seg(h.yoff[p], len, 0, B, B); g.end(); g.finish(be, pz, false, false); }
+        run_gemm(c, cx, pw1, h.Yall.p, Vs, W1p.p);
         const int np = pw1.tasks.n;
         const void* w1 = W1p.p;
         if (np > 1) {
           const void* xs[MAX_LC];
           double ones[2 * MAX_LC];
-          for (int pp = 0; pp < np; ++pp) { xs[pp] = (const char*)W1p.p + es * (size_t)pp * B * m; ones[2 * pp] = 1.0; ones[2 * pp + 1] = 0.0; }
-          lincomb(be, cx, np, xs, ones, 0.0, 0.0, W1.p, (int64_t)B * m);
+          for (int pp = 0; pp < np; ++pp) { xs[pp] = (const char*)W1p.p + es * (size_t)pp * B * mc; ones[2 * pp] = 1.0; ones[2 * pp + 1] = 0.0; }
+          lincomb(be, cx, np, xs, ones, 0.0, 0.0, W1.p, (int64_t)B * mc);
           w1 = W1.p;
         }
-        run_gemm(c, cx, pz, YT.p, w1, V.p);
+        run_gemm(c, cx, pz, YT.p, w1, Vs);
       }
     }
+    if (sliced) gather_cols(c, V.p, (int64_t)es * n, m);
   } else if (n < wy_min_n()) {
     launch_backtransform(be, h.cplx, h.A.p, n, h.tau.p, h.scl.p, (const double*)zc, m, V.p);
   } else if (wy_upfront()) {
@@ -1587,6 +1615,8 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   // the replicated truncation decision stays in lockstep).  Small bonds are not worth the barriers.
   const ShardState& sh = c->shard;
   const bool spread = tri && sh.world > 1 && sh.mode != 0 && nq > 1 && Dl.total() >= sh.min_dim;
+  // dense models (one block): the column-independent O(n^3) pieces are sliced over the ranks instead (see cols_sharded)
+  const bool dense_cols = tri && !spread && sh.world > 1 && sh.mode != 0 && Dl.total() >= sh.min_dim;
   auto owner = [&](int qm) { return spread ? qm % sh.world : sh.rank; };
   std::vector<Blk> blk(nq);
   // sizes: dir 0 orthogonalises (l,s1) [columns], long index (s2,r) [rows]; dir 1 the other way round
@@ -1640,13 +1670,21 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     if (tri) {
       // rho = X^H X (what ITensor's denmatDecomp forms); its eigenvalues are taken below, for all blocks of the bond at once
       Buf rho(be, (int64_t)es * b.n * b.n);
-      GemmBuilder gb(cplx);
-      gb.begin(0, b.n, b.n, b.n, GEMM_TRANS_A | GEMM_CONJ_A);
-      gb.seg(0, ld, 0, ld, b.rows);
-      gb.end();
-      GemmPlan gp;
-      gb.finish(be, gp, true, false);
-      run_gemm(c, cplx, gp, X.p, X.p, rho.p);
+      {
+        const bool sliced = dense_cols && cols_sharded(c, b.n);
+        int64_t c0 = 0, c1 = b.n;
+        if (sliced) col_slice(c, b.n, sh.rank, &c0, &c1);
+        if (c1 > c0) {
+          GemmBuilder gb(cplx);
+          gb.begin(c0 * b.n, b.n, b.n, c1 - c0, GEMM_TRANS_A | GEMM_CONJ_A);
+          gb.seg(0, ld, c0 * ld, ld, b.rows);
+          gb.end();
+          GemmPlan gp;
+          gb.finish(be, gp, true, false);
+          run_gemm(c, cplx, gp, X.p, X.p, rho.p);
+        }
+        if (sliced) gather_cols(c, rho.p, (int64_t)es * b.n, b.n);
+      }
       b.X = std::move(X);
       rhos.push_back(std::move(rho));
       rho_n.push_back(b.n);
@@ -1767,14 +1805,20 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     if (tri && owner(qm) != sh.rank) {
       b.Vk = Buf(be, (int64_t)es * ldvk * keep);               // filled by the broadcast below
     } else if (tri) {
-      b.Vk = heig_vectors(c, b.h, keep);                       // n x keep, orthonormal
-      GemmBuilder gb(cplx);
-      gb.begin(0, ldxk, b.rows, keep, 0);
-      gb.seg(0, ldxk, 0, ldvk, b.n);
-      gb.end();
-      GemmPlan gp;
-      gb.finish(be, gp, false, false);
-      run_gemm(c, cplx, gp, b.X.p, b.Vk.p, b.Xk.p);            // the weight-carrying factor X V_kept
+      b.Vk = heig_vectors(c, b.h, keep, dense_cols);           // n x keep, orthonormal
+      const bool sliced = dense_cols && cols_sharded(c, keep);
+      int64_t c0 = 0, c1 = keep;
+      if (sliced) col_slice(c, keep, sh.rank, &c0, &c1);
+      if (c1 > c0) {
+        GemmBuilder gb(cplx);
+        gb.begin(c0 * ldxk, ldxk, b.rows, c1 - c0, 0);
+        gb.seg(0, ldxk, c0 * ldvk, ldvk, b.n);
+        gb.end();
+        GemmPlan gp;
+        gb.finish(be, gp, false, false);
+        run_gemm(c, cplx, gp, b.X.p, b.Vk.p, b.Xk.p);          // the weight-carrying factor X V_kept
+      }
+      if (sliced) gather_cols(c, b.Xk.p, (int64_t)es * ldxk, keep);
       res.sweeps = std::max(res.sweeps, b.h.ns_iters);
     } else {
       b.Vk = Buf(be, (int64_t)es * ldvk * keep);

@@ -281,7 +281,7 @@ bool heig_values(Ctx* c, bool cplx, Buf&& A, int64_t n, Heig& h);   // false: ba
 // the same for several independent matrices at once (the charge blocks of one bond): batched tridiagonalisation, then bisection
 // per matrix; As[k] is consumed into hs[k]->A
 bool heig_values_batched(Ctx* c, bool cplx, std::vector<Buf>& As, const std::vector<int64_t>& ns, const std::vector<Heig*>& hs);
-Buf heig_vectors(Ctx* c, Heig& h, int64_t m);                       // n x m column-major, orthonormal, spans the top-m eigenspace
+Buf heig_vectors(Ctx* c, Heig& h, int64_t m, bool shard_cols = false);   // shard_cols: multi-GPU, back-transform a column slice per rank                       // n x m column-major, orthonormal, spans the top-m eigenspace
 
 
 // ---- import / export ---------------------------------------------------------------------------------------------

@@ -59,6 +59,30 @@ def _worker(rank, world, port, mode, q):
                 r2 = np.tensordot(A2, B2, axes=([2], [0]))
                 out["%s trunc %s rec" % (st, d)] = (float(np.abs(r1 - r2).max()) * 1e-3, 1.0)     # eigenvectors near the cut: 1e-8 abs
             B.close()
+        # dense truncation with its column-independent pieces sliced over the ranks (rho, the Q2 / Q1 back-transformation, X V): a dense
+        # bond large enough for the two-stage eigensolver once its threshold is lowered, against the unsharded context
+        os.environ["CB200_TWOSTAGE_MIN_N"] = "256"
+        rng = np.random.default_rng(77)
+        D, d, k = 96, 4, 3
+        z = np.zeros(D, np.int32)
+        for cplx in (False, True):
+            def rnd(*shape):
+                return rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0)
+            E, Wd = np.asfortranarray(rnd(D, k, D)), np.asfortranarray(rnd(k, d, d, k))
+            X = rnd(D * d, D * d) * (10.0 ** (-0.02 * np.arange(D * d)))[None, :]
+            phi = np.asfortranarray((X / np.linalg.norm(X)).reshape(D, d, d, D, order="F"))
+            kw = dict(ql=z, qr=z, qkl=np.zeros(k, np.int32), qkm=np.zeros(k, np.int32), qkr=np.zeros(k, np.int32), site_charges=np.zeros(d, np.int32), nq=1)
+            Bs = cb.Bond(E, Wd, Wd, E, ctx=ctx, **kw)
+            Bu = cb.Bond(E, Wd, Wd, E, ctx=ref, **kw)
+            for dirn in ("left", "right"):
+                A1, B1, _, sp1, te1 = Bs.truncate(phi, dirn, 150, 1e-12)
+                A2, B2, _, sp2, te2 = Bu.truncate(phi, dirn, 150, 1e-12)
+                tag = "dense two-stage %s %s" % ("c128" if cplx else "f64", dirn)
+                out[tag + " m"] = (float(abs(len(sp1) - len(sp2))), 0.0)
+                out[tag + " spec"] = (float(np.abs(np.sort(sp1) - np.sort(sp2)).max()), 0.01)
+                out[tag + " rec"] = (float(np.abs(np.tensordot(A1, B1, axes=([2], [0])) - np.tensordot(A2, B2, axes=([2], [0]))).max()) * 1e-2, 1.0)
+            Bs.close(); Bu.close()
+        del os.environ["CB200_TWOSTAGE_MIN_N"]
         # a short sharded DMRG run (every rank drives the same sweep in lockstep; min_dim=0 shards every bond)
         site, W, qk = common.build_model("golden", "p", 6, [-1.0])
         H = cb.MPO(W, qk, site.charges, nq=1)
