@@ -100,6 +100,10 @@ def _worker(rank, world, port, mode, q):
         e2, _ = cb.dmrg(H, [], psi0, sw, ctx=ctx)
         out["dmrg z3"] = (abs(e1 - e2), abs(e1) * 10)
         q.put((rank, out))
+    except BaseException:                      # report instead of leaving the parent to wait for its queue timeout
+        import traceback
+        q.put((rank, {"worker exception": traceback.format_exc()}))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -112,7 +116,9 @@ def _run(mode):
     procs = [mpc.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
+    for rank, out in res:
+        assert "worker exception" not in out, "rank %d:\n%s" % (rank, out.get("worker exception"))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -149,6 +155,10 @@ def _bench_worker(rank, world, port, q):
         rows = np.array([0, 266, 267, 533, 534, 1066, 1599])           # both ranks' row slices of every sector
         rel = tb._check_rows(ctx, w, rows, 1.0)
         q.put((rank, {"cfg2 rows": (rel, 1e11)}))                      # _check_rows asserted the bound already
+    except BaseException:
+        import traceback
+        q.put((rank, {"worker exception": traceback.format_exc()}))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -165,7 +175,9 @@ def test_cfg2_bench_workload_two_ranks_rows_match_numpy():
     procs = [mpc.Process(target=_bench_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=900) for _ in procs]
+    res = [q.get(timeout=600) for _ in procs]
+    for rank, out in res:
+        assert "worker exception" not in out, "rank %d:\n%s" % (rank, out.get("worker exception"))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
