@@ -72,7 +72,9 @@ def _worker(rank, world, port, mode, q):
             X = rnd(D * d, D * d) * (10.0 ** (-0.02 * np.arange(D * d)))[None, :]
             phi = np.asfortranarray((X / np.linalg.norm(X)).reshape(D, d, d, D, order="F"))
             kw = dict(ql=z, qr=z, qkl=np.zeros(k, np.int32), qkm=np.zeros(k, np.int32), qkr=np.zeros(k, np.int32), site_charges=np.zeros(d, np.int32), nq=1)
-            Bs = cb.Bond(E, Wd, Wd, E, ctx=ctx, **kw)
+            ctx2 = cb.Context(device=dev, lib_path=PRODUCT_LIB)               # landing area sized for THIS phi
+            ctx2.shard(rank, world, mode=mode, landing_bytes=16 * phi.size, min_dim=0)
+            Bs = cb.Bond(E, Wd, Wd, E, ctx=ctx2, **kw)
             Bu = cb.Bond(E, Wd, Wd, E, ctx=ref, **kw)
             for dirn in ("left", "right"):
                 A1, B1, _, sp1, te1 = Bs.truncate(phi, dirn, 150, 1e-12)
