@@ -483,17 +483,126 @@ void nccl_allreduce_sum(Backend* b, void* buf, int64_t n_doubles) {
 }
 
 // ------------------------------------------------------------------------------------------------ mix
-// out[row, oslot, r] = sum_e coef[e] * in[row, islot(e), r].  Two kernels:
-//   mix_smem_kernel: a CTA stages ALL input slots of (row chunk, r) in shared memory once (coalesced, read exactly once
-//                    from HBM) and then forms every output slot from shared memory -> HBM traffic = read T1 + write T2;
-//   mix_kernel     : generic fallback when the panel's inputs do not fit in shared memory (inputs re-read through L1/L2).
+// out[row, oslot, r] = sum_e coef[e] * in[row, islot(e), r].  Three kernels:
+//   mix_smem2_kernel: (default) a CTA stages ALL input slots of (row chunk, r) in shared memory once (coalesced, read exactly once from
+//                    HBM) and forms every output slot from shared memory -> HBM traffic = read T1 + write T2.  The row chunk (32 or 16
+//                    rows) is chosen so that at least TWO CTAs are resident per SM: one CTA's staging copies overlap another's output
+//                    phase (the round-1 kernel, one 512-thread CTA per SM, ran load -> compute -> store back to back and reached 0.35 of
+//                    the HBM copy rate); the descriptor of the next output slot is fetched while the current one is accumulated.
+//   mix_smem_kernel : the round-1 form of the same kernel (CB200_MIX=v1).
+//   mix_kernel      : generic fallback when the panel's inputs do not fit in shared memory (inputs re-read through L1/L2).
 static constexpr int MIX_ROWS = 128;          // fallback kernel: rows per CTA
-static constexpr int MIX_THREADS = 512;       // 16 warps; each warp owns 32 rows x (every 16th output slot)
+static constexpr int MIX_THREADS = 512;       // v1: 16 warps; each warp owns 32 rows x (every 16th output slot)
 static constexpr int MIX_RB = 32;
 static constexpr int MIX_SMEM_MAX = 208 * 1024;
-int mix_rows_per_block(bool cplx, int max_in) {
-  const size_t need = (size_t)max_in * MIX_RB * (cplx ? 16 : 8);
-  return need <= (size_t)MIX_SMEM_MAX ? MIX_RB : MIX_ROWS;
+static constexpr int MIX_SMEM_SM = 227 * 1024;   // shared memory of one SM that CTAs can share (1 KB reserved per CTA on top of its request)
+
+struct MixConfig {
+  int version;      // 2 = mix_smem2_kernel, 1 = mix_smem_kernel, 0 = mix_kernel (generic fallback)
+  int rb;           // rows per CTA
+  int threads;
+  size_t smem;
+};
+static MixConfig mix_config(bool cplx, int max_in) {
+  static const bool v1 = [] { const char* e = getenv("CB200_MIX"); return e && std::string(e) == "v1"; }();
+  static const int force_rb = [] { const char* e = getenv("CB200_MIX_RB"); return e ? atoi(e) : 0; }();
+  static const int force_threads = [] { const char* e = getenv("CB200_MIX_THREADS"); return e ? atoi(e) : 0; }();
+  const size_t es = cplx ? 16 : 8;
+  const size_t need32 = (size_t)max_in * 32 * es;
+  if (need32 > (size_t)MIX_SMEM_MAX && (v1 || (size_t)max_in * 16 * es > (size_t)MIX_SMEM_MAX)) return {0, MIX_ROWS, MIX_ROWS, 0};
+  if (v1) return {1, MIX_RB, MIX_THREADS, need32};
+  // 32 rows when two CTAs of that size fit on an SM, else 16 rows (runs of 256 B for complex128, 128 B for real data)
+  int rb = 2 * (need32 + 1024) <= (size_t)MIX_SMEM_SM ? 32 : 16;
+  if ((force_rb == 16 || force_rb == 32) && (size_t)max_in * force_rb * es <= (size_t)MIX_SMEM_MAX) rb = force_rb;
+  const size_t need = (size_t)max_in * rb * es;
+  const int fit = (int)((size_t)MIX_SMEM_SM / (need + 1024));
+  int threads = fit >= 4 ? 256 : 512;     // few resident CTAs: more warps per CTA keep the SM's load/store queues busy
+  if (force_threads == 256 || force_threads == 512) threads = force_threads;
+  return {2, rb, threads, need};
+}
+int mix_rows_per_block(bool cplx, int max_in) { return mix_config(cplx, max_in).rb; }
+
+template <bool CPLX, int RB, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 4) mix_smem2_kernel(const void* __restrict__ in_, void* __restrict__ out_,
+                                                                                     const MixPanel* __restrict__ panels, int npanels,
+                                                                                     const MixIn* __restrict__ ins, const MixOut* __restrict__ outs,
+                                                                                     const MixEntry* __restrict__ ents) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int G = THREADS / RB;              // groups of RB lanes; a group owns every G-th output slot
+  extern __shared__ __align__(16) char msm[];
+  T* sm = reinterpret_cast<T*>(msm);
+  int lo = 0, hi = npanels - 1;
+  const int blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (panels[mid].blk_begin <= blk) lo = mid; else hi = mid - 1;
+  }
+  const MixPanel p = panels[lo];
+  const int local = blk - p.blk_begin;
+  const int row0 = (local % p.row_chunks) * RB;
+  const int64_t r = local / p.row_chunks;
+  const int lrow = threadIdx.x % RB, grp = threadIdx.x / RB;
+  const bool row_ok = row0 + lrow < p.rows;
+  const T* in = reinterpret_cast<const T*>(in_);
+  // stage every input slot of this (row chunk, r) once: fire-and-forget async copies (zero-filled past the last row)
+  for (int s = grp; s < p.in_count; s += G) {
+    const MixIn mi = ins[p.in_begin + s];
+    const T* src = row_ok ? (in + mi.off + r * mi.rstride + row0 + lrow) : in;
+    if constexpr (CPLX) cp_async16(sm + s * RB + lrow, src, row_ok ? 16 : 0);
+    else cp_async8(sm + s * RB + lrow, src, row_ok ? 8 : 0);
+  }
+  cp_async_commit();
+  // the first output descriptor travels while the copies are in flight
+  int o = p.out_begin + grp;
+  MixOut mo{};
+  if (o < p.out_end) mo = outs[o];
+  cp_async_wait<0>();
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(out_);
+  const T* smr = sm + lrow;
+  while (o < p.out_end) {
+    const int on = o + G;
+    MixOut mn{};
+    if (on < p.out_end) mn = outs[on];          // next descriptor: its latency hides behind this slot's arithmetic
+    double ar = 0.0, ai = 0.0;
+    int e = mo.e_begin;
+    // entries are read as broadcast loads (every lane of the group the same address; L1-resident: all CTAs of a panel share them);
+    // two entries per trip so that both pairs of loads are in flight together; the accumulation order is the entry order
+    for (; e + 1 < mo.e_end; e += 2) {
+      const double2 c0 = __ldg(reinterpret_cast<const double2*>(&ents[e].cre));
+      const int s0 = __ldg(&ents[e].slot);
+      const double2 c1 = __ldg(reinterpret_cast<const double2*>(&ents[e + 1].cre));
+      const int s1 = __ldg(&ents[e + 1].slot);
+      const T v0 = smr[s0 * RB];
+      const T v1 = smr[s1 * RB];
+      if constexpr (!CPLX) {
+        ar = fma(c0.x, v0, ar);
+        ar = fma(c1.x, v1, ar);
+      } else {
+        ar = fma(c0.x, v0.x, ar); ar = fma(-c0.y, v0.y, ar);
+        ai = fma(c0.x, v0.y, ai); ai = fma(c0.y, v0.x, ai);
+        ar = fma(c1.x, v1.x, ar); ar = fma(-c1.y, v1.y, ar);
+        ai = fma(c1.x, v1.y, ai); ai = fma(c1.y, v1.x, ai);
+      }
+    }
+    if (e < mo.e_end) {
+      const double2 c0 = __ldg(reinterpret_cast<const double2*>(&ents[e].cre));
+      const int s0 = __ldg(&ents[e].slot);
+      const T v0 = smr[s0 * RB];
+      if constexpr (!CPLX) {
+        ar = fma(c0.x, v0, ar);
+      } else {
+        ar = fma(c0.x, v0.x, ar); ar = fma(-c0.y, v0.y, ar);
+        ai = fma(c0.x, v0.y, ai); ai = fma(c0.y, v0.x, ai);
+      }
+    }
+    if (row_ok) {
+      if constexpr (!CPLX) out[mo.off + r * mo.rstride + row0 + lrow] = ar;
+      else out[mo.off + r * mo.rstride + row0 + lrow] = make_double2(ar, ai);
+    }
+    mo = mn;
+    o = on;
+  }
 }
 
 template <bool CPLX>
@@ -610,19 +719,50 @@ __global__ void __launch_bounds__(MIX_ROWS) mix_kernel(const void* __restrict__ 
   }
 }
 
+template <bool CPLX, int RB, int THREADS>
+static void launch_mix2(Backend* b, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o, const MixEntry* e,
+                        int blocks, size_t smem) {
+  static bool attr_done = false;     // one device per process (backend_create enforces it)
+  if (!attr_done) {
+    cudaFuncSetAttribute(mix_smem2_kernel<CPLX, RB, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX);
+    attr_done = true;
+  }
+  // ask for a shared-memory carve-out that holds every CTA the register budget admits (2 x 512 or 4 x 256 threads): the overlap between
+  // CTAs is the point of this kernel; the rest of the 256 KB stays L1 for the descriptor / entry lists every CTA of a panel re-reads
+  static int carve_set = -1;
+  const int resident = std::min<int>((int)((size_t)MIX_SMEM_SM / (smem + 1024)), THREADS == 512 ? 2 : 4);
+  const int carve = std::min<int>(100, (int)(((size_t)std::max(resident, 1) * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+  if (carve != carve_set) {
+    cudaFuncSetAttribute(mix_smem2_kernel<CPLX, RB, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    carve_set = carve;
+  }
+  mix_smem2_kernel<CPLX, RB, THREADS><<<blocks, THREADS, smem, b->stream>>>(in, out, p, np, mi, o, e);
+}
+
 void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o,
                 const MixEntry* e, int blocks, int max_in) {
   if (blocks <= 0) return;
-  const size_t need = (size_t)max_in * MIX_RB * (cplx ? 16 : 8);
-  if (need <= (size_t)MIX_SMEM_MAX) {
+  const MixConfig cfg = mix_config(cplx, max_in);
+  if (cfg.version == 2) {
+#define CB_MIX2(C, R, T) launch_mix2<C, R, T>(b, in, out, p, np, mi, o, e, blocks, cfg.smem)
+    if (cplx) {
+      if (cfg.rb == 32) { if (cfg.threads == 512) CB_MIX2(true, 32, 512); else CB_MIX2(true, 32, 256); }
+      else { if (cfg.threads == 512) CB_MIX2(true, 16, 512); else CB_MIX2(true, 16, 256); }
+    } else {
+      if (cfg.rb == 32) { if (cfg.threads == 512) CB_MIX2(false, 32, 512); else CB_MIX2(false, 32, 256); }
+      else { if (cfg.threads == 512) CB_MIX2(false, 16, 512); else CB_MIX2(false, 16, 256); }
+    }
+#undef CB_MIX2
+    CB_LAUNCH_CHECK(b, "mix_smem2_kernel");
+  } else if (cfg.version == 1) {
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(mix_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX);
       cudaFuncSetAttribute(mix_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_MAX);
       attr_done = true;
     }
-    if (cplx) mix_smem_kernel<true><<<blocks, MIX_THREADS, need, b->stream>>>(in, out, p, np, mi, o, e);
-    else mix_smem_kernel<false><<<blocks, MIX_THREADS, need, b->stream>>>(in, out, p, np, mi, o, e);
+    if (cplx) mix_smem_kernel<true><<<blocks, MIX_THREADS, cfg.smem, b->stream>>>(in, out, p, np, mi, o, e);
+    else mix_smem_kernel<false><<<blocks, MIX_THREADS, cfg.smem, b->stream>>>(in, out, p, np, mi, o, e);
     CB_LAUNCH_CHECK(b, "mix_smem_kernel");
   } else {
     if (cplx) mix_kernel<true><<<blocks, MIX_ROWS, 0, b->stream>>>(in, out, p, np, mi, o, e);
