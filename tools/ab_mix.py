@@ -19,7 +19,7 @@ import bench
 bench.WORKLOADS["cfg5s"] = ("haagerupq", "p", 8, [-1.0, 0.0, 0.0], 1200, "haagerupq p j=(-1,0,0) synthetic D=1200 Z3 f64")
 
 old, new = sys.argv[1], sys.argv[2]
-names = sys.argv[3:] or ["tiny", "cfg3", "cfg5s", "cfg4s", "cfg2"]
+names = sys.argv[3:] or ["cfg2", "cfg4s", "cfg3"]
 t_start = time.time()
 TWO_STAGE_AB = {"cfg2": 3000, "cfg3": 1024}      # block sizes 3200 (complex) / 1600 (real): below the default thresholds 4096 / 2048
 for name in names:

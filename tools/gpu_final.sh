@@ -8,8 +8,8 @@ timeout ${AB_TIMEOUT:-120} python tools/ab_mix.py build/ab/libchain_b200_head.so
 echo "[final] ab_mix rc=$?"
 cat ${O}_ab_mix.jsonl
 tail -3 ${O}_ab_mix.err
-PYTHONUNBUFFERED=1 timeout ${TEST_TIMEOUT:-260} python -m pytest -m gpu -q -p no:cacheprovider tests/test_gpu_parity.py tests/test_gpu_shard.py tests/test_gpu_kernels.py \
-  tests/test_adapter.py tests/test_gpu_bench_parity.py > ${O}_pytest.log 2>&1
+PYTHONUNBUFFERED=1 timeout ${TEST_TIMEOUT:-260} python -m pytest -m gpu -q -p no:cacheprovider tests/test_gpu_parity.py tests/test_gpu_shard.py tests/test_adapter.py tests/test_gpu_kernels.py \
+  tests/test_gpu_bench_parity.py > ${O}_pytest.log 2>&1
 echo "[final] pytest rc=$?"
 tail -15 ${O}_pytest.log
 timeout ${BENCH_TIMEOUT:-150} python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-sweep > ${O}_bench_cfg2.json 2> ${O}_bench_cfg2.err
