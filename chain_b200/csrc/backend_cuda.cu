@@ -495,6 +495,7 @@ static constexpr int MIX_ROWS = 128;          // fallback kernel: rows per CTA
 static constexpr int MIX_THREADS = 512;       // v1: 16 warps; each warp owns 32 rows x (every 16th output slot)
 static constexpr int MIX_RB = 32;
 static constexpr int MIX_SMEM_MAX = 208 * 1024;
+static constexpr int MIX_CLUSTER_DEFAULT = 0;     // CTAs per cluster of mix_smem2_kernel (0 = plain launch); CB200_MIX_CLUSTER overrides
 static constexpr int MIX_SMEM_SM = 227 * 1024;   // shared memory of one SM that CTAs can share (1 KB reserved per CTA on top of its request)
 
 struct MixConfig {
@@ -504,9 +505,13 @@ struct MixConfig {
   size_t smem;
 };
 static MixConfig mix_config(bool cplx, int max_in) {
-  static const bool v1 = [] { const char* e = getenv("CB200_MIX"); return e && std::string(e) == "v1"; }();
-  static const int force_rb = [] { const char* e = getenv("CB200_MIX_RB"); return e ? atoi(e) : 0; }();
-  static const int force_threads = [] { const char* e = getenv("CB200_MIX_THREADS"); return e ? atoi(e) : 0; }();
+  // (read per call -- getenv is ~100 ns against a launch: tools/ab_mix.py switches variants inside one process)
+  const char* ev = getenv("CB200_MIX");
+  const bool v1 = ev && std::string(ev) == "v1";
+  const char* er = getenv("CB200_MIX_RB");
+  const int force_rb = er ? atoi(er) : 0;
+  const char* et = getenv("CB200_MIX_THREADS");
+  const int force_threads = et ? atoi(et) : 0;
   const size_t es = cplx ? 16 : 8;
   const size_t need32 = (size_t)max_in * 32 * es;
   if (need32 > (size_t)MIX_SMEM_MAX && (v1 || (size_t)max_in * 16 * es > (size_t)MIX_SMEM_MAX)) return {0, MIX_ROWS, MIX_ROWS, 0};
@@ -526,13 +531,14 @@ template <bool CPLX, int RB, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 4) mix_smem2_kernel(const void* __restrict__ in_, void* __restrict__ out_,
                                                                                      const MixPanel* __restrict__ panels, int npanels,
                                                                                      const MixIn* __restrict__ ins, const MixOut* __restrict__ outs,
-                                                                                     const MixEntry* __restrict__ ents) {
+                                                                                     const MixEntry* __restrict__ ents, int nblocks) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   constexpr int G = THREADS / RB;              // groups of RB lanes; a group owns every G-th output slot
   extern __shared__ __align__(16) char msm[];
   T* sm = reinterpret_cast<T*>(msm);
   int lo = 0, hi = npanels - 1;
   const int blk = blockIdx.x;
+  if (blk >= nblocks) return;                  // grid padded to a multiple of the cluster size (whole CTA leaves: no barrier is missed)
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
     if (panels[mid].blk_begin <= blk) lo = mid; else hi = mid - 1;
@@ -736,7 +742,24 @@ static void launch_mix2(Backend* b, const void* in, void* out, const MixPanel* p
     cudaFuncSetAttribute(mix_smem2_kernel<CPLX, RB, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     carve_set = carve;
   }
-  mix_smem2_kernel<CPLX, RB, THREADS><<<blocks, THREADS, smem, b->stream>>>(in, out, p, np, mi, o, e);
+  // CB200_MIX_CLUSTER=c (2, 4, 8): consecutive CTAs -- adjacent row chunks of the same (slot, r) runs -- are co-scheduled as one thread-block
+  // cluster, so that their requests for neighbouring 256-byte pieces reach the memory system together.  No distributed shared memory is used.
+  const char* ec = getenv("CB200_MIX_CLUSTER");
+  const int cl = ec ? atoi(ec) : MIX_CLUSTER_DEFAULT;
+  if (cl == 2 || cl == 4 || cl == 8) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)((blocks + cl - 1) / cl * cl));
+    lc.blockDim = dim3(THREADS);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = b->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, mix_smem2_kernel<CPLX, RB, THREADS>, in, out, p, np, mi, o, e, blocks) == cudaSuccess) return;
+    (void)cudaGetLastError();     // a cluster shape the device cannot place: plain launch below
+  }
+  mix_smem2_kernel<CPLX, RB, THREADS><<<blocks, THREADS, smem, b->stream>>>(in, out, p, np, mi, o, e, blocks);
 }
 
 void launch_mix(Backend* b, bool cplx, const void* in, void* out, const MixPanel* p, int np, const MixIn* mi, const MixOut* o,
