@@ -384,7 +384,7 @@ def main():
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
         return {"kernel": kernel, "bytes": nbytes, "ms": ms, "GB/s": gbs, "frac": gbs / hbm_peak if gbs else None, "what": what}
     roofline_hbm = {"peak_GB/s": hbm_peak, "peak_source": hbm_src, "kernels": [
-        hbm("mix_smem_kernel", by[1], st_ms[1], "Omega = W_b (x) W_{b+1} applied between the two GEMM stages: |T1| read + |T2| written"),
+        hbm("mix_smem2_kernel", by[1], st_ms[1], "Omega = W_b (x) W_{b+1} applied between the two GEMM stages: |T1| read + |T2| written"),
         hbm("dot_partial+dot_final (multi_dot)", (nvec + 1) * bond.phi_blocks_elems * es, l1[0], "Davidson Gram-Schmidt / penalty overlaps: %d dots in one pass over y" % nvec),
         hbm("lincomb_kernel", (nvec + 2) * bond.phi_blocks_elems * es, l1[1], "Davidson Ritz vector / residual / projector update: dst += sum of %d vectors" % nvec),
         hbm("device copy", 2 * bond.phi_blocks_elems * es, l1[2], "Krylov vector copy (cudaMemcpyAsync D2D)")]}
