@@ -60,6 +60,11 @@ def test_excited_state_in_charge_sector(emu_ctx):
     common.check_excited_qn(emu_ctx)
 
 
+def test_excited_state_in_qn_sector_converged(emu_ctx):
+    """north_star tolerances (energies 1e-10 relative, EE 1e-8) on the penalised Z3 state, at convergence (100 sweeps, ~25 s)."""
+    common.check_excited_qn_converged(emu_ctx)
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("n,m,decay", [(1, 1, 0.0), (2, 1, 0.5), (3, 3, 0.3), (37, 20, 0.4), (90, 90, 0.0), (120, 40, 0.1)])
 def test_hermitian_eigensolver_driver(emu_ctx, cplx, n, m, decay):
