@@ -13,6 +13,8 @@
 #   sweep:ARGS          tools/sweep_bench.py ARGS (comma-separated -> spaces, ';' -> ',')
 #   heig:ARGS           tools/heig_bench.py ARGS
 #   py:FILE             python FILE
+#   abmix[:OLD.so]      tools/ab_mix.py OLD.so (default build/ab/libchain_b200_head.so) against the product library; then tools/ab_mix_variants.py
+#   ncumix[:WORKLOAD]   one ncu --set full capture of the mix kernel (tools/ncu_mix.py, no torch import: starts in seconds)
 TAG=$1; shift
 mkdir -p gpurun_out
 O=gpurun_out/$TAG
@@ -54,6 +56,16 @@ for step in "$@"; do
     heig)
       args=$(echo "$a" | tr ',' ' ')
       timeout 1200 python tools/heig_bench.py $args > ${O}_heig.log 2>&1; echo "[$TAG] heig rc=$?"; tail -30 ${O}_heig.log ;;
+    abmix)
+      old=${a:-build/ab/libchain_b200_head.so}
+      timeout 300 python tools/ab_mix.py $old chain_b200/libchain_b200.so > ${O}_ab_mix.jsonl 2> ${O}_ab_mix.err; echo "[$TAG] ab_mix rc=$?"; cat ${O}_ab_mix.jsonl
+      timeout 300 python tools/ab_mix_variants.py cfg2 cfg4s > ${O}_mix_variants.jsonl 2> ${O}_mix_variants.err; echo "[$TAG] variants rc=$?"; cat ${O}_mix_variants.jsonl ;;
+    ncumix)
+      wl=${a:-cfg2}
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:mix_smem2 -s 1 -c 1 -o ${O}_ncu_mix2_${wl} -f python tools/ncu_mix.py $wl > ${O}_ncu_mix2_${wl}.out 2>&1; echo "[$TAG] ncu rc=$?"
+      ncu -i ${O}_ncu_mix2_${wl}.ncu-rep --page raw --csv > ${O}_ncu_mix2_${wl}_raw.csv 2>/dev/null
+      ncu -i ${O}_ncu_mix2_${wl}.ncu-rep --page details > ${O}_ncu_mix2_${wl}_details.txt 2>/dev/null
+      ncu -i ${O}_ncu_mix2_${wl}.ncu-rep --page source --csv > ${O}_ncu_mix2_${wl}_source.csv 2>/dev/null ;;
     py)
       timeout 1500 python $a > ${O}_py.log 2>&1; echo "[$TAG] py $a rc=$?"; tail -40 ${O}_py.log ;;
     *) echo "unknown step $step" ;;
