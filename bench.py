@@ -389,6 +389,16 @@ def main():
         hbm("lincomb_kernel", (nvec + 2) * bond.phi_blocks_elems * es, l1[1], "Davidson Ritz vector / residual / projector update: dst += sum of %d vectors" % nvec),
         hbm("device copy", 2 * bond.phi_blocks_elems * es, l1[2], "Krylov vector copy (cudaMemcpyAsync D2D)")]}
 
+    # DRAM traffic of the mix launch from the committed ncu --set full summary (cannot be measured outside a profiler), like roofline.traffic
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_mix2_%s_summary.json" % args.workload)) as f:
+            mj = json.load(f)
+        roofline_hbm["kernels"][0]["traffic"] = mj["dram_total_GB"] * 1e9
+        roofline_hbm["kernels"][0]["traffic_source"] = "profiles/r02_ncu_mix2_%s_summary.json (N=1 launch: dram__bytes_read.sum + dram__bytes_write.sum; %s)" % (
+            args.workload, "stalls: long scoreboard on the entry-list loads, L1 hit %.0f %%" % mj["l1_hit_rate_pct"])
+    except Exception:
+        pass
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
