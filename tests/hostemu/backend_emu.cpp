@@ -11,19 +11,44 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
 #include "../../chain_b200/csrc/backend.h"
 
 namespace cb200 {
 
 using cd = std::complex<double>;
 
+constexpr int64_t SYM_FLAG_BYTES = 256;    // arrival flags of the barrier (MAX_PEERS x u64), in front of the two landing halves
+
 struct Backend {
   uint64_t launches = 0;
   double ev[8] = {0};
+  // stand-in for the CUDA-IPC landing areas: one POSIX shared-memory segment per rank, [flags | landing 0 | landing 1], so that the
+  // engine's exchange logic (fused all-gather, broadcasts, slice-wise end-to-end call) runs between real processes on the CPU
+  char* sym = nullptr;
+  size_t sym_bytes = 0;
+  int64_t landing_each = 0;
+  char shm_name[SHARD_HANDLE_BYTES] = {0};
+  char* peer_sym[MAX_PEERS] = {nullptr};
+  size_t peer_bytes[MAX_PEERS] = {0};
+  int rank = 0, world = 1;
+  unsigned long long barrier_seq = 0;
+  std::string err;
+  bool has_err = false;
 };
 
 Backend* backend_create(int, char*, size_t) { return new Backend(); }
-void backend_destroy(Backend* b) { delete b; }
+void backend_destroy(Backend* b) {
+  for (int r = 0; r < MAX_PEERS; ++r)
+    if (b->peer_sym[r] && b->peer_sym[r] != b->sym) munmap(b->peer_sym[r], b->peer_bytes[r]);
+  if (b->sym) { munmap(b->sym, b->sym_bytes); shm_unlink(b->shm_name); }
+  delete b;
+}
 const char* backend_name() { return "host-emulation (tests only)"; }
 int backend_device(Backend*) { return -1; }
 void* dev_alloc(Backend*, size_t bytes) { return std::malloc(bytes ? bytes : 16); }
@@ -33,7 +58,7 @@ void dev_h2d(Backend*, void* d, const void* s, size_t n) { std::memcpy(d, s, n);
 void dev_d2h(Backend*, void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
 void dev_d2d(Backend*, void* d, const void* s, size_t n) { std::memmove(d, s, n); }
 void dev_sync(Backend*) {}
-const char* dev_last_error(Backend*) { return nullptr; }
+const char* dev_last_error(Backend* b) { return b->has_err ? b->err.c_str() : nullptr; }
 uint64_t dev_launch_count(Backend* b) { return b->launches; }
 void dev_event_record(Backend*, int) {}
 float dev_event_elapsed_ms(Backend*, int, int) { return 0.f; }
@@ -694,19 +719,111 @@ void launch_backtransform(Backend* b, bool cplx, const void* A, int64_t n, const
   else backtransform_t<double>((const double*)A, n, (const double*)tau, (const double*)scl, Zt, m, (double*)V);
 }
 
-// multi-GPU plumbing does not exist on the host emulation: only the exchange-free shard mode (0) is testable here
-int shard_alloc(Backend*, int64_t, void*) { return -1; }
-int shard_connect(Backend*, int, int, const void*) { return -1; }
-int64_t shard_landing_bytes(Backend*) { return 0; }
-void* shard_landing(Backend*, int) { return nullptr; }
-void shard_peer_bases(Backend*, int, PeerBases* out) { out->n = 0; }
-void shard_barrier(Backend*) {}
-void launch_gemm_peer(Backend*, bool, int, const void*, const void*, const PeerBases&, const GemmTask*, int, const GemmSeg*, int) {}
+// ---- multi-process plumbing of the host emulation: the p2p exchange (mode 2) over POSIX shared memory, same protocol as the CUDA backend
+// (per-rank segment [flags | landing 0 | landing 1], peers map each other's segments, arrival-counter barrier, broadcasts / all-gather as
+// stores into every landing half followed by the barrier).  NCCL (mode 1) has no stand-in.
+static void emu_err(Backend* b, const std::string& m) { if (!b->has_err) { b->err = m; b->has_err = true; } }
+int shard_alloc(Backend* b, int64_t landing_each, void* handle_out) {
+  if (b->sym) { emu_err(b, "shard_alloc: already allocated"); return -1; }
+  static int counter = 0;
+  landing_each = (landing_each + 255) / 256 * 256;
+  std::snprintf(b->shm_name, sizeof(b->shm_name), "/cb200emu_%d_%d", (int)getpid(), counter++);
+  const int fd = shm_open(b->shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) { emu_err(b, "shard_alloc: shm_open failed"); return -1; }
+  b->sym_bytes = (size_t)(SYM_FLAG_BYTES + 2 * landing_each);
+  if (ftruncate(fd, (off_t)b->sym_bytes) != 0) { close(fd); shm_unlink(b->shm_name); emu_err(b, "shard_alloc: ftruncate failed"); return -1; }
+  void* p = mmap(nullptr, b->sym_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) { shm_unlink(b->shm_name); emu_err(b, "shard_alloc: mmap failed"); return -1; }
+  b->sym = (char*)p;
+  b->landing_each = landing_each;
+  std::memset(b->sym, 0, SYM_FLAG_BYTES);
+  std::memcpy(handle_out, b->shm_name, SHARD_HANDLE_BYTES);
+  return 0;
+}
+int shard_connect(Backend* b, int rank, int world, const void* all_handles) {
+  if (!b->sym || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) { emu_err(b, "shard_connect: bad arguments or no landing area"); return -1; }
+  b->rank = rank; b->world = world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { b->peer_sym[r] = b->sym; b->peer_bytes[r] = b->sym_bytes; continue; }
+    char name[SHARD_HANDLE_BYTES + 1] = {0};
+    std::memcpy(name, (const char*)all_handles + (size_t)r * SHARD_HANDLE_BYTES, SHARD_HANDLE_BYTES);
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) { emu_err(b, "shard_connect: shm_open of a peer segment failed"); return -1; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size != b->sym_bytes) { close(fd); emu_err(b, "shard_connect: peer landing area has a different size"); return -1; }
+    void* p = mmap(nullptr, b->sym_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { emu_err(b, "shard_connect: mmap of a peer segment failed"); return -1; }
+    b->peer_sym[r] = (char*)p; b->peer_bytes[r] = b->sym_bytes;
+  }
+  return 0;
+}
+int64_t shard_landing_bytes(Backend* b) { return b->sym ? b->landing_each : 0; }
+void* shard_landing(Backend* b, int which) { return b->sym ? b->sym + SYM_FLAG_BYTES + (int64_t)(which & 1) * b->landing_each : nullptr; }
+void shard_peer_bases(Backend* b, int which, PeerBases* out) {
+  out->n = b->sym ? b->world : 0;
+  for (int r = 0; r < MAX_PEERS; ++r)
+    out->base[r] = (b->sym && r < b->world) ? b->peer_sym[r] + SYM_FLAG_BYTES + (int64_t)(which & 1) * b->landing_each : nullptr;
+}
+// rank publishes its arrival number in every peer's flag row (release) and waits for every peer's number in its own row (acquire)
+void shard_barrier(Backend* b) {
+  if (b->world <= 1 || !b->sym) return;
+  const unsigned long long seq = ++b->barrier_seq;
+  for (int t = 0; t < b->world; ++t)
+    __atomic_store_n(reinterpret_cast<unsigned long long*>(b->peer_sym[t]) + b->rank, seq, __ATOMIC_RELEASE);
+  struct timespec t0, now;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < b->world; ++t) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(b->sym) + t;
+    while (__atomic_load_n(src, __ATOMIC_ACQUIRE) < seq) {
+      sched_yield();
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if (now.tv_sec - t0.tv_sec > 120) { emu_err(b, "shard_barrier: a peer did not arrive within 120 s"); return; }
+    }
+  }
+  b->launches++;
+}
+void launch_gemm_peer(Backend* b, bool cplx, int, const void* A, const void* B, const PeerBases& peers, const GemmTask* t, int nt,
+                      const GemmSeg* s, int tiles) {
+  if (tiles <= 0 || nt <= 0) return;
+  b->launches++;
+  for (int r = 0; r < peers.n; ++r) {   // the R-stage product (A not transposed, B transposed) stored into every rank's landing half
+    if (cplx) gemm_t<cd>(false, true, (const cd*)A, (const cd*)B, (cd*)peers.base[r], t, nt, s);
+    else gemm_t<double>(false, true, (const double*)A, (const double*)B, (double*)peers.base[r], t, nt, s);
+  }
+}
 int nccl_unique_id(Backend*, void*) { return -1; }
 int nccl_init(Backend*, const void*, int, int) { return -1; }
 void nccl_allreduce_sum(Backend*, void*, int64_t) {}
-void shard_bcast_p2p(Backend*, void*, int64_t, int, int) {}
-void nccl_bcast(Backend*, void*, int64_t, int) {}
-void shard_allgather_p2p(Backend*, void*, int64_t, int64_t, int) {}
+void nccl_bcast(Backend* b, void*, int64_t, int) { emu_err(b, "nccl_bcast: the host emulation has no NCCL stand-in"); }
+void shard_bcast_p2p(Backend* b, void* buf, int64_t bytes, int root, int which) {
+  if (b->world <= 1 || bytes <= 0) return;
+  if (bytes > b->landing_each) { emu_err(b, "shard_bcast_p2p: message larger than the landing area"); return; }
+  if (b->rank == root) {
+    PeerBases pb;
+    shard_peer_bases(b, which, &pb);
+    for (int r = 0; r < pb.n; ++r) std::memcpy(pb.base[r], buf, (size_t)bytes);
+    b->launches++;
+  }
+  shard_barrier(b);
+  if (b->rank != root) std::memcpy(buf, shard_landing(b, which), (size_t)bytes);
+}
+void shard_allgather_p2p(Backend* b, void* buf, int64_t total_bytes, int64_t chunk_bytes, int which) {
+  if (b->world <= 1 || total_bytes <= 0) return;
+  if (total_bytes > b->landing_each || (chunk_bytes & 15)) { emu_err(b, "shard_allgather_p2p: message larger than the landing area / chunk not 16-byte granular"); return; }
+  const int64_t off = std::min<int64_t>((int64_t)b->rank * chunk_bytes, total_bytes);
+  const int64_t mine = std::min<int64_t>(chunk_bytes, total_bytes - off);
+  if (mine > 0) {
+    PeerBases pb;
+    shard_peer_bases(b, which, &pb);
+    for (int r = 0; r < pb.n; ++r) std::memcpy(pb.base[r] + off, (const char*)buf + off, (size_t)mine);
+    b->launches++;
+  }
+  shard_barrier(b);
+  const char* land = (const char*)shard_landing(b, which);
+  if (off > 0) std::memcpy(buf, land, (size_t)off);
+  if (off + mine < total_bytes) std::memcpy((char*)buf + off + mine, land + off + mine, (size_t)(total_bytes - off - mine));
+}
 
 }  // namespace cb200

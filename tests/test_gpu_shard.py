@@ -14,7 +14,7 @@ from conftest import PRODUCT_LIB, ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, mode, q):
+def _worker(rank, world, port, mode, q, lib=PRODUCT_LIB):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -25,14 +25,14 @@ def _worker(rank, world, port, mode, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        dev = rank % torch.cuda.device_count()
+        dev = rank % max(torch.cuda.device_count(), 1)          # (host emulation, tests/test_shard.py: no device)
         out = {}
         for case in (common.BOND_CASES[2], common.BOND_CASES[4]):           # dense real, complex Z3 block-sparse
             st, bc, n, cp, ch, bond = case
             site, W, qk, c = common.capture_bond(st, bc, n, cp, ch, bond)
-            ref = cb.Context(device=dev, lib_path=PRODUCT_LIB)
+            ref = cb.Context(device=dev, lib_path=lib)
             want = common.make_bond(ref, site, qk, c).apply(c["phi"])
-            ctx = cb.Context(device=dev, lib_path=PRODUCT_LIB)
+            ctx = cb.Context(device=dev, lib_path=lib)
             ctx.shard(rank, world, mode=mode, landing_bytes=16 * c["phi"].size, min_dim=0)
             B = common.make_bond(ctx, site, qk, c)
             for rep in range(3):                                              # both landing halves + reuse
@@ -72,7 +72,7 @@ def _worker(rank, world, port, mode, q):
             X = rnd(D * d, D * d) * (10.0 ** (-0.02 * np.arange(D * d)))[None, :]
             phi = np.asfortranarray((X / np.linalg.norm(X)).reshape(D, d, d, D, order="F"))
             kw = dict(ql=z, qr=z, qkl=np.zeros(k, np.int32), qkm=np.zeros(k, np.int32), qkr=np.zeros(k, np.int32), site_charges=np.zeros(d, np.int32), nq=1)
-            ctx2 = cb.Context(device=dev, lib_path=PRODUCT_LIB)               # landing area sized for THIS phi
+            ctx2 = cb.Context(device=dev, lib_path=lib)               # landing area sized for THIS phi
             ctx2.shard(rank, world, mode=mode, landing_bytes=16 * phi.size, min_dim=0)
             Bs = cb.Bond(E, Wd, Wd, E, ctx=ctx2, **kw)
             Bu = cb.Bond(E, Wd, Wd, E, ctx=ref, **kw)
@@ -110,15 +110,15 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-def _run(mode):
+def _run(mode, lib=PRODUCT_LIB, timeout=300):
     import torch.multiprocessing as mp
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = 29500 + os.getpid() % 2000
-    procs = [mpc.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    procs = [mpc.Process(target=_worker, args=(r, 2, port, mode, q, lib)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=timeout) for _ in procs]
     for rank, out in res:
         assert "worker exception" not in out, "rank %d:\n%s" % (rank, out.get("worker exception"))
     for p in procs:

@@ -117,3 +117,12 @@ def test_eigensolver_refuses_exchange_free_sharding(emu_ctx):
     psi0 = common.to_cb(common.warm_start(site, W, 6, 0, seed=3))
     with pytest.raises(cb.ChainB200Error):
         cb.dmrg(H, [], psi0, cb.Sweeps(1, 20, 1e-8), ctx=ctx)
+
+
+def test_two_processes_p2p_exchange_on_host_emulation():
+    """The exchange-dependent host logic between two REAL processes on the CPU: the body of tests/test_gpu_shard.py's worker (fused
+    all-gather of the R-stage, slice-wise end-to-end call, Davidson, truncation spread over the ranks / sliced by columns, sharded DMRG
+    runs in lockstep) on the host-emulation library, whose p2p landing areas are POSIX shared-memory segments with the CUDA backend's
+    barrier protocol; rendezvous over torch.distributed's gloo backend."""
+    import test_gpu_shard
+    test_gpu_shard._run("p2p", lib=EMU_LIB, timeout=900)
