@@ -54,7 +54,9 @@ def lowest_levels(site_type, bc, n, U, couplings, k=6, charge=None):
         idx = np.nonzero(total_charge(site, n) == charge)[0]
         H = H[idx][:, idx]
     dim = H.shape[0]
-    if dim <= 600:
+    if dim <= 2000:
+        # dense: a Krylov method returns one copy of a degenerate level unless rounding happens to split it -- how many copies of the 12-fold
+        # lowest level of the open haagerupq chain (6^4 = 1296 states) came back depended on the BLAS thread count
         w = np.linalg.eigvalsh(H.toarray())
         return w[:k]
     w = spla.eigsh(H, k=k, which="SA", tol=1e-13, ncv=max(40, 4 * k), return_eigenvectors=False)

@@ -325,6 +325,29 @@ def check_excited_qn_converged(ctx, nsweep=100):
 
 
 
+def check_truncation_survives_ns_failure(ctx, case, monkeypatch):
+    """split_bond's way out when heig_vectors cannot orthonormalise its inverse-iteration basis (forced: CB200_NS_MAXIT=-1 reports
+    non-convergence whatever the basis looks like): the block's kept columns come from the one-sided Jacobi SVD of the gathered matrix instead.
+    Same kept dimension per sector, same spectrum and truncation error, an isometry, and the same two-site tensor A.B as the default path."""
+    st, bc, n, cp, q, bond = case
+    site, W, qk, c = capture_bond(st, bc, n, cp, q, bond)
+    B = make_bond(ctx, site, qk, c)
+    phi = c["phi"] / np.linalg.norm(c["phi"])
+    for d in ("left", "right"):
+        monkeypatch.delenv("CB200_NS_MAXIT", raising=False)
+        A0, B0, qm0, spec0, terr0 = B.truncate(phi, d, 40, 1e-8)
+        monkeypatch.setenv("CB200_NS_MAXIT", "-1")
+        A1, B1, qm1, spec1, terr1 = B.truncate(phi, d, 40, 1e-8)
+        assert np.array_equal(qm0, qm1) and terr0 == terr1 and np.array_equal(spec0, spec1)     # decided before the vectors are formed
+        iso = A1 if d == "left" else B1
+        m = len(spec1)
+        g = np.tensordot(iso.conj(), iso, axes=([0, 1], [0, 1])) if d == "left" else np.tensordot(iso, iso.conj(), axes=([1, 2], [1, 2]))
+        assert np.abs(g - np.eye(m)).max() <= 1e-12
+        assert np.abs(np.tensordot(A1, B1, axes=([2], [0])) - np.tensordot(A0, B0, axes=([2], [0]))).max() <= 1e-9
+    monkeypatch.delenv("CB200_NS_MAXIT", raising=False)
+    B.close()
+
+
 def check_ground_state_kat(ctx, st, bc, n, cp, q, tol, nrep=12, seed=1):
     """Warm-up + reps of src/dmrg.h:538-609 through the C ABI; compare with the ED known answer."""
     site, W, qk = build_model(st, bc, n, cp)

@@ -110,3 +110,21 @@ def test_hermitian_eigensolver_two_stage_driver(emu_ctx, monkeypatch, cplx, n, m
 @pytest.mark.parametrize("direction", ["left", "right"])
 def test_true_svd_branch_below_cutoff_1e12(emu_ctx, cplx, direction):
     common.check_true_svd_branch(emu_ctx, cplx, direction, D=48)
+
+
+@pytest.mark.parametrize("case", [common.BOND_CASES[2], common.BOND_CASES[4]], ids=["dense-real", "z3-complex"])
+def test_truncation_falls_back_to_jacobi_when_orthonormalisation_fails(emu_ctx, monkeypatch, case):
+    common.check_truncation_survives_ns_failure(emu_ctx, case, monkeypatch)
+
+
+def test_dmrg_run_on_the_jacobi_fallback_matches_oracle(emu_ctx, monkeypatch):
+    """A whole run in which EVERY truncation takes the fallback: energy still 1e-10 from the oracle's."""
+    from oracle import dmrg as od
+    site, W, qk = common.build_model("haagerupq", "p", 6, [-1.0, 0.0, 0.0])
+    H = cb.MPO(W, qk, site.charges, nq=site.nq)
+    psi0 = od.product_mps(site, 6, 0, np.random.default_rng(0))
+    sw = ([10, 20, 40], [1e-6, 1e-7, 1e-8])
+    eo, _ = od.dmrg(W, [], psi0, od.Sweeps(4, *sw))
+    monkeypatch.setenv("CB200_NS_MAXIT", "-1")
+    eg, _ = cb.dmrg(H, [], common.to_cb(psi0), cb.Sweeps(4, *sw), ctx=emu_ctx)
+    assert abs(eo - eg) <= 1e-10 * abs(eo), (eo, eg)
