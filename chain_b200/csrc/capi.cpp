@@ -111,8 +111,66 @@ int cb200_shard_setup(cb200_ctx* ctx, int32_t rank, int32_t world, int32_t mode,
   });
 }
 
+// ---------------------------------------------------------------------------------------------- argument validation
+// Everything a caller can get wrong WITHOUT lying about how much memory it owns is refused here with CB200_ERR_INVALID, in front of any
+// allocation or launch (tools/fuzz_abi.py drives these under ASan/UBSan).  CB200_MAX_NQ / CB200_MAX_SITES / CB200_MAX_SITE_DIM are stated
+// in include/chain_b200.h.
+static void check_group(int nq, int d, const char* who) {
+  if (nq < 1 || nq > CB200_MAX_NQ) fail(CB200_ERR_INVALID, std::string(who) + ": nq must be in [1, " + std::to_string(CB200_MAX_NQ) + "]");
+  if (d < 1 || d > CB200_MAX_SITE_DIM) fail(CB200_ERR_INVALID, std::string(who) + ": site dimension d must be in [1, " + std::to_string(CB200_MAX_SITE_DIM) + "]");
+}
+static void check_chain(int n, const void* site, const void* link, const char* who) {
+  if (n < 1 || n > CB200_MAX_SITES) fail(CB200_ERR_INVALID, std::string(who) + ": n must be in [1, " + std::to_string(CB200_MAX_SITES) + "]");
+  if (!site || !link) fail(CB200_ERR_INVALID, std::string(who) + ": null site / link array");
+}
+static void check_index(const cb200_index* ix, const char* who) {
+  if (!ix) fail(CB200_ERR_INVALID, std::string(who) + ": null index");
+  if (ix->dim < 0 || ix->dim > ((int64_t)1 << 31)) fail(CB200_ERR_INVALID, std::string(who) + ": index dimension out of range");
+}
+static void check_tensor(const cb200_tensor& t, int rank, const std::string& who) {
+  if (t.rank != rank) fail(CB200_ERR_INVALID, who + " has rank " + std::to_string(t.rank) + ", expected " + std::to_string(rank));
+  if (t.dtype != 0 && t.dtype != 1) fail(CB200_ERR_INVALID, who + ": dtype must be 0 (float64) or 1 (complex128)");
+  if (!t.data) fail(CB200_ERR_INVALID, who + " has no data");
+}
+static void check_site_charges(int nq, int d, const int32_t* site_charge) {
+  if (!site_charge) return;                       // NULL = all zero (the dense case)
+  for (int s = 0; s < d; ++s)
+    if (site_charge[s] < 0 || site_charge[s] >= nq) fail(CB200_ERR_INVALID, "site charge label out of range");
+}
+
+// the MPO of a C-ABI call as the engine takes it (shared by cb200_dmrg and cb200_mps_mpo_element)
+static MpoIn to_mpo_in(const cb200_mpo* H, int nq, const int32_t* site_charge) {
+  check_group(nq, H->d, "MPO");
+  check_chain(H->n, H->site, H->link, "MPO");
+  check_site_charges(nq, H->d, site_charge);
+  MpoIn mi;
+  mi.n = H->n; mi.nq = nq; mi.d = H->d; mi.site_charge = site_charge;
+  mi.link.resize(H->n + 1);
+  for (int j = 0; j <= H->n; ++j) {
+    check_index(&H->link[j], "MPO link");
+    mi.link[j] = IndexMap::from_labels(nq, H->link[j].dim, H->link[j].charge);
+  }
+  mi.site.resize(H->n);
+  for (int j = 0; j < H->n; ++j) {
+    const cb200_tensor& t = H->site[j];
+    check_tensor(t, 4, "MPO site tensor " + std::to_string(j));
+    if (t.dims[0] != H->link[j].dim || t.dims[1] != H->d || t.dims[2] != H->d || t.dims[3] != H->link[j + 1].dim)
+      fail(CB200_ERR_INVALID, "MPO site tensor " + std::to_string(j) + " has inconsistent dimensions");
+    if (j == 0) mi.cplx = t.dtype == 1;
+    else if ((t.dtype == 1) != mi.cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside the MPO");
+    mi.site[j] = t.data;
+  }
+  return mi;
+}
+
 // ---------------------------------------------------------------------------------------------- coarse: dmrg
 static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
+  if (!m) fail(CB200_ERR_INVALID, "null MPS");
+  check_group(nq, d, "MPS");
+  check_chain(m->n, m->site, m->link, "MPS");
+  if (m->nq != nq) fail(CB200_ERR_INVALID, "MPS: nq differs from the symmetry group of the call");
+  if (m->ortho_center < 0 || m->ortho_center > m->n) fail(CB200_ERR_INVALID, "MPS: ortho_center must be 0 (unknown) or a 1-based site number");
+  for (int j = 0; j <= m->n; ++j) check_index(&m->link[j], "MPS link");
   HostMPS h;
   h.n = m->n;
   h.center = m->ortho_center;
@@ -124,11 +182,11 @@ static HostMPS to_host_mps(const cb200_mps* m, int nq, int d, bool* cplx) {
   *cplx = false;
   for (int j = 0; j < m->n; ++j) {
     const cb200_tensor& t = m->site[j];
-    if (t.rank != 3 || t.dims[0] != m->link[j].dim || t.dims[1] != d || t.dims[2] != m->link[j + 1].dim)
+    check_tensor(t, 3, "MPS site tensor " + std::to_string(j));
+    if (t.dims[0] != m->link[j].dim || t.dims[1] != d || t.dims[2] != m->link[j + 1].dim)
       fail(CB200_ERR_INVALID, "MPS site tensor " + std::to_string(j) + " has inconsistent dimensions");
     if (j == 0) *cplx = t.dtype == 1;
     else if ((t.dtype == 1) != *cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside one MPS");
-    if (!t.data) fail(CB200_ERR_INVALID, "MPS site tensor " + std::to_string(j) + " has no data");
     h.site[j] = t.data;
   }
   return h;
@@ -138,20 +196,16 @@ int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_
                const cb200_sweep* sweeps, int32_t nsweep, double weight, double* energy, cb200_result** out) {
   if (!ctx) return CB200_ERR_INVALID;
   return guard(ctx, [&] {
-    if (!H || !psi0 || !sweeps || !energy || !out || nsweep < 0 || nprev < 0) fail(CB200_ERR_INVALID, "null argument");
-    MpoIn mi;
-    mi.n = H->n; mi.nq = H->nq; mi.d = H->d; mi.site_charge = H->site_charge;
-    mi.link.resize(H->n + 1);
-    for (int j = 0; j <= H->n; ++j) mi.link[j] = IndexMap::from_labels(H->nq, H->link[j].dim, H->link[j].charge);
-    mi.site.resize(H->n);
-    for (int j = 0; j < H->n; ++j) {
-      const cb200_tensor& t = H->site[j];
-      if (t.rank != 4 || t.dims[0] != H->link[j].dim || t.dims[1] != H->d || t.dims[2] != H->d || t.dims[3] != H->link[j + 1].dim)
-        fail(CB200_ERR_INVALID, "MPO site tensor " + std::to_string(j) + " has inconsistent dimensions");
-      if (j == 0) mi.cplx = t.dtype == 1;
-      else if ((t.dtype == 1) != mi.cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside the MPO");
-      mi.site[j] = t.data;
+    if (!H || !psi0 || !sweeps || !energy || !out || nsweep < 0 || nprev < 0 || (nprev > 0 && !prev)) fail(CB200_ERR_INVALID, "null argument");
+    if (H->n != psi0->n) fail(CB200_ERR_INVALID, "MPO and MPS have different lengths");
+    for (int i = 0; i < nsweep; ++i) {
+      const cb200_sweep& w = sweeps[i];
+      if (w.maxdim < 1 || w.mindim < 0 || w.niter < 0) fail(CB200_ERR_INVALID, "sweep " + std::to_string(i) + ": maxdim >= 1, mindim >= 0 and niter >= 0 are required");
+      if (!(w.cutoff >= 0) || std::isinf(w.cutoff)) fail(CB200_ERR_INVALID, "sweep " + std::to_string(i) + ": cutoff must be a finite number >= 0");
+      if (std::isnan(w.noise)) fail(CB200_ERR_INVALID, "sweep " + std::to_string(i) + ": noise is NaN");
     }
+    if (!std::isfinite(weight)) fail(CB200_ERR_INVALID, "weight must be finite");
+    MpoIn mi = to_mpo_in(H, H->nq, H->site_charge);
     bool pc = false;
     HostMPS p0 = to_host_mps(psi0, H->nq, H->d, &pc);
     std::vector<HostMPS> pv;
@@ -164,6 +218,7 @@ int cb200_dmrg(cb200_ctx* ctx, const cb200_mpo* H, const cb200_mps* prev, int32_
     std::vector<SweepParams> sw(nsweep);
     for (int i = 0; i < nsweep; ++i) sw[i] = {sweeps[i].maxdim, sweeps[i].mindim, sweeps[i].niter, sweeps[i].cutoff, sweeps[i].noise};
     auto r = run_dmrg(&ctx->c, mi, pv, pvc, p0, pc, sw, weight);
+    if (!std::isfinite(r->energy)) fail(CB200_ERR_NOCONV, "dmrg: the energy is not finite (NaN / Inf in the MPO or the start state?)");
     *energy = r->energy;
     cb200_result* res = new cb200_result();
     res->r = std::move(r);
@@ -176,6 +231,7 @@ int cb200_mps_entropies(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const i
   return guard(ctx, [&] {
     bool cx = false;
     HostMPS h = to_host_mps(psi, psi->nq, d, &cx);
+    check_site_charges(psi->nq, d, site_charge);
     std::vector<double> ee = mps_entropies(&ctx->c, psi->nq, d, site_charge, h, cx);
     for (size_t i = 0; i < ee.size(); ++i) out[i] = ee[i];
   });
@@ -186,6 +242,8 @@ int cb200_mps_translate(cb200_ctx* ctx, const cb200_mps* psi, int32_t d, const i
   return guard(ctx, [&] {
     bool cx = false;
     HostMPS h = to_host_mps(psi, psi->nq, d, &cx);
+    check_site_charges(psi->nq, d, site_charge);
+    if (!(cutoff >= 0)) fail(CB200_ERR_INVALID, "translate: cutoff must be >= 0");
     auto r = mps_translate(&ctx->c, psi->nq, d, site_charge, h, cx, cutoff);
     cb200_result* res = new cb200_result();
     res->r = std::move(r);
@@ -199,6 +257,7 @@ int cb200_mps_overlap(cb200_ctx* ctx, const cb200_mps* a, const cb200_mps* b, in
     if (a->nq != b->nq) fail(CB200_ERR_INVALID, "overlap: the two states use different symmetry groups");
     bool ca = false, cbb = false;
     HostMPS ha = to_host_mps(a, a->nq, d, &ca), hb = to_host_mps(b, b->nq, d, &cbb);
+    check_site_charges(a->nq, d, site_charge);
     const cplx_t z = mps_overlap(&ctx->c, a->nq, d, site_charge, ha, ca, hb, cbb);
     re_im[0] = z.real(); re_im[1] = z.imag();
   });
@@ -208,19 +267,7 @@ int cb200_mps_mpo_element(cb200_ctx* ctx, const cb200_mps* bra, const cb200_mpo*
   if (!ctx || !bra || !O || !ket || !re_im) return CB200_ERR_INVALID;
   return guard(ctx, [&] {
     if (O->nq != 1 || bra->nq != 1 || ket->nq != 1) fail(CB200_ERR_INVALID, "mpo_element: dense (nq = 1) operands only");
-    MpoIn mi;
-    mi.n = O->n; mi.nq = 1; mi.d = O->d; mi.site_charge = nullptr;
-    mi.link.resize(O->n + 1);
-    for (int j = 0; j <= O->n; ++j) mi.link[j] = IndexMap::from_labels(1, O->link[j].dim, nullptr);
-    mi.site.resize(O->n);
-    for (int j = 0; j < O->n; ++j) {
-      const cb200_tensor& t = O->site[j];
-      if (t.rank != 4 || t.dims[0] != O->link[j].dim || t.dims[1] != O->d || t.dims[2] != O->d || t.dims[3] != O->link[j + 1].dim)
-        fail(CB200_ERR_INVALID, "MPO site tensor " + std::to_string(j) + " has inconsistent dimensions");
-      if (j == 0) mi.cplx = t.dtype == 1;
-      else if ((t.dtype == 1) != mi.cplx) fail(CB200_ERR_INVALID, "mixed dtypes inside the MPO");
-      mi.site[j] = t.data;
-    }
+    MpoIn mi = to_mpo_in(O, 1, nullptr);
     bool cbr = false, ck = false;
     HostMPS hb = to_host_mps(bra, 1, O->d, &cbr), hk = to_host_mps(ket, 1, O->d, &ck);
     const cplx_t z = mps_mpo_element(&ctx->c, O->d, hb, cbr, mi, hk, ck);
@@ -309,6 +356,11 @@ int cb200_bond_create(cb200_ctx* ctx, int32_t dtype, int32_t nq, int32_t d, cons
   cb200_bond* bp = new cb200_bond();
   int rc = guard(ctx, [&] {
     cb200_bond& B = *bp;
+    if (dtype != 0 && dtype != 1) fail(CB200_ERR_INVALID, "bond_create: dtype must be 0 (float64) or 1 (complex128)");
+    check_group(nq, d, "bond_create");
+    check_site_charges(nq, d, site_charge);
+    for (const cb200_index* ix : {l, r, kl, km, kr}) check_index(ix, "bond_create");
+    if (!L || !W1 || !W2 || !R) fail(CB200_ERR_INVALID, "bond_create: null environment / MPO tensor");
     B.ctx = ctx; B.cplx = dtype == 1; B.nq = nq;
     B.S = SiteInfo::make(nq, d, site_charge);
     B.l = IndexMap::from_labels(nq, l->dim, l->charge);

@@ -1593,6 +1593,9 @@ static void shard_broadcast(Ctx* c, void* buf, int64_t bytes, int root) {
 SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl, const void* phi, int dir, int64_t maxdim,
                        int64_t mindim, double cutoff, bool exact_rank, bool normalize, int use_svd) {
   Backend* be = c->be;
+  // (a maxdim < 1 would walk ITensor's `while (n >= maxdim)` loop off the front of the spectrum: refused here for every caller)
+  if (maxdim < 1 || mindim < 0 || !(cutoff >= 0) || (dir != 0 && dir != 1))
+    fail(-2, "split_bond: dir must be 0 / 1, maxdim >= 1, mindim >= 0 and cutoff a number >= 0");
   const int nq = pl.L.nq, d = S->d;
   const Grading& Dl = pl.L;
   const Grading& Dr = pl.R;

@@ -29,6 +29,12 @@ extern "C" {
 
 typedef struct cb200_ctx cb200_ctx;
 
+/* Argument limits (anything outside is refused with CB200_ERR_INVALID before any work is done, as are NULL arrays, ranks / dtypes / dimensions
+ * that contradict each other, charge labels outside [0, nq), maxdim < 1, a NaN or negative cutoff ...: tools/fuzz_abi.py). */
+#define CB200_MAX_NQ 64            /* order N of the Z_N symmetry (Chain uses 1 and 3) */
+#define CB200_MAX_SITES 65536      /* chain length */
+#define CB200_MAX_SITE_DIM 1024    /* physical dimension d (Chain: 2 and 6) */
+
 enum cb200_status {
   CB200_OK = 0,
   CB200_ERR_NO_DEVICE = -1,

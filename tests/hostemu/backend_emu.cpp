@@ -67,13 +67,51 @@ int gemm_tile_n(bool, int mode) { return mode == GEMM_TILE_WIDE ? 128 : (mode ==
 int mix_rows_per_block(bool, int) { return 128; }
 int copy_elems_per_block() { return 2048; }
 
+// Rounding audit (tools/rounding_audit.py): with CB200_EMU_ROUNDING=<seed> every GEMM result is perturbed before it is stored by what a
+// DIFFERENT summation order would have changed: u * ulps * 2^-53 * (sum_k |a_k b_k|) / sqrt(K), u uniform in [-1, 1) per real component
+// (a random walk of K roundings of terms of the average magnitude; for complex numbers both components get the perturbation of the whole
+// |a||b| sum -- normwise, which is what the 3M complex kernels of the product library do to a small component beside a large one).
+// CB200_EMU_ROUNDING_ULPS (default 1) scales it, to measure the margin of the tolerances in the shared test bodies against arithmetic that
+// differs from this serial loop the way the GPU's tile order / k-splitting / 3M products do.
+static uint64_t emu_rounding_seed() {
+  const char* e = getenv("CB200_EMU_ROUNDING");
+  return e && *e ? strtoull(e, nullptr, 10) : 0;
+}
+static double emu_rounding_ulps() {
+  const char* e = getenv("CB200_EMU_ROUNDING_ULPS");
+  return e && *e ? atof(e) : 1.0;
+}
+static inline double emu_u(uint64_t seed, uint64_t& ctr) {   // splitmix64 -> uniform in [-1, 1)
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * ++ctr;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(int64_t)z * (1.0 / 9223372036854775808.0);
+}
+// (the stream is keyed by the element's offset in C, so the same call repeated gives the same bits -- the suite asserts bit-identity between
+// some call forms, as the GPU kernels guarantee it)
+static inline double emu_perturb(double v, double mag, uint64_t seed, uint64_t key) {
+  uint64_t ctr = key * 2;
+  return v + mag * emu_u(seed, ctr);
+}
+static inline cd emu_perturb(cd v, double mag, uint64_t seed, uint64_t key) {
+  uint64_t ctr = key * 2;
+  const double u0 = emu_u(seed, ctr), u1 = emu_u(seed, ctr);
+  return cd(v.real() + mag * u0, v.imag() + mag * u1);
+}
+
 template <class T>
 static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTask* tasks, int nt, const GemmSeg* segs) {
+  const uint64_t rseed = emu_rounding_seed();
+  const double rulps = rseed ? emu_rounding_ulps() : 0.0;
   for (int ti = 0; ti < nt; ++ti) {
     const GemmTask& t = tasks[ti];
     const bool conjA = t.flags & GEMM_CONJ_A, acc = t.flags & GEMM_ACCUM, conjOut = t.flags & GEMM_CONJ_OUT;
     if (bool(t.flags & GEMM_TRANS_A) != ta && t.seg_count) { std::fprintf(stderr, "emu: transA flag mismatch\n"); std::abort(); }
     std::vector<T> tmp((size_t)t.M * t.N, T(0));
+    std::vector<double> mag(rseed ? (size_t)t.M * t.N : 0, 0.0);   // sum_k |a_k b_k| per output element (rounding audit only)
+    int64_t ktot = 0;
+    for (int s = 0; s < t.seg_count; ++s) ktot += segs[t.seg_begin + s].K;
     for (int s = 0; s < t.seg_count; ++s) {
       const GemmSeg& g = segs[t.seg_begin + s];
       for (int n = 0; n < t.N; ++n)
@@ -84,6 +122,7 @@ static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTas
             T a = ta ? A[g.a_off + k + (int64_t)m * g.lda] : A[g.a_off + m + (int64_t)k * g.lda];
             if constexpr (std::is_same<T, cd>::value) { if (conjA) a = std::conj(a); }
             tmp[(size_t)m + (size_t)n * t.M] += a * b;
+            if (rseed) mag[(size_t)m + (size_t)n * t.M] += std::abs(a) * std::abs(b);
           }
         }
     }
@@ -95,6 +134,7 @@ static void gemm_t(bool ta, bool tb, const T* A, const T* B, T* C, const GemmTas
         const int64_t nc = (int64_t)(n % t.chunk) + (int64_t)(n / t.chunk) * t.chunk_stride;
         T* p = (t.flags & GEMM_TRANS_C) ? &C[t.c_off + nc + (int64_t)m * t.ldc]
                : (n < t.n_split) ? &C[t.c_off + mc + (int64_t)n * t.ldc] : &C[t.c_off2 + mc + (int64_t)(n - t.n_split) * t.ldc];
+        if (rseed) v = emu_perturb(v, rulps * 0x1p-53 * mag[(size_t)m + (size_t)n * t.M] / std::sqrt((double)std::max<int64_t>(ktot, 1)), rseed, (uint64_t)(p - C));
         *p = acc ? *p + v : v;
       }
   }
