@@ -385,8 +385,11 @@ int cb200_bond_create(cb200_ctx* ctx, int32_t dtype, int32_t nq, int32_t d, cons
 void cb200_bond_free(cb200_bond* b) { delete b; }
 
 int cb200_bond_set_penalty(cb200_bond* B, int32_t nprev, const void* const* o, double weight) {
-  if (!B) return CB200_ERR_INVALID;
+  if (!B || nprev < 0 || (nprev > 0 && !o)) return CB200_ERR_INVALID;
   return guard(B->ctx, [&] {
+    for (int p = 0; p < nprev; ++p)
+      if (!o[p]) fail(CB200_ERR_INVALID, "set_penalty: null vector");
+    if (!std::isfinite(weight)) fail(CB200_ERR_INVALID, "set_penalty: weight must be finite");
     B->pen.clear();
     B->b.pen.clear();
     const size_t es = B->cplx ? 16 : 8;
@@ -628,6 +631,7 @@ int cb200_bond_env_update(cb200_bond* B, int32_t dir, int32_t m, const int32_t* 
   if (!B || !AorB || !out) return CB200_ERR_INVALID;
   return guard(B->ctx, [&] {
     Ctx* c = &B->ctx->c;
+    if ((dir != 0 && dir != 1) || m < 1) fail(CB200_ERR_INVALID, "env_update: dir must be 0 / 1 and m >= 1");
     IndexMap mid = IndexMap::from_labels(B->nq, m, charges_mid);
     DevSite3 T;
     DevEnv E;

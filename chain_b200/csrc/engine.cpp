@@ -417,21 +417,34 @@ OmegaMap build_omega(const HostW& W1, const HostW& W2) {
 }
 
 std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2) {
-  auto mix = [](uint64_t h, const void* p, size_t bytes) {   // FNV-1a over 8-byte words
+  // bucket key: every 8-byte word goes through a full-avalanche finaliser first (a plain multiply-xor chain never moves the
+  // exponent bits of round numbers like 1.0 or 2.0 downwards, so 0/1-valued tensors collided); equality is checked on a hit anyway
+  auto mix = [](uint64_t h, const void* p, size_t bytes) {
     const uint64_t* w = (const uint64_t*)p;
-    for (size_t i = 0; i < bytes / 8; ++i) { h ^= w[i]; h *= 0x100000001b3ull; }
+    for (size_t i = 0; i < bytes / 8; ++i) {
+      uint64_t k = w[i];
+      k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+      h = (h ^ k) * 0x100000001b3ull;
+      h ^= h >> 29;
+    }
     return h;
   };
   uint64_t h = 0xcbf29ce484222325ull;
   h = mix(h, W1.w.data(), W1.w.size() * sizeof(cplx_t));
   h = mix(h, W2.w.data(), W2.w.size() * sizeof(cplx_t));
-  const uint64_t dims[4] = {(uint64_t)W1.KL.total(), (uint64_t)W1.KR.total(), (uint64_t)W2.KR.total(), (uint64_t)W1.d};
+  const int64_t dims[4] = {W1.KL.total(), W1.KR.total(), W2.KR.total(), (int64_t)W1.d};
   h = mix(h, dims, sizeof(dims));
-  auto it = c->omega_cache.find(h);
-  if (it != c->omega_cache.end()) return it->second;
-  if (c->omega_cache.size() > 512) c->omega_cache.clear();
+  auto range = c->omega_cache.equal_range(h);
+  for (auto it = range.first; it != range.second; ++it) {
+    const Ctx::OmegaEntry& e = it->second;
+    if (std::equal(dims, dims + 4, e.dims) && e.w1 == W1.w && e.w2 == W2.w) return e.om;
+  }
+  if (c->omega_cache.size() >= 64) c->omega_cache.clear();      // (an entry keeps copies of both tensors: <= 0.8 MB at k = 26, d = 6)
   auto om = std::make_shared<OmegaMap>(build_omega(W1, W2));
-  c->omega_cache[h] = om;
+  Ctx::OmegaEntry e;
+  e.w1 = W1.w; e.w2 = W2.w; e.om = om;
+  std::copy(dims, dims + 4, e.dims);
+  c->omega_cache.emplace(h, std::move(e));
   return om;
 }
 
@@ -756,6 +769,7 @@ DavidsonResult davidson(Bond& b, void* phi, int niter) {
   const int miniter = 1;
   const int maxiter = niter;
   const int actual_maxiter = (int)std::min<int64_t>(maxiter, n - 1);
+  if (niter < 0) fail(-2, "davidson: niter must be >= 0");
   if (actual_maxiter + 1 > MAX_LC) fail(-2, "davidson: niter too large for this build (max " + std::to_string(MAX_LC - 1) + ")");
   // exchange-free shard mode returns PARTIAL products (the caller sums the ranks' vectors): an eigensolver on them would be silently wrong
   if (b.sharded && c->shard.mode == 0)
@@ -1715,7 +1729,9 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
       std::iota(b.order.begin(), b.order.end(), 0);
       std::stable_sort(b.order.begin(), b.order.end(), [&](int64_t x, int64_t y) { return b.jo.w[x] > b.jo.w[y]; });
       b.wd.resize(b.n);
-      for (int64_t k = 0; k < b.n; ++k) b.wd[k] = b.jo.w[b.order[k]];
+      // (an SVD of a rows x n block has min(rows, n) singular values -- ITensor's svd() returns no more; the column norms beyond that are
+      // rounding noise ~1e-33 which a cutoff of exactly 0 would otherwise keep)
+      for (int64_t k = 0; k < b.n; ++k) b.wd[k] = k < b.rows ? b.jo.w[b.order[k]] : 0.0;
     }
   }
   if (tri && !rhos.empty()) {

@@ -171,9 +171,16 @@ struct Ctx {
   std::string err;
   Timers tm;
   ShardState shard;
-  // Omega maps of MPO site pairs seen by this context, keyed by a hash of the two tensors: the reference calls dmrg() once per
-  // sweep with the same H (src/dmrg.h:596), so the planner's only O(k^2 d^4) host step is paid once per run, not per sweep
-  std::map<uint64_t, std::shared_ptr<OmegaMap>> omega_cache;
+  // Omega maps of MPO site pairs seen by this context: the reference calls dmrg() once per sweep with the same H (src/dmrg.h:596),
+  // so the planner's only O(k^2 d^4) host step is paid once per run, not per sweep.  The hash only picks the bucket; a hit is
+  // confirmed by comparing the two tensors element for element (tools/fuzz_dmrg.py found two different 0/1-valued boundary
+  // tensors with equal 64-bit hashes: a wrong Omega, silently).
+  struct OmegaEntry {
+    std::vector<cplx_t> w1, w2;
+    int64_t dims[4];
+    std::shared_ptr<OmegaMap> om;
+  };
+  std::multimap<uint64_t, OmegaEntry> omega_cache;
   // persistent scratch (matvec intermediates, Krylov basis): one buffer per slot, grown to the largest request and kept, so
   // a sweep does not churn multi-GB temporaries through the allocator at every bond
   std::vector<Buf> ws;

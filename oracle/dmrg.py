@@ -101,6 +101,9 @@ def heff_flops(Dl, Dr, d, kl, km, kr, cplx=False):
 
 
 # ----------------------------------------------------------------------------- Davidson (A.4)
+RANDOMIZED = [0]   # number of times davidson() replaced a dependent residual by a random vector
+
+
 def davidson(matvec, phi, maxiter=2, errgoal=1e-14, miniter=1, rng=None):
     size = phi.size
     actual_maxiter = min(maxiter, size - 1)
@@ -141,6 +144,7 @@ def davidson(matvec, phi, maxiter=2, errgoal=1e-14, miniter=1, rng=None):
         qn = np.linalg.norm(q)
         passes = 1
         while qn < 1e-10 and passes <= 3:
+            RANDOMIZED[0] += 1           # (test diagnostics: from here on the result depends on the generator, in ITensor too)
             q = (rng or np.random.default_rng(ii)).standard_normal(q.shape).astype(q.dtype)
             vq = [np.vdot(V[k], q) for k in range(ii + 1)]
             for k in range(ii + 1):
@@ -191,7 +195,7 @@ def truncate_probs(P, maxdim, mindim, cutoff):
     return m, truncerr, docut
 
 
-def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff, use_svd=False, normalize=True):
+def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff, use_svd=False, normalize=True, diag=None):
     """svdBond of A.5. phi[l,s1,s2,r]; returns (A_b, A_{b+1}, qmid, spectrum, truncerr).
     direction 'left'  (Fromleft):  A_b is the isometry, A_{b+1} carries the weight (normalised).
     direction 'right' (Fromright): A_{b+1} is the isometry, A_b carries the weight."""
@@ -222,6 +226,9 @@ def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff,
         blocks.append((q, idx, w, u))
     pooled = np.sort(np.concatenate([b[2] for b in blocks]))[::-1]
     m, truncerr, docut = truncate_probs(pooled, maxdim, mindim, cutoff)
+    if diag is not None:   # (test diagnostics: how close the cut runs to a multiplet / to zero-weight states)
+        diag["cut_gap"] = float((pooled[m - 1] - pooled[m]) / pooled[m - 1]) if m < len(pooled) and pooled[m - 1] > 0 else 1.0
+        diag["last_kept_rel"] = float(pooled[m - 1] / pooled[0]) if pooled[0] > 0 else 0.0
     Us, qmid, kept = [], [], []
     for q, idx, w, u in blocks:
         keep = int((w > docut).sum())
@@ -334,12 +341,13 @@ def dmrg(W, prev_states, psi0, sweeps, weight=1.0, stats=None, matvec_hook=None)
                 matvec_hook(dict(bond=b, dir=direction, L=L, W1=W1, W2=W2, R=R, phi=phi, proj=proj, ql=psi.q[b - 1], qr=psi.q[b + 1],
                                  sweep=sw, maxdim=maxdim, mindim=mindim, cutoff=cutoff, niter=niter, weight=weight))
             energy, phi, nmv = davidson(mv, phi, maxiter=niter)
+            dg = {}
             A1, A2, qmid, spec, terr = split_bond(phi, psi.q[b - 1], psi.q[b + 1], sq, nq, direction,
-                                                  maxdim, mindim, cutoff, use_svd=use_svd)
+                                                  maxdim, mindim, cutoff, use_svd=use_svd, diag=dg)
             psi.A[i], psi.A[i + 1], psi.q[b] = A1, A2, qmid
             if stats is not None:
                 stats.append(dict(sweep=sw, bond=b, dir=direction, energy=energy, m=len(qmid), truncerr=terr,
-                                  nmv=nmv, dims=(phi.shape[0], phi.shape[3])))
+                                  nmv=nmv, dims=(phi.shape[0], phi.shape[3]), cut_gap=dg["cut_gap"], last_kept_rel=dg["last_kept_rel"]))
             if direction == "left":
                 LE[b] = update_left(L, A1, W1)
                 for p, P in enumerate(prev_states):
