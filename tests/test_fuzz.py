@@ -62,3 +62,22 @@ def test_context_reuse_across_models_rebuilds_omega():
     used = cb.Context(lib_path=EMU_LIB)
     run(used, 41)
     assert run(used, 77) == fresh
+
+
+def test_measurement_entry_points_on_random_states(emu_ctx, monkeypatch, capsys):
+    """tools/fuzz_measure.py, 150 draws: entropies / overlap / exact translation / <a|O|b> of random flux-conserving MPS (unsorted link labels,
+    empty sectors, rank-deficient links, both storage layouts) against dense state-vector arithmetic."""
+    import fuzz_measure
+    monkeypatch.setattr(sys, "argv", ["fuzz_measure.py", "150", "0"])
+    rc = fuzz_measure.main()
+    out = capsys.readouterr().out
+    assert rc == 0 and "failures: 0" in out, out
+
+
+def test_bond_update_on_random_structures_with_penalties_and_virtual_ranks(emu_ctx, monkeypatch, capsys):
+    """tools/fuzz_bond.py, 25 draws: one bond update on random ragged structures incl. complex penalty vectors and 2-8 virtual ranks."""
+    import fuzz_bond
+    monkeypatch.setattr(sys, "argv", ["fuzz_bond.py", "25", "0"])
+    rc = fuzz_bond.main()
+    out = capsys.readouterr().out
+    assert rc == 0 and "failures: 0" in out, out

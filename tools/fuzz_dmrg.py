@@ -118,7 +118,7 @@ def main():
     from conftest import EMU_LIB
     ndraw = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    ctx = cb.Context(lib_path=EMU_LIB)
+    ctx = cb.Context(lib_path=os.environ.get("CB200_FUZZ_LIB", EMU_LIB))      # (tools/asan_engine.py's instrumented build, for a run under ASan)
     nfail = nedge = 0
     worst = dict(energy=0.0, terr=0.0, ee=0.0, ov=0.0)
     t0 = time.time()
