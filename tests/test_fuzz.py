@@ -81,3 +81,12 @@ def test_bond_update_on_random_structures_with_penalties_and_virtual_ranks(emu_c
     rc = fuzz_bond.main()
     out = capsys.readouterr().out
     assert rc == 0 and "failures: 0" in out, out
+
+
+def test_sharded_dmrg_is_bit_identical_to_unsharded_three_processes():
+    """tools/fuzz_shard.py, 12 draws on 3 real processes (gloo rendezvous, p2p exchange over shared memory, every bond sharded): the sharded
+    engine reproduces the unsharded run bit for bit and all ranks stay in lockstep."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_shard.py"), "12", "3", "0"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "failures: 0" in p.stdout and "worst energy gap to the unsharded run 0.00e+00" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
