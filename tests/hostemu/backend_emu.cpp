@@ -51,7 +51,14 @@ void backend_destroy(Backend* b) {
 }
 const char* backend_name() { return "host-emulation (tests only)"; }
 int backend_device(Backend*) { return -1; }
-void* dev_alloc(Backend*, size_t bytes) { return std::malloc(bytes ? bytes : 16); }
+// CB200_EMU_POISON=1: every allocation is filled with 0xFF bytes (NaN as a double, -1 as an integer) -- cudaMallocAsync hands out recycled,
+// non-zero memory, while a fresh malloc() of a large block is zero pages: anything the engine reads before writing it shows up as NaN here.
+void* dev_alloc(Backend*, size_t bytes) {
+  static const bool poison = [] { const char* e = getenv("CB200_EMU_POISON"); return e && atoi(e) != 0; }();
+  void* p = std::malloc(bytes ? bytes : 16);
+  if (p && poison) std::memset(p, 0xFF, bytes ? bytes : 16);
+  return p;
+}
 void dev_free(Backend*, void* p) { std::free(p); }
 void dev_memset0(Backend*, void* p, size_t bytes) { std::memset(p, 0, bytes); }
 void dev_h2d(Backend*, void* d, const void* s, size_t n) { std::memcpy(d, s, n); }
