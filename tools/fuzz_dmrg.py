@@ -4,7 +4,7 @@ randomly drawn problems, bond by bond.
 The committed parity cases use the documented models and Chain's schedule (maxdim 10..200, cutoff 1e-5..1e-9, niter 2, mindim 1).  This draws
 what those never reach: all three site types, every boundary condition of src/dmrg.h (p, o, s, sp), lengths 3..7, random couplings and U, every
 total charge, `niter` 1..4, `mindim` 1..5 (also above maxdim), maxdim schedules that shrink as well as grow and go down to 1, cutoffs from 1e-3
-to 1e-11 and 0, 1..3 sweeps, product-state and warm starts, and a penalised second state with a random weight.  Compared per bond update: the
+to 1e-11 and 0, 1..3 sweeps, product-state and warm starts, dense and block-packed start states, and a penalised second state with a random weight.  Compared per bond update: the
 kept dimension m, the Davidson eigenvalue and the truncation error; at the end energy, overlap of the states and the entanglement entropies.
 These schedules leave the state far from converged, where a rounding-level difference is amplified from bond to bond (the oracle against ITSELF
 from a start perturbed by 1e-15 drifts to 1e-6 within three sweeps at maxdim 2-3), so the yardstick is the oracle's own sensitivity: every draw
@@ -76,7 +76,11 @@ def run_one(ctx, p, seed):
         psi1.A = [a * (1 + 1e-15 * prng.standard_normal(a.shape)) for a in psi1.A]
         eo2, po2 = od.dmrg(W, done_o, psi1, swo, weight=p["weight"], stats=so2)
         info = cb.DmrgInfo()
-        eg, pg = cb.dmrg(H, done_g, common.to_cb(psi0), swg, weight=p["weight"], ctx=ctx, info=info)
+        packed = bool(np.random.default_rng(5 + seed + s).random() < 0.3)     # ITensor's block-packed QDense storage at the boundary (layout = 1)
+        start = cb.PackedMPS.from_dense(common.to_cb(psi0), site.charges) if packed else common.to_cb(psi0)
+        eg, pg = cb.dmrg(H, done_g, start, swg, weight=p["weight"], ctx=ctx, info=info)
+        if packed:
+            pg = pg.to_dense()
         if len(so) != len(info.stats):
             return "FAIL", "number of bond updates %d vs %d" % (len(so), len(info.stats)), worst
         self_e = self_t = 0.0
