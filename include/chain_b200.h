@@ -81,7 +81,9 @@ typedef struct cb200_tensor {
   int32_t dtype;              /* 0 f64, 1 c128 */
   int32_t rank;               /* 3 (MPS) or 4 (MPO) */
   int64_t dims[4];
-  const void* data;           /* column-major, dense with exact zeros in forbidden blocks */
+  const void* data;           /* column-major, dense with exact zeros in forbidden blocks (elements of an MPS tensor that sit in a
+                               * charge-forbidden block are ignored, not diagnosed: ITensor's QN storage cannot hold them; an MPO tensor
+                               * with such elements is refused) */
 } cb200_tensor;
 
 /* per-sweep parameters: what itensor::Sweeps holds (src/dmrg.h:538-543, :589-593) */
