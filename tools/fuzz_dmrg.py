@@ -31,6 +31,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def draw(rng):
+    if os.environ.get("CB200_FUZZ_BIG") == "1":
+        # fewer, larger problems: density-matrix blocks of order 250-500, where (with CB200_TWOSTAGE_MIN_N=256) the two-stage eigensolver and,
+        # under tools/fuzz_shard.py, the column-sliced dense truncation take over
+        st = ["haagerup", "haagerupq"][rng.integers(2)]
+        cp = [float(np.round(rng.uniform(-1.5, 1.5), 3)) for _ in range(3)]
+        return dict(st=st, bc=["p", "o"][rng.integers(2)], n=6, cp=cp, U=2.0, q=int(rng.integers(3)) if st == "haagerupq" else 0, nsweep=1,
+                    maxd=[int(rng.choice([45, 60, 80]))], cut=[float(rng.choice([1e-8, 1e-10]))], niter=[2], mind=[1], product=False, nstates=1,
+                    weight=1000.0)
     st = ["golden", "haagerup", "haagerupq"][rng.integers(3)]
     bc = ["p", "o", "s", "sp"][rng.integers(4)]
     n = int(rng.integers(3, 8 if st == "golden" else 6))
