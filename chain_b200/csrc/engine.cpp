@@ -1796,7 +1796,6 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
     dev_d2h(be, o3, out3.p, 24);
     m = (int64_t)o3[0]; terr = o3[1]; docut = o3[2];
   }
-  (void)m;
   SplitResult res;
   res.truncerr = terr;
   res.mid = Grading(nq);
@@ -1804,7 +1803,10 @@ SplitResult split_bond(Ctx* c, bool cplx, const SiteInfo* S, const PhiLayout& pl
   for (int qm = 0; qm < nq; ++qm) {
     Blk& b = blk[qm];
     int64_t keep = 0;
-    while (keep < b.n && b.wd[keep] > docut) ++keep;
+    // ITensor's diagHImpl / svdImpl: a tensor without QNs keeps exactly the m columns truncate() decided on (reduceCols(UU, m)); a QN tensor
+    // keeps, block by block, the eigenvalues above the pooled threshold docut (which drops a near-degenerate multiplet the cut would split)
+    if (nq == 1) keep = std::min<int64_t>(m, b.n);
+    else while (keep < b.n && b.wd[keep] > docut) ++keep;
     b.keep = keep;
     total_keep += keep;
   }

@@ -231,7 +231,10 @@ def split_bond(phi, ql, qr, site_charges, nq, direction, maxdim, mindim, cutoff,
         diag["last_kept_rel"] = float(pooled[m - 1] / pooled[0]) if pooled[0] > 0 else 0.0
     Us, qmid, kept = [], [], []
     for q, idx, w, u in blocks:
-        keep = int((w > docut).sum())
+        # ITensor's diagHImpl / svdImpl: a tensor WITHOUT QNs keeps exactly the m columns truncate() decided on (`reduceCols(UU, m)`); a QN
+        # tensor keeps, block by block, the eigenvalues above the pooled threshold docut -- which drops a (near-)degenerate multiplet the cut
+        # would have split (docut is raised by 1e-3 P(m-1) then) and any eigenvalue that is not positive.
+        keep = min(m, len(w)) if nq == 1 else int((w > docut).sum())
         if keep == 0:
             continue
         Uq = np.zeros((Mx.shape[0], keep), dtype=phi.dtype)

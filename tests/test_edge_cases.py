@@ -1,6 +1,9 @@
 """Edge cases and error behaviour of the boundary (host logic on the emulation backend; the CUDA library shares the engine):
 boundary conditions the reference supports (src/golden_site.cpp:68-117: p / o / s / d / sp), ragged and empty charge
 sectors, bond dimension 1, invalid input -> status codes (no exception crosses the C ABI, src/dmrg.h:454 contract)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -98,3 +101,42 @@ def test_invalid_inputs_give_status_codes(emu_ctx):
     # the context is still usable after the errors
     en, _ = cb.dmrg(H, [], psi, cb.Sweeps(2, 10, 1e-8), ctx=emu_ctx)
     assert np.isfinite(en)
+
+
+def test_cut_inside_a_degenerate_pair_dense_keeps_m_qn_drops_the_pair(emu_ctx):
+    """ITensor's two truncation conventions (diagHImpl / svdImpl): a tensor WITHOUT QNs keeps exactly the m columns truncate() decided on
+    (`reduceCols(UU, m)`), a QN tensor keeps per block the eigenvalues above the pooled threshold docut -- and docut is raised by 1e-3 P(m-1)
+    when the cut would split a (near-)degenerate pair, which drops the whole pair.  Designed spectrum (0.4, 0.3, 0.1, 0.1, 0.05, 0.05), maxdim 3."""
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    import fuzz_truncate as ft
+    p = np.array([0.4, 0.3, 0.1, 0.1, 0.05, 0.05])
+    for nq, want in ((1, 3), (3, 2)):
+        rng = np.random.default_rng(4)
+        d = 6 if nq == 3 else 2
+        sq = np.array([0, 1, 2, 0, 1, 2], np.int32) if nq == 3 else np.zeros(d, np.int32)
+        Dl = Dr = 6
+        ql = (np.arange(Dl) % nq).astype(np.int32)
+        qr = (np.arange(Dr) % nq).astype(np.int32)
+        qm = (np.arange(len(p)) % nq).astype(np.int32)
+        rowq = ((ql[:, None] + sq[None, :]) % nq).reshape(-1)
+        colq = ((qr[None, :] - sq[:, None]) % nq).reshape(-1)
+        U, V = ft.block_isometry(rng, rowq, qm, nq, False), ft.block_isometry(rng, colq, qm, nq, False)
+        phi = np.asfortranarray(((U * np.sqrt(p)) @ V.T).reshape(Dl, d, d, Dr))
+        k = 2
+        E = lambda D, q: rng.standard_normal((D, k, D)) * (q[:, None, None] == q[None, None, :])
+        W = np.zeros((k, d, d, k))
+        for a in range(k):
+            W[a, :, :, a] = np.eye(d)
+        zk = np.zeros(k, np.int32)
+        B = cb.Bond(np.asfortranarray(E(Dl, ql)), W, W, np.asfortranarray(E(Dr, qr)), ql=ql, qr=qr, qkl=zk, qkm=zk, qkr=zk, site_charges=sq, nq=nq, ctx=emu_ctx)
+        for direction in ("left", "right"):
+            A1, B1, qg, spec, terr = B.truncate(phi, direction, 3, 1e-12)
+            A2, B2, qo, speco, terro = od.split_bond(phi, ql, qr, sq, nq, direction, 3, 1, 1e-12)
+            assert len(spec) == len(speco) == want, (nq, direction, len(spec), len(speco))
+            assert abs(terr - 0.2) <= 1e-12 and abs(terro - 0.2) <= 1e-12          # truncate() itself discards 0.1 + 0.05 + 0.05 either way
+            iso = A1 if direction == "left" else B1
+            g = np.tensordot(iso.conj(), iso, axes=([0, 1], [0, 1])) if direction == "left" else np.tensordot(iso, iso.conj(), axes=([1, 2], [1, 2]))
+            assert np.abs(g - np.eye(want)).max() <= 1e-12
+        B.close()
