@@ -439,7 +439,8 @@ std::shared_ptr<OmegaMap> cached_omega(Ctx* c, const HostW& W1, const HostW& W2)
     const Ctx::OmegaEntry& e = it->second;
     if (std::equal(dims, dims + 4, e.dims) && e.w1 == W1.w && e.w2 == W2.w) return e.om;
   }
-  if (c->omega_cache.size() >= 64) c->omega_cache.clear();      // (an entry keeps copies of both tensors: <= 0.8 MB at k = 26, d = 6)
+  if (c->omega_cache.size() >= 256) c->omega_cache.clear();     // (an entry keeps copies of both tensors: <= 0.8 MB at k = 26, d = 6;
+                                                                 //  a sine-square-deformed chain has L - 1 distinct site pairs)
   auto om = std::make_shared<OmegaMap>(build_omega(W1, W2));
   Ctx::OmegaEntry e;
   e.w1 = W1.w; e.w2 = W2.w; e.om = om;
